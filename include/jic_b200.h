@@ -1,0 +1,152 @@
+/*
+ * jic_b200.h -- C ABI of the B200-native particle hot path that replaces JAX-in-Cell's explicit (Boris) time loop.
+ *
+ * The reference (uwplasma/JAX-in-Cell) has no FFI of its own: its hot path is Python traced under one jax.jit.
+ * The seam this library plugs into is the scan at jaxincell/_simulation.py:228-257 (initial carry -> lax.scan of
+ * jaxincell/_algorithms.py:17-95 `Boris_step` -> six stacked histories).  Each entry point below names the reference
+ * code it replaces.  Everything is plain C: opaque handle, POD structs, raw pointers, sizes, `void*` CUDA streams.
+ *
+ * Conventions
+ *   - return value: 0 = JIC_OK, negative = error; text via jic_last_error(ctx) (or jic_last_error(NULL) for
+ *     failures of jic_create / jic_simulate_host).  Nothing throws across this boundary.
+ *   - "real" = double when params.dtype == JIC_F64 (the reference's only precision, _simulation.py:32), float for JIC_F32.
+ *   - device pointers unless the function name ends in _host.  Buffers are owned by the caller; the library keeps
+ *     no reference to them after the call returns, except the history pointers of jic_run, which must stay valid
+ *     until the stream has drained.
+ *   - all work is enqueued on the given stream; no entry point except *_host, jic_create, jic_comm_init and
+ *     jic_destroy synchronises.  Scratch memory, the NCCL communicator and CUDA graphs belong to the context.
+ *   - a context is bound to one device and must not be used from two host threads at once; distinct contexts are
+ *     independent (no global mutable state).
+ *   - array layouts are the reference's: particles (N,3) row-major, fields (G,3) row-major, rho (G,).
+ */
+#ifndef JIC_B200_H
+#define JIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JIC_ABI_VERSION 1
+#define JIC_MAX_SPECIES 8
+#define JIC_MAX_STRIDES 8
+
+enum jic_status {
+  JIC_OK = 0,
+  JIC_ERR_INVALID_ARGUMENT = -1,
+  JIC_ERR_CUDA = -2,
+  JIC_ERR_BAD_STATE = -3,
+  JIC_ERR_NCCL = -4,
+  JIC_ERR_UNSUPPORTED = -5
+};
+
+enum jic_dtype { JIC_F64 = 0, JIC_F32 = 1 };
+
+/* Particle store.
+ *   INDEXED keeps particle p in slot p for the whole run (needed for the reference's (T,N,3) histories); one thread per
+ *           particle, deposition through global atomics or a CTA-private shared-memory copy of the grid.
+ *   BINNED  keeps particles binned by (species, cell) and re-bins them inside the push kernel every step, so that
+ *           gather coefficients and deposition stencils are CTA-uniform and accumulate in registers (the fast path
+ *           for >= ~1e6 particles).  Particle order is not preserved; particle histories are not available. */
+enum jic_engine { JIC_ENGINE_INDEXED = 0, JIC_ENGINE_BINNED = 1 };
+
+/* Boundary codes of jaxincell/_parameters/_domain_parameters.py:53-56 */
+enum jic_bc { JIC_BC_PERIODIC = 0, JIC_BC_REFLECTIVE = 1, JIC_BC_ABSORBING = 2 };
+
+enum jic_deposit { JIC_DEPOSIT_AUTO = 0, JIC_DEPOSIT_GLOBAL_ATOMICS = 1, JIC_DEPOSIT_SHARED_GRID = 2 };
+
+/* One contiguous block of identical macro-particles (jaxincell/_state_initialization.py:242-261:
+ * species are concatenated block-wise; charge and mass are already multiplied by the weight, q/m is not). */
+typedef struct jic_species {
+  int64_t count;          /* particles of this species ON THIS RANK */
+  double charge;          /* q_s * w   [C]  */
+  double mass;            /* m_s * w   [kg] */
+  double charge_to_mass;  /* q_s / m_s      */
+} jic_species;
+
+/* Static description of a run: what build_domain_state (jaxincell/_state_initialization.py:27-49), the four BC
+ * integers (_simulation.py:208-211) and solver_parameters (filter, relativistic) hand to Boris_step. */
+typedef struct jic_params {
+  uint32_t struct_bytes;  /* = sizeof(jic_params); checked */
+  int32_t dtype;          /* jic_dtype */
+  int32_t engine;         /* jic_engine */
+  int32_t device;         /* CUDA ordinal, -1 = current device */
+  int32_t n_grid;         /* G */
+  int32_t n_species;      /* <= JIC_MAX_SPECIES */
+  double length, length_y, length_z; /* box_size */
+  double dx, dt;          /* as the host computed them: dx = L/G, dt = CFL*dx/c */
+  double grid_first, grid_last; /* grid[0], grid[-1] of linspace(-L/2+dx/2, L/2-dx/2, G): edge tests use these bits */
+  int32_t particle_bc_left, particle_bc_right, field_bc_left, field_bc_right;
+  int32_t filter_passes;  /* >= 0 */
+  int32_t n_filter_strides;
+  int32_t filter_strides[JIC_MAX_STRIDES];
+  double filter_alpha;
+  int32_t relativistic;   /* solver_parameters["relativistic"] */
+  int32_t track_yz;       /* also advance and wrap y,z (only needed for the full (N,3) position outputs) */
+  int32_t deposit;        /* jic_deposit (INDEXED engine) */
+  int32_t steps_per_graph;/* steps captured per CUDA graph, 0 = default */
+  int32_t reserved[8];    /* must be zero */
+} jic_params;
+
+/* Where jic_run writes the per-step outputs (jaxincell/_algorithms.py:93, stacked at _simulation.py:256-257).
+ * Row t of every history is the state after step t of THIS call.  NULL = not recorded. */
+typedef struct jic_outputs {
+  void* electric_field;   /* real (T,G,3) */
+  void* magnetic_field;   /* real (T,G,3) */
+  void* current_density;  /* real (T,G,3) */
+  void* charge_density;   /* real (T,G)   */
+  void* positions;        /* real (T,N,3), INDEXED engine with track_yz only */
+  void* velocities;       /* real (T,N,3), INDEXED engine only */
+} jic_outputs;
+
+typedef struct jic_context jic_context;
+
+int jic_abi_version(void);
+const char* jic_last_error(const jic_context* ctx);
+
+/* Allocate all device state for `params` (replaces the carry construction at _simulation.py:228-231). */
+int jic_create(const jic_params* params, const jic_species* species, jic_context** out);
+int jic_destroy(jic_context* ctx);
+
+/* Multi-GPU: particles are sharded across ranks, fields replicated; one all-reduce of the raw [Jx,Jy,Jz,rho] grid per
+ * step.  Rank 0 creates an id (128 bytes), the host exchanges it (torch.distributed / MPI / files), every rank calls
+ * jic_comm_init before jic_initialize.  No reference counterpart (the reference is single-device). */
+int jic_comm_unique_id(void* id_128_bytes);
+int jic_comm_init(jic_context* ctx, const void* id_128_bytes, int rank, int world_size);
+
+/* External fields, float32 (G,3) as the reference stores them (_state_initialization.py:382-392); NULL = zeros. */
+int jic_set_external_fields(jic_context* ctx, const float* external_E, const float* external_B, void* stream);
+
+/* Initial particles at t=0: x0, v0 real (N,3).  Performs the leap-frog start-up of _simulation.py:217-225
+ * (x_{+1/2} with the full particle BC, x_{-1/2} with the post-BC velocity), the initial charge deposit and
+ * Gauss solve of _state_initialization.py:374-378, and the first current deposit of _algorithms.py:29-32. */
+int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* stream);
+
+/* Advance n_steps (the lax.scan of _simulation.py:253 over Boris_step).  Captured as CUDA graphs; no host sync. */
+int jic_run(jic_context* ctx, int64_t n_steps, const jic_outputs* outputs, void* stream);
+
+/* Current grid state: E, B (G,3) at integer time, filtered J (G,3) and rho (G,) of the last step.  Any may be NULL. */
+int jic_get_fields(jic_context* ctx, void* E, void* B, void* J, void* rho, void* stream);
+/* Initial fields (output key "fields") and post-BC initial velocities (key "initial_velocities", INDEXED only). */
+int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* initial_velocities, void* stream);
+/* Current particles: x_{n+1/2} (what the pusher carries) and v_n, real (N,3); y,z are zero unless track_yz.
+ * BINNED engine: bin order, not input order.  alive[N] (uint8, optional) is 0 for absorbed particles. */
+int jic_get_particles(jic_context* ctx, void* x_half, void* v, uint8_t* alive, void* stream);
+/* Sum over local particles of 0.5*m*v^2 (jaxincell/_diagnostics.py:131-138) into *kinetic_energy (device double). */
+int jic_kinetic_energy(jic_context* ctx, double* kinetic_energy, void* stream);
+/* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
+int64_t jic_launch_count(const jic_context* ctx);
+
+/* Whole-simulation call with HOST buffers (the drop-in for Simulation.run's device part, _simulation.py:169-257):
+ * host->device copies of x0, v0 and the external fields, jic_initialize, jic_run, device->host copies of the
+ * requested histories and a final synchronise are all inside.  `host_outputs` members point to host memory. */
+int jic_simulate_host(const jic_params* params, const jic_species* species, const void* x0_host, const void* v0_host,
+                      const float* external_E_host, const float* external_B_host, int64_t n_steps,
+                      const jic_outputs* host_outputs, void* fields0_E_host, void* fields0_B_host,
+                      void* initial_velocities_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JIC_B200_H */

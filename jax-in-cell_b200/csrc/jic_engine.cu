@@ -1,0 +1,483 @@
+// Host side of libjic_b200: contexts, CUDA-graph time loop, NCCL plumbing and the C ABI of include/jic_b200.h.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "jic_host.cuh"
+#include "jic_kernels.cuh"
+#include "jic_binned.cuh"
+
+namespace jic {
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time so that the library loads (and single-GPU runs work) without it.
+// ---------------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* env = getenv("JIC_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) { api.error = "libnccl.so.2 not found (set JIC_NCCL_LIB)"; return; }
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.error = "libnccl is missing symbols";
+  });
+  return api;
+}
+
+template <typename R>
+struct EngineT : Engine {
+  jic_params prm;
+  std::vector<jic_species> species;
+  DevParams<R> dp;
+  int device = 0, n_sm = 148;
+  bool initialized = false;
+  // particles (SoA)
+  R *xh = nullptr, *yh = nullptr, *zh = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr, *v_init = nullptr;
+  // grid
+  R *acc = nullptr, *F = nullptr;
+  double *E = nullptr, *B = nullptr, *E_int = nullptr, *B_int = nullptr, *J = nullptr, *rho = nullptr, *extE = nullptr, *extB = nullptr;
+  double *s0 = nullptr, *s1 = nullptr, *E0 = nullptr, *B0 = nullptr;
+  RunControl* ctl = nullptr;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // graphs, keyed by (outputs, steps)
+  struct GraphKey {
+    jic_outputs out;
+    int steps;
+    bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  bool shared_grid = false;
+  size_t shared_bytes = 0;
+  BinnedStore<R> bins;  // BINNED engine state (unused for INDEXED)
+
+  int dtype() const override { return prm.dtype; }
+  long long n_particles() const override { return dp.N; }
+  int n_grid() const override { return dp.G; }
+
+  template <typename T>
+  int alloc(T** p, size_t n) {
+    JIC_CUDA(cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)));
+    JIC_CUDA(cudaMemset(*p, 0, (n ? n : 1) * sizeof(T)));
+    return JIC_OK;
+  }
+
+  int create(const jic_params& params, const jic_species* sp) {
+    prm = params;
+    if (prm.device >= 0) JIC_CUDA(cudaSetDevice(prm.device));
+    JIC_CUDA(cudaGetDevice(&device));
+    JIC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    species.assign(sp, sp + prm.n_species);
+    memset(&dp, 0, sizeof(dp));
+    long long n = 0;
+    for (int s = 0; s < prm.n_species; ++s) {
+      if (sp[s].count < 0) return fail(JIC_ERR_INVALID_ARGUMENT, "negative species count");
+      n += sp[s].count;
+      dp.sp_end[s] = n;
+      dp.sp_q[s] = (R)sp[s].charge;
+      dp.sp_m[s] = (R)sp[s].mass;
+      dp.sp_qm[s] = (R)sp[s].charge_to_mass;
+    }
+    dp.N = n;
+    dp.G = prm.n_grid;
+    dp.n_species = prm.n_species;
+    dp.pbl = prm.particle_bc_left; dp.pbr = prm.particle_bc_right; dp.fbl = prm.field_bc_left; dp.fbr = prm.field_bc_right;
+    dp.relativistic = prm.relativistic;
+    dp.track_yz = prm.track_yz;
+    const double Ly = prm.length_y > 0 ? prm.length_y : prm.length, Lz = prm.length_z > 0 ? prm.length_z : prm.length;
+    dp.L = (R)prm.length; dp.Ly = (R)Ly; dp.Lz = (R)Lz;
+    dp.half_L = (R)(prm.length / 2); dp.half_Ly = (R)(Ly / 2); dp.half_Lz = (R)(Lz / 2);
+    dp.dx = (R)prm.dx; dp.inv_dx = (R)(1.0 / prm.dx); dp.half_dx = (R)(prm.dx / 2);
+    dp.dt = (R)prm.dt; dp.half_dt = (R)(prm.dt / 2);
+    dp.g0 = (R)prm.grid_first; dp.gl = (R)prm.grid_last;
+    dp.gs = (R)(prm.grid_first - prm.dx / 2);
+    dp.park_left = (R)(prm.grid_first - 1.5 * prm.dx);
+    dp.park_right = (R)(prm.grid_last + 3 * prm.dx);
+    const size_t N = (size_t)n, G = (size_t)prm.n_grid;
+    int rc;
+    if (prm.engine == JIC_ENGINE_INDEXED) {
+      if ((rc = alloc(&xh, N)) || (rc = alloc(&vx, N)) || (rc = alloc(&vy, N)) || (rc = alloc(&vz, N))) return rc;
+      if (prm.track_yz && ((rc = alloc(&yh, N)) || (rc = alloc(&zh, N)))) return rc;
+      if ((rc = alloc(&v_init, 3 * N))) return rc;
+    } else {
+      if ((rc = bins.create(*this, dp, prm, n_sm))) return rc;
+    }
+    if ((rc = alloc(&acc, G * kAccRow)) || (rc = alloc(&F, (G + 3) * kFieldRow))) return rc;
+    if ((rc = alloc(&E, G * 3)) || (rc = alloc(&B, G * 3)) || (rc = alloc(&E_int, G * 3)) || (rc = alloc(&B_int, G * 3))) return rc;
+    if ((rc = alloc(&J, G * 3)) || (rc = alloc(&rho, G)) || (rc = alloc(&extE, G * 3)) || (rc = alloc(&extB, G * 3))) return rc;
+    if ((rc = alloc(&s0, G * kAccRow)) || (rc = alloc(&s1, G * kAccRow)) || (rc = alloc(&E0, G * 3)) || (rc = alloc(&B0, G * 3))) return rc;
+    if ((rc = alloc(&ctl, 1))) return rc;
+    // deposition target of the INDEXED kernel
+    shared_bytes = G * kAccRow * sizeof(R);
+    int max_smem = 0;
+    JIC_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const bool fits = shared_bytes <= (size_t)max_smem;
+    if (prm.deposit == JIC_DEPOSIT_SHARED_GRID && !fits) return fail(JIC_ERR_UNSUPPORTED, "grid does not fit in shared memory");
+    shared_grid = prm.deposit == JIC_DEPOSIT_SHARED_GRID || (prm.deposit == JIC_DEPOSIT_AUTO && fits && N >= 4 * G);
+    if (shared_grid) {
+      JIC_CUDA(cudaFuncSetAttribute(k_step<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
+    }
+    return JIC_OK;
+  }
+
+  ~EngineT() override {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
+    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, F, E, B, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    bins.destroy();
+  }
+
+  int comm_init(const void* id, int rank_, int world_) override {
+    if (world_ <= 1) { rank = 0; world = 1; return JIC_OK; }
+    NcclApi& api = nccl_api();
+    if (!api.error.empty()) return fail(JIC_ERR_NCCL, api.error);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    JIC_CUDA(cudaSetDevice(device));
+    ncclResult_t r = api.CommInitRank(&comm, world_, uid, rank_);
+    if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
+    rank = rank_; world = world_;
+    return JIC_OK;
+  }
+
+  int set_external(const float* eE, const float* eB, cudaStream_t st) override {
+    const int n = dp.G * 3;
+    k_f32_to_f64<R><<<(n + 255) / 256, 256, 0, st>>>(eE, extE, n);
+    k_f32_to_f64<R><<<(n + 255) / 256, 256, 0, st>>>(eB, extB, n);
+    launches += 2;
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
+  int grid_for(long long n, int block, int per_sm) const {
+    long long b = (n + block - 1) / block;
+    long long cap = (long long)n_sm * per_sm;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+  }
+
+  int allreduce(cudaStream_t st) {
+    if (world <= 1) return JIC_OK;
+    NcclApi& api = nccl_api();
+    ncclResult_t r = api.AllReduce(acc, acc, (size_t)dp.G * kAccRow, sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, st);
+    if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
+    launches += 1;
+    return JIC_OK;
+  }
+
+  FieldArgs<R> field_args(bool init, const jic_outputs* out) const {
+    FieldArgs<R> a;
+    memset(&a, 0, sizeof(a));
+    a.G = dp.G; a.fbl = dp.fbl; a.fbr = dp.fbr; a.passes = prm.filter_passes; a.n_strides = prm.n_filter_strides; a.init = init;
+    for (int i = 0; i < prm.n_filter_strides; ++i) a.strides[i] = prm.filter_strides[i];
+    a.alpha = prm.filter_alpha; a.dx = prm.dx; a.dt = prm.dt;
+    a.acc = acc; a.E = E; a.B = B; a.E_int = E_int; a.B_int = B_int; a.J = J; a.rho = rho; a.extE = extE; a.extB = extB; a.F = F;
+    a.s0 = s0; a.s1 = s1; a.E0 = E0; a.B0 = B0; a.ctl = ctl;
+    if (out) { a.hE = (R*)out->electric_field; a.hB = (R*)out->magnetic_field; a.hJ = (R*)out->current_density; a.hrho = (R*)out->charge_density; }
+    return a;
+  }
+
+  int initialize(const void* x0, const void* v0, cudaStream_t st) override {
+    if (!x0 || !v0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
+    JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * kAccRow * sizeof(R), st));
+    JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
+    if (prm.engine == JIC_ENGINE_INDEXED) {
+      k_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x0, (const R*)v0, xh, yh, zh, vx, vy, vz, v_init, acc);
+      launches += 1;
+    } else {
+      int rc = bins.start(*this, dp, (const R*)x0, (const R*)v0, acc, st);
+      if (rc) return rc;
+    }
+    JIC_CUDA(cudaGetLastError());
+    int rc = allreduce(st);
+    if (rc) return rc;
+    k_fields<R><<<1, 1024, 0, st>>>(field_args(true, nullptr));
+    launches += 1;
+    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
+    JIC_CUDA(cudaGetLastError());
+    initialized = true;
+    return JIC_OK;
+  }
+
+  // enqueue one full step on `st` (used under stream capture)
+  int enqueue_step(const jic_outputs& out, cudaStream_t st) {
+    if (prm.engine == JIC_ENGINE_INDEXED) {
+      R* xhist = (R*)out.positions;
+      R* vhist = (R*)out.velocities;
+      if (shared_grid) {
+        // persistent CTAs: one shared copy of the grid each
+        const int per_sm = (int)((size_t)200 * 1024 / (shared_bytes + 1024));
+        const int g = grid_for(dp.N, 256, per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+        k_step<R, true><<<g, 256, shared_bytes, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, xhist, vhist, ctl);
+      } else {
+        k_step<R, false><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, xhist, vhist, ctl);
+      }
+      launches += 1;
+    } else {
+      int rc = bins.step(*this, dp, F, acc, st);
+      if (rc) return rc;
+    }
+    int rc = allreduce(st);
+    if (rc) return rc;
+    k_fields<R><<<1, 1024, 0, st>>>(field_args(false, &out));
+    launches += 1;
+    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
+    return JIC_OK;
+  }
+
+  int get_graph(const jic_outputs& out, int steps, cudaStream_t st, cudaGraphExec_t* exec) {
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.out = out; key.steps = steps;
+    auto it = graphs.find(key);
+    if (it != graphs.end()) { *exec = it->second; return JIC_OK; }
+    cudaStream_t cs;
+    JIC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const long long before = launches;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    int rc = JIC_OK;
+    if (e == cudaSuccess) {
+      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(out, cs);
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
+    launches = before;  // capture does not launch
+    cudaStreamDestroy(cs);
+    if (e != cudaSuccess) return fail(JIC_ERR_CUDA, format("begin capture: %s", cudaGetErrorString(e)));
+    if (rc != JIC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e2 != cudaSuccess) return fail(JIC_ERR_CUDA, format("end capture: %s", cudaGetErrorString(e2)));
+    cudaGraphExec_t ex;
+    e = cudaGraphInstantiate(&ex, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(JIC_ERR_CUDA, format("graph instantiate: %s", cudaGetErrorString(e)));
+    graphs[key] = ex;
+    launches_per_step = 0;
+    *exec = ex;
+    (void)st;
+    return JIC_OK;
+  }
+  long long launches_per_step = 0;
+
+  int run(long long n, const jic_outputs* outp, cudaStream_t st) override {
+    if (!initialized) return fail(JIC_ERR_BAD_STATE, "jic_run before jic_initialize");
+    if (n <= 0) return JIC_OK;
+    jic_outputs out;
+    memset(&out, 0, sizeof(out));
+    if (outp) out = *outp;
+    if (prm.engine == JIC_ENGINE_BINNED && (out.positions || out.velocities))
+      return fail(JIC_ERR_UNSUPPORTED, "particle histories need the INDEXED engine");
+    if (out.positions && !prm.track_yz) return fail(JIC_ERR_INVALID_ARGUMENT, "positions history needs track_yz=1");
+    // row 0 of the histories is the first step of this call
+    JIC_CUDA(cudaMemsetAsync(&ctl->hist_row, 0, sizeof(long long), st));
+    const int chunk = prm.steps_per_graph > 0 ? prm.steps_per_graph : 16;
+    const long long per_step = count_launches_per_step();
+    long long done = 0;
+    while (done < n) {
+      const int steps = (int)((n - done) >= chunk ? chunk : 1);
+      cudaGraphExec_t ex;
+      int rc = get_graph(out, steps, st, &ex);
+      if (rc) return rc;
+      JIC_CUDA(cudaGraphLaunch(ex, st));
+      launches += per_step * steps;
+      done += steps;
+    }
+    return JIC_OK;
+  }
+
+  long long count_launches_per_step() const {
+    long long k = 2 + (world > 1 ? 1 : 0);
+    if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
+    return k;
+  }
+
+  int get_fields(void* Eo, void* Bo, void* Jo, void* rhoo, cudaStream_t st) override {
+    const long long n3 = (long long)dp.G * 3;
+    if (Eo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(E_int, (R*)Eo, n3);
+    if (Bo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(B_int, (R*)Bo, n3);
+    if (Jo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(J, (R*)Jo, n3);
+    if (rhoo) k_convert<double, R><<<(dp.G + 255) / 256, 256, 0, st>>>(rho, (R*)rhoo, dp.G);
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
+  int get_initial(void* E0o, void* B0o, void* vinit, cudaStream_t st) override {
+    const long long n3 = (long long)dp.G * 3;
+    if (E0o) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(E0, (R*)E0o, n3);
+    if (B0o) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(B0, (R*)B0o, n3);
+    if (vinit) {
+      if (prm.engine != JIC_ENGINE_INDEXED) return fail(JIC_ERR_UNSUPPORTED, "initial_velocities need the INDEXED engine");
+      JIC_CUDA(cudaMemcpyAsync(vinit, v_init, (size_t)dp.N * 3 * sizeof(R), cudaMemcpyDeviceToDevice, st));
+    }
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
+  int get_particles(void* x, void* v, uint8_t* alive, cudaStream_t st) override {
+    if (prm.engine == JIC_ENGINE_BINNED) return bins.export_particles(*this, dp, (R*)x, (R*)v, alive, st);
+    k_export_particles<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, xh, yh, zh, vx, vy, vz, (R*)x, (R*)v, alive);
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
+  int kinetic(double* out, cudaStream_t st) override {
+    JIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (prm.engine == JIC_ENGINE_BINNED) return bins.kinetic(*this, dp, out, st);
+    k_kinetic<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, vx, vy, vz, out);
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+};
+
+static int validate(const jic_params* p, const jic_species* sp, std::string& why) {
+  if (!p || !sp) { why = "null params/species"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->struct_bytes != sizeof(jic_params)) { why = format("jic_params ABI mismatch: got %u bytes, expected %zu", p->struct_bytes, sizeof(jic_params)); return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->dtype != JIC_F64 && p->dtype != JIC_F32) { why = "dtype must be JIC_F64 or JIC_F32"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->engine != JIC_ENGINE_INDEXED && p->engine != JIC_ENGINE_BINNED) { why = "unknown engine"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->n_grid < 3) { why = "number_grid_points must be >= 3"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->n_species < 1 || p->n_species > JIC_MAX_SPECIES) { why = "n_species out of range"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (!(p->length > 0) || !(p->dx > 0) || !(p->dt > 0)) { why = "length, dx, dt must be positive"; return JIC_ERR_INVALID_ARGUMENT; }
+  const int bcs[4] = {p->particle_bc_left, p->particle_bc_right, p->field_bc_left, p->field_bc_right};
+  for (int b : bcs) if (b < 0 || b > 2) { why = "boundary codes are 0 (periodic), 1 (reflective), 2 (absorbing)"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->filter_passes < 0 || p->n_filter_strides < 0 || p->n_filter_strides > JIC_MAX_STRIDES) { why = "bad filter parameters"; return JIC_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < p->n_filter_strides; ++i) if (p->filter_strides[i] <= 0) { why = "filter strides must be positive"; return JIC_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < 8; ++i) if (p->reserved[i]) { why = "reserved fields must be zero"; return JIC_ERR_INVALID_ARGUMENT; }
+  return JIC_OK;
+}
+
+}  // namespace jic
+
+using namespace jic;
+
+struct jic_context {
+  Engine* eng;
+};
+
+extern "C" {
+
+int jic_abi_version(void) { return JIC_ABI_VERSION; }
+
+const char* jic_last_error(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->error.c_str() : g_last_error.c_str(); }
+
+int jic_create(const jic_params* params, const jic_species* species, jic_context** out) {
+  if (!out) { g_last_error = "out is null"; return JIC_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  std::string why;
+  int rc = validate(params, species, why);
+  if (rc) { g_last_error = why; return rc; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = "no CUDA device: libjic_b200 has no CPU path"; return JIC_ERR_CUDA; }
+  Engine* eng = nullptr;
+  if (params->dtype == JIC_F64) { auto* e = new EngineT<double>(); rc = e->create(*params, species); eng = e; }
+  else { auto* e = new EngineT<float>(); rc = e->create(*params, species); eng = e; }
+  if (rc) { g_last_error = eng->error; delete eng; return rc; }
+  *out = new jic_context{eng};
+  return JIC_OK;
+}
+
+int jic_destroy(jic_context* ctx) {
+  if (!ctx) return JIC_OK;
+  cudaDeviceSynchronize();
+  delete ctx->eng;
+  delete ctx;
+  return JIC_OK;
+}
+
+int jic_comm_unique_id(void* id) {
+  NcclApi& api = nccl_api();
+  if (!api.error.empty()) { g_last_error = api.error; return JIC_ERR_NCCL; }
+  ncclUniqueId uid;
+  if (api.GetUniqueId(&uid) != ncclSuccess) { g_last_error = "ncclGetUniqueId failed"; return JIC_ERR_NCCL; }
+  memcpy(id, &uid, sizeof(uid));
+  return JIC_OK;
+}
+
+#define CTX_OR_FAIL(ctx) if (!(ctx) || !(ctx)->eng) { g_last_error = "null context"; return JIC_ERR_INVALID_ARGUMENT; }
+
+int jic_comm_init(jic_context* ctx, const void* id, int rank, int world) { CTX_OR_FAIL(ctx); return ctx->eng->comm_init(id, rank, world); }
+int jic_set_external_fields(jic_context* ctx, const float* eE, const float* eB, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->set_external(eE, eB, (cudaStream_t)st); }
+int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize(x0, v0, (cudaStream_t)st); }
+int jic_run(jic_context* ctx, int64_t n, const jic_outputs* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->run(n, out, (cudaStream_t)st); }
+int jic_get_fields(jic_context* ctx, void* E, void* B, void* J, void* rho, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_fields(E, B, J, rho, (cudaStream_t)st); }
+int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* v, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_initial(E0, B0, v, (cudaStream_t)st); }
+int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_particles(x, v, alive, (cudaStream_t)st); }
+int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
+int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
+
+int jic_simulate_host(const jic_params* params, const jic_species* species, const void* x0_host, const void* v0_host,
+                      const float* eE_host, const float* eB_host, int64_t n_steps, const jic_outputs* host_out, void* E0_host,
+                      void* B0_host, void* vinit_host) {
+  jic_context* ctx = nullptr;
+  int rc = jic_create(params, species, &ctx);
+  if (rc) return rc;
+  Engine* e = ctx->eng;
+  const size_t rs = params->dtype == JIC_F64 ? 8 : 4;
+  const size_t N = (size_t)e->n_particles(), G = (size_t)e->n_grid(), T = (size_t)(n_steps > 0 ? n_steps : 0);
+  std::vector<void*> dev;
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; dev.push_back(p); return p; };
+  auto cleanup = [&](int code) { std::string msg = e->error; for (void* p : dev) cudaFree(p); jic_destroy(ctx); if (code) g_last_error = msg; return code; };
+  cudaStream_t st = nullptr;
+  void* dx0 = dalloc(N * 3 * rs);
+  void* dv0 = dalloc(N * 3 * rs);
+  float *deE = nullptr, *deB = nullptr;
+  if (!dx0 || !dv0) { e->error = "cudaMalloc failed for the particle upload"; return cleanup(JIC_ERR_CUDA); }
+  cudaMemcpyAsync(dx0, x0_host, N * 3 * rs, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dv0, v0_host, N * 3 * rs, cudaMemcpyHostToDevice, st);
+  if (eE_host) { deE = (float*)dalloc(G * 3 * 4); cudaMemcpyAsync(deE, eE_host, G * 3 * 4, cudaMemcpyHostToDevice, st); }
+  if (eB_host) { deB = (float*)dalloc(G * 3 * 4); cudaMemcpyAsync(deB, eB_host, G * 3 * 4, cudaMemcpyHostToDevice, st); }
+  if ((rc = e->set_external(deE, deB, st))) return cleanup(rc);
+  if ((rc = e->initialize(dx0, dv0, st))) return cleanup(rc);
+  jic_outputs d;
+  memset(&d, 0, sizeof(d));
+  const size_t sizes[6] = {T * G * 3 * rs, T * G * 3 * rs, T * G * 3 * rs, T * G * rs, T * N * 3 * rs, T * N * 3 * rs};
+  void* const* hsrc = host_out ? (void* const*)host_out : nullptr;
+  void** dptr = (void**)&d;
+  for (int k = 0; k < 6 && hsrc; ++k)
+    if (hsrc[k]) { dptr[k] = dalloc(sizes[k]); if (!dptr[k]) { e->error = "cudaMalloc failed for a history buffer"; return cleanup(JIC_ERR_CUDA); } }
+  if ((rc = e->run(n_steps, &d, st))) return cleanup(rc);
+  for (int k = 0; k < 6 && hsrc; ++k)
+    if (hsrc[k]) cudaMemcpyAsync(hsrc[k], dptr[k], sizes[k], cudaMemcpyDeviceToHost, st);
+  if (E0_host || B0_host || vinit_host) {
+    void* dE0 = E0_host ? dalloc(G * 3 * rs) : nullptr;
+    void* dB0 = B0_host ? dalloc(G * 3 * rs) : nullptr;
+    void* dvi = vinit_host ? dalloc(N * 3 * rs) : nullptr;
+    if ((rc = e->get_initial(dE0, dB0, dvi, st))) return cleanup(rc);
+    if (dE0) cudaMemcpyAsync(E0_host, dE0, G * 3 * rs, cudaMemcpyDeviceToHost, st);
+    if (dB0) cudaMemcpyAsync(B0_host, dB0, G * 3 * rs, cudaMemcpyDeviceToHost, st);
+    if (dvi) cudaMemcpyAsync(vinit_host, dvi, N * 3 * rs, cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { e->error = format("simulate_host: %s", cudaGetErrorString(ce)); return cleanup(JIC_ERR_CUDA); }
+  return cleanup(JIC_OK);
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// Kernels of the INDEXED engine (particle p stays in slot p) and the single-CTA field kernel shared by both engines.
+#pragma once
+#include "jic_device.cuh"
+
+namespace jic {
+
+// ---------------------------------------------------------------------------------------------------------
+// K0a  leap-frog start-up + initial deposits.
+//   jaxincell/_simulation.py:217-225   x_{+1/2}, v, q <- BC(x0 + dt/2 v0);  x_{-1/2} <- BCpos(x0 - dt/2 v) with post-BC v
+//   jaxincell/_state_initialization.py:374   rho0 from x0 with the ORIGINAL charges
+//   jaxincell/_algorithms.py:29-32    J^0 from (x_{-1/2}, x0, x_{+1/2}, v, q) with the post-BC charges
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) k_start(const DevParams<R> p, const R* __restrict__ x0, const R* __restrict__ v0,
+                                               R* __restrict__ xh, R* __restrict__ yh, R* __restrict__ zh, R* __restrict__ vx,
+                                               R* __restrict__ vy, R* __restrict__ vz, R* __restrict__ v_init, R* __restrict__ acc) {
+  const GlobalGrid<R> grid{acc};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    const int s = species_of(i, p);
+    const R q = p.sp_q[s];
+    const R X0 = x0[3 * i], Y0 = x0[3 * i + 1], Z0 = x0[3 * i + 2];
+    R v[3] = {v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]};
+    // rho0 (original charge, raw initial position)
+    const Cloud<R> c0 = make_cloud(X0, p);
+    deposit_cloud(grid, c0, p.G, R(0), R(0), q * p.inv_dx, false);
+    // x_{+1/2}
+    R xp = X0 + p.half_dt * v[0];
+    const int flag = bc_x(xp, p);
+    R qj = q;
+    if (flag == 1) v[0] = -v[0];
+    if (flag == 2) { v[0] = v[1] = v[2] = R(0); qj = R(0); }
+    // x_{-1/2} with the post-BC velocity
+    R xm = X0 - p.half_dt * v[0];
+    bc_x(xm, p);
+    if (qj != R(0)) {
+      const Cloud<R> cm = make_cloud(xm, p), cp = make_cloud(xp, p);
+      deposit_jx(grid, xm, cm, cp, qj / p.dt, p);
+      // J_y,z = rho(x_0) v_{y,z}: re-use the x0 cloud (same position, post-BC charge)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = c0.c + j - 1;
+        if (k >= 0 && k < p.G) { grid.add(k, 1, c0.w[j] * qj * p.inv_dx * v[1]); grid.add(k, 2, c0.w[j] * qj * p.inv_dx * v[2]); }
+      }
+      if (c0.first != R(0)) { grid.add(0, 1, c0.first * qj * p.inv_dx * v[1]); grid.add(0, 2, c0.first * qj * p.inv_dx * v[2]); }
+      if (c0.last != R(0)) { grid.add(p.G - 1, 1, c0.last * qj * p.inv_dx * v[1]); grid.add(p.G - 1, 2, c0.last * qj * p.inv_dx * v[2]); }
+    }
+    xh[i] = xp;
+    vx[i] = v[0]; vy[i] = v[1]; vz[i] = v[2];
+    if (p.track_yz) {
+      yh[i] = wrap_transverse(Y0 + p.half_dt * v0[3 * i + 1], p.Ly, p.half_Ly);
+      zh[i] = wrap_transverse(Z0 + p.half_dt * v0[3 * i + 2], p.Lz, p.half_Lz);
+    }
+    if (v_init) { v_init[3 * i] = v[0]; v_init[3 * i + 1] = v[1]; v_init[3 * i + 2] = v[2]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1  fused gather -> Boris push -> particle BC -> x_{n+1} -> deposit (J_x, J_y, J_z, rho), one pass over the
+//     particle arrays: jaxincell/_algorithms.py:40-66 and :90-92 (the first deposit of the next reference step,
+//     :29-32, is this same deposit -- SURVEY.md section 0).
+//     SHARED = CTA-private copy of the raw grid in shared memory (persistent CTAs, flushed once).
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, bool SHARED>
+__global__ void __launch_bounds__(256) k_step(const DevParams<R> p, R* __restrict__ xh, R* __restrict__ yh, R* __restrict__ zh,
+                                              R* __restrict__ vx, R* __restrict__ vy, R* __restrict__ vz, const R* __restrict__ F,
+                                              R* __restrict__ acc, R* __restrict__ x_hist, R* __restrict__ v_hist,
+                                              const RunControl* __restrict__ ctl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* sacc = reinterpret_cast<R*>(smem_raw);
+  if (SHARED) {
+    for (int k = threadIdx.x; k < p.G * kAccRow; k += blockDim.x) sacc[k] = R(0);
+    __syncthreads();
+  }
+  const long long row = (x_hist || v_hist) ? ctl->hist_row : 0;
+  R* xrow = x_hist ? x_hist + (size_t)row * 3 * p.N : nullptr;
+  R* vrow = v_hist ? v_hist + (size_t)row * 3 * p.N : nullptr;
+
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    const R x_old = xh[i];
+    R v[3] = {vx[i], vy[i], vz[i]};
+    // absorbed particles are parked outside the box with v = 0, q = 0 (_boundary_conditions.py:40,51,64,78): nothing moves
+    const bool dead = (x_old < -p.half_L) || (x_old > p.half_L);
+    R x_new = x_old, x_mid = x_old, y_mid = R(0), z_mid = R(0);
+    R vpre_y = R(0), vpre_z = R(0);  // transverse velocity the pusher advanced y,z with (before an absorption zeroes it)
+    if (!dead) {
+      const int s = species_of(i, p);
+      R E[3], B[3];
+      gather_fields(F, x_old, p, E, B);
+      if (p.relativistic) boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
+      else boris_velocity(v, E, B, p.sp_qm[s], p.dt);
+      vpre_y = v[1]; vpre_z = v[2];
+      x_new = x_old + p.dt * v[0];
+      const int flag = bc_x(x_new, p);
+      R q = p.sp_q[s];
+      if (flag == 1) v[0] = -v[0];
+      if (flag == 2) { v[0] = v[1] = v[2] = R(0); q = R(0); }
+      x_mid = x_new - p.half_dt * v[0];
+      bc_x(x_mid, p);
+      if (q != R(0)) {
+        const Cloud<R> c_old = make_cloud(x_old, p), c_new = make_cloud(x_new, p), c_mid = make_cloud(x_mid, p);
+        const R a = q * p.inv_dx;
+        if (SHARED) {
+          const SharedGrid<R> g{sacc};
+          deposit_jx(g, x_old, c_old, c_new, q / p.dt, p);
+          deposit_cloud(g, c_mid, p.G, a * v[1], a * v[2], a, true);
+        } else {
+          const GlobalGrid<R> g{acc};
+          deposit_jx(g, x_old, c_old, c_new, q / p.dt, p);
+          deposit_cloud(g, c_mid, p.G, a * v[1], a * v[2], a, true);
+        }
+      }
+      xh[i] = x_new;
+      vx[i] = v[0]; vy[i] = v[1]; vz[i] = v[2];
+    }
+    if (p.track_yz) {
+      // y,z: advanced with the pushed velocity (_particles.py:125), wrapped by the BC (_boundary_conditions.py:28-29),
+      // then x_{n+1} = BCpos(x_{n+3/2} - dt/2 v_{n+1}) with the post-BC velocity (_algorithms.py:60-61)
+      const R y = wrap_transverse(yh[i] + p.dt * vpre_y, p.Ly, p.half_Ly);
+      const R z = wrap_transverse(zh[i] + p.dt * vpre_z, p.Lz, p.half_Lz);
+      yh[i] = y; zh[i] = z;
+      y_mid = wrap_transverse(y - p.half_dt * v[1], p.Ly, p.half_Ly);
+      z_mid = wrap_transverse(z - p.half_dt * v[2], p.Lz, p.half_Lz);
+    }
+    if (xrow) { xrow[3 * i] = x_mid; xrow[3 * i + 1] = y_mid; xrow[3 * i + 2] = z_mid; }
+    if (vrow) { vrow[3 * i] = v[0]; vrow[3 * i + 1] = v[1]; vrow[3 * i + 2] = v[2]; }
+  }
+
+  if (SHARED) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.G * kAccRow; k += blockDim.x) {
+      const R v = sacc[k];
+      if (v != R(0)) atomicAdd(acc + k, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2  single-CTA field kernel: digital filter of the raw [Jx,Jy,Jz,rho] grid (jaxincell/_filters.py:52-153),
+//     second Maxwell half step of step n (B then E, _fields.py:185-193), emission of the step outputs
+//     (_algorithms.py:93), first Maxwell half step of step n+1 (E then B, _fields.py:175-183) and the padded
+//     total-field table for the next gather (_algorithms.py:36-37 + _boundary_conditions.py:233-245).
+//     In `init` mode it instead turns rho0 into E_x (prefix sum == the dense solve of _fields.py:76-81).
+//     Field arithmetic is always fp64; only the raw grid, the gather table and the histories are `R`.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct FieldArgs {
+  int G, fbl, fbr, passes, n_strides, init;
+  int strides[JIC_MAX_STRIDES];
+  double alpha, dx, dt;
+  R* acc;              // raw grid (G,4), consumed and zeroed
+  double *E, *B;       // (G,3) leap-frog state
+  double *E_int, *B_int;  // copies at integer time (what the step emits)
+  double *J, *rho;     // filtered (G,3), (G)
+  const double *extE, *extB;
+  R* F;                // padded gather table (G+3, 8)
+  double *s0, *s1;     // filter scratch (G,4) each
+  double *E0, *B0;     // initial fields (init mode)
+  R *hE, *hB, *hJ, *hrho;  // histories or null
+  RunControl* ctl;
+};
+
+__device__ __forceinline__ double filt_neighbour(const double* y, int j, int s, int G, int c, bool periodic, int fbl, int fbr) {
+  int k = j + s;
+  if (periodic) return y[mod_pos(k, G) * kAccRow + c];
+  if (k < 0) return fbl == JIC_BC_ABSORBING ? 0.0 : y[c];
+  if (k >= G) return fbr == JIC_BC_ABSORBING ? 0.0 : y[(G - 1) * kAccRow + c];
+  return y[k * kAccRow + c];
+}
+
+__device__ __forceinline__ void ghost_E_left(const double* E, const double* B, int G, int fbl, double g[3]) {
+  if (fbl == JIC_BC_PERIODIC) { g[0] = E[(G - 1) * 3]; g[1] = E[(G - 1) * 3 + 1]; g[2] = E[(G - 1) * 3 + 2]; }
+  else if (fbl == JIC_BC_REFLECTIVE) { g[0] = E[0]; g[1] = E[1]; g[2] = E[2]; }
+  else { g[0] = 0.0; g[1] = -2 * kC * B[2] - E[1]; g[2] = 2 * kC * B[1] - E[2]; }
+}
+
+__device__ __forceinline__ void ghost_B_right(const double* B, const double* E, int G, int fbr, double g[3]) {
+  const int l = (G - 1) * 3;
+  if (fbr == JIC_BC_PERIODIC) { g[0] = B[0]; g[1] = B[1]; g[2] = B[2]; }
+  else if (fbr == JIC_BC_REFLECTIVE) { g[0] = B[l]; g[1] = B[l + 1]; g[2] = B[l + 2]; }
+  else { g[0] = 0.0; g[1] = -(2 / kC) * E[l + 2] - B[l + 1]; g[2] = (2 / kC) * E[l + 1] - B[l + 2]; }
+}
+
+// B -= h curl E   (backward difference, left ghost; _fields.py:102-111, :182/:189)
+__device__ __forceinline__ void faraday(double* E, double* B, int G, int fbl, double dx, double h) {
+  double gl[3];
+  ghost_E_left(E, B, G, fbl, gl);
+  __syncthreads();  // every thread has read the ghost inputs before B[0] changes
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    const double ey_m = i ? E[(i - 1) * 3 + 1] : gl[1], ez_m = i ? E[(i - 1) * 3 + 2] : gl[2];
+    const double dFz = (E[i * 3 + 2] - ez_m) / dx, dFy = (E[i * 3 + 1] - ey_m) / dx;
+    B[i * 3 + 1] -= h * (-dFz);
+    B[i * 3 + 2] -= h * dFy;
+  }
+  __syncthreads();
+}
+
+// E += h (c^2 curl B - J/eps0)   (forward difference, right ghost; _fields.py:132-144, :179/:192)
+__device__ __forceinline__ void ampere(double* E, double* B, const double* J, int G, int fbr, double dx, double h) {
+  double gr[3];
+  ghost_B_right(B, E, G, fbr, gr);
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    const double by_p = (i + 1 < G) ? B[(i + 1) * 3 + 1] : gr[1], bz_p = (i + 1 < G) ? B[(i + 1) * 3 + 2] : gr[2];
+    const double dFz = (bz_p - B[i * 3 + 2]) / dx, dFy = (by_p - B[i * 3 + 1]) / dx;
+    E[i * 3 + 0] += h * ((kC * kC) * 0.0 - (J[i * 3 + 0] / kEps0));
+    E[i * 3 + 1] += h * ((kC * kC) * (-dFz) - (J[i * 3 + 1] / kEps0));
+    E[i * 3 + 2] += h * ((kC * kC) * dFy - (J[i * 3 + 2] / kEps0));
+  }
+  __syncthreads();
+}
+
+template <typename R>
+__global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
+  const int G = a.G, tid = threadIdx.x, nt = blockDim.x;
+  // 1. raw grid -> scratch (fp64), zero the raw grid for the next step
+  for (int k = tid; k < G * kAccRow; k += nt) { a.s0[k] = (double)a.acc[k]; a.acc[k] = R(0); }
+  __syncthreads();
+  // 2. digital filter, all four components at once
+  double* cur = a.s0;
+  double* nxt = a.s1;
+  if (a.passes > 0) {
+    const bool periodic = (a.fbl == JIC_BC_PERIODIC) && (a.fbr == JIC_BC_PERIODIC);
+    const int p_cl = a.passes < 17 ? a.passes : 17;
+    const int n_reg = (a.passes - 1) < 16 ? (a.passes - 1) : 16;
+    const double comp_alpha = p_cl - a.alpha * (p_cl - 1);
+    for (int si = 0; si < a.n_strides; ++si) {
+      const int s = a.strides[si];
+      for (int sweep = 0; sweep <= n_reg; ++sweep) {
+        const double al = sweep < n_reg ? a.alpha : comp_alpha;
+        const double co = (1 - al) * 0.5;
+        for (int k = tid; k < G * kAccRow; k += nt) {
+          const int j = k / kAccRow, c = k % kAccRow;
+          const double l = filt_neighbour(cur, j, -s, G, c, periodic, a.fbl, a.fbr);
+          const double r = filt_neighbour(cur, j, +s, G, c, periodic, a.fbl, a.fbr);
+          nxt[k] = al * cur[k] + co * (l + r);
+        }
+        __syncthreads();
+        double* t = cur; cur = nxt; nxt = t;
+      }
+    }
+  }
+  for (int i = tid; i < G; i += nt) {
+    a.J[i * 3 + 0] = cur[i * kAccRow + 0];
+    a.J[i * 3 + 1] = cur[i * kAccRow + 1];
+    a.J[i * 3 + 2] = cur[i * kAccRow + 2];
+    a.rho[i] = cur[i * kAccRow + 3];
+  }
+  __syncthreads();
+  const double h = a.dt / 2;
+  if (a.init) {
+    // 3a. E_x = (dx/eps0) cumsum(rho0); the reference's forward substitution is this same sequential sum
+    if (tid == 0) {
+      double run = 0.0;
+      for (int i = 0; i < G; ++i) { run += a.rho[i]; a.E[i * 3] = (a.dx / kEps0) * run; }
+    }
+    for (int i = tid; i < G; i += nt) {
+      a.E[i * 3 + 1] = 0.0; a.E[i * 3 + 2] = 0.0;
+      a.B[i * 3] = 0.0; a.B[i * 3 + 1] = 0.0; a.B[i * 3 + 2] = 0.0;
+    }
+    __syncthreads();
+    for (int k = tid; k < G * 3; k += nt) { a.E0[k] = a.E[k]; a.B0[k] = a.B[k]; a.E_int[k] = a.E[k]; a.B_int[k] = a.B[k]; }
+    __syncthreads();
+  } else {
+    // 3b. second half step of step n: B then E (_fields.py:185-193)
+    faraday(a.E, a.B, G, a.fbl, a.dx, h);
+    ampere(a.E, a.B, a.J, G, a.fbr, a.dx, h);
+    const long long row = a.ctl->hist_row;
+    for (int k = tid; k < G * 3; k += nt) {
+      a.E_int[k] = a.E[k]; a.B_int[k] = a.B[k];
+      if (a.hE) a.hE[(size_t)row * G * 3 + k] = (R)a.E[k];
+      if (a.hB) a.hB[(size_t)row * G * 3 + k] = (R)a.B[k];
+      if (a.hJ) a.hJ[(size_t)row * G * 3 + k] = (R)a.J[k];
+    }
+    if (a.hrho) for (int i = tid; i < G; i += nt) a.hrho[(size_t)row * G + i] = (R)a.rho[i];
+    __syncthreads();
+    if (tid == 0) { a.ctl->hist_row = row + 1; a.ctl->step += 1; }
+  }
+  // 4. first half step of the next step: E then B (_fields.py:175-183)
+  ampere(a.E, a.B, a.J, G, a.fbr, a.dx, h);
+  faraday(a.E, a.B, G, a.fbl, a.dx, h);
+  // 5. padded total fields for the gather: rows [L2, L1, f_0..f_{G-1}, R]
+  for (int r = tid; r < G + 3; r += nt) {
+    int src;  // source cell, -1 = zeros
+    if (r >= 2 && r < G + 2) src = r - 2;
+    else if (r < 2) src = a.fbl == JIC_BC_PERIODIC ? (G - 2 + r) : a.fbl == JIC_BC_REFLECTIVE ? (1 - r) : -1;
+    else src = a.fbr == JIC_BC_PERIODIC ? 0 : a.fbr == JIC_BC_REFLECTIVE ? (G - 1) : -1;
+    if (src >= G) src = G - 1;   // G == 1 corner
+    if (src < -1) src = 0;
+    R* f = a.F + (size_t)r * kFieldRow;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f[c] = src < 0 ? R(0) : (R)(a.E[src * 3 + c] + a.extE[src * 3 + c]);
+      f[3 + c] = src < 0 ? R(0) : (R)(a.B[src * 3 + c] + a.extB[src * 3 + c]);
+    }
+    f[6] = R(0); f[7] = R(0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_export_particles(const DevParams<R> p, const R* xh, const R* yh, const R* zh, const R* vx, const R* vy, const R* vz,
+                                   R* x_out, R* v_out, uint8_t* alive) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    const R x = xh[i];
+    if (x_out) { x_out[3 * i] = x; x_out[3 * i + 1] = p.track_yz ? yh[i] : R(0); x_out[3 * i + 2] = p.track_yz ? zh[i] : R(0); }
+    if (v_out) { v_out[3 * i] = vx[i]; v_out[3 * i + 1] = vy[i]; v_out[3 * i + 2] = vz[i]; }
+    if (alive) alive[i] = !((x < -p.half_L) || (x > p.half_L));
+  }
+}
+
+template <typename R>
+__global__ void k_kinetic(const DevParams<R> p, const R* vx, const R* vy, const R* vz, double* out) {
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    const int s = species_of(i, p);
+    const double a = vx[i], b = vy[i], c = vz[i];
+    acc += 0.5 * (double)p.sp_m[s] * (a * a + b * b + c * c);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+template <typename R>
+__global__ void k_f32_to_f64(const float* src, double* dst, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src ? (double)src[i] : 0.0;
+}
+
+template <typename Src, typename Dst>
+__global__ void k_convert(const Src* src, Dst* dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (Dst)src[i];
+}
+
+}  // namespace jic

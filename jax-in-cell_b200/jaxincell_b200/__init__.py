@@ -1,0 +1,5 @@
+"""jaxincell_b200 -- B200-native hot path (gather, Boris push, boundaries, deposition, filter, Maxwell update) behind
+JAX-in-Cell's Simulation API.  The arithmetic lives in libjic_b200.so (hand-written CUDA for sm_100a, C ABI in
+include/jic_b200.h); this package is the Python host side.  There is no CPU fallback."""
+from ._lib import JicError, LIB_PATH, load  # noqa: F401
+from ._engine import HotPath, make_params, make_species, simulate_host  # noqa: F401

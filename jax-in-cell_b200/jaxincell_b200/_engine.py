@@ -1,0 +1,215 @@
+"""Thin host wrapper around the C ABI: torch supplies device memory, streams and (for N>1) the rendezvous only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import JicError, Outputs, Params, Species
+
+_ENGINES = {"indexed": _lib.ENGINE_INDEXED, "binned": _lib.ENGINE_BINNED}
+_DEPOSITS = {"auto": _lib.DEPOSIT_AUTO, "global": _lib.DEPOSIT_GLOBAL_ATOMICS, "shared": _lib.DEPOSIT_SHARED_GRID}
+_HIST = ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities")
+
+
+def make_params(*, length, G, dt, n_species, length_y=0.0, length_z=0.0, pbl=0, pbr=0, fbl=0, fbr=0, filter_passes=5,
+                filter_alpha=0.5, filter_strides=(1, 2, 4), relativistic=False, dtype=torch.float64, engine="indexed",
+                track_yz=False, deposit="auto", steps_per_graph=0, device=-1):
+    """Fill a jic_params exactly as build_domain_state does (jaxincell/_state_initialization.py:27-49)."""
+    p = Params()
+    p.struct_bytes = C.sizeof(Params)
+    p.dtype = _lib.F64 if dtype == torch.float64 else _lib.F32
+    p.engine = _ENGINES[engine]
+    p.device = device
+    p.n_grid = int(G)
+    p.n_species = int(n_species)
+    dx = float(length) / int(G)
+    grid = np.linspace(-float(length) / 2 + dx / 2, float(length) / 2 - dx / 2, int(G))
+    p.length, p.length_y, p.length_z = float(length), float(length_y or 0.0), float(length_z or 0.0)
+    p.dx, p.dt = dx, float(dt)
+    p.grid_first, p.grid_last = float(grid[0]), float(grid[-1])
+    p.particle_bc_left, p.particle_bc_right, p.field_bc_left, p.field_bc_right = int(pbl), int(pbr), int(fbl), int(fbr)
+    strides = tuple(int(s) for s in filter_strides)
+    if len(strides) > _lib.JIC_MAX_STRIDES:
+        raise JicError(f"at most {_lib.JIC_MAX_STRIDES} filter strides")
+    p.filter_passes, p.n_filter_strides, p.filter_alpha = int(filter_passes), len(strides), float(filter_alpha)
+    for i, s in enumerate(strides):
+        p.filter_strides[i] = s
+    p.relativistic, p.track_yz = int(bool(relativistic)), int(bool(track_yz))
+    p.deposit, p.steps_per_graph = _DEPOSITS[deposit], int(steps_per_graph)
+    return p, grid
+
+
+def make_species(species):
+    arr = (Species * len(species))()
+    for i, s in enumerate(species):
+        arr[i].count, arr[i].charge, arr[i].mass, arr[i].charge_to_mass = int(s["count"]), float(s["q"]), float(s["m"]), float(s["qm"])
+    return arr
+
+
+class HotPath:
+    """One device context: the carry of jaxincell/_simulation.py:228-231 and the scan of :253, on one GPU."""
+
+    def __init__(self, *, species, dtype=torch.float64, device=None, **kw):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise JicError("no CUDA device: jaxincell_b200 has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = dtype
+        self.params, self.grid = make_params(n_species=len(species), dtype=dtype, device=self.device.index or 0, **kw)
+        self.species = make_species(species)
+        self.N = int(sum(int(s["count"]) for s in species))
+        self.G = self.params.n_grid
+        self.ctx = C.c_void_p()
+        _lib.check(self.lib.jic_create(C.byref(self.params), self.species, C.byref(self.ctx)))
+        self._keep = []
+
+    # ---- helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, rc):
+        _lib.check(rc, self.ctx)
+
+    def _ptr(self, t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    def _dev(self, a, dtype=None):
+        t = torch.as_tensor(a)
+        return t.to(device=self.device, dtype=dtype or self.dtype).contiguous()
+
+    # ---- multi-GPU rendezvous (torch.distributed is only the courier of the 128-byte NCCL id)
+    def comm_init_from_torch(self):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world == 1:
+            return
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(self.lib.jic_comm_unique_id(buf))
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._chk(self.lib.jic_comm_init(self.ctx, C.c_char_p(raw), rank, world))
+
+    # ---- state in
+    def set_external_fields(self, ext_E=None, ext_B=None):
+        e = None if ext_E is None else self._dev(ext_E, torch.float32)
+        b = None if ext_B is None else self._dev(ext_B, torch.float32)
+        self._chk(self.lib.jic_set_external_fields(self.ctx, self._ptr(e), self._ptr(b), self._stream()))
+        self._keep = [e, b]
+
+    def initialize(self, x0, v0):
+        x0, v0 = self._dev(x0), self._dev(v0)
+        if tuple(x0.shape) != (self.N, 3) or tuple(v0.shape) != (self.N, 3):
+            raise JicError(f"x0/v0 must have shape ({self.N}, 3)")
+        self._chk(self.lib.jic_initialize(self.ctx, self._ptr(x0), self._ptr(v0), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # x0/v0 may be freed by the caller afterwards
+
+    # ---- stepping
+    def alloc_outputs(self, n_steps, fields=True, particles=False):
+        out = {}
+        T, G, N = int(n_steps), self.G, self.N
+        if fields:
+            for k in _HIST[:3]:
+                out[k] = torch.empty((T, G, 3), dtype=self.dtype, device=self.device)
+            out["charge_density"] = torch.empty((T, G), dtype=self.dtype, device=self.device)
+        if particles:
+            out["positions"] = torch.empty((T, N, 3), dtype=self.dtype, device=self.device)
+            out["velocities"] = torch.empty((T, N, 3), dtype=self.dtype, device=self.device)
+        return out
+
+    def run(self, n_steps, outputs=None, fields=True, particles=False):
+        """Advance n_steps; returns the dict of history tensors (allocated here unless `outputs` is given)."""
+        if outputs is None:
+            outputs = self.alloc_outputs(n_steps, fields, particles)
+        o = Outputs()
+        for k in _HIST:
+            setattr(o, k, outputs[k].data_ptr() if k in outputs else None)
+        self._chk(self.lib.jic_run(self.ctx, int(n_steps), C.byref(o), self._stream()))
+        return outputs
+
+    # ---- state out
+    def fields(self):
+        G = self.G
+        E, B, J = (torch.empty((G, 3), dtype=self.dtype, device=self.device) for _ in range(3))
+        rho = torch.empty((G,), dtype=self.dtype, device=self.device)
+        self._chk(self.lib.jic_get_fields(self.ctx, self._ptr(E), self._ptr(B), self._ptr(J), self._ptr(rho), self._stream()))
+        return E, B, J, rho
+
+    def initial(self, velocities=True):
+        G = self.G
+        E0, B0 = (torch.empty((G, 3), dtype=self.dtype, device=self.device) for _ in range(2))
+        v = torch.empty((self.N, 3), dtype=self.dtype, device=self.device) if velocities else None
+        self._chk(self.lib.jic_get_initial(self.ctx, self._ptr(E0), self._ptr(B0), self._ptr(v), self._stream()))
+        return E0, B0, v
+
+    def particles(self):
+        x = torch.empty((self.N, 3), dtype=self.dtype, device=self.device)
+        v = torch.empty((self.N, 3), dtype=self.dtype, device=self.device)
+        alive = torch.empty((self.N,), dtype=torch.uint8, device=self.device)
+        self._chk(self.lib.jic_get_particles(self.ctx, self._ptr(x), self._ptr(v), self._ptr(alive), self._stream()))
+        return x, v, alive
+
+    def kinetic_energy(self):
+        ke = torch.zeros((1,), dtype=torch.float64, device=self.device)
+        self._chk(self.lib.jic_kinetic_energy(self.ctx, self._ptr(ke), self._stream()))
+        return ke
+
+    def launch_count(self):
+        return int(self.lib.jic_launch_count(self.ctx))
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.jic_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def simulate_host(*, species, x0, v0, n_steps, ext_E=None, ext_B=None, dtype=np.float64, fields=True, particles=False,
+                  initial=False, out=None, **kw):
+    """jic_simulate_host: HOST (NumPy) buffers in and out, every host<->device copy inside the call."""
+    lib = _lib.load()
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    if particles:
+        kw.setdefault("track_yz", True)
+    params, grid = make_params(n_species=len(species), dtype=tdt, **kw)
+    sp = make_species(species)
+    N = int(sum(int(s["count"]) for s in species))
+    G, T = params.n_grid, int(n_steps)
+    x0 = np.ascontiguousarray(x0, dtype=dtype)
+    v0 = np.ascontiguousarray(v0, dtype=dtype)
+    assert x0.shape == (N, 3) and v0.shape == (N, 3)
+    res = {} if out is None else out
+    if fields:
+        for k in _HIST[:3]:
+            res.setdefault(k, np.empty((T, G, 3), dtype=dtype))
+        res.setdefault("charge_density", np.empty((T, G), dtype=dtype))
+    if particles:
+        res.setdefault("positions", np.empty((T, N, 3), dtype=dtype))
+        res.setdefault("velocities", np.empty((T, N, 3), dtype=dtype))
+    o = Outputs()
+    for k in _HIST:
+        setattr(o, k, res[k].ctypes.data if k in res else None)
+    eE = None if ext_E is None else np.ascontiguousarray(ext_E, dtype=np.float32)
+    eB = None if ext_B is None else np.ascontiguousarray(ext_B, dtype=np.float32)
+    E0 = B0 = vi = None
+    if initial:
+        E0, B0 = np.empty((G, 3), dtype=dtype), np.empty((G, 3), dtype=dtype)
+        vi = np.empty((N, 3), dtype=dtype)
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
+    _lib.check(lib.jic_simulate_host(C.byref(params), sp, vp(x0), vp(v0), vp(eE), vp(eB), T, C.byref(o), vp(E0), vp(B0), vp(vi)))
+    res["grid"] = grid
+    if initial:
+        res["fields"] = (E0, B0)
+        res["initial_velocities"] = vi
+    return res

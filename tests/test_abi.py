@@ -1,0 +1,74 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/jic_b200.h declares (no compute calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("jic_build", os.path.join(ROOT, "jax-in-cell_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+    from jaxincell_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    header = open(os.path.join(ROOT, "include", "jic_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(jic_[a-z_0-9]+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 14
+    bound = {name for name, _, _ in lib.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    handle = lib.load()
+    for name in declared:
+        assert hasattr(handle, name)
+    assert handle.jic_abi_version() == 1
+
+
+def test_struct_layout_matches_header(lib, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "jic_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(jic_params),sizeof(jic_species),sizeof(jic_outputs),offsetof(jic_params,filter_alpha),offsetof(jic_params,grid_first));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(lib.Params), C.sizeof(lib.Species), C.sizeof(lib.Outputs), lib.Params.filter_alpha.offset, lib.Params.grid_first.offset]
+
+
+def test_invalid_arguments_are_reported_without_a_gpu(lib):
+    h = lib.load()
+    ctx = C.c_void_p()
+    p = lib.Params()
+    sp = (lib.Species * 1)()
+    assert h.jic_create(C.byref(p), sp, C.byref(ctx)) == -1  # struct_bytes == 0 -> ABI mismatch
+    assert b"ABI mismatch" in h.jic_last_error(None)
+    p.struct_bytes = C.sizeof(lib.Params)
+    p.n_grid, p.n_species, p.length, p.dx, p.dt = 2, 1, 1.0, 0.5, 1e-9
+    assert h.jic_create(C.byref(p), sp, C.byref(ctx)) == -1
+    assert b"number_grid_points" in h.jic_last_error(None)
+    assert h.jic_run(None, 1, None, None) == -1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from jaxincell_b200 import HotPath, JicError
+    with pytest.raises(JicError, match="no CUDA device"):
+        HotPath(species=[dict(count=1, q=1.0, m=1.0, qm=1.0)], length=1.0, G=8, dt=1e-9)
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "jax-in-cell_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,173 @@
+"""Parity of the CUDA hot path (through the C ABI) with the oracle on identical initial particles.
+
+Tolerance (BASELINE.json north_star): per-step E, B, J, rho, x, v within rtol 1e-5 in fp64 (1e-3 in fp32), measured
+against the largest magnitude of each history (atomic summation order is not deterministic).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as C
+from oracle import literal as L
+from plasma import cfl_dt, two_species
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {torch.float64: 1e-5, torch.float32: 1e-3}
+FIELD_KEYS = ("electric_field", "magnetic_field", "current_density", "charge_density")
+
+
+def run_gpu(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, ext_E=None, ext_B=None, dtype=torch.float64,
+            engine="indexed", deposit="auto", particles=True, box_yz=None, steps_per_graph=0):
+    from jaxincell_b200 import HotPath
+    solver = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "relativistic": False, **(solver or {})}
+    hp = HotPath(species=p["species"], dtype=dtype, length=length, G=G, dt=dt, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2], fbr=bcs[3],
+                 filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
+                 relativistic=solver["relativistic"], engine=engine, deposit=deposit, track_yz=particles,
+                 length_y=(box_yz or (0, 0))[0], length_z=(box_yz or (0, 0))[1], steps_per_graph=steps_per_graph)
+    hp.set_external_fields(ext_E, ext_B)
+    hp.initialize(p["x0"], p["v0"])
+    out = hp.run(T, particles=particles and engine == "indexed")
+    res = {k: v.cpu().numpy().astype(np.float64) for k, v in out.items()}
+    E0, B0, vi = hp.initial(velocities=engine == "indexed")
+    res["fields"] = (E0.cpu().numpy(), B0.cpu().numpy())
+    if vi is not None:
+        res["initial_velocities"] = vi.cpu().numpy()
+    res["launches"] = hp.launch_count()
+    res["hp"] = hp
+    return res
+
+
+def assert_parity(got, ref, keys, rtol):
+    for k in keys:
+        scale = np.abs(ref[k]).max()
+        if scale == 0:
+            assert np.abs(got[k]).max() == 0, k
+            continue
+        err = np.abs(got[k] - ref[k]).max() / scale
+        assert err < rtol, f"{k}: max rel err {err:.3e} >= {rtol}"
+
+
+@pytest.mark.parametrize("deposit", ["global", "shared"])
+@pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2), (1, 2, 1, 2), (2, 0, 2, 0), (0, 1, 0, 1)])
+def test_small_plasma_all_boundaries(bcs, deposit):
+    G, length, T = 16, 0.01, 25
+    p = two_species(300, 300, length=length, G=G, seed=21, vth_e=0.3, vth_yz=0.2, drift=5e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    rng = np.random.default_rng(5)
+    extE = 1e3 * rng.normal(size=(G, 3)); extB = 1e-3 * rng.normal(size=(G, 3))
+    solver = dict(filter_passes=3, filter_alpha=0.4, filter_strides=(1, 2))
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=bcs[0], pbr=bcs[1],
+                fbl=bcs[2], fbr=bcs[3], solver=solver, ext_E=extE, ext_B=extB)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, bcs=bcs, solver=solver, ext_E=extE, ext_B=extB, deposit=deposit)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+    np.testing.assert_allclose(got["initial_velocities"], ref["initial_velocities"], rtol=1e-14)
+    np.testing.assert_allclose(got["fields"][0], ref["fields"][0], rtol=1e-10, atol=1e-12 * np.abs(ref["fields"][0]).max())
+    if 2 in bcs[:2]:
+        x, v, alive = got["hp"].particles()
+        assert int((alive == 0).sum()) == int((ref["state"].q == 0).sum()) > 0
+
+
+def test_literal_oracle_direct():
+    """Straight against the expression-level restatement (both current deposits per step, O(N*G))."""
+    G, length, T = 12, 0.01, 8
+    p = two_species(60, 60, length=length, G=G, seed=3, vth_e=0.2, vth_yz=0.1, drift=3e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.8)
+    ref = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+
+
+def test_example_input_toml_regime():
+    """examples/input.toml: G=70, L=0.01, CFL 4.5, 3500+3500, drift +-6e7, v_y=v_z=0 (window truncation active)."""
+    G, length, T = 70, 0.01, 60
+    p = two_species(3500, 3500, length=length, G=G, seed=1701, vth_e=0.05, drift=6e7, plus_minus=True, gpdl=0.50265482457,
+                    amp=5e-7, k=1.0, random_x=False)
+    dt = cfl_dt(length, G, 4.5)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+
+
+def test_landau_regime_with_energy():
+    """examples/Landau_damping.py scaled down: G=32, L=1, CFL 1, vth 0.35c, heavy ions; energy history matches."""
+    G, length, T = 32, 1.0, 80
+    p = two_species(4000, 4000, length=length, G=G, seed=8, vth_e=0.35, gpdl=0.4, amp=0.025, k=1.02, random_x=False, ion_mass=1e9,
+                    ion_vth_scale=np.sqrt(1e-9))
+    dt = cfl_dt(length, G, 1.0)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+    eo = C.energies(ref, p["m"], ref["dx"]); eg = C.energies(got, p["m"], ref["dx"])
+    np.testing.assert_allclose(eg["total_energy"], eo["total_energy"], rtol=1e-8)
+    ke = float(got["hp"].kinetic_energy().cpu()[0])
+    np.testing.assert_allclose(ke, eo["kinetic_energy"][-1], rtol=1e-10)
+
+
+def test_weibel_regime_magnetic_growth():
+    """examples/Weibel_instability.py scaled: anisotropic vth_z >> vth_x, random x, full v x B rotation, B_y grows."""
+    G, length, T = 48, 0.3, 120
+    p = two_species(6000, 6000, length=length, G=G, seed=12, vth_e=0.01, vth_yz=0.10, gpdl=1.1)
+    p["v0"][:6000, 1] *= 0.0  # vth_y = 0 for electrons as in the example
+    dt = cfl_dt(length, G, 1.0)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+    assert np.abs(got["magnetic_field"][-1]).max() > 0
+
+
+def test_relativistic_pusher():
+    G, length, T = 24, 0.02, 30
+    p = two_species(500, 500, length=length, G=G, seed=31, vth_e=0.5, vth_yz=0.3, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    solver = dict(relativistic=True)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=solver)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, solver=solver)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+
+
+@pytest.mark.parametrize("G", [4, 5, 7])
+def test_tiny_grids(G):
+    """Reference fixtures use G=4 (tests/helpers.py:36): the J_x window degenerates to the whole grid."""
+    length, T = 0.01, 12
+    p = two_species(50, 50, length=length, G=G, seed=G, vth_e=0.2, vth_yz=0.1, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.7)
+    solver = dict(filter_passes=0)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=solver)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, solver=solver)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+
+
+def test_fp32_mode():
+    G, length, T = 32, 0.01, 30
+    p = two_species(2000, 2000, length=length, G=G, seed=5, vth_e=0.1, vth_yz=0.05, drift=4e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, dtype=torch.float32)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-3)
+
+
+def test_history_rows_and_graph_chunks():
+    """Two jic_run calls continue the same simulation; odd step counts exercise the 16-step and 1-step graphs."""
+    G, length = 20, 0.01
+    p = two_species(400, 400, length=length, G=G, seed=77, vth_e=0.1, drift=3e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=37)
+    a = run_gpu(p, length=length, G=G, dt=dt, T=19, particles=False)
+    b = a["hp"].run(18)
+    for k in FIELD_KEYS:
+        both = np.concatenate([a[k], b[k].cpu().numpy()])
+        assert np.abs(both - ref[k]).max() / np.abs(ref[k]).max() < 1e-5, k
+    assert a["hp"].launch_count() >= 2 * 37
+
+
+def test_host_buffer_entry_point():
+    """jic_simulate_host: NumPy in, NumPy out, all copies inside (the e2e boundary)."""
+    from jaxincell_b200 import simulate_host
+    G, length, T = 16, 0.01, 10
+    p = two_species(200, 200, length=length, G=G, seed=9, vth_e=0.1, vth_yz=0.05, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T)
+    got = simulate_host(species=p["species"], x0=p["x0"], v0=p["v0"], n_steps=T, length=length, G=G, dt=dt, particles=True, initial=True)
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+    np.testing.assert_allclose(got["initial_velocities"], ref["initial_velocities"], rtol=1e-14)
