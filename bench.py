@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark: particle-steps/s of the fused PIC hot path on the synthetic scaling plasma.
+
+  python bench.py --gpus 1 --steps K --warmup W            (torchrun launches N>1 ranks, one per GPU)
+  python bench.py --impl reference ...                     (the CPU restatement of the reference on the host cores)
+
+One JSON line on rank 0.  `value` is device-timed (CUDA events around the graph-captured time loop, barrier + sync on
+both sides, max over ranks) with the particles resident in HBM; `e2e` is the same metric through the host-buffer
+entry point (pinned host -> device copies of the initial particles and device -> host copies of the field histories
+inside the timed region).  Weak scaling: every rank owns --particles macro-particles.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "jax-in-cell_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+C_LIGHT = 2.99792458e8
+EPS0 = 8.85418782e-12
+QE = 1.60217663e-19
+ME = 9.10938371e-31
+MP = 1.67262193e-27
+BYTES_PER_PARTICLE_STEP = {"f64": 64, "f32": 32}  # read + write of x_{n+1/2}, v_x, v_y, v_z
+
+
+def workload(args, world):
+    """G=4096, dx=0.01/70 m, CFL 1, periodic, filter 5/0.5/(1,2,4); electrons N/2 as two
+    counter-streaming beams (+-0.2c, thermal 0.05c) with uniform-random x, ions N/2 cold (T_i/T_e = 1e-2)."""
+    G = args.grid
+    dx = 0.01 / 70
+    length = G * dx
+    dt = 1.0 * dx / C_LIGHT
+    n_e = args.particles // 2
+    n_i = args.particles - n_e
+    vth_e = 0.05
+    gpdl = 2.0
+
+    def weight(n_global):  # jaxincell/_state_initialization.py:172-185 with the GLOBAL species count
+        return EPS0 * ME * C_LIGHT ** 2 / QE ** 2 * G ** 2 / length / (2 * n_global) * vth_e ** 2 * gpdl ** 2
+
+    we, wi = weight(n_e * world), weight(n_i * world)
+    species = [dict(count=n_e, q=-QE * we, m=ME * we, qm=-QE / ME), dict(count=n_i, q=QE * wi, m=MP * wi, qm=QE / MP)]
+    return dict(G=G, length=length, dt=dt, species=species, vth_e=vth_e, n_e=n_e, n_i=n_i)
+
+
+def make_particles(w, torch, device, dtype, seed, order):
+    """Synthetic particles generated ON the device (Philox), (N,3) row-major like the reference's arrays."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n_e, n_i, L = w["n_e"], w["n_i"], w["length"]
+    N = n_e + n_i
+    x0 = torch.empty((N, 3), dtype=dtype, device=device)
+    v0 = torch.empty((N, 3), dtype=dtype, device=device)
+    if order == "random":
+        x0[:, 0].uniform_(-L / 2, L / 2, generator=g)
+    else:  # the reference default (random_positions_x=False): linspace per species -> sorted, the atomics worst case
+        x0[:n_e, 0] = torch.linspace(-L / 2, L / 2, n_e, dtype=dtype, device=device)
+        x0[n_e:, 0] = torch.linspace(-L / 2, L / 2, n_i, dtype=dtype, device=device)
+    x0[:, 1:].uniform_(-L / 2, L / 2, generator=g)
+    s = C_LIGHT / 2 ** 0.5
+    v0[:n_e, 0].normal_(0.0, 0.05 * s, generator=g)
+    v0[:n_e, 0] += 0.2 * C_LIGHT
+    v0[:n_e:2, 0] *= 1.0
+    v0[1:n_e:2, 0] *= -1.0  # velocity_plus_minus_x: alternate sign by index
+    v0[:n_e, 1:].normal_(0.0, 0.01 * s, generator=g)
+    vthi = 0.05 * (1e-2 * ME / MP) ** 0.5
+    v0[n_e:, 0].normal_(0.0, vthi * s, generator=g)
+    v0[n_e:, 1:].normal_(0.0, 0.2 * vthi * s, generator=g)
+    return x0, v0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000):
+    """Oracle port (NumPy closed form) on the host cores: particles split over threads, grids summed."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import closed_form as CF
+    threads = threads or os.cpu_count() or 1
+    rng = np.random.default_rng(1701)
+    L, G, dt = w["length"], w["G"], w["dt"]
+    n_e = n_i = n_sample // 2
+    x0 = np.zeros((n_sample, 3)); v0 = np.zeros((n_sample, 3))
+    x0[:, 0] = rng.uniform(-L / 2, L / 2, n_sample)
+    s = C_LIGHT / 2 ** 0.5
+    v0[:n_e, 0] = (0.2 * C_LIGHT + 0.05 * s * rng.standard_normal(n_e)) * (-1.0) ** np.arange(n_e)
+    v0[:n_e, 1:] = 0.01 * s * rng.standard_normal((n_e, 2))
+    sp = w["species"]
+    scale = (w["n_e"] / n_e)
+    q = np.concatenate([np.full(n_e, sp[0]["q"] * scale), np.full(n_i, sp[1]["q"] * scale)])
+    m = np.concatenate([np.full(n_e, sp[0]["m"] * scale), np.full(n_i, sp[1]["m"] * scale)])
+    qm = np.concatenate([np.full(n_e, sp[0]["qm"]), np.full(n_i, sp[1]["qm"])])
+    dom = CF.Domain(L, G, dt)
+    solver = dict(filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4))
+    chunks = np.array_split(np.arange(n_sample), threads)
+    states = [CF.start(x0[c], v0[c], q[c], m[c], qm[c], dom, 0, 0, 0, 0, solver) for c in chunks]
+    # the grid is shared: every chunk deposits, the sums are combined, one field solve (same as the multi-GPU scheme)
+    from oracle import literal as LT
+
+    def push_deposit(st, E, B):
+        E_p, B_p = CF.gather_EB(st.x_half[:, 0], E, B, dom, 0, 0)
+        x_pp, v_new = CF.push_boris(dt, st.x_half, st.v, st.qm, E_p, B_p)
+        x_pp, v_new, qq, mm, qqm = LT.set_BC_particles(x_pp, v_new, st.q, st.m, st.qm, dom.dx, dom.grid, *dom.box, 0, 0)
+        x_new = LT.set_BC_positions(x_pp - (dt / 2) * v_new, dom.dx, dom.grid, *dom.box, 0, 0)
+        J = CF.deposit_current_raw(st.x_half[:, 0], x_new[:, 0], x_pp[:, 0], v_new, qq, dom, 0, 0)
+        rho = CF.deposit_rho_raw(x_new[:, 0], qq, dom, 0, 0)
+        st.x_half, st.v = x_pp, v_new
+        return J, rho
+
+    E = sum(s_.E for s_ in states); B = states[0].B
+    J = sum(s_.J for s_ in states)  # start() filtered each chunk's J; the filter is linear
+    pool = ThreadPoolExecutor(threads)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        E, B = LT.field_update1(E, B, dom.dx, dt / 2, J, 0, 0)
+        parts = list(pool.map(lambda st: push_deposit(st, E, B), states))
+        J = LT.filter_vector_field(sum(p_[0] for p_ in parts), 5, 0.5, (1, 2, 4), 0, 0)
+        LT.filter_scalar_field(sum(p_[1] for p_ in parts), 5, 0.5, (1, 2, 4), 0, 0)
+        E, B = LT.field_update2(E, B, dom.dx, dt / 2, J, 0, 0)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > seconds_target or steps >= 200:
+            break
+    pool.shutdown()
+    return n_sample * steps / el, threads, f"{n_sample} particles x {steps} steps, G={G}, NumPy closed-form port of the reference, {threads} threads"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args, 1)
+    rate, cores, sample = cpu_port_rate(w, seconds_target=min(60.0, 4.0 * max(args.steps, 1)))
+    line = {"impl": "reference", "metric": "particle-steps/sec", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic two-beam plasma, G={args.grid}, CFL 1, periodic, filter 5/0.5/(1,2,4) (SURVEY 8d config 5), CPU sample"},
+            "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "JAX is not installable in this image, so the reference itself cannot run; this is the oracle port (NumPy) of its algorithm"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=100_000_000, help="macro-particles PER GPU (weak scaling)")
+    ap.add_argument("--grid", type=int, default=4096)
+    ap.add_argument("--engine", default=os.environ.get("JIC_BENCH_ENGINE", "auto"))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--order", default="random", choices=["random", "sorted"])
+    ap.add_argument("--deposit", default="auto", choices=["auto", "global", "shared"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from jaxincell_b200 import HotPath, JicError
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU restatement")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = workload(args, world)
+    engine = args.engine
+    if engine == "auto":
+        engine = "binned"
+        try:
+            HotPath(species=[dict(count=8, q=1.0, m=1.0, qm=1.0)], length=1.0, G=8, dt=1e-9, engine="binned").close()
+        except JicError:
+            engine = "indexed"
+    hp = HotPath(species=w["species"], dtype=dtype, length=w["length"], G=w["G"], dt=w["dt"], engine=engine, deposit=args.deposit)
+    if world > 1:
+        hp.comm_init_from_torch()
+    x0, v0 = make_particles(w, torch, device, dtype, 1701 + rank, args.order)
+    hp.set_external_fields(None, None)
+    hp.initialize(x0, v0)
+    N, G, K, W = hp.N, hp.G, args.steps, max(args.warmup, 3)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    outs = hp.alloc_outputs(K)
+    hp.run(W, outputs=hp.alloc_outputs(W))
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = hp.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    hp.run(K, outputs=outs)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = hp.launch_count() - l0
+    # dominant kernel, timed live with CUDA events on its own stream (jic_profile_steps), a few more real steps
+    n_prof = min(K, 10)
+    ms_push, ms_grid = hp.profile_steps(n_prof)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, ms_push / n_prof, ms_grid / n_prof], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_push_step, ms_grid_step = (float(v) for v in t.cpu())
+    value = N * world * K / (ms * 1e-3)
+    energy_ok = bool(torch.isfinite(outs["electric_field"][-1]).all().item())
+
+    # ---- end to end: host buffers in, host buffers out
+    e2e = None
+    if not args.no_e2e:
+        del outs
+        hx = torch.empty((N, 3), dtype=dtype, pin_memory=True)
+        hv = torch.empty((N, 3), dtype=dtype, pin_memory=True)
+        hx.copy_(x0); hv.copy_(v0)
+        del x0, v0
+        torch.cuda.empty_cache()
+        host_out = {k: torch.empty(s, dtype=dtype, pin_memory=True) for k, s in
+                    (("electric_field", (K, G, 3)), ("magnetic_field", (K, G, 3)), ("current_density", (K, G, 3)), ("charge_density", (K, G)))}
+        hp.close()
+        barrier()
+        t0 = time.perf_counter()
+        hp2 = HotPath(species=w["species"], dtype=dtype, length=w["length"], G=w["G"], dt=w["dt"], engine=engine)
+        if world > 1:
+            hp2.comm_init_from_torch()
+        hp2.set_external_fields(None, None)
+        dx0 = hx.to(device, non_blocking=True); dv0 = hv.to(device, non_blocking=True)
+        hp2.initialize(dx0, dv0)
+        del dx0, dv0
+        o2 = hp2.run(K)
+        for k, h in host_out.items():
+            h.copy_(o2[k], non_blocking=True)
+        barrier()
+        el = time.perf_counter() - t0
+        tt = torch.tensor([el], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        el = float(tt.cpu()[0])
+        es = dtype.itemsize
+        e2e = {"value": N * world * K / el, "unit": "particle-steps/s", "h2d_bytes_per_step": int(world * N * 6 * es / K),
+               "d2h_bytes_per_step": int(G * 10 * es), "seconds": el,
+               "what": f"HotPath create + pinned-host->device copy of x0,v0 + initialize + {K} steps + device->host copy of the E,B,J,rho histories"}
+        hp2.close()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bpp = BYTES_PER_PARTICLE_STEP[args.dtype]
+        achieved = bpp * N / (ms_push_step * 1e-3) / 1e9
+        line = {
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": f"synthetic two-beam plasma (SURVEY 8d config 5): G={G}, {N} macro-particles per GPU, CFL 1, periodic, "
+                                   f"filter 5/0.5/(1,2,4), x order {args.order}", "engine": engine, "particles_per_gpu": N, "grid": G,
+                       "l2": "particle state (>= 3.2 GB per GPU) is far larger than L2; no flush needed"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "k_step (fused gather+push+BC+deposit)" if engine == "indexed" else "k_push_binned",
+                         "kernel_ms": ms_push_step, "grid_part_ms": ms_grid_step,
+                         "algorithmic_bytes": f"{bpp} B per particle-step x {N} particles per launch"},
+            "finite": energy_ok,
+        }
+        if clocks:
+            line["clocks"] = clocks
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu:
+            rate, cores, sample = cpu_port_rate(w, seconds_target=12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,10 @@ int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* initial_velociti
 int jic_get_particles(jic_context* ctx, void* x_half, void* v, uint8_t* alive, void* stream);
 /* Sum over local particles of 0.5*m*v^2 (jaxincell/_diagnostics.py:131-138) into *kinetic_energy (device double). */
 int jic_kinetic_energy(jic_context* ctx, double* kinetic_energy, void* stream);
+/* Measurement aid: advance n_steps WITHOUT graphs or histories, bracketing the particle kernel(s) and the grid part
+ * (all-reduce + field kernel) of every step with CUDA events on `stream`; returns the summed milliseconds of each.
+ * Synchronises the stream. */
+int jic_profile_steps(jic_context* ctx, int64_t n_steps, double* ms_particle_kernels, double* ms_grid_kernels, void* stream);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 

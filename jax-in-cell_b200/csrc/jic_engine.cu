@@ -229,8 +229,8 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
-  // enqueue one full step on `st` (used under stream capture)
-  int enqueue_step(const jic_outputs& out, cudaStream_t st) {
+  // enqueue one full step on `st` (used under stream capture): particle kernel(s), all-reduce, field kernel
+  int enqueue_push(const jic_outputs& out, cudaStream_t st) {
     if (prm.engine == JIC_ENGINE_INDEXED) {
       R* xhist = (R*)out.positions;
       R* vhist = (R*)out.velocities;
@@ -243,16 +243,55 @@ struct EngineT : Engine {
         k_step<R, false><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, xhist, vhist, ctl);
       }
       launches += 1;
-    } else {
-      int rc = bins.step(*this, dp, F, acc, st);
-      if (rc) return rc;
+      return JIC_OK;
     }
+    return bins.step(*this, dp, F, acc, st);
+  }
+
+  int enqueue_fields(const jic_outputs& out, cudaStream_t st) {
     int rc = allreduce(st);
     if (rc) return rc;
     k_fields<R><<<1, 1024, 0, st>>>(field_args(false, &out));
     launches += 1;
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
     return JIC_OK;
+  }
+
+  int enqueue_step(const jic_outputs& out, cudaStream_t st) {
+    int rc = enqueue_push(out, st);
+    return rc ? rc : enqueue_fields(out, st);
+  }
+
+  // n real steps (no histories) with CUDA events around the particle kernel(s) and the grid part of every step
+  int profile(long long n, double* ms_push, double* ms_fields, cudaStream_t st) override {
+    if (!initialized) return fail(JIC_ERR_BAD_STATE, "jic_profile_steps before jic_initialize");
+    jic_outputs none;
+    memset(&none, 0, sizeof(none));
+    std::vector<cudaEvent_t> ev(3 * (size_t)n);
+    for (auto& e : ev) JIC_CUDA(cudaEventCreate(&e));
+    int rc = JIC_OK;
+    for (long long s = 0; s < n && rc == JIC_OK; ++s) {
+      cudaEventRecord(ev[3 * s], st);
+      rc = enqueue_push(none, st);
+      cudaEventRecord(ev[3 * s + 1], st);
+      if (rc == JIC_OK) rc = enqueue_fields(none, st);
+      cudaEventRecord(ev[3 * s + 2], st);
+    }
+    cudaError_t ce = cudaStreamSynchronize(st);
+    double a = 0, b = 0;
+    if (rc == JIC_OK && ce == cudaSuccess) {
+      for (long long s = 0; s < n; ++s) {
+        float t1 = 0, t2 = 0;
+        cudaEventElapsedTime(&t1, ev[3 * s], ev[3 * s + 1]);
+        cudaEventElapsedTime(&t2, ev[3 * s + 1], ev[3 * s + 2]);
+        a += t1; b += t2;
+      }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ce != cudaSuccess) return fail(JIC_ERR_CUDA, format("profile: %s", cudaGetErrorString(ce)));
+    if (ms_push) *ms_push = a;
+    if (ms_fields) *ms_fields = b;
+    return rc;
   }
 
   int get_graph(const jic_outputs& out, int steps, cudaStream_t st, cudaGraphExec_t* exec) {
@@ -431,6 +470,7 @@ int jic_get_fields(jic_context* ctx, void* E, void* B, void* J, void* rho, void*
 int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* v, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_initial(E0, B0, v, (cudaStream_t)st); }
 int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_particles(x, v, alive, (cudaStream_t)st); }
 int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
+int jic_profile_steps(jic_context* ctx, int64_t n, double* ms_push, double* ms_fields, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->profile(n, ms_push, ms_fields, (cudaStream_t)st); }
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
 
 int jic_simulate_host(const jic_params* params, const jic_species* species, const void* x0_host, const void* v0_host,

@@ -160,6 +160,12 @@ class HotPath:
         self._chk(self.lib.jic_kinetic_energy(self.ctx, self._ptr(ke), self._stream()))
         return ke
 
+    def profile_steps(self, n_steps):
+        """(ms in the particle kernels, ms in all-reduce + field kernel) summed over n_steps real steps (CUDA events)."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._chk(self.lib.jic_profile_steps(self.ctx, int(n_steps), C.byref(a), C.byref(b), self._stream()))
+        return a.value, b.value
+
     def launch_count(self):
         return int(self.lib.jic_launch_count(self.ctx))
 

@@ -58,6 +58,7 @@ SYMBOLS = [
     ("jic_get_initial", C.c_int, [_P, _P, _P, _P, _P]),
     ("jic_get_particles", C.c_int, [_P, _P, _P, _P, _P]),
     ("jic_kinetic_energy", C.c_int, [_P, _P, _P]),
+    ("jic_profile_steps", C.c_int, [_P, C.c_int64, _P, _P, _P]),
     ("jic_launch_count", C.c_int64, [_P]),
     ("jic_simulate_host", C.c_int, [C.POINTER(Params), C.POINTER(Species), _P, _P, _P, _P, C.c_int64, C.POINTER(Outputs), _P, _P, _P]),
 ]

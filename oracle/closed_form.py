@@ -93,14 +93,15 @@ def deposit_current_raw(x_old, x_mid, x_new, v_mid, q, dom, pbl, pbr):
     gs = grid[0] - dx / 2  # _algorithms.py:30
     cell = np.floor_divide(np.asarray(x_old, dtype=np.float64) - gs, dx).astype(np.int64)
     W = min(6, G)
-    short = np.zeros((n, W))
-    rows = np.arange(n)
+    flat = np.zeros(n * W)
+    rows = np.arange(n) * W
     for xx, sign in ((x_new, +1.0), (x_old, -1.0)):
         nodes, vals = s2_entries(xx, q, dom, pbl, pbr)
         rel = np.mod(nodes - (cell[:, None] - 3), G)
-        for e in range(nodes.shape[1]):
-            hit = rel[:, e] < W
-            np.add.at(short, (rows[hit], rel[hit, e]), sign * vals[hit, e] / dt)
+        hit = rel < W
+        idx = (rows[:, None] + rel)[hit]
+        flat += np.bincount(idx, weights=(sign * vals / dt)[hit], minlength=n * W)
+    short = flat.reshape(n, W)
     jwin = np.cumsum(-short * dx, axis=1)
     knodes = np.mod(cell[:, None] - 3 + np.arange(W)[None, :], G)
     J = np.zeros((G, 3))

@@ -119,6 +119,8 @@ def test_weibel_regime_magnetic_growth():
 def test_relativistic_pusher():
     G, length, T = 24, 0.02, 30
     p = two_species(500, 500, length=length, G=G, seed=31, vth_e=0.5, vth_yz=0.3, gpdl=0.5)
+    speed = np.linalg.norm(p["v0"], axis=1, keepdims=True)  # component-wise 0.99c clipping does not bound |v|; keep gamma real
+    p["v0"] = np.where(speed > 0.95 * L.speed_of_light, p["v0"] * (0.95 * L.speed_of_light / speed), p["v0"])
     dt = cfl_dt(length, G, 0.9)
     solver = dict(relativistic=True)
     ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=solver)
