@@ -326,6 +326,7 @@ struct EngineT : Engine {
     return JIC_OK;
   }
   long long launches_per_step = 0;
+  long long steps_run = 0;
 
   int run(long long n, const jic_outputs* outp, cudaStream_t st) override {
     if (!initialized) return fail(JIC_ERR_BAD_STATE, "jic_run before jic_initialize");
@@ -336,6 +337,12 @@ struct EngineT : Engine {
     if (prm.engine == JIC_ENGINE_BINNED && (out.positions || out.velocities))
       return fail(JIC_ERR_UNSUPPORTED, "particle histories need the INDEXED engine");
     if (out.positions && !prm.track_yz) return fail(JIC_ERR_INVALID_ARGUMENT, "positions history needs track_yz=1");
+    if (prm.engine == JIC_ENGINE_BINNED && steps_run > 0) {
+      // the store reports exhausted head-room through a sticky device flag: look at it before queueing more work
+      int rc = bins.check_error(*this, st);
+      if (rc) return rc;
+    }
+    steps_run += n;
     // row 0 of the histories is the first step of this call
     JIC_CUDA(cudaMemsetAsync(&ctl->hist_row, 0, sizeof(long long), st));
     const int chunk = prm.steps_per_graph > 0 ? prm.steps_per_graph : 16;
