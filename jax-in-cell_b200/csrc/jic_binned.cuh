@@ -25,14 +25,18 @@
 
 namespace jic {
 
-constexpr int kChunk = 2048;       // particles per work item
+constexpr int kMinChunk = 1024;    // particles per work item: chosen by k_plan in [kMinChunk, kMaxChunk]
+constexpr int kMaxChunk = 8192;
 constexpr int kPushThreads = 256;
+constexpr int kNumCoef = 21;       // CTA-uniform gather polynomial coefficients (see k_push_binned)
 
 struct PlanHeader {
   int flip;            // which buffer is the SOURCE of the next push
   int n_items;         // work items of the next push
   int ov_n[2];         // entries in the overflow list of each buffer
   int error;           // sticky: 1 = overflow list full, 2 = capacity exhausted
+  int chunk;           // particles per work item of the next push
+  int work;            // dynamic work queue head (reset by k_plan)
   int pad;
   long long n_stored;  // live particles (bins + overflow list) in the source buffer
   long long n_absorbed;
@@ -50,6 +54,7 @@ struct BinDev {
   unsigned* cur[2];       // [nb]   write cursors (count every attempt, also the overflowed ones)
   int* ov_bin[2]; R* ov_d[2]; R* ov_vx[2]; R* ov_vy[2]; R* ov_vz[2];
   int* item_bin; int* item_first; int item_cap;
+  int n_cta;              // CTAs of the push kernel (work-queue consumers)
   PlanHeader* hdr;
 };
 
@@ -130,60 +135,79 @@ __device__ __forceinline__ R warp_sum(R v) {
 template <typename R, bool REL>
 __global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams<R> p, const BinDev<R> bd, const R* __restrict__ F,
                                                                    R* __restrict__ acc) {
-  const PlanHeader* hdr = bd.hdr;
+  PlanHeader* hdr = bd.hdr;
   const int src = hdr->flip, dst = src ^ 1;
   const R* __restrict__ sd = bd.d[src]; const R* __restrict__ svx = bd.vx[src];
   const R* __restrict__ svy = bd.vy[src]; const R* __restrict__ svz = bd.vz[src];
-  const int n_items = hdr->n_items;
+  const int n_items = hdr->n_items, chunk = hdr->chunk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int G = p.G;
   const bool periodic = (p.pbl == JIC_BC_PERIODIC) && (p.pbr == JIC_BC_PERIODIC);
   const R cells_per_v = p.dt * p.inv_dx;  // displacement in cells per unit velocity
   __shared__ R red[kPushThreads / 32][20];
+  __shared__ R coef[24];
+  __shared__ int s_item;
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (;;) {
+    // ---- next work item from the queue (dynamic: items differ in size)
+    if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
     const int b = bd.item_bin[item];
     const int first = bd.item_first[item];
     const int s = b / G, c = b - s * G;
-    const int n = min(kChunk, bd.cnt[src][b] - first);
+    const int n = min(chunk, bd.cnt[src][b] - first);
     const long long base = bd.off[src][b] + first;
     const bool fast_bin = G >= 8 && (periodic || (c >= 2 && c <= G - 3));
     const int bl = s * G + (c == 0 ? G - 1 : c - 1), br = s * G + (c == G - 1 ? 0 : c + 1);
 
-    // CTA-uniform gather polynomials: rows c..c+3 of the padded table are f[c-2], f[c-1], f[c], f[c+1]
-    const R hs = REL ? R(1) : p.sp_qm[s] * p.half_dt;  // non-relativistic: fold (q/m)(dt/2) into the coefficients
-    R elo[3][3], ehi[3][3], bq[3][3];
-    {
-      const R* f = F + (size_t)c * kFieldRow;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const R f0 = __ldg(f + k), f1 = __ldg(f + kFieldRow + k), f2 = __ldg(f + 2 * kFieldRow + k), f3 = __ldg(f + 3 * kFieldRow + k);
-        elo[k][0] = hs * (R(0.5) * (f1 + f2)); elo[k][1] = hs * (f2 - f1); elo[k][2] = hs * (R(0.5) * (f0 + f2) - f1);
-        ehi[k][0] = hs * (R(0.5) * (f1 + f2)); ehi[k][1] = hs * (f2 - f1); ehi[k][2] = hs * (R(0.5) * (f1 + f3) - f2);
-        const R b1 = __ldg(f + kFieldRow + 3 + k), b2 = __ldg(f + 2 * kFieldRow + 3 + k), b3 = __ldg(f + 3 * kFieldRow + 3 + k);
-        bq[k][0] = hs * (R(0.125) * (b1 + b3) + R(0.75) * b2); bq[k][1] = hs * (R(0.5) * (b3 - b1)); bq[k][2] = hs * (R(0.5) * (b1 + b3) - b2);
+    // first particle of every thread is already in flight while the coefficients are set up
+    R nd = R(0), nv0 = R(0), nv1 = R(0), nv2 = R(0);
+    if ((int)threadIdx.x < n) { const long long k = base + threadIdx.x; nd = sd[k]; nv0 = svx[k]; nv1 = svy[k]; nv2 = svz[k]; }
+
+    // ---- CTA-uniform gather polynomials.  Rows c..c+3 of the padded table are f[c-2], f[c-1], f[c], f[c+1].
+    //   E lives on faces: for d < 0 the stencil is faces (c-2, c-1, c), for d >= 0 faces (c-1, c, c+1):
+    //     E(d) = 1/2 (f[c-1]+f[c]) + d (f[c]-f[c-1]) + d^2 a2,   a2 = 1/2 (f[c-2]+f[c]) - f[c-1]  (d<0),  1/2 (f[c-1]+f[c+1]) - f[c]  (d>=0)
+    //   B lives on centres (c-1, c, c+1):
+    //     B(d) = 1/8 (b[c-1]+b[c+1]) + 3/4 b[c] + d/2 (b[c+1]-b[c-1]) + d^2 (1/2 (b[c-1]+b[c+1]) - b[c])
+    //   coef[k*7 + {0: e0, 1: e1, 2: e2lo, 3: e2hi, 4: b0, 5: b1, 6: b2}], k = component.  Non-relativistic: pre-scaled by (q/m) dt/2.
+    if (threadIdx.x < kNumCoef) {
+      const int k = threadIdx.x / 7, w_ = threadIdx.x - 7 * k;
+      const R hs = REL ? R(1) : p.sp_qm[s] * p.half_dt;
+      const R* f = F + (size_t)c * kFieldRow + k;
+      R val;
+      if (w_ < 4) {
+        const R f0 = __ldg(f), f1 = __ldg(f + kFieldRow), f2 = __ldg(f + 2 * kFieldRow), f3 = __ldg(f + 3 * kFieldRow);
+        val = w_ == 0 ? R(0.5) * (f1 + f2) : w_ == 1 ? (f2 - f1) : w_ == 2 ? (R(0.5) * (f0 + f2) - f1) : (R(0.5) * (f1 + f3) - f2);
+      } else {
+        const R b1 = __ldg(f + kFieldRow + 3), b2 = __ldg(f + 2 * kFieldRow + 3), b3 = __ldg(f + 3 * kFieldRow + 3);
+        val = w_ == 4 ? (R(0.125) * (b1 + b3) + R(0.75) * b2) : w_ == 5 ? (R(0.5) * (b3 - b1)) : (R(0.5) * (b1 + b3) - b2);
       }
+      coef[threadIdx.x] = hs * val;
     }
-    // d < 0 uses faces (c-2, c-1, c):   E = 1/2 d^2 f0 + (1/2 - d - d^2) f1 + 1/2 (1+d)^2 f2
-    // d >= 0 uses faces (c-1, c, c+1):  E = 1/2 (1-d)^2 f1 + (1/2 + d - d^2) f2 + 1/2 d^2 f3
-    // (both written as a0 + a1 d + a2 d^2; note a0, a1 coincide, only the curvature differs)
+    __syncthreads();
 
     R a_rho[5] = {0, 0, 0, 0, 0}, a_jy[5] = {0, 0, 0, 0, 0}, a_jz[5] = {0, 0, 0, 0, 0}, a_jx[4] = {0, 0, 0, 0};
 
     const int n_pad = (n + 31) & ~31;
     for (int i = threadIdx.x; i < n_pad; i += kPushThreads) {
       const bool valid = i < n;
-      R d = R(0), v[3] = {R(0), R(0), R(0)};
-      if (valid) { d = sd[base + i]; v[0] = svx[base + i]; v[1] = svy[base + i]; v[2] = svz[base + i]; }
+      const R d = nd;
+      R v[3] = {nv0, nv1, nv2};
+      {  // software pipeline: the next particle's loads overlap this particle's arithmetic
+        const int j = i + kPushThreads;
+        if (j < n) { const long long k = base + j; nd = sd[k]; nv0 = svx[k]; nv1 = svy[k]; nv2 = svz[k]; }
+      }
       // ---- gather (quadratics in d)
       R E[3], B[3];
       const bool hi = d >= R(0);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const R a2 = hi ? ehi[k][2] : elo[k][2];
-        E[k] = fma(fma(a2, d, elo[k][1]), d, elo[k][0]);
-        B[k] = fma(fma(bq[k][2], d, bq[k][1]), d, bq[k][0]);
+        const R a2 = hi ? coef[7 * k + 3] : coef[7 * k + 2];
+        E[k] = fma(fma(a2, d, coef[7 * k + 1]), d, coef[7 * k]);
+        B[k] = fma(fma(coef[7 * k + 6], d, coef[7 * k + 5]), d, coef[7 * k + 4]);
       }
       // ---- velocity update
       if (REL) {
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams
         atomicAdd(acc + mod_pos(node, G) * kAccRow + comp, scale * t);
       }
     }
-    __syncthreads();
+    // (the __syncthreads at the head of the next iteration protects red[] and coef[])
   }
 
   // ---- particles that did not fit their bin last step: general path, one by one
@@ -367,7 +391,10 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
   if (t == 0) bd.off[next][nb] = tot_ll;
   __syncthreads();
   for (int b = lo; b < hi; ++b) bd.cur[next][b] = 0u;
-  // 3. work items over `written`
+  // 3. work items over `written`: about 4 per CTA of the push kernel, between kMinChunk and kMaxChunk particles each
+  long long want = n_total / (4ll * (bd.n_cta > 0 ? bd.n_cta : 1));
+  want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
+  const int kChunk = (int)((want + kPushThreads - 1) / kPushThreads) * kPushThreads;
   int my_items = 0;
   for (int b = lo; b < hi; ++b) my_items += (bd.cnt[written][b] + kChunk - 1) / kChunk;
   int it = block_exclusive_scan<int>(my_items, &tot_i, sh_i);
@@ -381,6 +408,8 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
   if (t == 0) {
     if (tot_i > bd.item_cap) atomicExch(&h->error, 2);
     h->n_items = tot_i < bd.item_cap ? tot_i : bd.item_cap;
+    h->chunk = kChunk;
+    h->work = 0;
     h->flip = written;
     h->ov_n[next] = 0;
     h->n_stored = n_total;
@@ -563,7 +592,8 @@ struct BinnedStore {
     bd.cap_total = (long long)((double)N * (1.0 + 3.0 * bd.slack)) + 48ll * bd.nb + 1024;
     if (bd.cap_total >= (1ll << 40)) return e.fail(JIC_ERR_UNSUPPORTED, "too many particles for one GPU");
     bd.ov_cap = (int)std::min<long long>(std::max<long long>(N / 16, 1 << 16), 1ll << 28);
-    bd.item_cap = (int)std::min<long long>(N / kChunk + bd.nb + 16, 1ll << 30);
+    bd.item_cap = (int)std::min<long long>(N / kMinChunk + bd.nb + 16, 1ll << 30);
+    bd.n_cta = n_sm * 2;
     int rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = alloc(e, &bd.d[k], bd.cap_total)) || (rc = alloc(e, &bd.vx[k], bd.cap_total)) || (rc = alloc(e, &bd.vy[k], bd.cap_total)) ||
@@ -621,7 +651,7 @@ struct BinnedStore {
   }
 
   int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, cudaStream_t st) {
-    const int g = n_sm * 2;
+    const int g = bd.n_cta;
     if (dp.relativistic) k_push_binned<R, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
     else k_push_binned<R, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
     e.launches += 1;
