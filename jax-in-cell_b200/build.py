@@ -40,6 +40,9 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false".replace("=false", ""),
            "-shared", "-Xcompiler", "-fPIC", "-I", nccl_include(), "-o", OUT, os.path.join(CSRC, "jic_engine.cu"), "-ldl"]
     cmd = [c for c in cmd if c != "--use_fast_math"]  # IEEE arithmetic: parity with the reference matters more than a few percent
+    for macro in ("JIC_PUSH_THREADS", "JIC_PUSH_MINBLOCKS"):  # tuning knobs of the binned push kernel
+        if os.environ.get(macro):
+            cmd.insert(1, f"-D{macro}={int(os.environ[macro])}")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

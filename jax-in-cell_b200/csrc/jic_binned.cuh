@@ -27,7 +27,14 @@ namespace jic {
 
 constexpr int kMinChunk = 1024;    // particles per work item: chosen by k_plan in [kMinChunk, kMaxChunk]
 constexpr int kMaxChunk = 8192;
-constexpr int kPushThreads = 256;
+#ifndef JIC_PUSH_THREADS
+#define JIC_PUSH_THREADS 64
+#endif
+#ifndef JIC_PUSH_MINBLOCKS
+#define JIC_PUSH_MINBLOCKS 6
+#endif
+constexpr int kPushThreads = JIC_PUSH_THREADS;
+constexpr int kPushMinBlocks = JIC_PUSH_MINBLOCKS;
 constexpr int kNumCoef = 21;       // CTA-uniform gather polynomial coefficients (see k_push_binned)
 
 struct PlanHeader {
@@ -133,7 +140,7 @@ __device__ __forceinline__ R warp_sum(R v) {
 // K1b  the binned push: gather -> Boris -> move -> deposit -> re-bin, one pass.
 // ---------------------------------------------------------------------------------------------------------
 template <typename R, bool REL>
-__global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams<R> p, const BinDev<R> bd, const R* __restrict__ F,
+__global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push_binned(const DevParams<R> p, const BinDev<R> bd, const R* __restrict__ F,
                                                                    R* __restrict__ acc) {
   PlanHeader* hdr = bd.hdr;
   const int src = hdr->flip, dst = src ^ 1;
@@ -148,6 +155,8 @@ __global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams
   __shared__ R red[kPushThreads / 32][20];
   __shared__ R coef[24];
   __shared__ int s_item;
+  __shared__ long long s_off[3];
+  __shared__ unsigned s_cap[3];
 
   for (;;) {
     // ---- next work item from the queue (dynamic: items differ in size)
@@ -186,10 +195,35 @@ __global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams
         val = w_ == 4 ? (R(0.125) * (b1 + b3) + R(0.75) * b2) : w_ == 5 ? (R(0.5) * (b3 - b1)) : (R(0.5) * (b1 + b3) - b2);
       }
       coef[threadIdx.x] = hs * val;
+    } else if (threadIdx.x >= 32 && threadIdx.x < 35) {
+      const int k = threadIdx.x - 32, bk = k == 0 ? b : (k == 1 ? bl : br);
+      const long long o = bd.off[dst][bk];
+      s_off[k] = o;
+      s_cap[k] = (unsigned)(bd.off[dst][bk + 1] - o);
     }
     __syncthreads();
 
     R a_rho[5] = {0, 0, 0, 0, 0}, a_jy[5] = {0, 0, 0, 0, 0}, a_jz[5] = {0, 0, 0, 0, 0}, a_jx[4] = {0, 0, 0, 0};
+
+    // A particle is STORED one iteration after its slot was claimed, so the cursor atomic's round trip overlaps the next
+    // particle's arithmetic instead of stalling the warp (q_* = claimed but not yet stored).  The first slot and capacity
+    // of the three fast-path destinations (stay / left / right) sit in shared memory (s_off, s_cap), indexed by kind.
+    R q_d = R(0), q_v0 = R(0), q_v1 = R(0), q_v2 = R(0);
+    int q_kind = -1;
+    unsigned q_m = 0, q_c = 0;
+    auto retire = [&]() {
+      // the leader lane of every destination group holds the base it claimed; one shuffle with a per-lane source
+      const unsigned base_slot = __shfl_sync(0xffffffffu, q_c, q_m ? __ffs(q_m) - 1 : 0);
+      if (q_kind >= 0) {
+        const unsigned slot = base_slot + __popc(q_m & lt_mask);
+        if (slot < s_cap[q_kind]) {
+          const long long k = s_off[q_kind] + slot;
+          bd.d[dst][k] = q_d; bd.vx[dst][k] = q_v0; bd.vy[dst][k] = q_v1; bd.vz[dst][k] = q_v2;
+        } else {
+          store_slot(bd, dst, q_kind == 0 ? b : (q_kind == 1 ? bl : br), slot, q_d, q_v0, q_v1, q_v2);  // -> overflow list
+        }
+      }
+    };
 
     const int n_pad = (n + 31) & ~31;
     for (int i = threadIdx.x; i < n_pad; i += kPushThreads) {
@@ -230,11 +264,12 @@ __global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams
       if (valid) kind = 3;
       R dn = d_new;
       if (fast) {
-        const int sh = (d_new >= R(0.5)) - (d_new < R(-0.5));
-        const int shm = (d_mid >= R(0.5)) - (d_mid < R(-0.5));
-        kind = sh == 0 ? 0 : (sh < 0 ? 1 : 2);
-        dn = d_new - R(sh);
-        const R dm = d_mid - R(shm);
+        const bool sr_ = d_new >= R(0.5), sl_ = d_new < R(-0.5), mr_ = d_mid >= R(0.5), ml_ = d_mid < R(-0.5);
+        const int sh = (int)sr_ - (int)sl_;
+        const int shm = (int)mr_ - (int)ml_;
+        kind = sr_ ? 2 : (sl_ ? 1 : 0);
+        dn = d_new - (sr_ ? R(1) : (sl_ ? R(-1) : R(0)));
+        const R dm = d_mid - (mr_ ? R(1) : (ml_ ? R(-1) : R(0)));
         // rho, J_y, J_z: S2 weights of x_{n+1} on nodes c-2..c+2 (its nearest node is c+shm)
         const R wl = R(0.5) * (R(0.5) - dm) * (R(0.5) - dm), wc = R(0.75) - dm * dm, wr = R(0.5) * (R(0.5) + dm) * (R(0.5) + dm);
         const bool ml = shm < 0, mc = shm == 0, mr = shm > 0;
@@ -255,24 +290,20 @@ __global__ void __launch_bounds__(kPushThreads, 2) k_push_binned(const DevParams
         a_jx[2] += (sl ? R(1) : (sc ? Bn : An)) - Bo;
         a_jx[3] += (sl || sc) ? R(0) : (Bn - R(1));
       }
-      // ---- claim slots in the destination bins (one atomic per warp and destination)
-      unsigned slot = 0;
-      int bdest = b;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const unsigned m = __ballot_sync(0xffffffffu, kind == k);
-        if (m) {
-          const int leader = __ffs(m) - 1;
-          const int bk = k == 0 ? b : (k == 1 ? bl : br);
-          unsigned b0 = 0;
-          if (lane == leader) b0 = atomicAdd(&bd.cur[dst][bk], (unsigned)__popc(m));
-          b0 = __shfl_sync(0xffffffffu, b0, leader);
-          if (kind == k) { slot = b0 + __popc(m & lt_mask); bdest = bk; }
-        }
-      }
-      if (kind >= 0 && kind < 3) store_slot(bd, dst, bdest, slot, dn, v[0], v[1], v[2]);
-      else if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d * p.dx, v[0], v[1], v[2]);
+      // ---- claim slots in the destination bins: one atomic per warp and destination (issued by the first lane of each
+      //      destination group), consumed next iteration
+      const unsigned m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1),
+                     m2 = __ballot_sync(0xffffffffu, kind == 2);
+      const unsigned m = kind == 0 ? m0 : (kind == 1 ? m1 : (kind == 2 ? m2 : 0u));
+      unsigned cl = 0;
+      if (m && lane == __ffs(m) - 1) cl = atomicAdd(bd.cur[dst] + (kind == 0 ? b : (kind == 1 ? bl : br)), (unsigned)__popc(m));
+      retire();  // the previous particle: its atomic has had a whole iteration to come back
+      q_d = dn; q_v0 = v[0]; q_v1 = v[1]; q_v2 = v[2];
+      q_kind = kind < 3 ? kind : -1;
+      q_m = m; q_c = cl;
+      if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d * p.dx, v[0], v[1], v[2]);
     }
+    retire();
 
     // ---- flush the register accumulators: warp shuffles -> shared memory -> 19 atomics on the raw grid
     R vals[19];
@@ -593,7 +624,7 @@ struct BinnedStore {
     if (bd.cap_total >= (1ll << 40)) return e.fail(JIC_ERR_UNSUPPORTED, "too many particles for one GPU");
     bd.ov_cap = (int)std::min<long long>(std::max<long long>(N / 16, 1 << 16), 1ll << 28);
     bd.item_cap = (int)std::min<long long>(N / kMinChunk + bd.nb + 16, 1ll << 30);
-    bd.n_cta = n_sm * 2;
+    bd.n_cta = n_sm * kPushMinBlocks;
     int rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = alloc(e, &bd.d[k], bd.cap_total)) || (rc = alloc(e, &bd.vx[k], bd.cap_total)) || (rc = alloc(e, &bd.vy[k], bd.cap_total)) ||
