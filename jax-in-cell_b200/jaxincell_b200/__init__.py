@@ -3,3 +3,4 @@ JAX-in-Cell's Simulation API.  The arithmetic lives in libjic_b200.so (hand-writ
 include/jic_b200.h); this package is the Python host side.  There is no CPU fallback."""
 from ._lib import JicError, LIB_PATH, load  # noqa: F401
 from ._engine import HotPath, make_params, make_species, simulate_host  # noqa: F401
+from ._parallel import shard_counts, shard_particles, shard_species  # noqa: F401

@@ -86,14 +86,11 @@ class HotPath:
         world, rank = dist.get_world_size(), dist.get_rank()
         if world == 1:
             return
+        from ._parallel import broadcast_bytes
         buf = C.create_string_buffer(128)
         if rank == 0:
             _lib.check(self.lib.jic_comm_unique_id(buf))
-        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        if dist.get_backend() == "nccl":
-            t = t.to(self.device)
-        dist.broadcast(t, src=0)
-        raw = bytes(t.cpu().numpy().tobytes())
+        raw = broadcast_bytes(buf.raw if rank == 0 else None, 128, 0, self.device)
         self._chk(self.lib.jic_comm_init(self.ctx, C.c_char_p(raw), rank, world))
 
     # ---- state in
