@@ -33,16 +33,19 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=None):
+    """defines: {macro: int} tuning knobs of the push kernel (also read from the environment); out: alternative .so path."""
+    if out is None and not force and not needs_build():
         return OUT
+    out = out or OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false".replace("=false", ""),
-           "-shared", "-Xcompiler", "-fPIC", "-I", nccl_include(), "-o", OUT, os.path.join(CSRC, "jic_engine.cu"), "-ldl"]
+           "-shared", "-Xcompiler", "-fPIC", "-I", nccl_include(), "-o", out, os.path.join(CSRC, "jic_engine.cu"), "-ldl"]
     cmd = [c for c in cmd if c != "--use_fast_math"]  # IEEE arithmetic: parity with the reference matters more than a few percent
-    for macro in ("JIC_PUSH_THREADS", "JIC_PUSH_MINBLOCKS"):  # tuning knobs of the binned push kernel
-        if os.environ.get(macro):
-            cmd.insert(1, f"-D{macro}={int(os.environ[macro])}")
+    for macro in ("JIC_PUSH_THREADS", "JIC_PUSH_MINBLOCKS", "JIC_PUSH_STAGES", "JIC_PUSH_STAGE_BLOCKS"):  # tuning knobs of the binned push kernel
+        val = (defines or {}).get(macro, os.environ.get(macro))
+        if val:
+            cmd.insert(1, f"-D{macro}={int(val)}")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -50,7 +53,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

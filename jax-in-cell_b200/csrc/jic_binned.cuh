@@ -10,12 +10,19 @@
 // Each particle's state crosses HBM once per step (4 reals in, 4 reals out); the out-write goes to the particle's NEW bin
 // (slots claimed through warp-aggregated cursor atomics), which is what keeps the store exactly binned with no sort pass.
 //
+// Memory layout: slots are grouped in BLOCKS of 32 (one warp); a block is [d x32][v_x x32][v_y x32][v_z x32], i.e. structure
+// of arrays inside 1 KiB (fp64) records.  Bins start on block boundaries.  A warp therefore reads a bin as a contiguous
+// stream of whole blocks (one 1-D bulk async copy per pipeline stage, any length), every lane's four values sit at
+// immediate offsets 0/256/512/768 B from one address, and re-binned particles of one warp land in runs of consecutive
+// slots that fill whole 32-byte sectors.
+//
 // The arithmetic is that of jaxincell/_algorithms.py:40-66,90-92 (see jic_device.cuh for the per-function citations); the
 // "fast path" below is the closed form of the reference's 6-node windowed prefix sum for a particle that moves by at most
 // one cell and stays clear of non-periodic walls.  Everything else (multi-cell jumps, wall cells, overflowed bins) takes
 // the exact general code of the INDEXED engine, particle by particle -- the deposit is additive, so paths can be mixed.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -27,15 +34,26 @@ namespace jic {
 
 constexpr int kMinChunk = 1024;    // particles per work item: chosen by k_plan in [kMinChunk, kMaxChunk]
 constexpr int kMaxChunk = 8192;
+constexpr int kChunkAlign = 256;   // items start on multiples of this inside a bin (a multiple of the block size)
+constexpr int kBlk = 32;           // slots per block
+constexpr int kBlkElems = 4 * kBlk;  // reals per block
 #ifndef JIC_PUSH_THREADS
-#define JIC_PUSH_THREADS 64
+#define JIC_PUSH_THREADS 128
 #endif
 #ifndef JIC_PUSH_MINBLOCKS
-#define JIC_PUSH_MINBLOCKS 6
+#define JIC_PUSH_MINBLOCKS 3
+#endif
+#ifndef JIC_PUSH_STAGES
+#define JIC_PUSH_STAGES 4          // ring slots per warp (power of two)
+#endif
+#ifndef JIC_PUSH_STAGE_BLOCKS
+#define JIC_PUSH_STAGE_BLOCKS 2    // 32-particle blocks per ring slot
 #endif
 constexpr int kPushThreads = JIC_PUSH_THREADS;
 constexpr int kPushMinBlocks = JIC_PUSH_MINBLOCKS;
-constexpr int kNumCoef = 21;       // CTA-uniform gather polynomial coefficients (see k_push_binned)
+constexpr int kPushStages = JIC_PUSH_STAGES;
+constexpr int kPushStageBlocks = JIC_PUSH_STAGE_BLOCKS;
+constexpr int kPushWarps = kPushThreads / 32;
 
 struct PlanHeader {
   int flip;            // which buffer is the SOURCE of the next push
@@ -55,13 +73,13 @@ struct BinDev {
   long long cap_total;    // slots per buffer
   int ov_cap;             // overflow list capacity
   float slack;            // head-room fraction per neighbour
-  R* d[2]; R* vx[2]; R* vy[2]; R* vz[2];
+  R* rec[2];              // blocked particle records of each buffer: 4 * cap_total reals
   long long* off[2];      // [nb+1] first slot of each bin
   int* cnt[2];            // [nb]   particles stored in each bin
   unsigned* cur[2];       // [nb]   write cursors (count every attempt, also the overflowed ones)
   int* ov_bin[2]; R* ov_d[2]; R* ov_vx[2]; R* ov_vy[2]; R* ov_vz[2];
   int* item_bin; int* item_first; int item_cap;
-  int n_cta;              // CTAs of the push kernel (work-queue consumers)
+  int n_workers;          // warps of the push kernel (work-queue consumers)
   PlanHeader* hdr;
 };
 
@@ -78,14 +96,18 @@ __device__ __forceinline__ float rcp_fast(float a) { return __frcp_rn(a); }
 template <typename R>
 __device__ __forceinline__ R node_pos(int c, const DevParams<R>& p) { return p.g0 + R(c) * p.dx; }
 
+// component a of slot k lives at slot_ptr(rec, k)[kBlk * a]
+template <typename R>
+__device__ __forceinline__ R* slot_ptr(R* rec, long long k) { return rec + ((k >> 5) << 7) + (k & 31); }
+
 // Put one particle into bin `b` of the destination buffer (or into its overflow list when the bin is full).
 template <typename R>
 __device__ __forceinline__ void store_slot(const BinDev<R>& bd, int dst, int b, unsigned slot, R d, R vx, R vy, R vz) {
   const long long o = bd.off[dst][b];
   const long long cap = bd.off[dst][b + 1] - o;
   if ((long long)slot < cap) {
-    const long long k = o + slot;
-    bd.d[dst][k] = d; bd.vx[dst][k] = vx; bd.vy[dst][k] = vy; bd.vz[dst][k] = vz;
+    R* q = slot_ptr(bd.rec[dst], o + slot);
+    q[0] = d; q[kBlk] = vx; q[2 * kBlk] = vy; q[3 * kBlk] = vz;
   } else {
     const int k = atomicAdd(&bd.hdr->ov_n[dst], 1);
     if (k < bd.ov_cap) {
@@ -136,218 +158,9 @@ __device__ __forceinline__ R warp_sum(R v) {
   return v;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// K1b  the binned push: gather -> Boris -> move -> deposit -> re-bin, one pass.
-// ---------------------------------------------------------------------------------------------------------
-template <typename R, bool REL>
-__global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push_binned(const DevParams<R> p, const BinDev<R> bd, const R* __restrict__ F,
-                                                                   R* __restrict__ acc) {
-  PlanHeader* hdr = bd.hdr;
-  const int src = hdr->flip, dst = src ^ 1;
-  const R* __restrict__ sd = bd.d[src]; const R* __restrict__ svx = bd.vx[src];
-  const R* __restrict__ svy = bd.vy[src]; const R* __restrict__ svz = bd.vz[src];
-  const int n_items = hdr->n_items, chunk = hdr->chunk;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int G = p.G;
-  const bool periodic = (p.pbl == JIC_BC_PERIODIC) && (p.pbr == JIC_BC_PERIODIC);
-  const R cells_per_v = p.dt * p.inv_dx;  // displacement in cells per unit velocity
-  __shared__ R red[kPushThreads / 32][20];
-  __shared__ R coef[24];
-  __shared__ int s_item;
-  __shared__ long long s_off[3];
-  __shared__ unsigned s_cap[3];
-
-  for (;;) {
-    // ---- next work item from the queue (dynamic: items differ in size)
-    if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work, 1);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= n_items) break;
-    const int b = bd.item_bin[item];
-    const int first = bd.item_first[item];
-    const int s = b / G, c = b - s * G;
-    const int n = min(chunk, bd.cnt[src][b] - first);
-    const long long base = bd.off[src][b] + first;
-    const bool fast_bin = G >= 8 && (periodic || (c >= 2 && c <= G - 3));
-    const int bl = s * G + (c == 0 ? G - 1 : c - 1), br = s * G + (c == G - 1 ? 0 : c + 1);
-
-    // first particle of every thread is already in flight while the coefficients are set up
-    R nd = R(0), nv0 = R(0), nv1 = R(0), nv2 = R(0);
-    if ((int)threadIdx.x < n) { const long long k = base + threadIdx.x; nd = sd[k]; nv0 = svx[k]; nv1 = svy[k]; nv2 = svz[k]; }
-
-    // ---- CTA-uniform gather polynomials.  Rows c..c+3 of the padded table are f[c-2], f[c-1], f[c], f[c+1].
-    //   E lives on faces: for d < 0 the stencil is faces (c-2, c-1, c), for d >= 0 faces (c-1, c, c+1):
-    //     E(d) = 1/2 (f[c-1]+f[c]) + d (f[c]-f[c-1]) + d^2 a2,   a2 = 1/2 (f[c-2]+f[c]) - f[c-1]  (d<0),  1/2 (f[c-1]+f[c+1]) - f[c]  (d>=0)
-    //   B lives on centres (c-1, c, c+1):
-    //     B(d) = 1/8 (b[c-1]+b[c+1]) + 3/4 b[c] + d/2 (b[c+1]-b[c-1]) + d^2 (1/2 (b[c-1]+b[c+1]) - b[c])
-    //   coef[k*7 + {0: e0, 1: e1, 2: e2lo, 3: e2hi, 4: b0, 5: b1, 6: b2}], k = component.  Non-relativistic: pre-scaled by (q/m) dt/2.
-    if (threadIdx.x < kNumCoef) {
-      const int k = threadIdx.x / 7, w_ = threadIdx.x - 7 * k;
-      const R hs = REL ? R(1) : p.sp_qm[s] * p.half_dt;
-      const R* f = F + (size_t)c * kFieldRow + k;
-      R val;
-      if (w_ < 4) {
-        const R f0 = __ldg(f), f1 = __ldg(f + kFieldRow), f2 = __ldg(f + 2 * kFieldRow), f3 = __ldg(f + 3 * kFieldRow);
-        val = w_ == 0 ? R(0.5) * (f1 + f2) : w_ == 1 ? (f2 - f1) : w_ == 2 ? (R(0.5) * (f0 + f2) - f1) : (R(0.5) * (f1 + f3) - f2);
-      } else {
-        const R b1 = __ldg(f + kFieldRow + 3), b2 = __ldg(f + 2 * kFieldRow + 3), b3 = __ldg(f + 3 * kFieldRow + 3);
-        val = w_ == 4 ? (R(0.125) * (b1 + b3) + R(0.75) * b2) : w_ == 5 ? (R(0.5) * (b3 - b1)) : (R(0.5) * (b1 + b3) - b2);
-      }
-      coef[threadIdx.x] = hs * val;
-    } else if (threadIdx.x >= 32 && threadIdx.x < 35) {
-      const int k = threadIdx.x - 32, bk = k == 0 ? b : (k == 1 ? bl : br);
-      const long long o = bd.off[dst][bk];
-      s_off[k] = o;
-      s_cap[k] = (unsigned)(bd.off[dst][bk + 1] - o);
-    }
-    __syncthreads();
-
-    R a_rho[5] = {0, 0, 0, 0, 0}, a_jy[5] = {0, 0, 0, 0, 0}, a_jz[5] = {0, 0, 0, 0, 0}, a_jx[4] = {0, 0, 0, 0};
-
-    // A particle is STORED one iteration after its slot was claimed, so the cursor atomic's round trip overlaps the next
-    // particle's arithmetic instead of stalling the warp (q_* = claimed but not yet stored).  The first slot and capacity
-    // of the three fast-path destinations (stay / left / right) sit in shared memory (s_off, s_cap), indexed by kind.
-    R q_d = R(0), q_v0 = R(0), q_v1 = R(0), q_v2 = R(0);
-    int q_kind = -1;
-    unsigned q_m = 0, q_c = 0;
-    auto retire = [&]() {
-      // the leader lane of every destination group holds the base it claimed; one shuffle with a per-lane source
-      const unsigned base_slot = __shfl_sync(0xffffffffu, q_c, q_m ? __ffs(q_m) - 1 : 0);
-      if (q_kind >= 0) {
-        const unsigned slot = base_slot + __popc(q_m & lt_mask);
-        if (slot < s_cap[q_kind]) {
-          const long long k = s_off[q_kind] + slot;
-          bd.d[dst][k] = q_d; bd.vx[dst][k] = q_v0; bd.vy[dst][k] = q_v1; bd.vz[dst][k] = q_v2;
-        } else {
-          store_slot(bd, dst, q_kind == 0 ? b : (q_kind == 1 ? bl : br), slot, q_d, q_v0, q_v1, q_v2);  // -> overflow list
-        }
-      }
-    };
-
-    const int n_pad = (n + 31) & ~31;
-    for (int i = threadIdx.x; i < n_pad; i += kPushThreads) {
-      const bool valid = i < n;
-      const R d = nd;
-      R v[3] = {nv0, nv1, nv2};
-      {  // software pipeline: the next particle's loads overlap this particle's arithmetic
-        const int j = i + kPushThreads;
-        if (j < n) { const long long k = base + j; nd = sd[k]; nv0 = svx[k]; nv1 = svy[k]; nv2 = svz[k]; }
-      }
-      // ---- gather (quadratics in d)
-      R E[3], B[3];
-      const bool hi = d >= R(0);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const R a2 = hi ? coef[7 * k + 3] : coef[7 * k + 2];
-        E[k] = fma(fma(a2, d, coef[7 * k + 1]), d, coef[7 * k]);
-        B[k] = fma(fma(coef[7 * k + 6], d, coef[7 * k + 5]), d, coef[7 * k + 4]);
-      }
-      // ---- velocity update
-      if (REL) {
-        boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
-      } else {
-        // E, B already carry the factor (q/m) dt/2:  v- = v + E ; t = B ; v+ = (R x t + (R.t) t + R)/(1 + t.t) ; v = v+ + E
-        const R vm0 = v[0] + E[0], vm1 = v[1] + E[1], vm2 = v[2] + E[2];
-        const R R0 = fma(vm1, B[2], fma(-vm2, B[1], vm0)), R1 = fma(vm2, B[0], fma(-vm0, B[2], vm1)), R2 = fma(vm0, B[1], fma(-vm1, B[0], vm2));
-        const R Rt = fma(R0, B[0], fma(R1, B[1], R2 * B[2]));
-        const R inv = rcp_fast(fma(B[0], B[0], fma(B[1], B[1], fma(B[2], B[2], R(1)))));
-        v[0] = fma(fma(R1, B[2], fma(-R2, B[1], fma(Rt, B[0], R0))), inv, E[0]);
-        v[1] = fma(fma(R2, B[0], fma(-R0, B[2], fma(Rt, B[1], R1))), inv, E[1]);
-        v[2] = fma(fma(R0, B[1], fma(-R1, B[0], fma(Rt, B[2], R2))), inv, E[2]);
-      }
-      // ---- move (in cell units)
-      const R u = v[0] * cells_per_v;
-      const R d_new = d + u, d_mid = fma(R(0.5), u, d);
-      const bool fast = valid && fast_bin && (fabs(d_new) < R(1.5));
-      int kind = -1;  // 0 stay, 1 left, 2 right, 3 general
-      if (valid) kind = 3;
-      R dn = d_new;
-      if (fast) {
-        const bool sr_ = d_new >= R(0.5), sl_ = d_new < R(-0.5), mr_ = d_mid >= R(0.5), ml_ = d_mid < R(-0.5);
-        const int sh = (int)sr_ - (int)sl_;
-        const int shm = (int)mr_ - (int)ml_;
-        kind = sr_ ? 2 : (sl_ ? 1 : 0);
-        dn = d_new - (sr_ ? R(1) : (sl_ ? R(-1) : R(0)));
-        const R dm = d_mid - (mr_ ? R(1) : (ml_ ? R(-1) : R(0)));
-        // rho, J_y, J_z: S2 weights of x_{n+1} on nodes c-2..c+2 (its nearest node is c+shm)
-        const R wl = R(0.5) * (R(0.5) - dm) * (R(0.5) - dm), wc = R(0.75) - dm * dm, wr = R(0.5) * (R(0.5) + dm) * (R(0.5) + dm);
-        const bool ml = shm < 0, mc = shm == 0, mr = shm > 0;
-        R w[5];
-        w[0] = ml ? wl : R(0);
-        w[1] = ml ? wc : (mc ? wl : R(0));
-        w[2] = ml ? wr : (mc ? wc : wl);
-        w[3] = mc ? wr : (mr ? wc : R(0));
-        w[4] = mr ? wr : R(0);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) { a_rho[j] += w[j]; a_jy[j] = fma(w[j], v[1], a_jy[j]); a_jz[j] = fma(w[j], v[2], a_jz[j]); }
-        // J_x on nodes c-2..c+1: difference of the cumulative S2 weights of x_{n+3/2} and x_{n+1/2}
-        const R An = R(0.5) * (R(0.5) - dn) * (R(0.5) - dn), Bn = R(1) - R(0.5) * (R(0.5) + dn) * (R(0.5) + dn);
-        const R Ao = R(0.5) * (R(0.5) - d) * (R(0.5) - d), Bo = R(1) - R(0.5) * (R(0.5) + d) * (R(0.5) + d);
-        const bool sl = sh < 0, sc = sh == 0;
-        a_jx[0] += sl ? An : R(0);
-        a_jx[1] += (sl ? Bn : (sc ? An : R(0))) - Ao;
-        a_jx[2] += (sl ? R(1) : (sc ? Bn : An)) - Bo;
-        a_jx[3] += (sl || sc) ? R(0) : (Bn - R(1));
-      }
-      // ---- claim slots in the destination bins: one atomic per warp and destination (issued by the first lane of each
-      //      destination group), consumed next iteration
-      const unsigned m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1),
-                     m2 = __ballot_sync(0xffffffffu, kind == 2);
-      const unsigned m = kind == 0 ? m0 : (kind == 1 ? m1 : (kind == 2 ? m2 : 0u));
-      unsigned cl = 0;
-      if (m && lane == __ffs(m) - 1) cl = atomicAdd(bd.cur[dst] + (kind == 0 ? b : (kind == 1 ? bl : br)), (unsigned)__popc(m));
-      retire();  // the previous particle: its atomic has had a whole iteration to come back
-      q_d = dn; q_v0 = v[0]; q_v1 = v[1]; q_v2 = v[2];
-      q_kind = kind < 3 ? kind : -1;
-      q_m = m; q_c = cl;
-      if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d * p.dx, v[0], v[1], v[2]);
-    }
-    retire();
-
-    // ---- flush the register accumulators: warp shuffles -> shared memory -> 19 atomics on the raw grid
-    R vals[19];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { vals[j] = a_rho[j]; vals[5 + j] = a_jy[j]; vals[10 + j] = a_jz[j]; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) vals[15 + j] = a_jx[j];
-#pragma unroll
-    for (int j = 0; j < 19; ++j) {
-      const R t = warp_sum(vals[j]);
-      if (lane == 0) red[warp][j] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x < 19) {
-      R t = R(0);
-#pragma unroll
-      for (int w_ = 0; w_ < kPushThreads / 32; ++w_) t += red[w_][threadIdx.x];
-      if (t != R(0)) {
-        const int j = threadIdx.x;
-        const R q = p.sp_q[s];
-        int node, comp;
-        R scale;
-        if (j < 15) { node = c - 2 + (j % 5); comp = j < 5 ? 3 : (j < 10 ? 1 : 2); scale = q * p.inv_dx; }
-        else { node = c - 2 + (j - 15); comp = 0; scale = -(q / p.dt); }
-        atomicAdd(acc + mod_pos(node, G) * kAccRow + comp, scale * t);
-      }
-    }
-    // (the __syncthreads at the head of the next iteration protects red[] and coef[])
-  }
-
-  // ---- particles that did not fit their bin last step: general path, one by one
-  const int n_ov = min(hdr->ov_n[src], bd.ov_cap);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ov; i += gridDim.x * blockDim.x) {
-    const int b = bd.ov_bin[src][i];
-    const int s = b / G, c = b - s * G;
-    const R x_old = node_pos(c, p) + bd.ov_d[src][i] * p.dx;
-    R v[3] = {bd.ov_vx[src][i], bd.ov_vy[src][i], bd.ov_vz[src][i]};
-    R E[3], B[3];
-    gather_fields(F, x_old, p, E, B);
-    if (REL) boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
-    else boris_velocity(v, E, B, p.sp_qm[s], p.dt);
-    slow_tail(p, bd, dst, acc, s, x_old, v[0], v[1], v[2]);
-  }
-}
+}  // namespace jic
+#include "jic_push.cuh"
+namespace jic {
 
 // ---------------------------------------------------------------------------------------------------------
 // K3  plan (single CTA): close the buffer that was just written, lay out the NEXT destination buffer with head-room
@@ -395,7 +208,7 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
   // 2. capacities of `next`: population + slack * (itself and both neighbours in the same species) + a constant
   double f = bd.slack;
   {
-    const double room = (double)bd.cap_total - (double)n_total - 40.0 * nb;
+    const double room = (double)bd.cap_total - (double)n_total - 72.0 * nb;
     const double fmax = n_total > 0 ? room / (3.0 * (double)n_total) : 0.0;
     if (f > fmax) f = fmax;
     if (f < 0) { f = 0; if (t == 0 && room < 0) atomicExch(&h->error, 2); }
@@ -406,7 +219,7 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
     const long long a0 = bd.cur[written][b];
     const long long al = bd.cur[written][s * G + (c == 0 ? G - 1 : c - 1)], ar = bd.cur[written][s * G + (c == G - 1 ? 0 : c + 1)];
     long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
-    cap = (cap + 3) & ~3ll;  // keep bins 32-byte aligned
+    cap = (cap + kBlk - 1) & ~(long long)(kBlk - 1);  // bins start on block boundaries
     cap_sum += cap;
   }
   long long run = block_exclusive_scan<long long>(cap_sum, &tot_ll, sh_ll);
@@ -415,17 +228,17 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
     const long long a0 = bd.cur[written][b];
     const long long al = bd.cur[written][s * G + (c == 0 ? G - 1 : c - 1)], ar = bd.cur[written][s * G + (c == G - 1 ? 0 : c + 1)];
     long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
-    cap = (cap + 3) & ~3ll;
+    cap = (cap + kBlk - 1) & ~(long long)(kBlk - 1);
     bd.off[next][b] = run;
     run += cap;
   }
   if (t == 0) bd.off[next][nb] = tot_ll;
   __syncthreads();
   for (int b = lo; b < hi; ++b) bd.cur[next][b] = 0u;
-  // 3. work items over `written`: about 4 per CTA of the push kernel, between kMinChunk and kMaxChunk particles each
-  long long want = n_total / (4ll * (bd.n_cta > 0 ? bd.n_cta : 1));
+  // 3. work items over `written`: about 4 per warp of the push kernel, between kMinChunk and kMaxChunk particles each
+  long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
   want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
-  const int kChunk = (int)((want + kPushThreads - 1) / kPushThreads) * kPushThreads;
+  const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
   int my_items = 0;
   for (int b = lo; b < hi; ++b) my_items += (bd.cnt[written][b] + kChunk - 1) / kChunk;
   int it = block_exclusive_scan<int>(my_items, &tot_i, sh_i);
@@ -500,9 +313,9 @@ __global__ void __launch_bounds__(1024) k_first_layout(const BinDev<R> bd) {
   const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb;
   const int per = (nb + nt - 1) / nt, lo = min(t * per, nb), hi = min(lo + per, nb);
   long long mine = 0;
-  for (int b = lo; b < hi; ++b) mine += ((long long)bd.cur[0][b] + 3) & ~3ll;
+  for (int b = lo; b < hi; ++b) mine += ((long long)bd.cur[0][b] + kBlk - 1) & ~(long long)(kBlk - 1);
   long long run = block_exclusive_scan<long long>(mine, &tot, sh_ll);
-  for (int b = lo; b < hi; ++b) { bd.off[0][b] = run; run += ((long long)bd.cur[0][b] + 3) & ~3ll; }
+  for (int b = lo; b < hi; ++b) { bd.off[0][b] = run; run += ((long long)bd.cur[0][b] + kBlk - 1) & ~(long long)(kBlk - 1); }
   if (t == 0) {
     bd.off[0][nb] = tot;
     if (tot > bd.cap_total) atomicExch(&bd.hdr->error, 2);
@@ -549,8 +362,9 @@ __global__ void k_export_binned(const DevParams<R> p, const BinDev<R> bd, const 
     const long long o = bd.off[src][b], q0 = dense[b];
     for (int i = threadIdx.x; i < bd.cnt[src][b]; i += blockDim.x) {
       const long long k = q0 + i;
-      if (x_out) { x_out[3 * k] = node_pos(c, p) + bd.d[src][o + i] * p.dx; x_out[3 * k + 1] = R(0); x_out[3 * k + 2] = R(0); }
-      if (v_out) { v_out[3 * k] = bd.vx[src][o + i]; v_out[3 * k + 1] = bd.vy[src][o + i]; v_out[3 * k + 2] = bd.vz[src][o + i]; }
+      const R* q = slot_ptr(bd.rec[src], o + i);
+      if (x_out) { x_out[3 * k] = node_pos(c, p) + q[0] * p.dx; x_out[3 * k + 1] = R(0); x_out[3 * k + 2] = R(0); }
+      if (v_out) { v_out[3 * k] = q[kBlk]; v_out[3 * k + 1] = q[2 * kBlk]; v_out[3 * k + 2] = q[3 * kBlk]; }
       if (alive) alive[k] = 1;
     }
   }
@@ -578,7 +392,8 @@ __global__ void k_kinetic_binned(const DevParams<R> p, const BinDev<R> bd, doubl
     const double m = (double)p.sp_m[b / p.G];
     const long long o = bd.off[src][b];
     for (int i = threadIdx.x; i < bd.cnt[src][b]; i += blockDim.x) {
-      const double a = bd.vx[src][o + i], b_ = bd.vy[src][o + i], c_ = bd.vz[src][o + i];
+      const R* q = slot_ptr(bd.rec[src], o + i);
+      const double a = q[kBlk], b_ = q[2 * kBlk], c_ = q[3 * kBlk];
       acc += 0.5 * m * (a * a + b_ * b_ + c_ * c_);
     }
   }
@@ -620,16 +435,15 @@ struct BinnedStore {
     const long long N = dp.N;
     bd.nb = dp.n_species * dp.G;
     bd.slack = 0.125f;
-    bd.cap_total = (long long)((double)N * (1.0 + 3.0 * bd.slack)) + 48ll * bd.nb + 1024;
+    bd.cap_total = (long long)((double)N * (1.0 + 3.0 * bd.slack)) + 96ll * bd.nb + 1024;
+    bd.cap_total = (bd.cap_total + kBlk - 1) & ~(long long)(kBlk - 1);
     if (bd.cap_total >= (1ll << 40)) return e.fail(JIC_ERR_UNSUPPORTED, "too many particles for one GPU");
     bd.ov_cap = (int)std::min<long long>(std::max<long long>(N / 16, 1 << 16), 1ll << 28);
     bd.item_cap = (int)std::min<long long>(N / kMinChunk + bd.nb + 16, 1ll << 30);
-    bd.n_cta = n_sm * kPushMinBlocks;
+    bd.n_workers = n_sm * kPushMinBlocks * kPushWarps;
     int rc;
     for (int k = 0; k < 2; ++k) {
-      if ((rc = alloc(e, &bd.d[k], bd.cap_total)) || (rc = alloc(e, &bd.vx[k], bd.cap_total)) || (rc = alloc(e, &bd.vy[k], bd.cap_total)) ||
-          (rc = alloc(e, &bd.vz[k], bd.cap_total)))
-        return rc;
+      if ((rc = alloc(e, &bd.rec[k], 4 * (size_t)bd.cap_total))) return rc;
       if ((rc = alloc(e, &bd.off[k], bd.nb + 1)) || (rc = alloc(e, &bd.cnt[k], bd.nb)) || (rc = alloc(e, &bd.cur[k], bd.nb))) return rc;
       if ((rc = alloc(e, &bd.ov_bin[k], bd.ov_cap)) || (rc = alloc(e, &bd.ov_d[k], bd.ov_cap)) || (rc = alloc(e, &bd.ov_vx[k], bd.ov_cap)) ||
           (rc = alloc(e, &bd.ov_vy[k], bd.ov_cap)) || (rc = alloc(e, &bd.ov_vz[k], bd.ov_cap)))
@@ -661,9 +475,11 @@ struct BinnedStore {
     cudaError_t ce = cudaMallocAsync((void**)&st_bin, sizeof(int) * (size_t)(dp.N ? dp.N : 1), st);
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("staging allocation: %s", cudaGetErrorString(ce)));
     const int g = grid_for(dp.N, 256, 8);
-    k_start_binned<R><<<g, 256, 0, st>>>(dp, bd, x0, v0, bd.d[1], bd.vx[1], bd.vy[1], bd.vz[1], st_bin, acc);
+    // buffer 1 is free until the first push: use it as four linear staging arrays
+    R* sx = bd.rec[1]; R* svx = sx + bd.cap_total; R* svy = svx + bd.cap_total; R* svz = svy + bd.cap_total;
+    k_start_binned<R><<<g, 256, 0, st>>>(dp, bd, x0, v0, sx, svx, svy, svz, st_bin, acc);
     k_first_layout<R><<<1, 1024, 0, st>>>(bd);
-    k_scatter_binned<R><<<g, 256, 0, st>>>(dp, bd, bd.d[1], bd.vx[1], bd.vy[1], bd.vz[1], st_bin);
+    k_scatter_binned<R><<<g, 256, 0, st>>>(dp, bd, sx, svx, svy, svz, st_bin);
     cudaFreeAsync(st_bin, st);
     e.launches += 3;
     ce = cudaGetLastError();
@@ -682,9 +498,9 @@ struct BinnedStore {
   }
 
   int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, cudaStream_t st) {
-    const int g = bd.n_cta;
-    if (dp.relativistic) k_push_binned<R, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
-    else k_push_binned<R, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+    const int g = n_sm * kPushMinBlocks;
+    if (dp.relativistic) k_push<R, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+    else k_push<R, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
     e.launches += 1;
     return JIC_OK;
   }

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjic_b200.so")
+LIB_PATH = os.environ.get("JIC_B200_LIB") or os.path.join(_HERE, "libjic_b200.so")  # override: tuning variants of the same ABI
 
 JIC_MAX_SPECIES = 8
 JIC_MAX_STRIDES = 8

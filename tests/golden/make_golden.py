@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/*.npz:  python tests/golden/make_golden.py
+
+The vectors are produced by oracle/literal.py -- the expression-by-expression NumPy restatement of the reference, itself
+pinned to the known-answer vectors of the reference's unit tests (tests/test_oracle_kat.py).  They are NOT outputs of the
+reference: JAX is not installable in the build image, so the reference cannot be imported here.  If it ever
+can be, regenerate them from `jaxincell.Simulation` with explicit initial_positions/initial_velocities and keep the names.
+Each file holds the inputs (x0, v0, per-particle q, m, q/m, geometry, BCs, solver switches, external fields) and the six
+per-step histories of jaxincell/_algorithms.py:93 plus the initial fields / post-BC initial velocities."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+from oracle import literal as L  # noqa: E402
+from plasma import cfl_dt, two_species  # noqa: E402
+
+CASES = {
+    # name: (two_species kwargs, G, length, cfl, T, bcs(pbl,pbr,fbl,fbr), solver overrides, external field amplitude)
+    "two_stream_periodic": (dict(n_e=160, n_i=120, seed=5, vth_e=0.05, vth_yz=0.02, drift=6e7, plus_minus=True, gpdl=0.6), 16, 0.01, 0.9, 10, (0, 0, 0, 0), {}, 0.0),
+    "large_cfl_jumps": (dict(n_e=120, n_i=80, seed=6, vth_e=0.05, drift=6e7, plus_minus=True, gpdl=0.6), 20, 0.01, 4.5, 8, (0, 0, 0, 0), {}, 0.0),
+    "reflective_absorbing": (dict(n_e=140, n_i=100, seed=7, vth_e=0.08, vth_yz=0.03, gpdl=0.6), 12, 0.01, 1.3, 10, (1, 2, 1, 2), {}, 0.0),
+    "absorbing_reflective_nofilter": (dict(n_e=100, n_i=100, seed=8, vth_e=0.08, vth_yz=0.03, gpdl=0.6), 9, 0.01, 1.1, 8, (2, 1, 2, 1), {"filter_passes": 0}, 0.0),
+    "weibel_external_B": (dict(n_e=150, n_i=150, seed=9, vth_e=0.01, vth_yz=0.1, gpdl=0.6, ion_vth_scale=1.0), 14, 0.02, 1.0, 8, (0, 0, 0, 0), {"filter_passes": 2, "filter_strides": (1, 3)}, 1.0),
+    "relativistic": (dict(n_e=100, n_i=60, seed=10, vth_e=0.3, vth_yz=0.2, gpdl=0.6), 10, 0.01, 0.7, 8, (0, 0, 0, 0), {"relativistic": True}, 0.3),
+}
+
+
+def build(name):
+    kw, G, length, cfl, T, bcs, solver, ext = CASES[name]
+    kw = dict(kw)
+    n_e, n_i = kw.pop("n_e"), kw.pop("n_i")
+    p = two_species(n_e, n_i, length=length, G=G, **kw)
+    dt = cfl_dt(length, G, cfl)
+    rng = np.random.default_rng(99)
+    ext_E = (ext * 1e3 * rng.standard_normal((G, 3))).astype(np.float32) if ext else None
+    ext_B = (ext * 1e-3 * rng.standard_normal((G, 3))).astype(np.float32) if ext else None
+    pbl, pbr, fbl, fbr = bcs
+    out = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=pbl, pbr=pbr, fbl=fbl,
+                fbr=fbr, solver=solver, ext_E=ext_E, ext_B=ext_B)
+    sol = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "relativistic": False, **solver}
+    return dict(x0=p["x0"], v0=p["v0"], q=p["q"], m=p["m"], qm=p["qm"], n_e=n_e, n_i=n_i, length=length, G=G, dt=dt, T=T,
+                bcs=np.array(bcs), filter_passes=sol["filter_passes"], filter_alpha=sol["filter_alpha"],
+                filter_strides=np.array(sol["filter_strides"]), relativistic=int(sol["relativistic"]),
+                ext_E=np.zeros((G, 3), np.float32) if ext_E is None else ext_E, ext_B=np.zeros((G, 3), np.float32) if ext_B is None else ext_B,
+                positions=out["positions"], velocities=out["velocities"], electric_field=out["electric_field"],
+                magnetic_field=out["magnetic_field"], current_density=out["current_density"], charge_density=out["charge_density"],
+                E0=out["fields"][0], B0=out["fields"][1], initial_velocities=out["initial_velocities"])
+
+
+if __name__ == "__main__":
+    for name in CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **build(name))
+        print("wrote", name)

@@ -1,0 +1,74 @@
+"""Committed golden vectors (tests/golden/*.npz, written by tests/golden/make_golden.py from the literal oracle).
+
+CPU: the O(N) closed-form oracle must reproduce them (guards the oracle against drift).
+GPU: both CUDA engines, through the C ABI, must reproduce them within the north-star tolerance (1e-5 fp64)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import closed_form as C
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FIELDS = ("electric_field", "magnetic_field", "current_density", "charge_density")
+RTOL_F64 = 1e-5  # BASELINE.json north_star: per-step E, B, J and particle x/v within 1e-5 relative in fp64
+
+
+def _load(path):
+    g = dict(np.load(path))
+    g["solver"] = dict(filter_passes=int(g["filter_passes"]), filter_alpha=float(g["filter_alpha"]),
+                       filter_strides=tuple(int(s) for s in g["filter_strides"]), relativistic=bool(g["relativistic"]))
+    return g
+
+
+def _relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_fixtures_exist():
+    assert len(FILES) >= 6
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_closed_form_oracle_reproduces_golden(path):
+    g = _load(path)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    out = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]),
+                total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"], ext_E=g["ext_E"], ext_B=g["ext_B"])
+    for k in FIELDS + ("positions", "velocities"):
+        assert _relerr(out[k], g[k]) < 1e-10, k
+    assert _relerr(out["fields"][0], g["E0"]) < 1e-12
+    assert _relerr(out["initial_velocities"], g["initial_velocities"]) < 1e-15
+
+
+def _species(g):
+    ne, ni = int(g["n_e"]), int(g["n_i"])
+    return [dict(count=ne, q=float(g["q"][0]), m=float(g["m"][0]), qm=float(g["qm"][0])),
+            dict(count=ni, q=float(g["q"][ne]), m=float(g["m"][ne]), qm=float(g["qm"][ne]))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_cuda_reproduces_golden(path, engine):
+    import torch
+    from jaxincell_b200 import HotPath
+    g = _load(path)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    s = g["solver"]
+    hp = HotPath(species=_species(g), length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                 filter_passes=s["filter_passes"], filter_alpha=s["filter_alpha"], filter_strides=s["filter_strides"],
+                 relativistic=s["relativistic"], engine=engine, track_yz=engine == "indexed")
+    hp.set_external_fields(g["ext_E"], g["ext_B"])
+    hp.initialize(g["x0"], g["v0"])
+    out = hp.run(int(g["T"]), particles=engine == "indexed")
+    torch.cuda.synchronize()
+    for k in FIELDS + (("positions", "velocities") if engine == "indexed" else ()):
+        assert _relerr(out[k].cpu().numpy(), g[k]) < RTOL_F64, (k, engine)
+    E0, B0, vi = hp.initial(velocities=engine == "indexed")
+    assert _relerr(E0.cpu().numpy(), g["E0"]) < RTOL_F64
+    if engine == "indexed":
+        assert _relerr(vi.cpu().numpy(), g["initial_velocities"]) < 1e-14
+    hp.close()
