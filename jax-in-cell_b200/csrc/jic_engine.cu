@@ -69,13 +69,8 @@ struct EngineT : Engine {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
-  // graphs, keyed by (outputs, steps)
-  struct GraphKey {
-    jic_outputs out;
-    int steps;
-    bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
-  };
-  std::map<GraphKey, cudaGraphExec_t> graphs;
+  // captured time loops, keyed by the number of steps (the kernels read the output pointers from RunControl at run time)
+  std::map<int, cudaGraphExec_t> graphs;
   bool shared_grid = false;
   size_t shared_bytes = 0;
   BinnedStore<R> bins;  // BINNED engine state (unused for INDEXED)
@@ -195,7 +190,7 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
-  FieldArgs<R> field_args(bool init, const jic_outputs* out) const {
+  FieldArgs<R> field_args(bool init, bool record) const {
     FieldArgs<R> a;
     memset(&a, 0, sizeof(a));
     a.G = dp.G; a.fbl = dp.fbl; a.fbr = dp.fbr; a.passes = prm.filter_passes; a.n_strides = prm.n_filter_strides; a.init = init;
@@ -203,7 +198,7 @@ struct EngineT : Engine {
     a.alpha = prm.filter_alpha; a.dx = prm.dx; a.dt = prm.dt;
     a.acc = acc; a.E = E; a.B = B; a.E_int = E_int; a.B_int = B_int; a.J = J; a.rho = rho; a.extE = extE; a.extB = extB; a.F = F;
     a.s0 = s0; a.s1 = s1; a.E0 = E0; a.B0 = B0; a.ctl = ctl;
-    if (out) { a.hE = (R*)out->electric_field; a.hB = (R*)out->magnetic_field; a.hJ = (R*)out->current_density; a.hrho = (R*)out->charge_density; }
+    a.record = record ? 1 : 0;
     return a;
   }
 
@@ -221,7 +216,7 @@ struct EngineT : Engine {
     JIC_CUDA(cudaGetLastError());
     int rc = allreduce(st);
     if (rc) return rc;
-    k_fields<R><<<1, 1024, 0, st>>>(field_args(true, nullptr));
+    k_fields<R><<<1, 1024, 0, st>>>(field_args(true, false));
     launches += 1;
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
     JIC_CUDA(cudaGetLastError());
@@ -230,17 +225,15 @@ struct EngineT : Engine {
   }
 
   // enqueue one full step on `st` (used under stream capture): particle kernel(s), all-reduce, field kernel
-  int enqueue_push(const jic_outputs& out, cudaStream_t st) {
+  int enqueue_push(cudaStream_t st) {
     if (prm.engine == JIC_ENGINE_INDEXED) {
-      R* xhist = (R*)out.positions;
-      R* vhist = (R*)out.velocities;
       if (shared_grid) {
         // persistent CTAs: one shared copy of the grid each
         const int per_sm = (int)((size_t)200 * 1024 / (shared_bytes + 1024));
         const int g = grid_for(dp.N, 256, per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
-        k_step<R, true><<<g, 256, shared_bytes, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, xhist, vhist, ctl);
+        k_step<R, true><<<g, 256, shared_bytes, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, ctl);
       } else {
-        k_step<R, false><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, xhist, vhist, ctl);
+        k_step<R, false><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, xh, yh, zh, vx, vy, vz, F, acc, ctl);
       }
       launches += 1;
       return JIC_OK;
@@ -248,18 +241,25 @@ struct EngineT : Engine {
     return bins.step(*this, dp, F, acc, st);
   }
 
-  int enqueue_fields(const jic_outputs& out, cudaStream_t st) {
+  int enqueue_fields(cudaStream_t st) {
     int rc = allreduce(st);
     if (rc) return rc;
-    k_fields<R><<<1, 1024, 0, st>>>(field_args(false, &out));
+    k_fields<R><<<1, 1024, 0, st>>>(field_args(false, true));
     launches += 1;
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
     return JIC_OK;
   }
 
-  int enqueue_step(const jic_outputs& out, cudaStream_t st) {
-    int rc = enqueue_push(out, st);
-    return rc ? rc : enqueue_fields(out, st);
+  int enqueue_step(cudaStream_t st) {
+    int rc = enqueue_push(st);
+    return rc ? rc : enqueue_fields(st);
+  }
+
+  int begin_run(const jic_outputs& out, cudaStream_t st) {
+    k_begin_run<<<1, 1, 0, st>>>(ctl, out);
+    launches += 1;
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
   }
 
   // n real steps (no histories) with CUDA events around the particle kernel(s) and the grid part of every step
@@ -267,14 +267,16 @@ struct EngineT : Engine {
     if (!initialized) return fail(JIC_ERR_BAD_STATE, "jic_profile_steps before jic_initialize");
     jic_outputs none;
     memset(&none, 0, sizeof(none));
+    int rc0 = begin_run(none, st);
+    if (rc0) return rc0;
     std::vector<cudaEvent_t> ev(3 * (size_t)n);
     for (auto& e : ev) JIC_CUDA(cudaEventCreate(&e));
     int rc = JIC_OK;
     for (long long s = 0; s < n && rc == JIC_OK; ++s) {
       cudaEventRecord(ev[3 * s], st);
-      rc = enqueue_push(none, st);
+      rc = enqueue_push(st);
       cudaEventRecord(ev[3 * s + 1], st);
-      if (rc == JIC_OK) rc = enqueue_fields(none, st);
+      if (rc == JIC_OK) rc = enqueue_fields(st);
       cudaEventRecord(ev[3 * s + 2], st);
     }
     cudaError_t ce = cudaStreamSynchronize(st);
@@ -294,10 +296,8 @@ struct EngineT : Engine {
     return rc;
   }
 
-  int get_graph(const jic_outputs& out, int steps, cudaStream_t st, cudaGraphExec_t* exec) {
-    GraphKey key;
-    memset(&key, 0, sizeof(key));
-    key.out = out; key.steps = steps;
+  int get_graph(int steps, cudaStream_t st, cudaGraphExec_t* exec) {
+    const int key = steps;
     auto it = graphs.find(key);
     if (it != graphs.end()) { *exec = it->second; return JIC_OK; }
     cudaStream_t cs;
@@ -306,7 +306,7 @@ struct EngineT : Engine {
     cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     int rc = JIC_OK;
     if (e == cudaSuccess) {
-      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(out, cs);
+      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs);
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
@@ -343,15 +343,15 @@ struct EngineT : Engine {
       if (rc) return rc;
     }
     steps_run += n;
-    // row 0 of the histories is the first step of this call
-    JIC_CUDA(cudaMemsetAsync(&ctl->hist_row, 0, sizeof(long long), st));
+    int rcb = begin_run(out, st);
+    if (rcb) return rcb;
     const int chunk = prm.steps_per_graph > 0 ? prm.steps_per_graph : 16;
     const long long per_step = count_launches_per_step();
     long long done = 0;
     while (done < n) {
       const int steps = (int)((n - done) >= chunk ? chunk : 1);
       cudaGraphExec_t ex;
-      int rc = get_graph(out, steps, st, &ex);
+      int rc = get_graph(steps, st, &ex);
       if (rc) return rc;
       JIC_CUDA(cudaGraphLaunch(ex, st));
       launches += per_step * steps;

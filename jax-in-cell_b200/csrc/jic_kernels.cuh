@@ -63,14 +63,15 @@ __global__ void __launch_bounds__(256) k_start(const DevParams<R> p, const R* __
 template <typename R, bool SHARED>
 __global__ void __launch_bounds__(256) k_step(const DevParams<R> p, R* __restrict__ xh, R* __restrict__ yh, R* __restrict__ zh,
                                               R* __restrict__ vx, R* __restrict__ vy, R* __restrict__ vz, const R* __restrict__ F,
-                                              R* __restrict__ acc, R* __restrict__ x_hist, R* __restrict__ v_hist,
-                                              const RunControl* __restrict__ ctl) {
+                                              R* __restrict__ acc, const RunControl* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* sacc = reinterpret_cast<R*>(smem_raw);
   if (SHARED) {
     for (int k = threadIdx.x; k < p.G * kAccRow; k += blockDim.x) sacc[k] = R(0);
     __syncthreads();
   }
+  R* x_hist = (R*)ctl->hist[4];
+  R* v_hist = (R*)ctl->hist[5];
   const long long row = (x_hist || v_hist) ? ctl->hist_row : 0;
   R* xrow = x_hist ? x_hist + (size_t)row * 3 * p.N : nullptr;
   R* vrow = v_hist ? v_hist + (size_t)row * 3 * p.N : nullptr;
@@ -155,7 +156,7 @@ struct FieldArgs {
   R* F;                // padded gather table (G+3, 8)
   double *s0, *s1;     // filter scratch (G,4) each
   double *E0, *B0;     // initial fields (init mode)
-  R *hE, *hB, *hJ, *hrho;  // histories or null
+  int record;          // write this step's outputs to the history buffers named in ctl->hist
   RunControl* ctl;
 };
 
@@ -265,13 +266,17 @@ __global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
     faraday(a.E, a.B, G, a.fbl, a.dx, h);
     ampere(a.E, a.B, a.J, G, a.fbr, a.dx, h);
     const long long row = a.ctl->hist_row;
+    R* hE = a.record ? (R*)a.ctl->hist[0] : nullptr;
+    R* hB = a.record ? (R*)a.ctl->hist[1] : nullptr;
+    R* hJ = a.record ? (R*)a.ctl->hist[2] : nullptr;
+    R* hrho = a.record ? (R*)a.ctl->hist[3] : nullptr;
     for (int k = tid; k < G * 3; k += nt) {
       a.E_int[k] = a.E[k]; a.B_int[k] = a.B[k];
-      if (a.hE) a.hE[(size_t)row * G * 3 + k] = (R)a.E[k];
-      if (a.hB) a.hB[(size_t)row * G * 3 + k] = (R)a.B[k];
-      if (a.hJ) a.hJ[(size_t)row * G * 3 + k] = (R)a.J[k];
+      if (hE) hE[(size_t)row * G * 3 + k] = (R)a.E[k];
+      if (hB) hB[(size_t)row * G * 3 + k] = (R)a.B[k];
+      if (hJ) hJ[(size_t)row * G * 3 + k] = (R)a.J[k];
     }
-    if (a.hrho) for (int i = tid; i < G; i += nt) a.hrho[(size_t)row * G + i] = (R)a.rho[i];
+    if (hrho) for (int i = tid; i < G; i += nt) hrho[(size_t)row * G + i] = (R)a.rho[i];
     __syncthreads();
     if (tid == 0) { a.ctl->hist_row = row + 1; a.ctl->step += 1; }
   }
@@ -320,6 +325,13 @@ __global__ void k_kinetic(const DevParams<R> p, const R* vx, const R* vy, const 
   }
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// start of a jic_run: row 0 of the caller's history buffers is the first step of this call
+__global__ void k_begin_run(RunControl* ctl, jic_outputs out) {
+  ctl->hist_row = 0;
+  ctl->hist[0] = out.electric_field; ctl->hist[1] = out.magnetic_field; ctl->hist[2] = out.current_density;
+  ctl->hist[3] = out.charge_density; ctl->hist[4] = out.positions; ctl->hist[5] = out.velocities;
 }
 
 template <typename R>

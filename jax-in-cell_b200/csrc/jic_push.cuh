@@ -72,6 +72,16 @@ struct __align__(16) DestSlot {
   int bin;
 };
 
+template <typename R>
+__device__ __forceinline__ void store_slot_at(const BinDev<R>& bd, int dst, const DestSlot<R>& ds, unsigned slot, R d, R vx, R vy, R vz) {
+  if (slot < ds.cap) {
+    R* q = ds.base + (size_t)(slot >> 5) * kBlkElems + (slot & 31u);
+    q[0] = d; q[kBlk] = vx; q[2 * kBlk] = vy; q[3 * kBlk] = vz;
+  } else {
+    store_slot(bd, dst, ds.bin, slot, d, vx, vy, vz);  // -> overflow list
+  }
+}
+
 template <typename R, bool REL>
 __global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
                                                                        const R* __restrict__ F, R* __restrict__ acc) {
@@ -82,12 +92,15 @@ __global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __g
   __shared__ __align__(16) R coef_s[NW][24];  // per component k: [e0, e1, a2lo, a2hi, b0, b1, b2, -]
   __shared__ DestSlot<R> dest_s[NW][3];
   __shared__ R tot_s[NW][20];
+  __shared__ __align__(16) R stash[NW][KB][kBlkElems];  // re-binned particles waiting for their claimed slots
 
   PlanHeader* hdr = bd.hdr;
   const int src = hdr->flip, dst = src ^ 1;
   const R* __restrict__ srec = bd.rec[src];
   const int n_items = hdr->n_items, chunk = hdr->chunk;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5;
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-reading SR_TID in the loop
   const unsigned lt_mask = (1u << lane) - 1u;
   const int G = p.G;
   const bool periodic = (p.pbl == JIC_BC_PERIODIC) && (p.pbr == JIC_BC_PERIODIC);
@@ -172,24 +185,31 @@ __global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __g
     R y0 = 0, y1 = 0, y2 = 0, yP = 0, yN = 0;
     R z0 = 0, z1 = 0, z2 = 0, zP = 0, zN = 0;
     R a1 = 0, a2 = 0, aP = 0, aN = 0;
-    int n_slow = 0;  // warp-uniform
+    int n_slow = 0;  // warp-uniform: particles of this item that took the general path
 
-    // A particle is STORED one iteration after its slot was claimed, so the cursor atomic's round trip overlaps the next
-    // particle's arithmetic instead of stalling the warp (q_* = claimed but not yet stored).
-    R q_d = R(0), q_v0 = R(0), q_v1 = R(0), q_v2 = R(0);
-    int q_kind = -1;
-    unsigned q_rank = 0, q_claim = 0;
-    auto retire = [&]() {
-      const unsigned base_slot = __shfl_sync(0xffffffffu, q_claim, q_kind < 0 ? 0 : q_kind);
-      if (q_kind >= 0) {
-        const DestSlot<R> ds = dest_s[warp][q_kind];
-        const unsigned slot = base_slot + q_rank;
-        if (slot < ds.cap) {
-          R* q = ds.base + (size_t)(slot >> 5) * kBlkElems + (slot & 31u);
-          q[0] = q_d; q[kBlk] = q_v0; q[2 * kBlk] = q_v1; q[3 * kBlk] = q_v2;
-        } else {
-          store_slot(bd, dst, ds.bin, slot, q_d, q_v0, q_v1, q_v2);  // -> overflow list
-        }
+    // A particle is STORED one group (KB blocks) after its slot was claimed, so that the cursor atomic's round trip
+    // (> 1 us under load: profiles/r01_push_warpworkers_*) overlaps a whole group's arithmetic instead of stalling the warp.
+    // Until then its new state waits in the lane's own slot of a shared-memory stash (no cross-lane traffic, no conflicts)
+    // and only (destination, rank) and the claimed base stay in registers.  q_meta < 0 = nothing pending.
+    int q_meta[KB];
+    unsigned q_claim[KB];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) { q_meta[kb] = -1; q_claim[kb] = 0; }
+    R* my_stash = &stash[warp][0][0] + lane;
+    auto retire = [&](int kb) {
+      const int kind = q_meta[kb] < 0 ? 0 : (q_meta[kb] & 3);
+      const unsigned base_slot = __shfl_sync(0xffffffffu, q_claim[kb], kind);
+      const DestSlot<R> ds = dest_s[warp][kind];
+      const unsigned sl_ = base_slot + ((unsigned)q_meta[kb] >> 2);
+      const bool pending = q_meta[kb] >= 0, fits = pending && sl_ < ds.cap;
+      const R* st_ = my_stash + kb * kBlkElems;
+      const R o_d = st_[0], o_v0 = st_[kBlk], o_v1 = st_[2 * kBlk], o_v2 = st_[3 * kBlk];
+      if (fits) {
+        R* q = ds.base + (size_t)(sl_ >> 5) * kBlkElems + (sl_ & 31u);
+        q[0] = o_d; q[kBlk] = o_v0; q[2 * kBlk] = o_v1; q[3 * kBlk] = o_v2;
+      }
+      if (__any_sync(0xffffffffu, pending && !fits)) {
+        if (pending && !fits) store_slot(bd, dst, ds.bin, sl_, o_d, o_v0, o_v1, o_v2);  // -> overflow list
       }
     };
 
@@ -199,12 +219,12 @@ __global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __g
       const R* stage = my_ring + slot * (KB * kBlkElems);
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        const int blk = g * KB + kb;
-        if (blk >= nblk) break;
-        const bool valid = blk * kBlk + lane < n;
+        // (blocks past the end of the item run with every lane invalid: no early exit, so the loop body stays one
+        //  straight line and the pending claim never has to be copied out of the atomic's destination register)
+        const bool valid = (g * KB + kb) * kBlk + lane < n;
         const R d = stage[kb * kBlkElems + lane];
         R v[3] = {stage[kb * kBlkElems + kBlk + lane], stage[kb * kBlkElems + 2 * kBlk + lane], stage[kb * kBlkElems + 3 * kBlk + lane]};
-        if (kb == KB - 1 || blk == nblk - 1) {
+        if (kb == KB - 1) {
           // every lane has taken its particle of the slot's last block: the slot can be refilled
           __syncwarp();
           if (lane == 0 && g + NS < ngroups) load_group(g + NS);
@@ -235,41 +255,49 @@ __global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __g
         const R u = v[0] * cells_per_v;
         const R tn = d + u, tm = fma(R(0.5), u, d);
         const bool fast = valid && fast_bin && (fabs(tn) < R(1.5));
-        int kind = valid ? 3 : -1;  // 0 stay, 1 left, 2 right, 3 general
-        R dn = tn;
-        if (fast) {
-          const bool sr_ = tn >= R(0.5), sl_ = tn < R(-0.5);
-          kind = sr_ ? 2 : (sl_ ? 1 : 0);
-          dn = tn - (sr_ ? R(1) : (sl_ ? R(-1) : R(0)));
+        const bool all_fast = __all_sync(0xffffffffu, fast);  // the common case, warp-uniform: no per-lane branches below
+        if (all_fast || fast) {
           // truncated powers 4 P(t) = (y + |y|)^2 with y = t - 1/2, 4 N(t) likewise with y = -t - 1/2
           const R pn_ = (tn - R(0.5)) + fabs(tn - R(0.5)), nn_ = (-tn - R(0.5)) + fabs(-tn - R(0.5));
           const R pm_ = (tm - R(0.5)) + fabs(tm - R(0.5)), nm_ = (-tm - R(0.5)) + fabs(-tm - R(0.5));
-          const R Pn = pn_ * pn_, Nn = nn_ * nn_, Pm = pm_ * pm_, Nm = nm_ * nm_, tm2 = tm * tm;
-          a1 += u; a2 = fma(u, tn + d, a2); aP += Pn; aN += Nn;
+          const R Pm = pm_ * pm_, Nm = nm_ * nm_, tm2 = tm * tm;
+          a1 += u; a2 = fma(u, tn + d, a2); aP = fma(pn_, pn_, aP); aN = fma(nn_, nn_, aN);
           r1 += tm; r2 += tm2; rP += Pm; rN += Nm;
           y0 += v[1]; y1 = fma(v[1], tm, y1); y2 = fma(v[1], tm2, y2); yP = fma(v[1], Pm, yP); yN = fma(v[1], Nm, yN);
           z0 += v[2]; z1 = fma(v[2], tm, z1); z2 = fma(v[2], tm2, z2); zP = fma(v[2], Pm, zP); zN = fma(v[2], Nm, zN);
         }
-        // ---- claim slots in the destination bins: one atomic per warp and destination, consumed next iteration
-        const unsigned m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1),
-                       m2 = __ballot_sync(0xffffffffu, kind == 2);
+        // ---- destination: 0 stay, 1 left, 2 right (3 = general path, -1 = no particle)
+        const bool go_r = fast && tn >= R(0.5), go_l = fast && tn < R(-0.5);
+        R dn = tn;
+        if (go_r) dn -= R(1);
+        if (go_l) dn += R(1);
+        const int kind = fast ? (go_r ? 2 : (go_l ? 1 : 0)) : (valid ? 3 : -1);
+        // ---- claim slots in the destination bins: one atomic per warp and destination, consumed one block later
+        const unsigned m1 = __ballot_sync(0xffffffffu, go_l), m2 = __ballot_sync(0xffffffffu, go_r);
+        const unsigned m0 = __ballot_sync(0xffffffffu, fast) & ~(m1 | m2);
+        const unsigned my_cnt = __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
         unsigned claim = 0;
-        if (lane < 3) {
-          const int cnt = __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
-          if (cnt) claim = atomicAdd(my_cursor, (unsigned)cnt);
+        if (lane < 3 && my_cnt) claim = atomicAdd(my_cursor, my_cnt);
+        const unsigned rank = __popc((go_r ? m2 : (go_l ? m1 : m0)) & lt_mask);
+        // ---- retire the block stashed in this slot one group ago, then stash the new one
+        retire(kb);
+        {
+          R* st_ = my_stash + kb * kBlkElems;
+          st_[0] = dn; st_[kBlk] = v[0]; st_[2 * kBlk] = v[1]; st_[3 * kBlk] = v[2];
         }
-        const unsigned rank = __popc((kind == 0 ? m0 : (kind == 1 ? m1 : m2)) & lt_mask);
-        retire();  // the previous particle: its atomic has had a whole iteration to come back
-        q_d = dn; q_v0 = v[0]; q_v1 = v[1]; q_v2 = v[2];
-        q_kind = kind < 3 ? kind : -1;
-        q_rank = rank; q_claim = claim;
-        if (__any_sync(0xffffffffu, kind == 3)) {
-          n_slow += __popc(__ballot_sync(0xffffffffu, kind == 3));
-          if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d * p.dx, v[0], v[1], v[2]);
+        q_meta[kb] = fast ? (int)((rank << 2) | (unsigned)kind) : -1;
+        q_claim[kb] = claim;
+        if (!all_fast) {
+          const unsigned ms = __ballot_sync(0xffffffffu, kind == 3);
+          if (ms) {
+            n_slow += __popc(ms);
+            if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d * p.dx, v[0], v[1], v[2]);
+          }
         }
       }
     }
-    retire();
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) retire(kb);  // the last group of the item
 
     // ---- flush: warp totals of the moments -> 19 node values -> atomics on the raw (L2-resident) grid
     if (n_slow < n) {
