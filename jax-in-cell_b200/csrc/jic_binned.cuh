@@ -167,45 +167,68 @@ namespace jic {
 //     proportional to the population of each bin and its neighbours, build the work-item list, flip.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ T block_exclusive_scan(T v, T* total, T* smem /* blockDim.x */) {
-  // simple Hillis-Steele over blockDim.x partial values (called once or twice per step on 1024 threads)
-  const int t = threadIdx.x, n = blockDim.x;
-  smem[t] = v;
-  __syncthreads();
-  for (int o = 1; o < n; o <<= 1) {
-    T x = t >= o ? smem[t - o] : T(0);
-    __syncthreads();
-    smem[t] += x;
-    __syncthreads();
+__device__ T block_exclusive_scan(T v, T* total, T* smem /* >= 33 */) {
+  // warp shuffles inside the warps, one more warp scan over the warp totals (blockDim.x <= 1024, a multiple of 32)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  T incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const T x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += x;
   }
-  const T incl = smem[t];
-  if (total) *total = smem[n - 1];
+  if (lane == 31) smem[w] = incl;
   __syncthreads();
-  return incl - v;
+  if (w == 0) {
+    const T t = lane < nw ? smem[lane] : T(0);
+    T ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const T x = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += x;
+    }
+    smem[lane] = ti - t;
+    if (lane == 31) smem[32] = ti;
+  }
+  __syncthreads();
+  const T res = incl - v + smem[w];
+  if (total && threadIdx.x == 0) *total = smem[32];
+  __syncthreads();
+  return res;
 }
 
-template <typename R>
+// SMEM: the per-bin cursor values and counts are staged in shared memory (2 * nb ints), so that global memory is read once
+// and the three phases are not separated by L2 round trips; without it (nb too large) the same code re-reads global memory.
+template <typename R, bool SMEM>
 __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int first_call) {
-  __shared__ long long sh_ll[1024];
-  __shared__ int sh_i[1024];
+  extern __shared__ int plan_sm[];  // SMEM: [nb] attempts, [nb] counts
+  __shared__ long long sh_ll[33];
+  __shared__ int sh_i[33];
   __shared__ long long tot_ll;
   __shared__ int tot_i;
   PlanHeader* h = bd.hdr;
   const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb;
   const int written = first_call ? h->flip : (h->flip ^ 1);  // buffer the last kernel wrote = source of the next push
   const int next = written ^ 1;                               // destination of the next push
-  const int per = (nb + nt - 1) / nt, lo = min(t * per, nb), hi = min(lo + per, nb);
-  // 1. close `written`: cnt = min(cursor, capacity); everything beyond sits in its overflow list
+  const unsigned* __restrict__ g_att = bd.cur[written];
+  int* s_att = plan_sm;
+  int* s_cnt = plan_sm + nb;
+  auto att_of = [&](int b) -> long long { return SMEM ? (long long)(unsigned)s_att[b] : (long long)g_att[b]; };
+  auto cnt_of = [&](int b) -> int { return SMEM ? s_cnt[b] : bd.cnt[written][b]; };
+  // 1. close `written`: cnt = min(cursor, capacity); everything beyond sits in its overflow list (bins interleaved over threads)
   long long mine = 0;
-  for (int b = lo; b < hi; ++b) {
+  for (int b = t; b < nb; b += nt) {
     const long long cap = bd.off[written][b + 1] - bd.off[written][b];
-    const long long att = bd.cur[written][b];
-    bd.cnt[written][b] = (int)(att < cap ? att : cap);
+    const long long att = g_att[b];
+    const int cnt = (int)(att < cap ? att : cap);
+    bd.cnt[written][b] = cnt;
+    if (SMEM) { s_att[b] = (int)att; s_cnt[b] = cnt; }
     mine += att;
   }
   block_exclusive_scan<long long>(mine, &tot_ll, sh_ll);
   const long long n_total = tot_ll;
-  // 2. capacities of `next`: population + slack * (itself and both neighbours in the same species) + a constant
+  // 2. capacities of `next`: population + slack * (itself and both neighbours in the same species) + a constant.
+  //    From here on every thread owns a contiguous range of bins (offsets are a running sum).
+  const int per = (nb + nt - 1) / nt, lo = min(t * per, nb), hi = min(lo + per, nb);
   double f = bd.slack;
   {
     const double room = (double)bd.cap_total - (double)n_total - 72.0 * nb;
@@ -213,37 +236,30 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
     if (f > fmax) f = fmax;
     if (f < 0) { f = 0; if (t == 0 && room < 0) atomicExch(&h->error, 2); }
   }
-  long long cap_sum = 0;
-  for (int b = lo; b < hi; ++b) {
+  auto cap_of = [&](int b) -> long long {
     const int s = b / G, c = b - s * G;
-    const long long a0 = bd.cur[written][b];
-    const long long al = bd.cur[written][s * G + (c == 0 ? G - 1 : c - 1)], ar = bd.cur[written][s * G + (c == G - 1 ? 0 : c + 1)];
-    long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
-    cap = (cap + kBlk - 1) & ~(long long)(kBlk - 1);  // bins start on block boundaries
-    cap_sum += cap;
-  }
+    const long long a0 = att_of(b), al = att_of(s * G + (c == 0 ? G - 1 : c - 1)), ar = att_of(s * G + (c == G - 1 ? 0 : c + 1));
+    const long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
+    return (cap + kBlk - 1) & ~(long long)(kBlk - 1);  // bins start on block boundaries
+  };
+  long long cap_sum = 0;
+  for (int b = lo; b < hi; ++b) cap_sum += cap_of(b);
   long long run = block_exclusive_scan<long long>(cap_sum, &tot_ll, sh_ll);
   for (int b = lo; b < hi; ++b) {
-    const int s = b / G, c = b - s * G;
-    const long long a0 = bd.cur[written][b];
-    const long long al = bd.cur[written][s * G + (c == 0 ? G - 1 : c - 1)], ar = bd.cur[written][s * G + (c == G - 1 ? 0 : c + 1)];
-    long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
-    cap = (cap + kBlk - 1) & ~(long long)(kBlk - 1);
     bd.off[next][b] = run;
-    run += cap;
+    run += cap_of(b);
+    bd.cur[next][b] = 0u;
   }
   if (t == 0) bd.off[next][nb] = tot_ll;
-  __syncthreads();
-  for (int b = lo; b < hi; ++b) bd.cur[next][b] = 0u;
   // 3. work items over `written`: about 4 per warp of the push kernel, between kMinChunk and kMaxChunk particles each
   long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
   want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
   const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
   int my_items = 0;
-  for (int b = lo; b < hi; ++b) my_items += (bd.cnt[written][b] + kChunk - 1) / kChunk;
+  for (int b = lo; b < hi; ++b) my_items += (cnt_of(b) + kChunk - 1) / kChunk;
   int it = block_exclusive_scan<int>(my_items, &tot_i, sh_i);
   for (int b = lo; b < hi; ++b) {
-    const int n = bd.cnt[written][b];
+    const int n = cnt_of(b);
     for (int k = 0; k < n; k += kChunk) {
       if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
       ++it;
@@ -417,6 +433,7 @@ struct BinnedStore {
   long long* dense = nullptr;
   int n_sm = 148;
   bool built = false;
+  size_t plan_smem_max = 0;
 
   template <typename T>
   int alloc(Engine& e, T** ptr, size_t n) {
@@ -452,6 +469,14 @@ struct BinnedStore {
     if ((rc = alloc(e, &bd.item_bin, bd.item_cap)) || (rc = alloc(e, &bd.item_first, bd.item_cap)) || (rc = alloc(e, &bd.hdr, 1))) return rc;
     if ((rc = alloc(e, &dense, bd.nb + 1))) return rc;
     (void)prm;
+    {
+      int dev = 0, max_smem = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      plan_smem_max = max_smem > 4096 ? (size_t)max_smem - 4096 : 0;
+      if ((size_t)2 * bd.nb * sizeof(int) > 48 * 1024 && (size_t)2 * bd.nb * sizeof(int) <= plan_smem_max)
+        cudaFuncSetAttribute(k_plan<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * bd.nb * sizeof(int)));
+    }
     built = true;
     return JIC_OK;
   }
@@ -489,9 +514,11 @@ struct BinnedStore {
   }
   bool first_plan = true;
 
-  // runs after the field kernel of every step (and of the start-up): plan the next push
-  int after_fields(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
-    k_plan<R><<<1, 1024, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
+  // runs after every push (and after the start-up scatter), concurrently with the field kernel: plan the next push
+  int plan(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
+    const size_t sm = (size_t)2 * bd.nb * sizeof(int);
+    if (sm <= plan_smem_max) k_plan<R, true><<<1, 1024, sm, st>>>(bd, dp.G, first_plan ? 1 : 0);
+    else k_plan<R, false><<<1, 1024, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
     first_plan = false;
     e.launches += 1;
     return JIC_OK;

@@ -73,6 +73,10 @@ struct EngineT : Engine {
   std::map<int, cudaGraphExec_t> graphs;
   bool shared_grid = false;
   size_t shared_bytes = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int field_smem_comps = 0;
+  size_t field_smem_bytes = 0;
   BinnedStore<R> bins;  // BINNED engine state (unused for INDEXED)
 
   int dtype() const override { return prm.dtype; }
@@ -141,11 +145,24 @@ struct EngineT : Engine {
     if (shared_grid) {
       JIC_CUDA(cudaFuncSetAttribute(k_step<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
     }
+    JIC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    JIC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    JIC_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    // field kernel: filter in shared memory, as many of the four components at a time as fit (double-buffered)
+    field_smem_comps = 0;
+    for (int c = 4; c >= 1; c >>= 1)
+      if ((size_t)2 * c * G * sizeof(double) <= (size_t)max_smem - 2048) { field_smem_comps = c; break; }
+    field_smem_bytes = (size_t)2 * field_smem_comps * G * sizeof(double);
+    if (field_smem_bytes > 48 * 1024)
+      JIC_CUDA(cudaFuncSetAttribute(k_fields<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)field_smem_bytes));
     return JIC_OK;
   }
 
   ~EngineT() override {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
     if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
     void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, F, E, B, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -199,6 +216,7 @@ struct EngineT : Engine {
     a.acc = acc; a.E = E; a.B = B; a.E_int = E_int; a.B_int = B_int; a.J = J; a.rho = rho; a.extE = extE; a.extB = extB; a.F = F;
     a.s0 = s0; a.s1 = s1; a.E0 = E0; a.B0 = B0; a.ctl = ctl;
     a.record = record ? 1 : 0;
+    a.smem_comps = field_smem_comps;
     return a;
   }
 
@@ -216,9 +234,9 @@ struct EngineT : Engine {
     JIC_CUDA(cudaGetLastError());
     int rc = allreduce(st);
     if (rc) return rc;
-    k_fields<R><<<1, 1024, 0, st>>>(field_args(true, false));
+    k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));
     launches += 1;
-    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
+    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.plan(*this, dp, st))) return rc;
     JIC_CUDA(cudaGetLastError());
     initialized = true;
     return JIC_OK;
@@ -241,12 +259,21 @@ struct EngineT : Engine {
     return bins.step(*this, dp, F, acc, st);
   }
 
+  // grid part of a step.  BINNED: the plan of the next push only depends on the push that just ran, so it runs on a side
+  // stream next to the all-reduce + field kernel (fork/join through events; inside a capture this becomes a parallel branch).
   int enqueue_fields(cudaStream_t st) {
-    int rc = allreduce(st);
-    if (rc) return rc;
-    k_fields<R><<<1, 1024, 0, st>>>(field_args(false, true));
+    const bool binned = prm.engine == JIC_ENGINE_BINNED;
+    int rc;
+    if (binned) {
+      JIC_CUDA(cudaEventRecord(ev_fork, st));
+      JIC_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      if ((rc = bins.plan(*this, dp, side))) return rc;
+      JIC_CUDA(cudaEventRecord(ev_join, side));
+    }
+    if ((rc = allreduce(st))) return rc;
+    k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(false, true));
     launches += 1;
-    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.after_fields(*this, dp, st))) return rc;
+    if (binned) JIC_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     return JIC_OK;
   }
 

@@ -156,16 +156,22 @@ struct FieldArgs {
   R* F;                // padded gather table (G+3, 8)
   double *s0, *s1;     // filter scratch (G,4) each
   double *E0, *B0;     // initial fields (init mode)
+  int smem_comps;      // components filtered at a time in shared memory (0 = global scratch)
   int record;          // write this step's outputs to the history buffers named in ctl->hist
   RunControl* ctl;
 };
 
-__device__ __forceinline__ double filt_neighbour(const double* y, int j, int s, int G, int c, bool periodic, int fbl, int fbr) {
+// neighbour j+s of a component stored contiguously (y[0..G)): jaxincell/_filters.py:9-50 (_shift_with_bc_1d)
+__device__ __forceinline__ double filt_neighbour(const double* y, int j, int s, int G, bool periodic, int fbl, int fbr) {
   int k = j + s;
-  if (periodic) return y[mod_pos(k, G) * kAccRow + c];
-  if (k < 0) return fbl == JIC_BC_ABSORBING ? 0.0 : y[c];
-  if (k >= G) return fbr == JIC_BC_ABSORBING ? 0.0 : y[(G - 1) * kAccRow + c];
-  return y[k * kAccRow + c];
+  if (periodic) {
+    if (k < 0) { k += G; if (k < 0) k = mod_pos(k, G); }
+    else if (k >= G) { k -= G; if (k >= G) k = mod_pos(k, G); }
+    return y[k];
+  }
+  if (k < 0) return fbl == JIC_BC_ABSORBING ? 0.0 : y[0];
+  if (k >= G) return fbr == JIC_BC_ABSORBING ? 0.0 : y[G - 1];
+  return y[k];
 }
 
 __device__ __forceinline__ void ghost_E_left(const double* E, const double* B, int G, int fbl, double g[3]) {
@@ -210,43 +216,96 @@ __device__ __forceinline__ void ampere(double* E, double* B, const double* J, in
   __syncthreads();
 }
 
-template <typename R>
-__global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
-  const int G = a.G, tid = threadIdx.x, nt = blockDim.x;
-  // 1. raw grid -> scratch (fp64), zero the raw grid for the next step
-  for (int k = tid; k < G * kAccRow; k += nt) { a.s0[k] = (double)a.acc[k]; a.acc[k] = R(0); }
-  __syncthreads();
-  // 2. digital filter, all four components at once
-  double* cur = a.s0;
-  double* nxt = a.s1;
-  if (a.passes > 0) {
-    const bool periodic = (a.fbl == JIC_BC_PERIODIC) && (a.fbr == JIC_BC_PERIODIC);
-    const int p_cl = a.passes < 17 ? a.passes : 17;
-    const int n_reg = (a.passes - 1) < 16 ? (a.passes - 1) : 16;
-    const double comp_alpha = p_cl - a.alpha * (p_cl - 1);
-    for (int si = 0; si < a.n_strides; ++si) {
-      const int s = a.strides[si];
-      for (int sweep = 0; sweep <= n_reg; ++sweep) {
-        const double al = sweep < n_reg ? a.alpha : comp_alpha;
-        const double co = (1 - al) * 0.5;
-        for (int k = tid; k < G * kAccRow; k += nt) {
-          const int j = k / kAccRow, c = k % kAccRow;
-          const double l = filt_neighbour(cur, j, -s, G, c, periodic, a.fbl, a.fbr);
-          const double r = filt_neighbour(cur, j, +s, G, c, periodic, a.fbl, a.fbr);
-          nxt[k] = al * cur[k] + co * (l + r);
+// Digital filter of `cg` components held contiguously in cur[c * G + j] (double-buffered with nxt), all strides and sweeps:
+// jaxincell/_filters.py:52-153.  Returns the buffer holding the result.  Called with shared-memory or global pointers; kept
+// as a separate function so that the shared-memory instantiation compiles to 32-bit LDS/STS addressing.
+template <typename Ptr>
+__device__ __forceinline__ Ptr filter_components(Ptr cur, Ptr nxt, int cg, int G, int passes, double alpha, int n_strides, const int* strides,
+                                                 int fbl, int fbr) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (passes <= 0) return cur;
+  const bool periodic = (fbl == JIC_BC_PERIODIC) && (fbr == JIC_BC_PERIODIC);
+  const int p_cl = passes < 17 ? passes : 17;
+  const int n_reg = (passes - 1) < 16 ? (passes - 1) : 16;
+  const double comp_alpha = p_cl - alpha * (p_cl - 1);
+  const double zl = fbl == JIC_BC_ABSORBING ? 0.0 : 1.0, zr = fbr == JIC_BC_ABSORBING ? 0.0 : 1.0;
+  for (int si = 0; si < n_strides; ++si) {
+    const int s = strides[si];
+    for (int sweep = 0; sweep <= n_reg; ++sweep) {
+      const double al = sweep < n_reg ? alpha : comp_alpha;
+      const double co = (1 - al) * 0.5;
+      if (periodic && s < G) {
+        for (int c = 0; c < cg; ++c) {
+          const int o = c * G;
+          for (int j = tid; j < G; j += nt) {
+            int jm = j - s, jp = j + s;
+            jm += jm < 0 ? G : 0;
+            jp -= jp >= G ? G : 0;
+            nxt[o + j] = al * cur[o + j] + co * (cur[o + jm] + cur[o + jp]);
+          }
         }
-        __syncthreads();
-        double* t = cur; cur = nxt; nxt = t;
+      } else if (periodic) {
+        for (int c = 0; c < cg; ++c) {
+          const int o = c * G;
+          for (int j = tid; j < G; j += nt) nxt[o + j] = al * cur[o + j] + co * (cur[o + mod_pos(j - s, G)] + cur[o + mod_pos(j + s, G)]);
+        }
+      } else {  // index clamp, and zero where the overrun side is absorbing (_filters.py:26-50)
+        for (int c = 0; c < cg; ++c) {
+          const int o = c * G;
+          for (int j = tid; j < G; j += nt) {
+            const int jm = j - s, jp = j + s;
+            const double l = jm < 0 ? zl * cur[o] : cur[o + jm];
+            const double r = jp >= G ? zr * cur[o + G - 1] : cur[o + jp];
+            nxt[o + j] = al * cur[o + j] + co * (l + r);
+          }
+        }
       }
+      __syncthreads();
+      Ptr t = cur; cur = nxt; nxt = t;
     }
   }
-  for (int i = tid; i < G; i += nt) {
-    a.J[i * 3 + 0] = cur[i * kAccRow + 0];
-    a.J[i * 3 + 1] = cur[i * kAccRow + 1];
-    a.J[i * 3 + 2] = cur[i * kAccRow + 2];
-    a.rho[i] = cur[i * kAccRow + 3];
+  return cur;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
+  extern __shared__ __align__(16) double fsm[];  // 2 * smem_comps * G doubles (0 = filter through the global scratch s0/s1)
+  const int G = a.G, tid = threadIdx.x, nt = blockDim.x;
+  // 1.+2. digital filter of the raw grid, `cg` components at a time
+  {
+    const int cg = a.smem_comps > 0 ? a.smem_comps : kAccRow;
+    for (int c0 = 0; c0 < kAccRow; c0 += cg) {
+      if (a.smem_comps > 0) {
+        double* cur = fsm;
+        for (int c = 0; c < cg; ++c)
+          for (int j = tid; j < G; j += nt) cur[c * G + j] = (double)a.acc[j * kAccRow + c0 + c];
+        __syncthreads();
+        const double* res = filter_components<double*>(cur, fsm + cg * G, cg, G, a.passes, a.alpha, a.n_strides, a.strides, a.fbl, a.fbr);
+        for (int c = 0; c < cg; ++c) {
+          const int comp = c0 + c;
+          for (int j = tid; j < G; j += nt) {
+            if (comp < 3) a.J[j * 3 + comp] = res[c * G + j];
+            else a.rho[j] = res[c * G + j];
+          }
+        }
+      } else {
+        double* cur = a.s0;
+        for (int c = 0; c < cg; ++c)
+          for (int j = tid; j < G; j += nt) cur[c * G + j] = (double)a.acc[j * kAccRow + c0 + c];
+        __syncthreads();
+        const double* res = filter_components<double*>(cur, a.s1, cg, G, a.passes, a.alpha, a.n_strides, a.strides, a.fbl, a.fbr);
+        for (int c = 0; c < cg; ++c) {
+          const int comp = c0 + c;
+          for (int j = tid; j < G; j += nt) {
+            if (comp < 3) a.J[j * 3 + comp] = res[c * G + j];
+            else a.rho[j] = res[c * G + j];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int k = tid; k < G * kAccRow; k += nt) a.acc[k] = R(0);  // the raw grid is consumed: zero it for the next step
   }
-  __syncthreads();
   const double h = a.dt / 2;
   if (a.init) {
     // 3a. E_x = (dx/eps0) cumsum(rho0); the reference's forward substitution is this same sequential sum
