@@ -77,39 +77,65 @@ def make_particles(w, torch, device, dtype, seed, order):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in-process (a sample
+    every few ms; the timed region is tens of ms), falling back to polling nvidia-smi."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((mhz, self.max_mhz, {k for k, b in self.BITS.items() if mask & b}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            c = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.rows.append((float(c[0]), float(c[1]), {n for n, v in zip(names, c[3:7]) if v.lower().startswith("active")}))
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.002 if self.nvml else 0.1)
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: lets the caller cut out the samples taken inside the timed region."""
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        rows = self.rows[lo:hi] or self.rows
+        sm = sorted(r[0] for r in rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+        for r in rows:
+            reasons |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[1] for r in rows), default=None),
+                "reasons": sorted(reasons), "samples": len(rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def peaks():
@@ -173,11 +199,25 @@ def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000):
     return n_sample * steps / el, threads, f"{n_sample} particles x {steps} steps, G={G}, NumPy closed-form port of the reference, {threads} threads"
 
 
+def real_reference_status():
+    """The unmodified reference lives in baseline/_ref when it could be installed.  It is pure Python on
+    JAX; importing it needs jax, jax_tqdm and matplotlib, none of which exist in this image."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        import jaxincell  # noqa: F401
+        return None
+    except Exception as e:  # noqa: BLE001
+        return f"{type(e).__name__}: {e}"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = workload(args, 1)
+    why_not = real_reference_status()
     rate, cores, sample = cpu_port_rate(w, seconds_target=min(60.0, 4.0 * max(args.steps, 1)))
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
@@ -185,7 +225,8 @@ def run_reference(args):
             "config": {"workload": f"synthetic two-beam plasma, G={args.grid}, CFL 1, periodic, filter 5/0.5/(1,2,4) (SURVEY 8d config 5), CPU sample"},
             "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "JAX is not installable in this image, so the reference itself cannot run; this is the oracle port (NumPy) of its algorithm"}
+            "note": "the reference itself cannot run here (import jaxincell from baseline/_ref -> " + str(why_not) + "); "
+                    "this is the oracle port (NumPy) of its algorithm on the host cores"}
     print(json.dumps(line), flush=True)
 
 
@@ -253,17 +294,19 @@ def main():
     l0 = hp.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    m0 = sampler.mark() if sampler else 0
     e0.record()
     hp.run(K, outputs=outs)
     e1.record()
     barrier()
+    m1 = sampler.mark() if sampler else 0
     ms = e0.elapsed_time(e1)
     launches = hp.launch_count() - l0
     # dominant kernel, timed live with CUDA events on its own stream (jic_profile_steps), a few more real steps
     n_prof = min(K, 10)
     ms_push, ms_grid = hp.profile_steps(n_prof)
     barrier()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(m0, max(m1, m0 + 1)) if sampler else None
     t = torch.tensor([ms, ms_push / n_prof, ms_grid / n_prof], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1,0 +1,72 @@
+"""Two ranks, two GPUs, one NCCL all-reduce of the raw grid per step: fields must match the single-rank oracle and be
+bit-identical across ranks.  Skipped unless the box has >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import closed_form as C
+from plasma import cfl_dt, two_species
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, engine, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from jaxincell_b200 import HotPath, shard_particles, shard_species
+        G, length, T = 64, 0.01, 12
+        p = two_species(6000, 5000, length=length, G=G, seed=21, vth_e=0.05, vth_yz=0.02, drift=5e7, plus_minus=True, gpdl=0.7)
+        dt = cfl_dt(length, G, 0.9)
+        x, v, idx = shard_particles(p["x0"], p["v0"], p["species"], rank, world)
+        hp = HotPath(species=shard_species(p["species"], rank, world), length=length, G=G, dt=dt, engine=engine)
+        hp.comm_init_from_torch()
+        hp.set_external_fields(None, None)
+        hp.initialize(x, v)
+        out = hp.run(T)
+        torch.cuda.synchronize()
+        E = out["electric_field"]
+        others = [torch.empty_like(E) for _ in range(world)]
+        dist.all_gather(others, E)
+        assert all(torch.equal(o, E) for o in others), "ranks hold different fields"
+        if rank == 0:
+            ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, keep_particles=False)
+            for k in ("electric_field", "magnetic_field", "current_density", "charge_density"):
+                err = np.abs(out[k].cpu().numpy() - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-300)
+                assert err < 1e-5, (k, err)  # north-star tolerance, fp64
+        hp.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+def test_two_gpus_match_single_rank_oracle(engine):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, engine, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
