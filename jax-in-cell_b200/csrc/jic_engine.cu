@@ -62,9 +62,15 @@ struct EngineT : Engine {
   // particles (SoA)
   R *xh = nullptr, *yh = nullptr, *zh = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr, *v_init = nullptr;
   // grid
-  R *acc = nullptr, *F = nullptr;
+  R *acc = nullptr, *acc2 = nullptr, *F = nullptr;   // raw deposit grid (two of them when the multi-CTA field kernel is on)
   double *E = nullptr, *B = nullptr, *E_int = nullptr, *B_int = nullptr, *J = nullptr, *rho = nullptr, *extE = nullptr, *extB = nullptr;
   double *s0 = nullptr, *s1 = nullptr, *E0 = nullptr, *B0 = nullptr;
+  double *E2 = nullptr, *B2 = nullptr;  // ping-pong partners of E, B (multi-CTA field kernel)
+  unsigned* mc_done = nullptr;
+  bool mc = false;                      // multi-CTA field kernel in use
+  int mc_S = 0, mc_H = 0, mc_NC = 0;
+  size_t mc_smem = 0;
+  int par = 0;                          // which of the ping-pong buffers the next step reads (mc only)
   RunControl* ctl = nullptr;
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -135,6 +141,33 @@ struct EngineT : Engine {
     if ((rc = alloc(&J, G * 3)) || (rc = alloc(&rho, G)) || (rc = alloc(&extE, G * 3)) || (rc = alloc(&extB, G * 3))) return rc;
     if ((rc = alloc(&s0, G * kAccRow)) || (rc = alloc(&s1, G * kAccRow)) || (rc = alloc(&E0, G * 3)) || (rc = alloc(&B0, G * 3))) return rc;
     if ((rc = alloc(&ctl, 1))) return rc;
+    if ((rc = alloc(&acc2, G * kAccRow)) || (rc = alloc(&E2, G * 3)) || (rc = alloc(&B2, G * 3)) || (rc = alloc(&mc_done, 1))) return rc;
+    {
+      // multi-CTA field kernel: slices of S nodes with a halo of H = filter reach + 2; needs >= 2 slices of >= H + 2 nodes
+      long long reach = 0;
+      if (prm.filter_passes > 0) {
+        const int sweeps = (prm.filter_passes - 1 < 16 ? prm.filter_passes - 1 : 16) + 1;
+        for (int i = 0; i < prm.n_filter_strides; ++i) reach += (long long)sweeps * prm.filter_strides[i];
+      }
+      const char* env = getenv("JIC_FIELDS_MC");  // "0" forces the single-CTA kernel
+      mc = false;
+      // (one periodic and one non-periodic field boundary couples the two ends of the domain through the curl ghosts,
+      //  _boundary_conditions.py:148-207: that case stays on the single-CTA kernel)
+      const bool mixed = (prm.field_bc_left == JIC_BC_PERIODIC) != (prm.field_bc_right == JIC_BC_PERIODIC);
+      if (!(env && env[0] == '0') && !mixed && reach + 2 < (long long)G) {
+        mc_H = (int)reach + 2;
+        int nc = 16;
+        while (nc >= 2) {
+          const int S = (int)((G + nc - 1) / nc);
+          const long long last = (long long)G - (long long)(nc - 1) * S;
+          const size_t smem = ((size_t)8 * (S + 2 * mc_H) + (size_t)6 * (S + 4)) * sizeof(double);
+          if (S >= 2 * mc_H && S >= 64 && last >= 1 && smem <= (size_t)max_smem_optin() - 1024) { mc = true; mc_S = S; mc_NC = nc; mc_smem = smem; break; }
+          nc >>= 1;
+        }
+        if (mc && mc_smem > 48 * 1024)
+          JIC_CUDA(cudaFuncSetAttribute(k_fields_mc<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mc_smem));
+      }
+    }
     // deposition target of the INDEXED kernel
     shared_bytes = G * kAccRow * sizeof(R);
     int max_smem = 0;
@@ -164,7 +197,7 @@ struct EngineT : Engine {
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
     if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
-    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, F, E, B, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl};
+    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, acc2, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
   }
@@ -191,6 +224,12 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
+  int max_smem_optin() const {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    return v;
+  }
+
   int grid_for(long long n, int block, int per_sm) const {
     long long b = (n + block - 1) / block;
     long long cap = (long long)n_sm * per_sm;
@@ -198,10 +237,15 @@ struct EngineT : Engine {
     return (int)(b < 1 ? 1 : b);
   }
 
-  int allreduce(cudaStream_t st) {
+  R* acc_of(int p) const { return (mc && p) ? acc2 : acc; }
+  double* E_of(int p) const { return (mc && p) ? E2 : E; }
+  double* B_of(int p) const { return (mc && p) ? B2 : B; }
+
+  int allreduce(cudaStream_t st, int p) {
     if (world <= 1) return JIC_OK;
     NcclApi& api = nccl_api();
-    ncclResult_t r = api.AllReduce(acc, acc, (size_t)dp.G * kAccRow, sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, st);
+    R* buf = acc_of(p);
+    ncclResult_t r = api.AllReduce(buf, buf, (size_t)dp.G * kAccRow, sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, st);
     if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
     launches += 1;
     return JIC_OK;
@@ -223,7 +267,10 @@ struct EngineT : Engine {
   int initialize(const void* x0, const void* v0, cudaStream_t st) override {
     if (!x0 || !v0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
     JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * kAccRow * sizeof(R), st));
+    JIC_CUDA(cudaMemsetAsync(acc2, 0, (size_t)dp.G * kAccRow * sizeof(R), st));
+    JIC_CUDA(cudaMemsetAsync(mc_done, 0, sizeof(unsigned), st));
     JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
+    par = 0;
     if (prm.engine == JIC_ENGINE_INDEXED) {
       k_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x0, (const R*)v0, xh, yh, zh, vx, vy, vz, v_init, acc);
       launches += 1;
@@ -232,9 +279,9 @@ struct EngineT : Engine {
       if (rc) return rc;
     }
     JIC_CUDA(cudaGetLastError());
-    int rc = allreduce(st);
+    int rc = allreduce(st, 0);
     if (rc) return rc;
-    k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));
+    k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));  // init mode is always the single-CTA kernel
     launches += 1;
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.plan(*this, dp, st))) return rc;
     JIC_CUDA(cudaGetLastError());
@@ -243,7 +290,8 @@ struct EngineT : Engine {
   }
 
   // enqueue one full step on `st` (used under stream capture): particle kernel(s), all-reduce, field kernel
-  int enqueue_push(cudaStream_t st) {
+  int enqueue_push(cudaStream_t st, int p) {
+    R* acc = acc_of(p);  // (shadows the member: the raw grid this step deposits into)
     if (prm.engine == JIC_ENGINE_INDEXED) {
       if (shared_grid) {
         // persistent CTAs: one shared copy of the grid each
@@ -261,7 +309,21 @@ struct EngineT : Engine {
 
   // grid part of a step.  BINNED: the plan of the next push only depends on the push that just ran, so it runs on a side
   // stream next to the all-reduce + field kernel (fork/join through events; inside a capture this becomes a parallel branch).
-  int enqueue_fields(cudaStream_t st) {
+  FieldArgsMC<R> field_args_mc(int p) const {
+    FieldArgsMC<R> a;
+    memset(&a, 0, sizeof(a));
+    a.G = dp.G; a.fbl = dp.fbl; a.fbr = dp.fbr; a.passes = prm.filter_passes; a.n_strides = prm.n_filter_strides;
+    for (int i = 0; i < prm.n_filter_strides; ++i) a.strides[i] = prm.filter_strides[i];
+    a.alpha = prm.filter_alpha; a.dx = prm.dx; a.dt = prm.dt;
+    a.S = mc_S; a.H = mc_H; a.NC = mc_NC;
+    a.acc_cur = acc_of(p); a.acc_next = acc_of(p ^ 1);
+    a.E_r = E_of(p); a.B_r = B_of(p); a.E_w = E_of(p ^ 1); a.B_w = B_of(p ^ 1);
+    a.E_int = E_int; a.B_int = B_int; a.J = J; a.rho = rho; a.extE = extE; a.extB = extB; a.F = F;
+    a.record = 1; a.ctl = ctl; a.done = mc_done;
+    return a;
+  }
+
+  int enqueue_fields(cudaStream_t st, int p) {
     const bool binned = prm.engine == JIC_ENGINE_BINNED;
     int rc;
     if (binned) {
@@ -270,16 +332,18 @@ struct EngineT : Engine {
       if ((rc = bins.plan(*this, dp, side))) return rc;
       JIC_CUDA(cudaEventRecord(ev_join, side));
     }
-    if ((rc = allreduce(st))) return rc;
-    k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(false, true));
+    if ((rc = allreduce(st, p))) return rc;
+    if (mc) k_fields_mc<R><<<mc_NC, kFieldsMcThreads, mc_smem, st>>>(field_args_mc(p));
+    else k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(false, true));
     launches += 1;
     if (binned) JIC_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     return JIC_OK;
   }
 
-  int enqueue_step(cudaStream_t st) {
-    int rc = enqueue_push(st);
-    return rc ? rc : enqueue_fields(st);
+  // one step reading the ping-pong buffers `p` (always 0 without the multi-CTA field kernel)
+  int enqueue_step(cudaStream_t st, int p) {
+    int rc = enqueue_push(st, p);
+    return rc ? rc : enqueue_fields(st, p);
   }
 
   int begin_run(const jic_outputs& out, cudaStream_t st) {
@@ -301,10 +365,11 @@ struct EngineT : Engine {
     int rc = JIC_OK;
     for (long long s = 0; s < n && rc == JIC_OK; ++s) {
       cudaEventRecord(ev[3 * s], st);
-      rc = enqueue_push(st);
+      rc = enqueue_push(st, par);
       cudaEventRecord(ev[3 * s + 1], st);
-      if (rc == JIC_OK) rc = enqueue_fields(st);
+      if (rc == JIC_OK) rc = enqueue_fields(st, par);
       cudaEventRecord(ev[3 * s + 2], st);
+      if (mc) par ^= 1;
     }
     cudaError_t ce = cudaStreamSynchronize(st);
     double a = 0, b = 0;
@@ -324,7 +389,7 @@ struct EngineT : Engine {
   }
 
   int get_graph(int steps, cudaStream_t st, cudaGraphExec_t* exec) {
-    const int key = steps;
+    const int key = steps * 2 + par;  // the buffer pointers baked into the graph depend on the starting parity
     auto it = graphs.find(key);
     if (it != graphs.end()) { *exec = it->second; return JIC_OK; }
     cudaStream_t cs;
@@ -333,7 +398,7 @@ struct EngineT : Engine {
     cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     int rc = JIC_OK;
     if (e == cudaSuccess) {
-      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs);
+      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, mc ? (par ^ (s & 1)) : 0);
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
@@ -383,6 +448,7 @@ struct EngineT : Engine {
       JIC_CUDA(cudaGraphLaunch(ex, st));
       launches += per_step * steps;
       done += steps;
+      if (mc) par ^= steps & 1;
     }
     return JIC_OK;
   }

@@ -361,6 +361,201 @@ __global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K2m  the field kernel on NC CTAs (used when the grid is large enough; same arithmetic as k_fields, non-init mode).
+//   The filter and the Maxwell half steps are local stencils, so every CTA owns a slice of S nodes and recomputes a halo of
+//   H = (total filter reach) + 2 nodes on each side from the raw grid: no inter-CTA communication, no grid-wide barrier.
+//   Because CTAs read each other's slices (halos), the state is ping-ponged: this step reads acc_cur / E_r / B_r and writes
+//   E_w / B_w, and zeroes its slice of acc_next (the buffer the NEXT push deposits into; it was consumed one step ago).
+//   Non-periodic boundaries are handled by the edge CTAs with the clamp / zero rule of _filters.py:26-50 and the ghost-cell
+//   formulas of _boundary_conditions.py:148-207; S >= H + 2 is guaranteed by the host so only they see the domain edge.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct FieldArgsMC {
+  int G, fbl, fbr, passes, n_strides;
+  int strides[JIC_MAX_STRIDES];
+  double alpha, dx, dt;
+  int S, H, NC;
+  const R* acc_cur; R* acc_next;
+  const double *E_r, *B_r;
+  double *E_w, *B_w, *E_int, *B_int, *J, *rho;
+  const double *extE, *extB;
+  R* F;
+  int record;
+  RunControl* ctl;
+  unsigned* done;  // CTAs finished (the last one advances ctl->step / hist_row and resets it)
+};
+
+constexpr int kFieldsMcThreads = 512;
+
+template <typename R>
+__global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsMC<R> a) {
+  extern __shared__ __align__(16) double fsm[];
+  const int G = a.G, S = a.S, H = a.H, tid = threadIdx.x, nt = blockDim.x;
+  const int lo = blockIdx.x * S, hi = min(lo + S, G);
+  const int W = S + 2 * H;           // filter window: local li <-> global node lo - H + li
+  const int Wm = S + 4;              // Maxwell window: local mi <-> global node lo - 2 + mi  (li = mi + H - 2)
+  double* cur = fsm;                 // [4][W]
+  double* nxt = fsm + 4 * W;         // [4][W]
+  double* Em = fsm + 8 * W;          // [3][Wm]
+  double* Bm = Em + 3 * Wm;          // [3][Wm]
+  const bool periodic = (a.fbl == JIC_BC_PERIODIC) && (a.fbr == JIC_BC_PERIODIC);
+  const int idx0 = H - lo;           // local (filter window) index of node 0
+  const int idxL = G - 1 - lo + H;   // local (filter window) index of node G - 1
+  const bool edgeL = !periodic && idx0 >= 0, edgeR = !periodic && idxL <= W - 1;  // the window reaches the domain edge
+  const long long row = a.ctl->hist_row;
+
+  // ---- raw grid window -> shared memory (periodic: wrapped; outside a non-periodic domain: unused)
+  for (int li = tid; li < W; li += nt) {
+    int g = lo - H + li;
+    if (periodic) g = g < 0 ? g + G : (g >= G ? g - G : g);
+    const bool in = g >= 0 && g < G;
+#pragma unroll
+    for (int c = 0; c < kAccRow; ++c) cur[c * W + li] = in ? (double)a.acc_cur[g * kAccRow + c] : 0.0;
+  }
+  // the other raw buffer was consumed by the previous step: zero our slice of it for the next push
+  for (int k = tid; k < (hi - lo) * kAccRow; k += nt) a.acc_next[lo * kAccRow + k] = R(0);
+  __syncthreads();
+
+  // ---- digital filter on a shrinking valid range [va, vb); the domain edge (non-periodic) does not shrink
+  int va = edgeL ? idx0 : 0, vb = edgeR ? idxL + 1 : W;
+  if (a.passes > 0) {
+    const int p_cl = a.passes < 17 ? a.passes : 17;
+    const int n_reg = (a.passes - 1) < 16 ? (a.passes - 1) : 16;
+    const double comp_alpha = p_cl - a.alpha * (p_cl - 1);
+    const double zl = a.fbl == JIC_BC_ABSORBING ? 0.0 : 1.0, zr = a.fbr == JIC_BC_ABSORBING ? 0.0 : 1.0;
+    for (int si = 0; si < a.n_strides; ++si) {
+      const int s = a.strides[si];
+      for (int sweep = 0; sweep <= n_reg; ++sweep) {
+        const double al = sweep < n_reg ? a.alpha : comp_alpha;
+        const double co = (1 - al) * 0.5;
+        const int b0 = edgeL ? va : va + s, b1 = edgeR ? vb : vb - s;
+        const int c = tid & 3;  // four components side by side: thread -> (component, every (nt/4)-th node)
+        for (int li = b0 + (tid >> 2); li < b1; li += nt >> 2) {
+          const double* y = cur + c * W;
+          const double l = (edgeL && li - s < idx0) ? zl * y[idx0] : y[li - s];
+          const double r = (edgeR && li + s > idxL) ? zr * y[idxL] : y[li + s];
+          nxt[c * W + li] = al * y[li] + co * (l + r);
+        }
+        __syncthreads();
+        double* t = cur; cur = nxt; nxt = t;
+        va = b0; vb = b1;
+      }
+    }
+  }
+  // filtered J, rho of the owned nodes
+  for (int i = tid; i < hi - lo; i += nt) {
+    const int li = i + H, g = lo + i;
+    a.J[g * 3 + 0] = cur[li]; a.J[g * 3 + 1] = cur[W + li]; a.J[g * 3 + 2] = cur[2 * W + li];
+    a.rho[g] = cur[3 * W + li];
+  }
+
+  // ---- Maxwell window
+  for (int mi = tid; mi < Wm; mi += nt) {
+    int g = lo - 2 + mi;
+    if (periodic) g = g < 0 ? g + G : (g >= G ? g - G : g);
+    const bool in = g >= 0 && g < G;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { Em[c * Wm + mi] = in ? a.E_r[g * 3 + c] : 0.0; Bm[c * Wm + mi] = in ? a.B_r[g * 3 + c] : 0.0; }
+  }
+  __syncthreads();
+  const double h = a.dt / 2;
+  // window nodes that exist: [m_first, m_last]; wallL / wallR: the window starts / ends at a non-periodic wall
+  const int m_first = periodic ? 0 : max(0, 2 - lo), m_last = periodic ? Wm - 1 : min(Wm - 1, G - 1 - lo + 2);
+  const bool wallL = !periodic && lo - 2 + m_first == 0, wallR = !periodic && lo - 2 + m_last == G - 1;
+  auto faraday_mc = [&](int from, int to) {  // B -= h curl E on mi in [from, to]   (_fields.py:102-111)
+    for (int mi = from + tid; mi <= to; mi += nt) {
+      double ey_m, ez_m;
+      if (wallL && mi == m_first) {  // left ghost of E (_boundary_conditions.py:148-176)
+        if (a.fbl == JIC_BC_REFLECTIVE) { ey_m = Em[Wm + mi]; ez_m = Em[2 * Wm + mi]; }
+        else { ey_m = -2 * kC * Bm[2 * Wm + mi] - Em[Wm + mi]; ez_m = 2 * kC * Bm[Wm + mi] - Em[2 * Wm + mi]; }
+      } else { ey_m = Em[Wm + mi - 1]; ez_m = Em[2 * Wm + mi - 1]; }
+      const double dFz = (Em[2 * Wm + mi] - ez_m) / a.dx, dFy = (Em[Wm + mi] - ey_m) / a.dx;
+      Bm[Wm + mi] -= h * (-dFz);
+      Bm[2 * Wm + mi] -= h * dFy;
+    }
+    __syncthreads();
+  };
+  auto ampere_mc = [&](int from, int to) {  // E += h (c^2 curl B - J/eps0) on mi in [from, to]   (_fields.py:132-144)
+    for (int mi = from + tid; mi <= to; mi += nt) {
+      const int li = mi + H - 2;
+      double by_p, bz_p;
+      if (wallR && mi == m_last) {  // right ghost of B (_boundary_conditions.py:178-207)
+        if (a.fbr == JIC_BC_REFLECTIVE) { by_p = Bm[Wm + mi]; bz_p = Bm[2 * Wm + mi]; }
+        else { by_p = -(2 / kC) * Em[2 * Wm + mi] - Bm[Wm + mi]; bz_p = (2 / kC) * Em[Wm + mi] - Bm[2 * Wm + mi]; }
+      } else { by_p = Bm[Wm + mi + 1]; bz_p = Bm[2 * Wm + mi + 1]; }
+      const double dFz = (bz_p - Bm[2 * Wm + mi]) / a.dx, dFy = (by_p - Bm[Wm + mi]) / a.dx;
+      Em[mi] += h * ((kC * kC) * 0.0 - (cur[li] / kEps0));
+      Em[Wm + mi] += h * ((kC * kC) * (-dFz) - (cur[W + li] / kEps0));
+      Em[2 * Wm + mi] += h * ((kC * kC) * dFy - (cur[2 * W + li] / kEps0));
+    }
+    __syncthreads();
+  };
+  // second half step of step n: B then E (_fields.py:185-193).  Valid ranges shrink by one node per neighbour access.
+  const int fa = wallL ? m_first : m_first + 1;     // B valid on [fa, m_last]
+  faraday_mc(fa, m_last);
+  const int ab = wallR ? m_last : m_last - 1;       // E valid on [fa, ab]
+  ampere_mc(fa, ab);
+  {  // step outputs (_algorithms.py:93) for the owned nodes
+    R* hE = a.record ? (R*)a.ctl->hist[0] : nullptr;
+    R* hB = a.record ? (R*)a.ctl->hist[1] : nullptr;
+    R* hJ = a.record ? (R*)a.ctl->hist[2] : nullptr;
+    R* hrho = a.record ? (R*)a.ctl->hist[3] : nullptr;
+    for (int k = tid; k < (hi - lo) * 3; k += nt) {
+      const int i = k / 3, c = k - 3 * i, mi = i + 2, g = lo + i;
+      const double e = Em[c * Wm + mi], b = Bm[c * Wm + mi];
+      a.E_int[g * 3 + c] = e; a.B_int[g * 3 + c] = b;
+      if (hE) hE[(size_t)row * G * 3 + g * 3 + c] = (R)e;
+      if (hB) hB[(size_t)row * G * 3 + g * 3 + c] = (R)b;
+      if (hJ) hJ[(size_t)row * G * 3 + g * 3 + c] = (R)cur[c * W + i + H];
+    }
+    if (hrho) for (int i = tid; i < hi - lo; i += nt) hrho[(size_t)row * G + lo + i] = (R)cur[3 * W + i + H];
+  }
+  // first half step of step n+1: E then B (_fields.py:175-183)
+  ampere_mc(fa, ab);
+  const int fb = wallL ? fa : fa + 1;               // B valid on [fb, ab]
+  faraday_mc(fb, ab);
+  // ---- new leap-frog state and the padded total-field table of the owned nodes (+ the ghost rows they source)
+  for (int i = tid; i < hi - lo; i += nt) {
+    const int mi = i + 2, g = lo + i;
+    double tE[3], tB[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double e = Em[c * Wm + mi], b = Bm[c * Wm + mi];
+      a.E_w[g * 3 + c] = e; a.B_w[g * 3 + c] = b;
+      tE[c] = e + a.extE[g * 3 + c]; tB[c] = b + a.extB[g * 3 + c];
+    }
+    auto put = [&](int r) {
+      R* f = a.F + (size_t)r * kFieldRow;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { f[c] = (R)tE[c]; f[3 + c] = (R)tB[c]; }
+      f[6] = R(0); f[7] = R(0);
+    };
+    put(g + 2);
+    // rows [L2, L1 | ... | R]: periodic f[G-2], f[G-1] | f[0]; reflective f[1], f[0] | f[G-1]; absorbing zeros (written below)
+    if (a.fbl == JIC_BC_PERIODIC) { if (g == G - 2) put(0); if (g == G - 1) put(1); }
+    else if (a.fbl == JIC_BC_REFLECTIVE) { if (g == 1) put(0); if (g == 0) put(1); }
+    if (a.fbr == JIC_BC_PERIODIC) { if (g == 0) put(G + 2); }
+    else if (a.fbr == JIC_BC_REFLECTIVE) { if (g == G - 1) put(G + 2); }
+  }
+  if (blockIdx.x == 0 && tid < 3 * kFieldRow) {  // absorbing ghost rows are zeros
+    const int r = tid / kFieldRow, c = tid - r * kFieldRow;
+    if (r < 2 && a.fbl == JIC_BC_ABSORBING) a.F[(size_t)r * kFieldRow + c] = R(0);
+    if (r == 2 && a.fbr == JIC_BC_ABSORBING) a.F[(size_t)(G + 2) * kFieldRow + c] = R(0);
+  }
+  // ---- the last CTA to finish advances the run counters (every CTA has read hist_row by then)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned k = atomicAdd(a.done, 1u);
+    if (k == gridDim.x - 1) {
+      a.ctl->hist_row = row + 1;
+      a.ctl->step += 1;
+      *a.done = 0u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------------------------------------
 template <typename R>

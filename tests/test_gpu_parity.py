@@ -252,3 +252,40 @@ def test_binned_matches_indexed_at_scale():
     a = run_gpu(p, length=length, G=G, dt=dt, T=T, engine="indexed", particles=False)
     b = run_gpu(p, length=length, G=G, dt=dt, T=T, engine="binned", particles=False)
     assert_parity(b, a, FIELD_KEYS, 1e-7)
+
+
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("G,bcs,solver", [
+    (300, (0, 0, 0, 0), {}),                                                   # 4 slices of 75 nodes, halo 37
+    (333, (0, 0, 0, 0), dict(filter_passes=2, filter_strides=(1, 3))),         # uneven last slice
+    (300, (1, 1, 1, 1), {}),
+    (300, (2, 2, 2, 2), {}),
+    (310, (1, 2, 1, 2), dict(filter_passes=3, filter_alpha=0.4, filter_strides=(2, 5))),
+    (300, (2, 0, 2, 0), dict(filter_passes=0)),                                # no filter: halo 2
+    (4096, (0, 0, 0, 0), {}),                                                  # the bench grid: 16 slices of 256
+])
+def test_multi_cta_field_kernel(G, bcs, solver, engine):
+    """Grids large enough for k_fields_mc (slices + recomputed halos, ping-ponged state) against the oracle, every BC."""
+    length, T = 0.05, 14
+    p = two_species(12000, 9000, length=length, G=G, seed=77, vth_e=0.05, vth_yz=0.03, drift=5e7, plus_minus=True, gpdl=2.0)
+    dt = cfl_dt(length, G, 0.9)
+    rng = np.random.default_rng(8)
+    extE = 1e2 * rng.normal(size=(G, 3)); extB = 1e-4 * rng.normal(size=(G, 3))
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=bcs[0], pbr=bcs[1],
+                fbl=bcs[2], fbr=bcs[3], solver=solver, ext_E=extE, ext_B=extB, keep_particles=False)
+    # odd number of steps per graph and a second call: exercises both parities of the ping-pong buffers
+    from jaxincell_b200 import HotPath
+    s = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), **solver}
+    hp = HotPath(species=p["species"], length=length, G=G, dt=dt, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2], fbr=bcs[3],
+                 filter_passes=s["filter_passes"], filter_alpha=s["filter_alpha"], filter_strides=s["filter_strides"],
+                 engine=engine, steps_per_graph=3)
+    hp.set_external_fields(extE, extB)
+    hp.initialize(p["x0"], p["v0"])
+    a = hp.run(5)
+    b = hp.run(T - 5)
+    got = {k: torch.cat([a[k], b[k]]).cpu().numpy() for k in FIELD_KEYS}
+    assert_parity(got, ref, FIELD_KEYS, 1e-5)
+    E, B, J, rho = (t.cpu().numpy() for t in hp.fields())
+    np.testing.assert_array_equal(E, got["electric_field"][-1])
+    np.testing.assert_array_equal(rho, got["charge_density"][-1])
+    hp.close()
