@@ -208,11 +208,13 @@ def simulate_host(*, species, x0, v0, n_steps, ext_E=None, ext_B=None, dtype=np.
     E0 = B0 = vi = None
     if initial:
         E0, B0 = np.empty((G, 3), dtype=dtype), np.empty((G, 3), dtype=dtype)
-        vi = np.empty((N, 3), dtype=dtype)
+        if kw.get("engine", "indexed") == "indexed":  # the binned store does not keep particle order
+            vi = np.empty((N, 3), dtype=dtype)
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
     _lib.check(lib.jic_simulate_host(C.byref(params), sp, vp(x0), vp(v0), vp(eE), vp(eB), T, C.byref(o), vp(E0), vp(B0), vp(vi)))
     res["grid"] = grid
     if initial:
         res["fields"] = (E0, B0)
-        res["initial_velocities"] = vi
+        if vi is not None:
+            res["initial_velocities"] = vi
     return res

@@ -1,0 +1,364 @@
+"""Host driver with the reference's public shape: ``Simulation(parameters_or_toml).run()`` -> output dictionary, ``load_parameters``,
+``diagnostics``.  It mirrors jaxincell/_simulation.py:36-344 (interface, defaults, output keys) on top of the C ABI; the
+per-step arithmetic all happens in libjic_b200.so.  Host code is NumPy: there is no JAX here, so
+
+  * ``input_parameters`` are plain overrides (no autodiff through the path -- out of scope per BASELINE.json);
+  * random initial particles come from ``numpy.random.default_rng`` with the reference's seed schedule
+    (_state_initialization.py:87-96), NOT from ``jax.random`` -- same distributions, different streams.  Bit-level parity with the
+    reference needs explicit ``initial_positions`` / ``initial_velocities`` per species, which the reference also accepts
+    (_parameters/_species_definitions.py:57-58);
+  * ``time_evolution_algorithm = 1`` (Crank-Nicolson) and ``field_solver != 0`` raise: they are not part of this path.
+
+Extra, optional ``solver_parameters`` understood here only: ``engine`` ("auto" | "indexed" | "binned"), ``particle_history``
+(default True, like the reference; False drops the (T,N,3) histories and lets large runs use the binned engine) and ``dtype``
+("float64" | "float32").
+"""
+from __future__ import annotations
+
+import copy
+import os
+
+import numpy as np
+
+from ._lib import JicError
+
+try:  # jaxincell/_simulation.py:27-30
+    import tomllib
+except ModuleNotFoundError:  # pragma: no cover
+    import pip._vendor.tomli as tomllib
+
+# jaxincell/_constants.py:1-7 (the rounded values are part of the results)
+epsilon_0 = 8.85418782e-12
+mu_0 = 1.25663706e-6
+speed_of_light = 2.99792458e8
+elementary_charge = 1.60217663e-19
+mass_electron = 9.10938371e-31
+mass_proton = 1.67262193e-27
+
+AXES = ("x", "y", "z")
+SECTIONS = ("domain_parameters", "species_parameters", "external_field_parameters", "source_parameters", "solver_parameters")
+
+# defaults: _parameters/_domain_parameters.py:12-25, _solver_parameters.py:10-22, _external_field_parameters.py:10-17
+DOMAIN_DEFAULTS = dict(total_steps=350, timestep_over_spatialstep_times_c=1.0, number_grid_points=50, number_grid_points_y=0,
+                       number_grid_points_z=0, length=1e-2, length_y=0, length_z=0, particle_BC_left=0, particle_BC_right=0,
+                       field_BC_left=0, field_BC_right=0)
+SOLVER_DEFAULTS = dict(print_info=True, field_solver=0, relativistic=False, time_evolution_algorithm=0,
+                       max_number_of_Picard_iterations_implicit_CN=20, number_of_particle_substeps_implicit_CN=2,
+                       tolerance_Picard_iterations_implicit_CN=1e-6, filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4),
+                       seed=1701, engine="auto", particle_history=True, dtype="float64")
+EXTERNAL_DEFAULTS = dict(external_electric_field_amplitude=0.0, external_electric_field_wavenumber=0.0,
+                         external_magnetic_field_amplitude=0.0, external_magnetic_field_wavenumber=0.0,
+                         external_electric_field_function=None, external_magnetic_field_function=None)
+
+
+def _species_defaults(kind, first):
+    """_parameters/_species_definitions.py:33-101: the first species of each type gets the two-stream-like 'initial' defaults."""
+    d = dict(number_pseudoparticles=500, grid_points_per_Debye_length=2, weight=0, seed_position_override=False, seed_position=None,
+             initial_positions=None, initial_velocities=None)
+    for a in AXES:
+        d.update({f"perturbation_amplitude_{a}": 0.0, f"perturbation_wavenumber_{a}": 0, f"random_positions_{a}": a != "x",
+                  f"vth_over_c_{a}": 0, f"drift_speed_{a}": 0, f"velocity_plus_minus_{a}": False})
+    if kind == "electrons":
+        d["charge_over_elementary_charge"] = -1
+        if first:
+            d.update(perturbation_amplitude_x=1e-7, perturbation_wavenumber_x=8, vth_over_c_x=0.05, drift_speed_x=1e8, velocity_plus_minus_x=True)
+    else:
+        d.update(charge_over_elementary_charge=1, mass_over_proton_mass=1)
+        for a in AXES:
+            d[f"ion_temperature_over_electron_temperature_{a}"] = 1
+        if first:
+            d.update(perturbation_amplitude_x=1e-7, vth_over_c_x="_electrons0", vth_over_c_y="_electrons0", vth_over_c_z="_electrons0")
+    return d
+
+
+def load_parameters(input_file):
+    """jaxincell/_simulation.py:36-41"""
+    with open(input_file, "rb") as f:
+        return tomllib.load(f)
+
+
+def _clean_species(species_parameters):
+    """Canonical labels `_electrons<i>` / `_ions<i>`, defaults, cross references (_species_parameters.py:52-200)."""
+    out = {}
+    for kind in ("electrons", "ions"):
+        values = dict(species_parameters.get(kind, {}) or {})
+        if not values:
+            values = {f"{kind}0": {}}
+        elif not any(isinstance(v, dict) for v in values.values()):
+            values = {f"{kind}0": values}
+        out[kind] = {}
+        for i, (label, v) in enumerate(values.items()):
+            sp = {**_species_defaults(kind, i == 0), **v, "user_label": label}
+            if not (isinstance(sp["number_pseudoparticles"], int) and sp["number_pseudoparticles"] > 0):
+                raise AssertionError(f"Number of pseudoparticles for {label} must be a positive integer. Got {sp['number_pseudoparticles']}.")
+            if not sp["grid_points_per_Debye_length"] > 0:
+                raise AssertionError(f"Grid points per Debye length must be positive. Got {sp['grid_points_per_Debye_length']}.")
+            out[kind][f"_{kind}{i}"] = sp
+    labels = {k: {sp["user_label"]: canon for canon, sp in out[k].items()} for k in out}
+
+    def find(ref):
+        for k in ("ions", "electrons"):
+            if ref in out[k]:
+                return k, ref
+            if ref in labels[k]:
+                return k, labels[k][ref]
+        raise ValueError(f"Cross referenced species value did not reference another species: {ref!r}")
+
+    for kind in out:
+        for canon, sp in out[kind].items():
+            for key, val in list(sp.items()):
+                if key == "user_label" or not isinstance(val, str):
+                    continue
+                rk, rl = find(val)
+                ref = out[rk][rl]
+                if isinstance(ref[key], str):
+                    raise AssertionError("Cross referenced species values cannot reference another reference.")
+                if key.startswith("vth_over_c_") and kind == "ions" and rk == "electrons":
+                    a = key[-1]
+                    sp[key] = float(np.sqrt(sp[f"ion_temperature_over_electron_temperature_{a}"]) * ref[key]
+                                    * np.sqrt(mass_electron / (sp["mass_over_proton_mass"] * mass_proton)))
+                elif key.startswith("vth_over_c_") and kind == "electrons" and rk == "ions":
+                    a = key[-1]
+                    sp[key] = float(np.sqrt(1 / ref[f"ion_temperature_over_electron_temperature_{a}"]) * ref[key]
+                                    * np.sqrt(ref["mass_over_proton_mass"] * mass_proton / mass_electron))
+                else:
+                    sp[key] = ref[key]
+    return out
+
+
+def _seed_pair(seed, kind, rng_index, extra):
+    """_state_initialization.py:87-96"""
+    if rng_index == 0:
+        return (seed, seed + 3) if kind == "electrons" else (seed, seed + 6)
+    s = seed + 12 + extra * 6
+    return s, s
+
+
+class Simulation:
+    """Same call shape as jaxincell.Simulation (jaxincell/_simulation.py:43-121)."""
+
+    def __init__(self, parameters=None):
+        if parameters is None:
+            parameters = {}
+        if not isinstance(parameters, dict):
+            parameters = load_parameters(parameters)
+        parameters = copy.deepcopy(parameters)
+        self.input_parameters = dict(parameters.pop("input_parameters", {}) or {})
+        unknown = set(parameters) - set(SECTIONS)
+        if unknown:
+            raise AssertionError(f"Unknown parameter sections: {sorted(unknown)}")
+        self.domain_parameters = self._clean_domain({**DOMAIN_DEFAULTS, **parameters.get("domain_parameters", {})})
+        self.solver_parameters = self._clean_solver({**SOLVER_DEFAULTS, **parameters.get("solver_parameters", {})})
+        self.external_field_parameters = {**EXTERNAL_DEFAULTS, **parameters.get("external_field_parameters", {})}
+        self.source_parameters = dict(parameters.get("source_parameters", {}))  # validated nowhere in the step
+        self.species_parameters = _clean_species(parameters.get("species_parameters", {}))
+
+    # ---- cleaning -------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _clean_domain(d):
+        assert type(d["total_steps"]) == int and d["total_steps"] > 0, "Total number of time steps must be an integer."
+        assert d["length"] > 0, "Length of the simulation box must be positive."
+        for k in ("particle_BC_left", "particle_BC_right", "field_BC_left", "field_BC_right"):
+            assert d[k] in (0, 1, 2), f"Invalid boundary condition {k}. Must be 0 (periodic), 1 (reflecting), or 2 (absorbing)."
+        return d
+
+    @staticmethod
+    def _clean_solver(s):
+        s["filter_strides"] = tuple(s["filter_strides"])
+        assert s["field_solver"] in (0, 1), "Invalid field solver."
+        assert s["time_evolution_algorithm"] in (0, 1), "Invalid time evolution algorithm."
+        assert type(s["filter_passes"]) == int and s["filter_passes"] >= 0, "Number of passes of the digital filter must be a non-negative integer."
+        assert 0 < s["filter_alpha"] < 1, "Filter strength must be a float between 0 and 1."
+        assert all(type(v) == int and v > 0 for v in s["filter_strides"]), "Filter strides must be a tuple of positive integers."
+        return s
+
+    def _sections(self, input_parameters):
+        """Overrides: a key is routed to whichever section declares it; species overrides are nested {electrons|ions: {label: {...}}}."""
+        sec = {k: copy.deepcopy(getattr(self, k)) for k in SECTIONS}
+        raw_species = None
+        for key, val in {**self.input_parameters, **(input_parameters or {})}.items():
+            if key in ("electrons", "ions"):
+                raw_species = raw_species or {k: {sp["user_label"]: {kk: vv for kk, vv in sp.items() if kk != "user_label"} for sp in v.values()}
+                                              for k, v in self.species_parameters.items()}
+                for label, over in (val.items() if any(isinstance(v, dict) for v in val.values()) else [(next(iter(raw_species[key])), val)]):
+                    raw_species[key].setdefault(label, {}).update(over)
+                continue
+            for name in ("domain_parameters", "solver_parameters", "external_field_parameters", "source_parameters"):
+                if key in sec[name] or name == "source_parameters":
+                    sec[name][key] = val
+                    break
+        if raw_species is not None:
+            sec["species_parameters"] = _clean_species(raw_species)
+        sec["domain_parameters"] = self._clean_domain(sec["domain_parameters"])
+        sec["solver_parameters"] = self._clean_solver(sec["solver_parameters"])
+        return sec
+
+    # ---- state initialisation (NumPy) -----------------------------------------------------------------------------
+    @staticmethod
+    def build_domain_state(dom):
+        """_state_initialization.py:27-49"""
+        length = float(dom["length"])
+        G = int(dom["number_grid_points"])
+        dx = length / G
+        return dict(box_size=(length, float(dom["length_y"]) or length, float(dom["length_z"]) or length), dx=dx,
+                    dt=dom["timestep_over_spatialstep_times_c"] * dx / speed_of_light,
+                    grid=np.linspace(-length / 2 + dx / 2, length / 2 - dx / 2, G))
+
+    @staticmethod
+    def initialize_particle_state(species_parameters, dom, solver, state):
+        """_state_initialization.py:51-286 with numpy.random.default_rng streams."""
+        box, G = state["box_size"], int(dom["number_grid_points"])
+        pos, vel, wts, sidx, table = [], [], [], [], []
+        charge_l, mass_l, qm_l = [], [], []
+        ref = None
+        extra = 0
+        for kind in ("electrons", "ions"):
+            for i, (canon, sp) in enumerate(species_parameters[kind].items()):
+                sp_seed, sv_seed = _seed_pair(int(solver["seed"]), kind, i, extra)
+                if i != 0:
+                    extra += 1
+                if sp["seed_position_override"]:
+                    sp_seed = sp["seed_position"]
+                n = sp["number_pseudoparticles"]
+                x = np.empty((n, 3)); v = np.empty((n, 3))
+                for a, ax in enumerate(AXES):
+                    if sp[f"random_positions_{ax}"]:
+                        xa = np.random.default_rng(sp_seed + a + 1).uniform(-box[a] / 2, box[a] / 2, n)
+                    else:
+                        xa = np.linspace(-box[a] / 2, box[a] / 2, n)
+                    xa = xa + sp[f"perturbation_amplitude_{ax}"] * np.sin(sp[f"perturbation_wavenumber_{ax}"] * 2 * np.pi / box[a] * xa)
+                    va = sp[f"vth_over_c_{ax}"] * speed_of_light / np.sqrt(2) * np.random.default_rng(sv_seed + a + 4).standard_normal(n)
+                    va = va + sp[f"drift_speed_{ax}"]
+                    if sp[f"velocity_plus_minus_{ax}"]:
+                        va = va * (-1.0) ** np.arange(n)
+                    x[:, a], v[:, a] = xa, va
+                for key, arr in (("initial_positions", x), ("initial_velocities", v)):
+                    if sp[key] is not None:
+                        given = np.asarray(sp[key], dtype=float)
+                        assert given.shape == (n, 3), f"{key} for {kind}{i} must have shape {(n, 3)}. Got {given.shape}."
+                        arr[...] = given
+                mass = mass_electron if kind == "electrons" else sp["mass_over_proton_mass"] * mass_proton
+                charge = sp["charge_over_elementary_charge"] * elementary_charge
+                if kind == "electrons" and i == 0:
+                    vths = [sp[f"vth_over_c_{ax}"] for ax in AXES]
+                    ref = dict(vth_electrons=max(vths) * speed_of_light, vth_electrons_over_c=max(vths), charge_electrons=charge)
+                if ref is None:
+                    raise ValueError("Electron reference species must be initialized before ions.")
+                w = (epsilon_0 * mass_electron * speed_of_light ** 2 / ref["charge_electrons"] ** 2 * G ** 2 / box[0] / (2 * n)
+                     * ref["vth_electrons_over_c"] ** 2 * sp["grid_points_per_Debye_length"] ** 2)
+                w = w if sp["weight"] == 0 else float(sp["weight"])
+                pos.append(x); vel.append(v); wts.append(np.full((n, 1), w)); sidx.append(np.full(n, len(table), dtype=np.int32))
+                table.append(dict(count=n, q=charge * w, m=mass * w, qm=charge / mass))
+                charge_l.append(charge); mass_l.append(mass); qm_l.append(charge / mass)
+        positions, velocities = np.concatenate(pos), np.concatenate(vel)
+        weights, species_integer_index = np.concatenate(wts), np.concatenate(sidx)
+        lim = 0.99 * speed_of_light
+        velocities = np.where(np.abs(velocities) >= lim, np.sign(velocities) * lim, velocities)
+        cl, ml, ql = np.array(charge_l), np.array(mass_l), np.array(qm_l)
+        return dict(positions=positions, velocities=velocities, weights=weights, species_integer_index=species_integer_index,
+                    charge_integer_lookup=cl, mass_integer_lookup=ml, charge_mass_integer_lookup=ql,
+                    charges=cl[species_integer_index].reshape(-1, 1) * weights, masses=ml[species_integer_index].reshape(-1, 1) * weights,
+                    charge_to_mass_ratios=ql[species_integer_index].reshape(-1, 1), species_table=table, **ref)
+
+    # ---- run ------------------------------------------------------------------------------------------------------
+    def simulation(self, input_parameters=None):
+        from ._engine import simulate_host
+        sec = self._sections(input_parameters)
+        dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
+        if solver["time_evolution_algorithm"] != 0 or solver["field_solver"] != 0:
+            raise JicError("only the explicit Boris path with the Maxwell update (time_evolution_algorithm=0, field_solver=0) is implemented")
+        state = self.build_domain_state(dom)
+        ps = self.initialize_particle_state(sec["species_parameters"], dom, solver, state)
+        G, T = int(dom["number_grid_points"]), int(dom["total_steps"])
+        N = len(ps["positions"])
+        dtype = np.float64 if str(solver["dtype"]) in ("float64", "f64") else np.float32
+        eE = ext.get("external_electric_field"); eB = ext.get("external_magnetic_field")
+        ext_E = np.asarray(eE["E"], np.float32) if isinstance(eE, dict) and "E" in eE else np.zeros((G, 3), np.float32)
+        ext_B = np.asarray(eB["B"], np.float32) if isinstance(eB, dict) and "B" in eB else np.zeros((G, 3), np.float32)
+        history = bool(solver["particle_history"])
+        engine = solver["engine"]
+        if engine == "auto":
+            engine = "indexed" if history or N < 1_000_000 else "binned"
+        if history and engine == "binned":
+            raise JicError("particle_history=True needs engine='indexed' (the binned store does not keep particle order)")
+        res = simulate_host(species=ps["species_table"], x0=ps["positions"], v0=ps["velocities"], n_steps=T, ext_E=ext_E, ext_B=ext_B,
+                            dtype=dtype, fields=True, particles=history, initial=True, engine=engine,
+                            length=state["box_size"][0], length_y=state["box_size"][1], length_z=state["box_size"][2], G=G, dt=state["dt"],
+                            pbl=dom["particle_BC_left"], pbr=dom["particle_BC_right"], fbl=dom["field_BC_left"], fbr=dom["field_BC_right"],
+                            filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
+                            relativistic=bool(solver["relativistic"]), track_yz=history)
+        e0 = next(iter(sec["species_parameters"]["electrons"].values()))
+        we = ps["weights"][0, 0]
+        plasma_frequency = (np.sqrt(e0["number_pseudoparticles"] * we * ps["charge_electrons"] ** 2) / np.sqrt(mass_electron)
+                            / np.sqrt(epsilon_0) / np.sqrt(state["box_size"][0]))
+        out = {  # jaxincell/_simulation.py:269-312
+            "positions": res.get("positions"), "velocities": res.get("velocities"), "masses": ps["masses"], "charges": ps["charges"],
+            "charge_to_mass_ratios": ps["charge_to_mass_ratios"], "initial_positions": ps["positions"],
+            "initial_velocities": res["initial_velocities"] if "initial_velocities" in res else ps["velocities"],
+            "weights": ps["weights"], "species_integer_index": ps["species_integer_index"],
+            "charge_integer_lookup": ps["charge_integer_lookup"], "mass_integer_lookup": ps["mass_integer_lookup"],
+            "charge_mass_integer_lookup": ps["charge_mass_integer_lookup"],
+            "electric_field": res["electric_field"], "magnetic_field": res["magnetic_field"], "current_density": res["current_density"],
+            "charge_density": res["charge_density"], "number_grid_points": G, "number_pseudoelectrons": e0["number_pseudoparticles"],
+            "total_steps": T, "time_array": np.linspace(0, T * state["dt"], T), "grid": state["grid"], "dt": state["dt"],
+            "plasma_frequency": plasma_frequency, "max_initial_vth_electrons": ps["vth_electrons"],
+            "vth_electrons_over_c": ps["vth_electrons_over_c"], "charge_electrons": ps["charge_electrons"], "dx": state["dx"],
+            "length": state["box_size"][0], "box_size": state["box_size"],
+            "fields": res["fields"], "external_electric_field": ext_E, "external_magnetic_field": ext_B,
+        }
+        return {**dom, **ext, **sec["source_parameters"], **solver, **out, "domain_parameters": dom,
+                "species_parameters": sec["species_parameters"], "external_field_parameters": ext,
+                "source_parameters": sec["source_parameters"], "solver_parameters": solver, "parameter_sections": sec}
+
+    def run(self, input_parameters=None):
+        return self.simulation(input_parameters)
+
+
+def diagnostics(output):
+    """jaxincell/_diagnostics.py:8-147 in NumPy: species split, energies, dominant frequency.  Mutates and returns `output`."""
+    if output.get("positions") is None or output.get("velocities") is None:
+        raise JicError("diagnostics() needs the particle histories (solver_parameters['particle_history']=True)")
+    q = np.asarray(output["charges"]).reshape(-1); m = np.asarray(output["masses"]).reshape(-1)
+    esel, isel = q < 0, q >= 0
+    output.update(position_electrons=output["positions"][:, esel, :], velocity_electrons=output["velocities"][:, esel, :],
+                  mass_electrons=output["masses"][esel], charge_electrons=output["charges"][esel],
+                  position_ions=output["positions"][:, isel, :], velocity_ions=output["velocities"][:, isel, :],
+                  mass_ions=output["masses"][isel], charge_ions=output["charges"][isel])
+    pairs, labels = np.unique(np.stack([q, m], axis=1), axis=0, return_inverse=True)
+    labels = labels.reshape(-1)
+    species = []
+    for si, (qv, mv) in enumerate(pairs):
+        mask = labels == si
+        if qv < 0 and not any(s["name"] == "electrons" for s in species):
+            name = "electrons"
+        elif qv > 0 and not any(s["name"] == "ions" for s in species):
+            name = "ions"
+        else:
+            name = f"species_{si}"
+        species.append(dict(name=name, charge=float(qv), mass=float(mv), positions=output["positions"][:, mask, :],
+                            velocities=output["velocities"][:, mask, :]))
+    output["species"] = species
+    for k in ("positions", "velocities", "masses", "charges"):
+        del output[k]
+    T, dt, dx = int(output["total_steps"]), float(output["dt"]), output["dx"]
+    sig = output["electric_field"][:, len(output["grid"]) // 2, 0]
+    sig = (sig - np.mean(sig)) / np.max(sig)
+    half = T // 2
+    mag = np.abs(np.fft.fft(sig)[:half])
+    freqs = np.fft.fftfreq(T, d=dt)[:half] * 2 * np.pi
+    dominant = np.abs(freqs[np.argmax(mag)])
+    E2 = np.sum(output["electric_field"] ** 2, axis=-1); B2 = np.sum(output["magnetic_field"] ** 2, axis=-1)
+    eE2 = np.sum(np.asarray(output["external_electric_field"], np.float64) ** 2, axis=-1)
+    eB2 = np.sum(np.asarray(output["external_magnetic_field"], np.float64) ** 2, axis=-1)
+    ke_e = 0.5 * np.sum(output["mass_electrons"].reshape(-1) * np.sum(output["velocity_electrons"] ** 2, axis=-1), axis=-1)
+    ke_i = 0.5 * np.sum(output["mass_ions"].reshape(-1) * np.sum(output["velocity_ions"] ** 2, axis=-1), axis=-1)
+    output.update({
+        "electric_field_energy_density": epsilon_0 / 2 * E2, "electric_field_energy": epsilon_0 / 2 * np.sum(E2, axis=-1) * dx,
+        "magnetic_field_energy_density": 1 / (2 * mu_0) * B2, "magnetic_field_energy": 1 / (2 * mu_0) * np.sum(B2, axis=-1) * dx,
+        "dominant_frequency": dominant, "kinetic_energy": ke_e + ke_i, "kinetic_energy_electrons": ke_e, "kinetic_energy_ions": ke_i,
+        "external_electric_field_energy_density": epsilon_0 / 2 * eE2, "external_electric_field_energy": epsilon_0 / 2 * np.sum(eE2) * dx,
+        "external_magnetic_field_energy_density": 1 / (2 * mu_0) * eB2, "external_magnetic_field_energy": 1 / (2 * mu_0) * np.sum(eB2) * dx,
+    })
+    output["total_energy"] = (output["electric_field_energy"] + output["external_electric_field_energy"] + output["magnetic_field_energy"]
+                              + output["external_magnetic_field_energy"] + output["kinetic_energy"])
+    return output

@@ -1,0 +1,173 @@
+"""The Simulation-shaped host driver (jaxincell_b200/_simulation.py) against the reference's public contract:
+jaxincell/_simulation.py:43-344 and tests/test_simulation.py:79-144,246-262,668-721 of the reference, re-expressed without JAX."""
+import numpy as np
+import pytest
+
+from jaxincell_b200 import JicError, Simulation, diagnostics, load_parameters
+from jaxincell_b200 import _simulation as S
+from oracle import closed_form as C
+
+SMALL = {
+    "domain_parameters": {"number_grid_points": 16, "total_steps": 12, "length": 0.01, "timestep_over_spatialstep_times_c": 0.9},
+    "species_parameters": {
+        "electrons": {"e": {"number_pseudoparticles": 300, "vth_over_c_x": 0.05, "vth_over_c_y": 0.02, "drift_speed_x": 5e7,
+                            "velocity_plus_minus_x": True, "random_positions_x": True, "grid_points_per_Debye_length": 0.6}},
+        "ions": {"i": {"number_pseudoparticles": 200, "vth_over_c_x": "e", "vth_over_c_y": "e", "vth_over_c_z": "e",
+                       "random_positions_x": True, "grid_points_per_Debye_length": 0.6}},
+    },
+    "solver_parameters": {"print_info": False},
+}
+
+
+def test_defaults_match_the_reference_tables():
+    sim = Simulation()
+    assert sim.domain_parameters["number_grid_points"] == 50 and sim.domain_parameters["total_steps"] == 350  # _domain_parameters.py:12-25
+    assert sim.solver_parameters["filter_strides"] == (1, 2, 4) and sim.solver_parameters["seed"] == 1701        # _solver_parameters.py:10-22
+    e0 = sim.species_parameters["electrons"]["_electrons0"]
+    assert e0["number_pseudoparticles"] == 500 and e0["drift_speed_x"] == 1e8 and e0["velocity_plus_minus_x"]  # _species_definitions.py:86-101
+    i0 = sim.species_parameters["ions"]["_ions0"]
+    # "_electrons0" reference: sqrt(T_i/T_e) * vth_e * sqrt(m_e / m_i)   (_species_parameters.py:112-121)
+    np.testing.assert_allclose(i0["vth_over_c_x"], 0.05 * np.sqrt(S.mass_electron / S.mass_proton), rtol=1e-15)
+    assert i0["vth_over_c_y"] == 0
+
+
+def test_species_cross_references_and_validation():
+    sim = Simulation(SMALL)
+    i = sim.species_parameters["ions"]["_ions0"]
+    np.testing.assert_allclose(i["vth_over_c_y"], 0.02 * np.sqrt(S.mass_electron / S.mass_proton), rtol=1e-15)
+    assert i["user_label"] == "i"
+    bad = {"species_parameters": {"ions": {"vth_over_c_x": "nobody"}}}
+    with pytest.raises(ValueError):
+        Simulation(bad)
+    with pytest.raises(AssertionError):
+        Simulation({"domain_parameters": {"total_steps": 0}})
+    with pytest.raises(AssertionError):
+        Simulation({"solver_parameters": {"filter_alpha": 1.5}})
+    with pytest.raises(AssertionError):
+        Simulation({"species_parameters": {"electrons": {"number_pseudoparticles": 0}}})
+
+
+def test_particle_state_shapes_weights_and_seed_schedule():
+    sim = Simulation(SMALL)
+    st = sim.build_domain_state(sim.domain_parameters)
+    np.testing.assert_allclose(st["dt"], 0.9 * st["dx"] / S.speed_of_light)
+    np.testing.assert_allclose(st["grid"][0], -0.005 + st["dx"] / 2)
+    ps = sim.initialize_particle_state(sim.species_parameters, sim.domain_parameters, sim.solver_parameters, st)
+    N = 500
+    assert ps["positions"].shape == (N, 3) and ps["velocities"].shape == (N, 3) and ps["charges"].shape == (N, 1)
+    assert (np.abs(ps["positions"]) <= 0.005 + 1e-12).all()
+    # auto weight (_state_initialization.py:172-185)
+    w = S.epsilon_0 * S.mass_electron * S.speed_of_light ** 2 / S.elementary_charge ** 2 * 16 ** 2 / 0.01 / (2 * 300) * 0.05 ** 2 * 0.6 ** 2
+    np.testing.assert_allclose(ps["weights"][0, 0], w, rtol=1e-14)
+    np.testing.assert_allclose(ps["charges"][0, 0], -S.elementary_charge * w, rtol=1e-14)
+    np.testing.assert_allclose(ps["charge_to_mass_ratios"][-1, 0], S.elementary_charge / S.mass_proton, rtol=1e-14)
+    # alternating drift sign, thermal spread of the right size
+    vx = ps["velocities"][:300, 0]
+    assert (np.sign(vx[::2]) > 0).mean() > 0.95 and (np.sign(vx[1::2]) < 0).mean() > 0.95
+    assert abs(np.std(np.abs(vx)) / (0.05 * S.speed_of_light / np.sqrt(2)) - 1) < 0.2
+    again = sim.initialize_particle_state(sim.species_parameters, sim.domain_parameters, sim.solver_parameters, st)
+    np.testing.assert_array_equal(ps["positions"], again["positions"])
+    assert S._seed_pair(1701, "electrons", 0, 0) == (1701, 1704) and S._seed_pair(1701, "ions", 0, 0) == (1701, 1707)
+    assert S._seed_pair(1701, "electrons", 1, 0) == (1713, 1713) and S._seed_pair(1701, "ions", 1, 1) == (1719, 1719)
+
+
+def test_load_parameters_toml(tmp_path):
+    f = tmp_path / "input.toml"
+    f.write_text('[domain_parameters]\nlength = 0.01\nnumber_grid_points = 70\ntotal_steps = 5\n'
+                 '[solver_parameters]\nfilter_strides = [1, 2, 4]\nprint_info = false\n'
+                 '[species_parameters.electrons.electrons0]\nnumber_pseudoparticles = 40\nvth_over_c_x = 0.05\n'
+                 '[species_parameters.ions.ions0]\nnumber_pseudoparticles = 40\nvth_over_c_x = "_electrons0"\n')
+    p = load_parameters(str(f))
+    assert p["domain_parameters"]["number_grid_points"] == 70
+    sim = Simulation(str(f))
+    assert sim.solver_parameters["filter_strides"] == (1, 2, 4)
+    assert sim.species_parameters["electrons"]["_electrons0"]["number_pseudoparticles"] == 40
+
+
+def test_out_of_scope_algorithms_are_rejected_loudly():
+    for over in ({"time_evolution_algorithm": 1}, {"field_solver": 1}):
+        sim = Simulation({**SMALL, "solver_parameters": {"print_info": False, **over}})
+        with pytest.raises(JicError):
+            sim.run()
+
+
+def test_diagnostics_energies_on_a_fabricated_output():
+    T, N, G = 6, 5, 8
+    rng = np.random.default_rng(0)
+    q = np.array([-1.0, -1.0, 2.0, 2.0, 2.0]).reshape(-1, 1); m = np.array([1.0, 1.0, 3.0, 3.0, 3.0]).reshape(-1, 1)
+    out = dict(positions=rng.normal(size=(T, N, 3)), velocities=rng.normal(size=(T, N, 3)), charges=q, masses=m,
+               electric_field=rng.normal(size=(T, G, 3)), magnetic_field=rng.normal(size=(T, G, 3)),
+               external_electric_field=np.zeros((G, 3), np.float32), external_magnetic_field=np.ones((G, 3), np.float32),
+               grid=np.arange(G) * 0.5, total_steps=T, dt=0.1, dx=0.5, plasma_frequency=1.0)
+    v = out["velocities"].copy(); E = out["electric_field"].copy()
+    d = diagnostics(out)
+    assert "positions" not in d and d["position_electrons"].shape == (T, 2, 3) and d["velocity_ions"].shape == (T, 3, 3)
+    np.testing.assert_allclose(d["kinetic_energy"], 0.5 * np.sum(m.reshape(-1) * np.sum(v ** 2, axis=-1), axis=-1))
+    np.testing.assert_allclose(d["electric_field_energy"], S.epsilon_0 / 2 * np.sum(E ** 2, axis=(1, 2)) * 0.5)
+    np.testing.assert_allclose(d["external_magnetic_field_energy"], 1 / (2 * S.mu_0) * 3 * G * 0.5)
+    assert [s["name"] for s in d["species"]] == ["electrons", "ions"]
+    assert d["total_energy"].shape == (T,)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_output_contract_and_determinism():
+    out = Simulation(SMALL).run()
+    T, G, N = 12, 16, 500
+    for k, shp in (("positions", (T, N, 3)), ("velocities", (T, N, 3)), ("masses", (N, 1)), ("charges", (N, 1)), ("weights", (N, 1)),
+                   ("initial_positions", (N, 3)), ("initial_velocities", (N, 3)), ("species_integer_index", (N,)),
+                   ("electric_field", (T, G, 3)), ("magnetic_field", (T, G, 3)), ("current_density", (T, G, 3)), ("charge_density", (T, G)),
+                   ("grid", (G,)), ("time_array", (T,)), ("external_electric_field", (G, 3)), ("external_magnetic_field", (G, 3))):
+        assert np.asarray(out[k]).shape == shp, k
+    assert out["fields"][0].shape == (G, 3) and out["fields"][1].shape == (G, 3)
+    assert out["number_grid_points"] == G and out["total_steps"] == T and out["plasma_frequency"] > 0
+    assert all(np.isfinite(out[k]).all() for k in ("positions", "velocities", "electric_field", "charge_density"))
+    assert (np.abs(out["positions"][..., 0]) <= 0.005).all()
+    for k in ("domain_parameters", "species_parameters", "solver_parameters", "parameter_sections", "length", "filter_passes"):
+        assert k in out
+    again = Simulation(SMALL).run()
+    np.testing.assert_allclose(again["electric_field"], out["electric_field"], rtol=1e-9, atol=1e-9 * np.abs(out["electric_field"]).max())
+    d = diagnostics(out)
+    drift = np.abs(d["total_energy"] - d["total_energy"][0]).max() / d["total_energy"][0]
+    assert drift < 0.05
+
+
+@pytest.mark.gpu
+def test_explicit_initial_conditions_match_the_oracle():
+    """The parity route that needs no RNG compatibility: initial_positions / initial_velocities per species
+    (reference tests/test_simulation.py:668-721)."""
+    rng = np.random.default_rng(3)
+    ne, ni, G, L = 200, 150, 12, 0.01
+    xe = rng.uniform(-L / 2, L / 2, (ne, 3)); xi = rng.uniform(-L / 2, L / 2, (ni, 3))
+    ve = 1e7 * rng.standard_normal((ne, 3)); vi = 1e4 * rng.standard_normal((ni, 3))
+    par = {"domain_parameters": {"number_grid_points": G, "total_steps": 15, "length": L, "timestep_over_spatialstep_times_c": 0.8,
+                                 "particle_BC_left": 1, "particle_BC_right": 2, "field_BC_left": 1, "field_BC_right": 2},
+           "species_parameters": {"electrons": {"number_pseudoparticles": ne, "vth_over_c_x": 0.05, "initial_positions": xe, "initial_velocities": ve,
+                                                "grid_points_per_Debye_length": 0.6},
+                                  "ions": {"number_pseudoparticles": ni, "initial_positions": xi, "initial_velocities": vi,
+                                           "grid_points_per_Debye_length": 0.6}},
+           "solver_parameters": {"print_info": False, "filter_passes": 3, "filter_strides": [1, 2]}}
+    out = Simulation(par).run()
+    dt = 0.8 * (L / G) / S.speed_of_light
+    ref = C.run(np.concatenate([xe, xi]), np.concatenate([ve, vi]), out["charges"][:, 0], out["masses"][:, 0], out["charge_to_mass_ratios"][:, 0],
+                length=L, G=G, dt=dt, total_steps=15, pbl=1, pbr=2, fbl=1, fbr=2,
+                solver=dict(filter_passes=3, filter_alpha=0.5, filter_strides=(1, 2)))
+    for k in ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities"):
+        err = np.abs(out[k] - ref[k]).max() / np.abs(ref[k]).max()
+        assert err < 1e-5, (k, err)
+    np.testing.assert_allclose(out["initial_velocities"], ref["initial_velocities"], rtol=1e-14)
+    np.testing.assert_allclose(out["time_array"], np.linspace(0, 15 * dt, 15))
+
+
+@pytest.mark.gpu
+def test_large_run_without_particle_history_uses_the_binned_engine():
+    par = {"domain_parameters": {"number_grid_points": 256, "total_steps": 10, "length": 0.05},
+           "species_parameters": {"electrons": {"number_pseudoparticles": 600_000, "random_positions_x": True, "drift_speed_x": 5e7},
+                                  "ions": {"number_pseudoparticles": 600_000, "random_positions_x": True}},
+           "solver_parameters": {"print_info": False, "particle_history": False}}
+    out = Simulation(par).run()
+    assert out["positions"] is None and out["electric_field"].shape == (10, 256, 3) and np.isfinite(out["electric_field"]).all()
+    rho_sum = out["charge_density"].sum(axis=1) * out["dx"]
+    assert np.abs(rho_sum - out["charges"].sum()).max() < 1e-9 * np.abs(out["charges"]).sum()
+    with pytest.raises(JicError):
+        diagnostics(out)
