@@ -33,7 +33,10 @@
 namespace jic {
 
 constexpr int kMinChunk = 1024;    // particles per work item: chosen by k_plan in [kMinChunk, kMaxChunk]
-constexpr int kMaxChunk = 8192;
+#ifndef JIC_MAX_CHUNK
+#define JIC_MAX_CHUNK 8192
+#endif
+constexpr int kMaxChunk = JIC_MAX_CHUNK;
 constexpr int kChunkAlign = 256;   // items start on multiples of this inside a bin (a multiple of the block size)
 constexpr int kBlk = 32;           // slots per block
 constexpr int kBlkElems = 4 * kBlk;  // reals per block

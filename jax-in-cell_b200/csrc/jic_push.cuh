@@ -217,81 +217,94 @@ __global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __g
       const unsigned slot = gt & (NS - 1);
       mbar_wait(bar_u32 + 8u * slot, (gt / NS) & 1u);
       const R* stage = my_ring + slot * (KB * kBlkElems);
+      // The KB particles of a lane go through the arithmetic TOGETHER (phases A-C are straight-line code over kb, so the
+      // compiler interleaves the independent FP64 dependency chains and shares the coefficient loads); the warp-level
+      // bookkeeping (votes, claims, stash) follows per block in phase D.  Blocks past the end of the item run with every lane
+      // invalid: no early exit, the loop body stays one straight line.
+      R d[KB], v[KB][3], u[KB], tn[KB], tm[KB];
+      bool valid[KB], fast[KB], all_fast[KB];
+      // ---- A. take the particles
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        // (blocks past the end of the item run with every lane invalid: no early exit, so the loop body stays one
-        //  straight line and the pending claim never has to be copied out of the atomic's destination register)
-        const bool valid = (g * KB + kb) * kBlk + lane < n;
-        const R d = stage[kb * kBlkElems + lane];
-        R v[3] = {stage[kb * kBlkElems + kBlk + lane], stage[kb * kBlkElems + 2 * kBlk + lane], stage[kb * kBlkElems + 3 * kBlk + lane]};
-        if (kb == KB - 1) {
-          // every lane has taken its particle of the slot's last block: the slot can be refilled
-          __syncwarp();
-          if (lane == 0 && g + NS < ngroups) load_group(g + NS);
-        }
-
-        // ---- gather (quadratics in d)
+        valid[kb] = (g * KB + kb) * kBlk + lane < n;
+        d[kb] = stage[kb * kBlkElems + lane];
+        v[kb][0] = stage[kb * kBlkElems + kBlk + lane]; v[kb][1] = stage[kb * kBlkElems + 2 * kBlk + lane]; v[kb][2] = stage[kb * kBlkElems + 3 * kBlk + lane];
+      }
+      __syncwarp();  // every lane has taken its particles: the ring slot can be refilled
+      if (lane == 0 && g + NS < ngroups) load_group(g + NS);
+      // ---- B. gather (quadratics in d), velocity update, move
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
         R E[3], B[3];
-        const int hi = d >= R(0) ? 3 : 2;
+        const int hi = d[kb] >= R(0) ? 3 : 2;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          E[k] = fma(fma(coef[8 * k + hi], d, coef[8 * k + 1]), d, coef[8 * k]);
-          B[k] = fma(fma(coef[8 * k + 6], d, coef[8 * k + 5]), d, coef[8 * k + 4]);
+          E[k] = fma(fma(coef[8 * k + hi], d[kb], coef[8 * k + 1]), d[kb], coef[8 * k]);
+          B[k] = fma(fma(coef[8 * k + 6], d[kb], coef[8 * k + 5]), d[kb], coef[8 * k + 4]);
         }
-        // ---- velocity update
         if (REL) {
-          boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
+          boris_velocity_relativistic(v[kb], E, B, p.sp_q[s], p.sp_m[s], p.dt);
         } else {
           // E, B already carry the factor (q/m) dt/2:  v- = v + E ; t = B ; v+ = (R x t + (R.t) t + R)/(1 + t.t) ; v = v+ + E
-          const R vm0 = v[0] + E[0], vm1 = v[1] + E[1], vm2 = v[2] + E[2];
+          const R vm0 = v[kb][0] + E[0], vm1 = v[kb][1] + E[1], vm2 = v[kb][2] + E[2];
           const R R0 = fma(vm1, B[2], fma(-vm2, B[1], vm0)), R1 = fma(vm2, B[0], fma(-vm0, B[2], vm1)), R2 = fma(vm0, B[1], fma(-vm1, B[0], vm2));
           const R Rt = fma(R0, B[0], fma(R1, B[1], R2 * B[2]));
           const R inv = rcp_fast(fma(B[0], B[0], fma(B[1], B[1], fma(B[2], B[2], R(1)))));
-          v[0] = fma(fma(R1, B[2], fma(-R2, B[1], fma(Rt, B[0], R0))), inv, E[0]);
-          v[1] = fma(fma(R2, B[0], fma(-R0, B[2], fma(Rt, B[1], R1))), inv, E[1]);
-          v[2] = fma(fma(R0, B[1], fma(-R1, B[0], fma(Rt, B[2], R2))), inv, E[2]);
+          v[kb][0] = fma(fma(R1, B[2], fma(-R2, B[1], fma(Rt, B[0], R0))), inv, E[0]);
+          v[kb][1] = fma(fma(R2, B[0], fma(-R0, B[2], fma(Rt, B[1], R1))), inv, E[1]);
+          v[kb][2] = fma(fma(R0, B[1], fma(-R1, B[0], fma(Rt, B[2], R2))), inv, E[2]);
         }
-        // ---- move (offsets from node c in cells): new offset tn, mid offset tm
-        const R u = v[0] * cells_per_v;
-        const R tn = d + u, tm = fma(R(0.5), u, d);
-        const bool fast = valid && fast_bin && (fabs(tn) < R(1.5));
-        const bool all_fast = __all_sync(0xffffffffu, fast);  // the common case, warp-uniform: no per-lane branches below
-        if (all_fast || fast) {
+        // offsets from node c in cells: new offset tn, mid offset tm
+        u[kb] = v[kb][0] * cells_per_v;
+        tn[kb] = d[kb] + u[kb];
+        tm[kb] = fma(R(0.5), u[kb], d[kb]);
+        fast[kb] = valid[kb] && fast_bin && (fabs(tn[kb]) < R(1.5));
+      }
+      // ---- C. deposit moments (all_fast: the common case, warp-uniform, no per-lane branches)
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) all_fast[kb] = __all_sync(0xffffffffu, fast[kb]);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        if (all_fast[kb] || fast[kb]) {
           // truncated powers 4 P(t) = (y + |y|)^2 with y = t - 1/2, 4 N(t) likewise with y = -t - 1/2
-          const R pn_ = (tn - R(0.5)) + fabs(tn - R(0.5)), nn_ = (-tn - R(0.5)) + fabs(-tn - R(0.5));
-          const R pm_ = (tm - R(0.5)) + fabs(tm - R(0.5)), nm_ = (-tm - R(0.5)) + fabs(-tm - R(0.5));
-          const R Pm = pm_ * pm_, Nm = nm_ * nm_, tm2 = tm * tm;
-          a1 += u; a2 = fma(u, tn + d, a2); aP = fma(pn_, pn_, aP); aN = fma(nn_, nn_, aN);
-          r1 += tm; r2 += tm2; rP += Pm; rN += Nm;
-          y0 += v[1]; y1 = fma(v[1], tm, y1); y2 = fma(v[1], tm2, y2); yP = fma(v[1], Pm, yP); yN = fma(v[1], Nm, yN);
-          z0 += v[2]; z1 = fma(v[2], tm, z1); z2 = fma(v[2], tm2, z2); zP = fma(v[2], Pm, zP); zN = fma(v[2], Nm, zN);
+          const R tn_ = tn[kb], tm_ = tm[kb], vy = v[kb][1], vz = v[kb][2];
+          const R pn_ = (tn_ - R(0.5)) + fabs(tn_ - R(0.5)), nn_ = (-tn_ - R(0.5)) + fabs(-tn_ - R(0.5));
+          const R pm_ = (tm_ - R(0.5)) + fabs(tm_ - R(0.5)), nm_ = (-tm_ - R(0.5)) + fabs(-tm_ - R(0.5));
+          const R Pm = pm_ * pm_, Nm = nm_ * nm_, tm2 = tm_ * tm_;
+          a1 += u[kb]; a2 = fma(u[kb], tn_ + d[kb], a2); aP = fma(pn_, pn_, aP); aN = fma(nn_, nn_, aN);
+          r1 += tm_; r2 += tm2; rP += Pm; rN += Nm;
+          y0 += vy; y1 = fma(vy, tm_, y1); y2 = fma(vy, tm2, y2); yP = fma(vy, Pm, yP); yN = fma(vy, Nm, yN);
+          z0 += vz; z1 = fma(vz, tm_, z1); z2 = fma(vz, tm2, z2); zP = fma(vz, Pm, zP); zN = fma(vz, Nm, zN);
         }
-        // ---- destination: 0 stay, 1 left, 2 right (3 = general path, -1 = no particle)
-        const bool go_r = fast && tn >= R(0.5), go_l = fast && tn < R(-0.5);
-        R dn = tn;
+      }
+      // ---- D. per block: destination, slot claim, retire the block stashed one group ago, stash the new one
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        // destination: 0 stay, 1 left, 2 right (3 = general path, -1 = no particle)
+        const bool go_r = fast[kb] && tn[kb] >= R(0.5), go_l = fast[kb] && tn[kb] < R(-0.5);
+        R dn = tn[kb];
         if (go_r) dn -= R(1);
         if (go_l) dn += R(1);
-        const int kind = fast ? (go_r ? 2 : (go_l ? 1 : 0)) : (valid ? 3 : -1);
-        // ---- claim slots in the destination bins: one atomic per warp and destination, consumed one block later
+        const int kind = fast[kb] ? (go_r ? 2 : (go_l ? 1 : 0)) : (valid[kb] ? 3 : -1);
+        // claim slots in the destination bins: one atomic per warp and destination, consumed one group later
         const unsigned m1 = __ballot_sync(0xffffffffu, go_l), m2 = __ballot_sync(0xffffffffu, go_r);
-        const unsigned m0 = __ballot_sync(0xffffffffu, fast) & ~(m1 | m2);
+        const unsigned m0 = __ballot_sync(0xffffffffu, fast[kb]) & ~(m1 | m2);
         const unsigned my_cnt = __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
         unsigned claim = 0;
         if (lane < 3 && my_cnt) claim = atomicAdd(my_cursor, my_cnt);
         const unsigned rank = __popc((go_r ? m2 : (go_l ? m1 : m0)) & lt_mask);
-        // ---- retire the block stashed in this slot one group ago, then stash the new one
         retire(kb);
         {
           R* st_ = my_stash + kb * kBlkElems;
-          st_[0] = dn; st_[kBlk] = v[0]; st_[2 * kBlk] = v[1]; st_[3 * kBlk] = v[2];
+          st_[0] = dn; st_[kBlk] = v[kb][0]; st_[2 * kBlk] = v[kb][1]; st_[3 * kBlk] = v[kb][2];
         }
-        q_meta[kb] = fast ? (int)((rank << 2) | (unsigned)kind) : -1;
+        q_meta[kb] = fast[kb] ? (int)((rank << 2) | (unsigned)kind) : -1;
         q_claim[kb] = claim;
-        if (!all_fast) {
+        if (!all_fast[kb]) {
           const unsigned ms = __ballot_sync(0xffffffffu, kind == 3);
           if (ms) {
             n_slow += __popc(ms);
-            if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d * p.dx, v[0], v[1], v[2]);
+            if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d[kb] * p.dx, v[kb][0], v[kb][1], v[kb][2]);
           }
         }
       }
