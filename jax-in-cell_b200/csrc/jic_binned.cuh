@@ -54,6 +54,11 @@ constexpr int kBlkElems = 4 * kBlk;  // reals per block
 #endif
 constexpr int kPushThreads = JIC_PUSH_THREADS;
 constexpr int kPushMinBlocks = JIC_PUSH_MINBLOCKS;
+#ifndef JIC_PUSH_MINBLOCKS_F32
+#define JIC_PUSH_MINBLOCKS_F32 5   // the fp32 kernel fits 96 registers: 20 warps per SM (measured best of 3..6)
+#endif
+template <typename R>
+constexpr int push_min_blocks() { return sizeof(R) == 8 ? kPushMinBlocks : JIC_PUSH_MINBLOCKS_F32; }
 constexpr int kPushStages = JIC_PUSH_STAGES;
 constexpr int kPushStageBlocks = JIC_PUSH_STAGE_BLOCKS;
 constexpr int kPushWarps = kPushThreads / 32;
@@ -460,7 +465,7 @@ struct BinnedStore {
     if (bd.cap_total >= (1ll << 40)) return e.fail(JIC_ERR_UNSUPPORTED, "too many particles for one GPU");
     bd.ov_cap = (int)std::min<long long>(std::max<long long>(N / 16, 1 << 16), 1ll << 28);
     bd.item_cap = (int)std::min<long long>(N / kMinChunk + bd.nb + 16, 1ll << 30);
-    bd.n_workers = n_sm * kPushMinBlocks * kPushWarps;
+    bd.n_workers = n_sm * push_min_blocks<R>() * kPushWarps;
     int rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = alloc(e, &bd.rec[k], 4 * (size_t)bd.cap_total))) return rc;
@@ -528,7 +533,7 @@ struct BinnedStore {
   }
 
   int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, cudaStream_t st) {
-    const int g = n_sm * kPushMinBlocks;
+    const int g = n_sm * push_min_blocks<R>();
     if (dp.relativistic) k_push<R, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
     else k_push<R, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
     e.launches += 1;

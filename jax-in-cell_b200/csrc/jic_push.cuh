@@ -83,7 +83,7 @@ __device__ __forceinline__ void store_slot_at(const BinDev<R>& bd, int dst, cons
 }
 
 template <typename R, bool REL>
-__global__ void __launch_bounds__(kPushThreads, kPushMinBlocks) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
+__global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
                                                                        const R* __restrict__ F, R* __restrict__ acc) {
   constexpr int NW = kPushWarps, NS = kPushStages, KB = kPushStageBlocks;
   constexpr unsigned kBlockBytes = kBlkElems * sizeof(R);
