@@ -86,7 +86,10 @@ typedef struct jic_params {
   int32_t track_yz;       /* also advance and wrap y,z (only needed for the full (N,3) position outputs) */
   int32_t deposit;        /* jic_deposit (INDEXED engine) */
   int32_t steps_per_graph;/* steps captured per CUDA graph, 0 = default */
-  int32_t reserved[8];    /* must be zero */
+  int32_t field_solver;   /* per-step electrostatic correction of jaxincell/_algorithms.py:69-78 (the `field_solver` argument of
+                           * Boris_step): 0 = none, 1 = E_from_Gauss_1D_FFT, 2 = E_from_Gauss_1D_Cartesian, 3 = E_from_Poisson_1D_FFT
+                           * (_fields.py:9-81).  E_x is replaced every step by the solve of rho(x_n) deposited on the faces. */
+  int32_t reserved[7];    /* must be zero */
 } jic_params;
 
 /* Where jic_run writes the per-step outputs (jaxincell/_algorithms.py:93, stacked at _simulation.py:256-257).

@@ -138,7 +138,7 @@ __device__ __forceinline__ void insert_particle(const BinDev<R>& bd, int dst, in
 
 // General (exact) tail of one particle after its velocity update: BC, x_{n+1}, deposit through global atomics, re-insert.
 template <typename R>
-__device__ __noinline__ void slow_tail(const DevParams<R>& p, const BinDev<R>& bd, int dst, R* acc, int species, R x_old, R v0, R v1, R v2) {
+__device__ __noinline__ void slow_tail(const DevParams<R>& p, const BinDev<R>& bd, int dst, R* acc, int species, R x_old, R vx_old, R v0, R v1, R v2) {
   R v[3] = {v0, v1, v2};
   R x_new = x_old + p.dt * v[0];
   const int flag = bc_x(x_new, p);
@@ -153,6 +153,11 @@ __device__ __noinline__ void slow_tail(const DevParams<R>& p, const BinDev<R>& b
     const GlobalGrid<R> g{acc};
     deposit_jx(g, x_old, c_old, c_new, q / p.dt, p);
     deposit_cloud(g, c_mid, p.G, a * v[1], a * v[2], a, true);
+    if (p.stag) {  // rho(x_n) on the faces (field_solver != 0), as in k_step
+      R x_n = x_old - p.half_dt * vx_old;
+      bc_x(x_n, p);
+      deposit_faces(acc + (size_t)p.G * kAccRow, make_cloud_faces(x_n, p), p.G, a);
+    }
     insert_particle(bd, dst, species, x_new, v[0], v[1], v[2], p);
   } else {
     atomicAdd((unsigned long long*)&bd.hdr->n_absorbed, 1ull);  // absorbed: leaves the store, contributes nothing from now on
@@ -534,8 +539,13 @@ struct BinnedStore {
 
   int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, cudaStream_t st) {
     const int g = n_sm * push_min_blocks<R>();
-    if (dp.relativistic) k_push<R, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
-    else k_push<R, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+    if (dp.stag) {
+      if (dp.relativistic) k_push<R, true, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+      else k_push<R, false, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+    } else {
+      if (dp.relativistic) k_push<R, true, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+      else k_push<R, false, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+    }
     e.launches += 1;
     return JIC_OK;
   }

@@ -36,6 +36,7 @@ struct DevParams {
   int pbl, pbr, fbl, fbr;
   int relativistic;
   int track_yz;
+  int stag;        // field_solver != 0: also deposit rho(x_n) on the faces g_k + dx/2 (_algorithms.py:69-72)
   R L, Ly, Lz, half_L, half_Ly, half_Lz;
   R dx, inv_dx, half_dx, dt, half_dt;
   R g0, gl;        // grid[0], grid[-1]
@@ -117,6 +118,40 @@ __device__ __forceinline__ R cloud_at(const Cloud<R>& cl, int k, int G) {
   if (k == 0) v += cl.first;
   if (k == G - 1) v += cl.last;
   return v;
+}
+
+// The same cloud on the FACES g_k + dx/2 (`grid + dx/2` of jaxincell/_algorithms.py:70).  The nearest face of a particle in the
+// left half cell is face -1: no clamp, its weights are dropped like the reference's `where` over the grid does, and the ghost
+// fold only exists for |x - f_0| <= dx/2 resp. |x - f_{G-1}| <= dx/2 (_sources.py:60-69 with the shifted grid).
+template <typename R>
+__device__ __forceinline__ Cloud<R> make_cloud_faces(R x, const DevParams<R>& p) {
+  Cloud<R> cl;
+  const R f0 = p.g0 + p.half_dx, fl = p.gl + p.half_dx;
+  const R s = (x - f0) * p.inv_dx;
+  const int c = (int)floor(s + R(0.5));
+  const R d = s - R(c);
+  cl.c = c;
+  cl.w[0] = R(0.5) * (R(0.5) - d) * (R(0.5) - d);
+  cl.w[1] = R(0.75) - d * d;
+  cl.w[2] = R(0.5) * (R(0.5) + d) * (R(0.5) + d);
+  R exl = R(0), exr = R(0);
+  if (fabs(x - f0) <= p.half_dx) { const R t = R(0.5) + (f0 - x) * p.inv_dx; exl = R(0.5) * t * t; }
+  if (fabs(x - fl) <= p.half_dx) { const R t = R(0.5) + (x - fl) * p.inv_dx; exr = R(0.5) * t * t; }
+  cl.first = (p.pbl == JIC_BC_PERIODIC ? exr : R(0)) + (p.pbl == JIC_BC_REFLECTIVE ? exl : R(0));
+  cl.last = (p.pbr == JIC_BC_PERIODIC ? exl : R(0)) + (p.pbr == JIC_BC_REFLECTIVE ? exr : R(0));
+  return cl;
+}
+
+// rho(x_n) on the faces into the fifth raw component, stored behind the (G,4) grid: accS[k] = acc[G * kAccRow + k]
+template <typename R>
+__device__ __forceinline__ void deposit_faces(R* accS, const Cloud<R>& cl, int G, R a) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int k = cl.c + j - 1;
+    if (k >= 0 && k < G) atomicAdd(accS + k, cl.w[j] * a);
+  }
+  if (cl.first != R(0)) atomicAdd(accS, cl.first * a);
+  if (cl.last != R(0)) atomicAdd(accS + G - 1, cl.last * a);
 }
 
 __device__ __forceinline__ int mod_pos(int a, int n) {

@@ -62,7 +62,10 @@ struct EngineT : Engine {
   // particles (SoA)
   R *xh = nullptr, *yh = nullptr, *zh = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr, *v_init = nullptr;
   // grid
-  R *acc = nullptr, *acc2 = nullptr, *F = nullptr;   // raw deposit grid (two of them when the multi-CTA field kernel is on)
+  R *acc = nullptr, *acc2 = nullptr, *F = nullptr;   // raw deposit grid (two of them when the multi-CTA field kernel is on):
+                                                     // (G,4) [Jx,Jy,Jz,rho] followed by (G) rho on the faces (field_solver != 0)
+  double *gauss_h = nullptr, *ExC = nullptr;         // field_solver != 0: circulant kernel of the spectral solve, E_x of the step
+  size_t gauss_smem = 0;
   double *E = nullptr, *B = nullptr, *E_int = nullptr, *B_int = nullptr, *J = nullptr, *rho = nullptr, *extE = nullptr, *extB = nullptr;
   double *s0 = nullptr, *s1 = nullptr, *E0 = nullptr, *B0 = nullptr;
   double *E2 = nullptr, *B2 = nullptr;  // ping-pong partners of E, B (multi-CTA field kernel)
@@ -118,6 +121,7 @@ struct EngineT : Engine {
     dp.pbl = prm.particle_bc_left; dp.pbr = prm.particle_bc_right; dp.fbl = prm.field_bc_left; dp.fbr = prm.field_bc_right;
     dp.relativistic = prm.relativistic;
     dp.track_yz = prm.track_yz;
+    dp.stag = prm.field_solver != 0 ? 1 : 0;
     const double Ly = prm.length_y > 0 ? prm.length_y : prm.length, Lz = prm.length_z > 0 ? prm.length_z : prm.length;
     dp.L = (R)prm.length; dp.Ly = (R)Ly; dp.Lz = (R)Lz;
     dp.half_L = (R)(prm.length / 2); dp.half_Ly = (R)(Ly / 2); dp.half_Lz = (R)(Lz / 2);
@@ -136,12 +140,22 @@ struct EngineT : Engine {
     } else {
       if ((rc = bins.create(*this, dp, prm, n_sm))) return rc;
     }
-    if ((rc = alloc(&acc, G * kAccRow)) || (rc = alloc(&F, (G + 3) * kFieldRow))) return rc;
+    if ((rc = alloc(&acc, G * (kAccRow + 1))) || (rc = alloc(&F, (G + 3) * kFieldRow))) return rc;
     if ((rc = alloc(&E, G * 3)) || (rc = alloc(&B, G * 3)) || (rc = alloc(&E_int, G * 3)) || (rc = alloc(&B_int, G * 3))) return rc;
     if ((rc = alloc(&J, G * 3)) || (rc = alloc(&rho, G)) || (rc = alloc(&extE, G * 3)) || (rc = alloc(&extB, G * 3))) return rc;
     if ((rc = alloc(&s0, G * kAccRow)) || (rc = alloc(&s1, G * kAccRow)) || (rc = alloc(&E0, G * 3)) || (rc = alloc(&B0, G * 3))) return rc;
     if ((rc = alloc(&ctl, 1))) return rc;
-    if ((rc = alloc(&acc2, G * kAccRow)) || (rc = alloc(&E2, G * 3)) || (rc = alloc(&B2, G * 3)) || (rc = alloc(&mc_done, 1))) return rc;
+    if ((rc = alloc(&acc2, G * (kAccRow + 1))) || (rc = alloc(&E2, G * 3)) || (rc = alloc(&B2, G * 3)) || (rc = alloc(&mc_done, 1))) return rc;
+    if (dp.stag) {
+      // per-step electrostatic correction (_algorithms.py:69-78): circulant kernel of the spectral solvers, built once
+      if ((rc = alloc(&gauss_h, G)) || (rc = alloc(&ExC, G))) return rc;
+      gauss_smem = 2 * G * sizeof(double);
+      if (gauss_smem > (size_t)max_smem_optin() - 1024) return fail(JIC_ERR_UNSUPPORTED, "field_solver != 0 needs 16 G bytes of shared memory: grid too large");
+      if (gauss_smem > 48 * 1024) JIC_CUDA(cudaFuncSetAttribute(k_gauss<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gauss_smem));
+      k_gauss_kernel<<<(int)((G + 127) / 128), 128>>>((int)G, prm.dx, gauss_h);
+      JIC_CUDA(cudaGetLastError());
+      JIC_CUDA(cudaDeviceSynchronize());
+    }
     {
       // multi-CTA field kernel: slices of S nodes with a halo of H = filter reach + 2; needs >= 2 slices of >= H + 2 nodes
       long long reach = 0;
@@ -197,7 +211,7 @@ struct EngineT : Engine {
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
     if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
-    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, acc2, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done};
+    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, acc2, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
   }
@@ -245,7 +259,7 @@ struct EngineT : Engine {
     if (world <= 1) return JIC_OK;
     NcclApi& api = nccl_api();
     R* buf = acc_of(p);
-    ncclResult_t r = api.AllReduce(buf, buf, (size_t)dp.G * kAccRow, sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, st);
+    ncclResult_t r = api.AllReduce(buf, buf, (size_t)dp.G * (kAccRow + dp.stag), sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, st);
     if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
     launches += 1;
     return JIC_OK;
@@ -261,13 +275,14 @@ struct EngineT : Engine {
     a.s0 = s0; a.s1 = s1; a.E0 = E0; a.B0 = B0; a.ctl = ctl;
     a.record = record ? 1 : 0;
     a.smem_comps = field_smem_comps;
+    a.ExC = (dp.stag && !init) ? ExC : nullptr;
     return a;
   }
 
   int initialize(const void* x0, const void* v0, cudaStream_t st) override {
     if (!x0 || !v0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
-    JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * kAccRow * sizeof(R), st));
-    JIC_CUDA(cudaMemsetAsync(acc2, 0, (size_t)dp.G * kAccRow * sizeof(R), st));
+    JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));
+    JIC_CUDA(cudaMemsetAsync(acc2, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));
     JIC_CUDA(cudaMemsetAsync(mc_done, 0, sizeof(unsigned), st));
     JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
     par = 0;
@@ -320,7 +335,23 @@ struct EngineT : Engine {
     a.E_r = E_of(p); a.B_r = B_of(p); a.E_w = E_of(p ^ 1); a.B_w = B_of(p ^ 1);
     a.E_int = E_int; a.B_int = B_int; a.J = J; a.rho = rho; a.extE = extE; a.extB = extB; a.F = F;
     a.record = 1; a.ctl = ctl; a.done = mc_done;
+    a.ExC = dp.stag ? ExC : nullptr;
     return a;
+  }
+
+  // field_solver != 0: E_x of this step from the face charge density the push just deposited (k_gauss), before the field kernel
+  int enqueue_gauss(cudaStream_t st, int p) {
+    GaussArgs<R> a;
+    memset(&a, 0, sizeof(a));
+    a.G = dp.G; a.fbl = dp.fbl; a.fbr = dp.fbr; a.passes = prm.filter_passes; a.n_strides = prm.n_filter_strides; a.mode = prm.field_solver;
+    for (int i = 0; i < prm.n_filter_strides; ++i) a.strides[i] = prm.filter_strides[i];
+    a.alpha = prm.filter_alpha; a.dx = prm.dx;
+    a.accS = acc_of(p) + (size_t)dp.G * kAccRow; a.h = gauss_h; a.Ex = ExC;
+    int nc = (dp.G + 7) / 8;  // >= 8 nodes (one per warp) per CTA
+    if (nc > n_sm) nc = n_sm;
+    k_gauss<R><<<nc, kGaussThreads, gauss_smem, st>>>(a);
+    launches += 1;
+    return JIC_OK;
   }
 
   int enqueue_fields(cudaStream_t st, int p) {
@@ -333,6 +364,7 @@ struct EngineT : Engine {
       JIC_CUDA(cudaEventRecord(ev_join, side));
     }
     if ((rc = allreduce(st, p))) return rc;
+    if (dp.stag && (rc = enqueue_gauss(st, p))) return rc;
     if (mc) k_fields_mc<R><<<mc_NC, kFieldsMcThreads, mc_smem, st>>>(field_args_mc(p));
     else k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(false, true));
     launches += 1;
@@ -454,7 +486,7 @@ struct EngineT : Engine {
   }
 
   long long count_launches_per_step() const {
-    long long k = 2 + (world > 1 ? 1 : 0);
+    long long k = 2 + (world > 1 ? 1 : 0) + dp.stag;
     if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
     return k;
   }
@@ -509,7 +541,8 @@ static int validate(const jic_params* p, const jic_species* sp, std::string& why
   for (int b : bcs) if (b < 0 || b > 2) { why = "boundary codes are 0 (periodic), 1 (reflective), 2 (absorbing)"; return JIC_ERR_INVALID_ARGUMENT; }
   if (p->filter_passes < 0 || p->n_filter_strides < 0 || p->n_filter_strides > JIC_MAX_STRIDES) { why = "bad filter parameters"; return JIC_ERR_INVALID_ARGUMENT; }
   for (int i = 0; i < p->n_filter_strides; ++i) if (p->filter_strides[i] <= 0) { why = "filter strides must be positive"; return JIC_ERR_INVALID_ARGUMENT; }
-  for (int i = 0; i < 8; ++i) if (p->reserved[i]) { why = "reserved fields must be zero"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->field_solver < 0 || p->field_solver > 3) { why = "field_solver must be 0 (none), 1 (Gauss FFT), 2 (Gauss Cartesian) or 3 (Poisson FFT)"; return JIC_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < 7; ++i) if (p->reserved[i]) { why = "reserved fields must be zero"; return JIC_ERR_INVALID_ARGUMENT; }
   return JIC_OK;
 }
 

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) k_step(const DevParams<R> p, R* __restric
     if (!dead) {
       const int s = species_of(i, p);
       R E[3], B[3];
+      const R vx_old = v[0];
       gather_fields(F, x_old, p, E, B);
       if (p.relativistic) boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
       else boris_velocity(v, E, B, p.sp_qm[s], p.dt);
@@ -108,6 +109,13 @@ __global__ void __launch_bounds__(256) k_step(const DevParams<R> p, R* __restric
           const GlobalGrid<R> g{acc};
           deposit_jx(g, x_old, c_old, c_new, q / p.dt, p);
           deposit_cloud(g, c_mid, p.G, a * v[1], a * v[2], a, true);
+        }
+        if (p.stag) {
+          // rho on the faces at x_n = BCpos(x_{n+1/2} - dt/2 v_n), the position the reference still holds in `positions` at
+          // _algorithms.py:70 (bit-identical recomputation of _algorithms.py:60-61 of the previous step), post-BC charge
+          R x_n = x_old - p.half_dt * vx_old;
+          bc_x(x_n, p);
+          deposit_faces(acc + (size_t)p.G * kAccRow, make_cloud_faces(x_n, p), p.G, a);
         }
       }
       xh[i] = x_new;
@@ -157,6 +165,7 @@ struct FieldArgs {
   double *s0, *s1;     // filter scratch (G,4) each
   double *E0, *B0;     // initial fields (init mode)
   int smem_comps;      // components filtered at a time in shared memory (0 = global scratch)
+  const double* ExC;   // field_solver != 0: E_x of this step from k_gauss (G), else null; the raw grid then has a fifth component
   int record;          // write this step's outputs to the history buffers named in ctl->hist
   RunControl* ctl;
 };
@@ -304,7 +313,8 @@ __global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
       }
       __syncthreads();
     }
-    for (int k = tid; k < G * kAccRow; k += nt) a.acc[k] = R(0);  // the raw grid is consumed: zero it for the next step
+    // the raw grid is consumed: zero it for the next step (with the face component behind it when it is in use)
+    for (int k = tid; k < G * (kAccRow + (a.ExC ? 1 : 0)); k += nt) a.acc[k] = R(0);
   }
   const double h = a.dt / 2;
   if (a.init) {
@@ -324,6 +334,10 @@ __global__ void __launch_bounds__(1024) k_fields(const FieldArgs<R> a) {
     // 3b. second half step of step n: B then E (_fields.py:185-193)
     faraday(a.E, a.B, G, a.fbl, a.dx, h);
     ampere(a.E, a.B, a.J, G, a.fbr, a.dx, h);
+    if (a.ExC) {  // _algorithms.py:78: E_x is replaced by the Gauss / Poisson solve
+      for (int i = tid; i < G; i += nt) a.E[i * 3] = a.ExC[i];
+      __syncthreads();
+    }
     const long long row = a.ctl->hist_row;
     R* hE = a.record ? (R*)a.ctl->hist[0] : nullptr;
     R* hB = a.record ? (R*)a.ctl->hist[1] : nullptr;
@@ -376,6 +390,7 @@ struct FieldArgsMC {
   double alpha, dx, dt;
   int S, H, NC;
   const R* acc_cur; R* acc_next;
+  const double* ExC;   // field_solver != 0: E_x of this step from k_gauss (G), else null
   const double *E_r, *B_r;
   double *E_w, *B_w, *E_int, *B_int, *J, *rho;
   const double *extE, *extB;
@@ -414,6 +429,7 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
   }
   // the other raw buffer was consumed by the previous step: zero our slice of it for the next push
   for (int k = tid; k < (hi - lo) * kAccRow; k += nt) a.acc_next[lo * kAccRow + k] = R(0);
+  if (a.ExC) for (int k = tid; k < hi - lo; k += nt) a.acc_next[(size_t)G * kAccRow + lo + k] = R(0);  // face component
   __syncthreads();
 
   // ---- digital filter on a shrinking valid range [va, vb); the domain edge (non-periodic) does not shrink
@@ -495,6 +511,14 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
   faraday_mc(fa, m_last);
   const int ab = wallR ? m_last : m_last - 1;       // E valid on [fa, ab]
   ampere_mc(fa, ab);
+  if (a.ExC) {  // _algorithms.py:78: E_x is replaced by the Gauss / Poisson solve
+    for (int mi = fa + tid; mi <= ab; mi += nt) {
+      int g = lo - 2 + mi;
+      if (periodic) g = g < 0 ? g + G : (g >= G ? g - G : g);
+      Em[mi] = a.ExC[g];
+    }
+    __syncthreads();
+  }
   {  // step outputs (_algorithms.py:93) for the owned nodes
     R* hE = a.record ? (R*)a.ctl->hist[0] : nullptr;
     R* hB = a.record ? (R*)a.ctl->hist[1] : nullptr;
@@ -552,6 +576,68 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
       a.ctl->step += 1;
       *a.done = 0u;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2g  per-step electrostatic correction (field_solver != 0, jaxincell/_algorithms.py:69-78): E_x from the filtered charge
+//      density on the faces.  The two spectral solvers (_fields.py:9-60) are the same circulant operator, E = h (*) rho with
+//      h[d] = 1/(G eps0) sum_{m != 0} sin(2 pi m d / G) / k_m  (k = 0 and Nyquist terms have no real part), evaluated here as a
+//      direct circular convolution: G^2 multiply-adds spread over the SMs is ~1 us at G = 4096 and needs no transform library
+//      inside the captured graph.  field_solver = 2 (_fields.py:62-81) is the prefix sum (dx/eps0) sum_{j<=i} rho_j.
+//      Every CTA filters the whole face component itself (O(15 G), shared memory) and then produces its own slice of E_x,
+//      one warp per node, lanes striding over the sources.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_gauss_kernel(int G, double dx, double* h) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= G) return;
+  const int n_pos = (G - 1) / 2 + 1;  // numpy/jnp fftfreq: indices [0, n_pos) are >= 0, the rest are m - G
+  double sum = 0.0;
+  for (int m = 1; m < G; ++m) {
+    const int mm = m < n_pos ? m : m - G;
+    const double k = ((double)mm * (1.0 / ((double)G * dx))) * 2.0 * 3.14159265358979323846;
+    const long long ph = ((long long)m * d) % G;
+    sum += sinpi(2.0 * (double)ph / (double)G) / k;
+  }
+  h[d] = sum / ((double)G * kEps0);
+}
+
+template <typename R>
+struct GaussArgs {
+  int G, fbl, fbr, passes, n_strides, mode;  // mode = field_solver (1 Gauss FFT, 2 Gauss Cartesian, 3 Poisson FFT)
+  int strides[JIC_MAX_STRIDES];
+  double alpha, dx;
+  const R* accS;    // raw rho on the faces (already all-reduced)
+  const double* h;  // circulant kernel of the spectral solvers (G)
+  double* Ex;       // out: E_x (G)
+};
+
+constexpr int kGaussThreads = 256;
+
+template <typename R>
+__global__ void __launch_bounds__(kGaussThreads) k_gauss(const GaussArgs<R> a) {
+  extern __shared__ __align__(16) double gsm[];  // 2 G doubles
+  const int G = a.G, tid = threadIdx.x, nt = blockDim.x;
+  for (int j = tid; j < G; j += nt) gsm[j] = (double)a.accS[j];
+  __syncthreads();
+  const double* rho = filter_components<double*>(gsm, gsm + G, 1, G, a.passes, a.alpha, a.n_strides, a.strides, a.fbl, a.fbr);
+  const int S = (G + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * S, hi = min(lo + S, G);
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int i = lo + warp; i < hi; i += nw) {
+    double sum = 0.0;
+    if (a.mode == 2) {
+      for (int j = lane; j <= i; j += 32) sum += rho[j];
+      sum *= a.dx / kEps0;
+    } else {
+      // h[(i - j) mod G]: lanes read consecutive (descending) addresses
+      for (int j = lane; j < G; j += 32) {
+        int k = i - j;
+        k += k < 0 ? G : 0;
+        sum = fma(rho[j], __ldg(a.h + k), sum);
+      }
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) a.Ex[i] = sum;
   }
 }
 

@@ -82,7 +82,15 @@ __device__ __forceinline__ void store_slot_at(const BinDev<R>& bd, int dst, cons
   }
 }
 
-template <typename R, bool REL>
+// STAG (field_solver != 0): additionally rho(x_n) on the FACES c-3..c+2 (jaxincell/_algorithms.py:69-72), x_n = x_{n+1/2} - dt/2 v_n
+// at offset ts from node c.  The face weights are the same B-spline seen from half a cell away, so their knots inside
+// (-3/2, 3/2) sit at -1, 0, 1:  with Nm = max(-ts-1,0)^2, Z = max(ts,0)^2, Pp = max(ts-1,0)^2
+//     W(c-3) = Nm/2                               W(c)   = ((ts+1)^2 - Nm - 3Z + 3Pp)/2
+//     W(c-2) = (ts^2 - 3Nm - Z)/2                 W(c+1) = (Z - 3Pp)/2
+//     W(c-1) = (1 - 2ts - 2ts^2 + 3Nm + 3Z - Pp)/2     W(c+2) = Pp/2
+// Five more sums per lane, six more node values per item.  Bins next to the domain ends take the general path: there the
+// reference drops the weight of faces -1 and -2 instead of wrapping it (make_cloud_faces).
+template <typename R, bool REL, bool STAG>
 __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
                                                                        const R* __restrict__ F, R* __restrict__ acc) {
   constexpr int NW = kPushWarps, NS = kPushStages, KB = kPushStageBlocks;
@@ -91,7 +99,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
   __shared__ __align__(8) unsigned long long full[NW][NS];
   __shared__ __align__(16) R coef_s[NW][24];  // per component k: [e0, e1, a2lo, a2hi, b0, b1, b2, -]
   __shared__ DestSlot<R> dest_s[NW][3];
-  __shared__ R tot_s[NW][20];
+  __shared__ R tot_s[NW][24];
   __shared__ __align__(16) R stash[NW][KB][kBlkElems];  // re-binned particles waiting for their claimed slots
 
   PlanHeader* hdr = bd.hdr;
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     const int n = min(chunk, bd.cnt[src][b] - first);
     const int nblk = (n + kBlk - 1) / kBlk, ngroups = (nblk + KB - 1) / KB;
     const R* item_rec = srec + ((bd.off[src][b] + first) >> 5) * (long long)kBlkElems;
-    const bool fast_bin = G >= 8 && (periodic || (c >= 2 && c <= G - 3));
+    const bool fast_bin = STAG ? (G >= 10 && c >= 3 && c <= G - 4) : (G >= 8 && (periodic || (c >= 2 && c <= G - 3)));
 
     // lane 0 starts streaming the item at once; the other lanes set up the item-uniform tables meanwhile
     const unsigned gt0 = gt;
@@ -185,6 +193,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     R y0 = 0, y1 = 0, y2 = 0, yP = 0, yN = 0;
     R z0 = 0, z1 = 0, z2 = 0, zP = 0, zN = 0;
     R a1 = 0, a2 = 0, aP = 0, aN = 0;
+    R s1 = 0, s2 = 0, sN = 0, sZ = 0, sP = 0;  // STAG
     int n_slow = 0;  // warp-uniform: particles of this item that took the general path
 
     // A particle is STORED one group (KB blocks) after its slot was claimed, so that the cursor atomic's round trip
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
       // compiler interleaves the independent FP64 dependency chains and shares the coefficient loads); the warp-level
       // bookkeeping (votes, claims, stash) follows per block in phase D.  Blocks past the end of the item run with every lane
       // invalid: no early exit, the loop body stays one straight line.
-      R d[KB], v[KB][3], u[KB], tn[KB], tm[KB];
+      R d[KB], v[KB][3], u[KB], tn[KB], tm[KB], vx_old[KB], ts[KB];
       bool valid[KB], fast[KB], all_fast[KB];
       // ---- A. take the particles
 #pragma unroll
@@ -237,6 +246,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
       for (int kb = 0; kb < KB; ++kb) {
         R E[3], B[3];
         const int hi = d[kb] >= R(0) ? 3 : 2;
+        if (STAG) { vx_old[kb] = v[kb][0]; ts[kb] = fma(R(-0.5) * cells_per_v, v[kb][0], d[kb]); }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           E[k] = fma(fma(coef[8 * k + hi], d[kb], coef[8 * k + 1]), d[kb], coef[8 * k]);
@@ -259,6 +269,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
         tn[kb] = d[kb] + u[kb];
         tm[kb] = fma(R(0.5), u[kb], d[kb]);
         fast[kb] = valid[kb] && fast_bin && (fabs(tn[kb]) < R(1.5));
+        if (STAG) fast[kb] = fast[kb] && (fabs(ts[kb]) < R(1.5));
       }
       // ---- C. deposit moments (all_fast: the common case, warp-uniform, no per-lane branches)
 #pragma unroll
@@ -275,6 +286,11 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
           r1 += tm_; r2 += tm2; rP += Pm; rN += Nm;
           y0 += vy; y1 = fma(vy, tm_, y1); y2 = fma(vy, tm2, y2); yP = fma(vy, Pm, yP); yN = fma(vy, Nm, yN);
           z0 += vz; z1 = fma(vz, tm_, z1); z2 = fma(vz, tm2, z2); zP = fma(vz, Pm, zP); zN = fma(vz, Nm, zN);
+          if (STAG) {
+            const R t_ = ts[kb];
+            const R n_ = (-t_ - R(1)) + fabs(-t_ - R(1)), z_ = t_ + fabs(t_), p_ = (t_ - R(1)) + fabs(t_ - R(1));
+            s1 += t_; s2 = fma(t_, t_, s2); sN = fma(n_, n_, sN); sZ = fma(z_, z_, sZ); sP = fma(p_, p_, sP);
+          }
         }
       }
       // ---- D. per block: destination, slot claim, retire the block stashed one group ago, stash the new one
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
           const unsigned ms = __ballot_sync(0xffffffffu, kind == 3);
           if (ms) {
             n_slow += __popc(ms);
-            if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d[kb] * p.dx, v[kb][0], v[kb][1], v[kb][2]);
+            if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d[kb] * p.dx, STAG ? vx_old[kb] : R(0), v[kb][0], v[kb][1], v[kb][2]);
           }
         }
       }
@@ -320,7 +336,28 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
         const R tsum = warp_sum(vals[j]);
         if (lane == j) tot_s[warp][j] = tsum;
       }
+      if (STAG) {
+        R sv[5] = {s1, s2, sN, sZ, sP};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const R tsum = warp_sum(sv[j]);
+          if (lane == j) tot_s[warp][18 + j] = tsum;
+        }
+      }
       __syncwarp();
+      if (STAG && lane >= 19 && lane < 25) {  // rho(x_n) on the faces c-3..c+2 (the truncated-power sums carry a factor 4)
+        const R* tot = tot_s[warp];
+        const R X0 = (R)(n - n_slow), X1 = tot[18], X2 = tot[19], Nm = R(0.25) * tot[20], Z = R(0.25) * tot[21], Pp = R(0.25) * tot[22];
+        const int o = lane - 19;
+        R val = o == 0 ? Nm
+              : o == 1 ? X2 - R(3) * Nm - Z
+              : o == 2 ? X0 - R(2) * (X1 + X2) + R(3) * (Nm + Z) - Pp
+              : o == 3 ? X2 + R(2) * X1 + X0 - Nm - R(3) * (Z - Pp)
+              : o == 4 ? Z - R(3) * Pp
+                       : Pp;
+        val *= R(0.5) * p.sp_q[s] * p.inv_dx;
+        if (val != R(0)) atomicAdd(acc + (size_t)G * kAccRow + mod_pos(c - 3 + o, G), val);
+      }
       if (lane < 19) {
         const R* tot = tot_s[warp];
         const R cnt = (R)(n - n_slow);
@@ -359,11 +396,12 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     const int s = b / G, c = b - s * G;
     const R x_old = node_pos(c, p) + bd.ov_d[src][i] * p.dx;
     R v[3] = {bd.ov_vx[src][i], bd.ov_vy[src][i], bd.ov_vz[src][i]};
+    const R vx_old = v[0];
     R E[3], B[3];
     gather_fields(F, x_old, p, E, B);
     if (REL) boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
     else boris_velocity(v, E, B, p.sp_qm[s], p.dt);
-    slow_tail(p, bd, dst, acc, s, x_old, v[0], v[1], v[2]);
+    slow_tail(p, bd, dst, acc, s, x_old, vx_old, v[0], v[1], v[2]);
   }
 }
 

@@ -16,7 +16,7 @@ _HIST = ("electric_field", "magnetic_field", "current_density", "charge_density"
 
 def make_params(*, length, G, dt, n_species, length_y=0.0, length_z=0.0, pbl=0, pbr=0, fbl=0, fbr=0, filter_passes=5,
                 filter_alpha=0.5, filter_strides=(1, 2, 4), relativistic=False, dtype=torch.float64, engine="indexed",
-                track_yz=False, deposit="auto", steps_per_graph=0, device=-1):
+                track_yz=False, deposit="auto", steps_per_graph=0, device=-1, field_solver=0):
     """Fill a jic_params exactly as build_domain_state does (jaxincell/_state_initialization.py:27-49)."""
     p = Params()
     p.struct_bytes = C.sizeof(Params)
@@ -39,6 +39,7 @@ def make_params(*, length, G, dt, n_species, length_y=0.0, length_z=0.0, pbl=0, 
         p.filter_strides[i] = s
     p.relativistic, p.track_yz = int(bool(relativistic)), int(bool(track_yz))
     p.deposit, p.steps_per_graph = _DEPOSITS[deposit], int(steps_per_graph)
+    p.field_solver = int(field_solver)  # Boris_step's `field_solver` argument (jaxincell/_algorithms.py:20,69-78)
     return p, grid
 
 

@@ -33,7 +33,7 @@ class Params(C.Structure):
         ("filter_passes", C.c_int32), ("n_filter_strides", C.c_int32), ("filter_strides", C.c_int32 * JIC_MAX_STRIDES),
         ("filter_alpha", C.c_double),
         ("relativistic", C.c_int32), ("track_yz", C.c_int32), ("deposit", C.c_int32), ("steps_per_graph", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("field_solver", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 

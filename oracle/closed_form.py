@@ -42,7 +42,7 @@ class Domain:
 # ----------------------------------------------------------------------------------------------------
 # S2 stencil of a particle (jaxincell/_sources.py:83-110 + :43-81), as (node, value) entries
 # ----------------------------------------------------------------------------------------------------
-def s2_entries(x, q, dom: Domain, pbl, pbr):
+def s2_entries(x, q, dom: Domain, pbl, pbr, faces=False):
     """Five (node, value) entries per particle: nodes c-1, c, c+1 (dropped if off-grid) + the two end nodes,
     which receive the folded ghost weight according to the particle BCs.
 
@@ -52,12 +52,20 @@ def s2_entries(x, q, dom: Domain, pbl, pbr):
     G, dx, grid, L = dom.G, dom.dx, dom.grid, dom.L
     x = np.asarray(x, dtype=np.float64)
     q = np.asarray(q, dtype=np.float64)
-    s = (x - grid[0]) / dx
-    c = np.floor(s + 0.5).astype(np.int64)
-    inside = (x >= -L / 2) & (x <= L / 2)
-    c = np.where(inside, np.clip(c, 0, G - 1), c)
-    cc = np.clip(c, 0, G - 1)
-    d = np.where(inside, (x - grid[cc]) / dx, s - c)
+    if faces:
+        # nodes g_k + dx/2 (`grid + dx/2` of _algorithms.py:70): the nearest face of a particle in the left half cell is
+        # face -1, which is not on the grid -- its weight is dropped, exactly as single_particle_charge_density does
+        grid = grid + dx / 2
+        s = (x - grid[0]) / dx
+        c = np.floor(s + 0.5).astype(np.int64)
+        d = s - c
+    else:
+        s = (x - grid[0]) / dx
+        c = np.floor(s + 0.5).astype(np.int64)
+        inside = (x >= -L / 2) & (x <= L / 2)
+        c = np.where(inside, np.clip(c, 0, G - 1), c)
+        cc = np.clip(c, 0, G - 1)
+        d = np.where(inside, (x - grid[cc]) / dx, s - c)
     w = np.stack([0.5 * (0.5 - d) ** 2, 0.75 - d ** 2, 0.5 * (0.5 + d) ** 2], axis=1)
     a = (q / dx)[:, None] * w
     nodes = c[:, None] + np.array([-1, 0, 1])[None, :]
@@ -75,10 +83,31 @@ def s2_entries(x, q, dom: Domain, pbl, pbr):
     return nodes, vals
 
 
-def deposit_rho_raw(x, q, dom, pbl, pbr):
-    """Unfiltered rho on cell centres: sum of S2 clouds (`_sources.py:136-142`)."""
-    nodes, vals = s2_entries(x, q, dom, pbl, pbr)
+def deposit_rho_raw(x, q, dom, pbl, pbr, faces=False):
+    """Unfiltered rho on cell centres (or on the faces g_k + dx/2): sum of S2 clouds (`_sources.py:136-142`)."""
+    nodes, vals = s2_entries(x, q, dom, pbl, pbr, faces)
     return np.bincount(nodes.ravel(), weights=vals.ravel(), minlength=dom.G)
+
+
+def gauss_kernel(G, dx):
+    """The spectral solvers of `_fields.py:9-60` are one circulant operator: E = h (*) rho (circular convolution) with
+    h[d] = 1/(G eps0) sum_{m != 0} sin(2 pi m d / G) / k_m, k_m = 2 pi fftfreq(G, dx)[m]; the k = 0 and Nyquist terms vanish
+    in the real part.  This is what the CUDA path evaluates (k_gauss)."""
+    m = np.arange(1, G)
+    k = 2 * np.pi * np.fft.fftfreq(G, d=dx)[1:]
+    d = np.arange(G)
+    phase = (np.outer(d, m) % G) / G
+    return (np.sin(2 * np.pi * phase) / k[None, :]).sum(axis=1) / (G * epsilon_0)
+
+
+def solve_Ex(rho_faces, dx, field_solver):
+    """E_x of `_algorithms.py:73-78` in the form the kernels use: circular convolution (1, 3) or prefix sum (2)."""
+    G = len(rho_faces)
+    if field_solver == 2:
+        return (dx / epsilon_0) * np.cumsum(rho_faces)
+    h = gauss_kernel(G, dx)
+    idx = (np.arange(G)[:, None] - np.arange(G)[None, :]) % G
+    return (h[idx] * rho_faces[None, :]).sum(axis=1)
 
 
 def deposit_current_raw(x_old, x_mid, x_new, v_mid, q, dom, pbl, pbr):
@@ -202,6 +231,7 @@ def start(x0, v0, qs, ms, q_ms, dom: Domain, pbl, pbr, fbl, fbr, solver, ext_E=N
                                                np.asarray(q_ms, np.float64).reshape(-1), dx, grid, *dom.box, pbl, pbr)
     x_m = lit.set_BC_positions(x0 - (dt / 2) * v, dx, grid, *dom.box, pbl, pbr)
     st.x_half, st.v, st.q, st.m, st.qm = x_p, v, q1, m1, qm1
+    st.x_n = x0.copy()
     st.initial_velocities = v.copy()
     Jraw = deposit_current_raw(x_m[:, 0], x0[:, 0], x_p[:, 0], v, q1, dom, pbl, pbr)
     st.J = lit.filter_vector_field(Jraw, fp, fa, fs, fbl, fbr)
@@ -225,8 +255,14 @@ def step(st):
     Jraw = deposit_current_raw(st.x_half[:, 0], x_new[:, 0], x_pp[:, 0], v_new, q, dom, pbl, pbr)
     J = lit.filter_vector_field(Jraw, fp, fa, fs, fbl, fbr)
     E, B = lit.field_update2(E, B, dx, dt / 2, J, fbl, fbr)
+    field_solver = st.solver.get("field_solver", 0)
+    if field_solver != 0:  # _algorithms.py:69-78: rho of x_n (start of the step) with the post-BC charges, on the faces
+        rho_f = lit.filter_scalar_field(deposit_rho_raw(st.x_n[:, 0], q, dom, pbl, pbr, faces=True), fp, fa, fs, fbl, fbr)
+        E = E.copy()
+        E[:, 0] = solve_Ex(rho_f, dx, field_solver)
     rho = lit.filter_scalar_field(deposit_rho_raw(x_new[:, 0], q, dom, pbl, pbr), fp, fa, fs, fbl, fbr)
     st.E, st.B, st.J = E, B, J
+    st.x_n = x_new
     st.x_half, st.v, st.q, st.m, st.qm = x_pp, v_new, q, m, qm
     return x_new, v_new, E, B, J, rho
 

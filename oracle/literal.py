@@ -333,6 +333,32 @@ def E_from_Gauss_1D_Cartesian(charge_density, dx):
     return (dx / epsilon_0) * np.linalg.solve(D, rho)
 
 
+def _gauss_wavenumbers(n, dx):
+    kx = np.fft.fftfreq(n, d=dx) * 2 * np.pi
+    kx[0] = 1.0  # "prevent division by zero" (_fields.py:26, :50)
+    return kx
+
+
+def E_from_Gauss_1D_FFT(charge_density, dx):
+    """E_k = -i rho_k / (k eps0), real part of the inverse transform.  _fields.py:9-31."""
+    rho = np.asarray(charge_density, dtype=np.float64)
+    kx = _gauss_wavenumbers(len(rho), dx)
+    E_k = -1j * np.fft.fft(rho) / kx / epsilon_0
+    return np.fft.ifft(E_k).real
+
+
+def E_from_Poisson_1D_FFT(charge_density, dx):
+    """phi_k = -rho_k / (k^2 eps0) with phi_0 = 0, E_k = i k phi_k.  _fields.py:33-60."""
+    rho = np.asarray(charge_density, dtype=np.float64)
+    kx = _gauss_wavenumbers(len(rho), dx)
+    phi_k = -np.fft.fft(rho) / kx ** 2 / epsilon_0
+    phi_k[0] = 0.0
+    return np.fft.ifft(1j * kx * phi_k).real
+
+
+FIELD_SOLVERS = {1: E_from_Gauss_1D_FFT, 2: E_from_Gauss_1D_Cartesian, 3: E_from_Poisson_1D_FFT}  # _algorithms.py:73-77
+
+
 def curlE(E, B, dx, dt, bc_left, bc_right):
     """Backward difference with a left ghost row.  _fields.py:102-111."""
     E = np.asarray(E, dtype=np.float64)
@@ -400,6 +426,11 @@ def Boris_step(carry, solver, ext_E, ext_B, dx, dt, grid, box_size, pbl, pbr, fb
     x_new = set_BC_positions(x_pp - (dt / 2) * v_new, dx, grid, *box_size, pbl, pbr)  # :60-61
     J = current_density(x_p, x_new, x_pp, v_new, qs, dx, dt, grid, gs, pbl, pbr, fp, fa, fs, fbl, fbr)  # :63-66
     E, B = field_update2(E, B, dx, dt / 2, J, fbl, fbr)  # :67
+    field_solver = solver.get("field_solver", 0)
+    if field_solver != 0:  # :69-78 -- `positions` is still x_n here (rebound at :84), `qs` already the post-BC charges of :56
+        rho_faces = calculate_charge_density(x_n, qs, dx, grid + dx / 2, pbl, pbr, fp, fa, fs, fbl, fbr)
+        E = E.copy()
+        E[:, 0] = FIELD_SOLVERS[field_solver](rho_faces, dx)
     carry = (E, B, x_p, x_new, x_pp, v_new, qs, ms, q_ms)  # :81-87
     rho = calculate_charge_density(x_new, qs, dx, grid, pbl, pbr, fp, fa, fs, fbl, fbr)  # :90-92
     return carry, (x_new, v_new, E, B, J, rho)

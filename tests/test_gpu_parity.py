@@ -20,8 +20,8 @@ FIELD_KEYS = ("electric_field", "magnetic_field", "current_density", "charge_den
 def run_gpu(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, ext_E=None, ext_B=None, dtype=torch.float64,
             engine="indexed", deposit="auto", particles=True, box_yz=None, steps_per_graph=0):
     from jaxincell_b200 import HotPath
-    solver = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "relativistic": False, **(solver or {})}
-    hp = HotPath(species=p["species"], dtype=dtype, length=length, G=G, dt=dt, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2], fbr=bcs[3],
+    solver = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "relativistic": False, "field_solver": 0, **(solver or {})}
+    hp = HotPath(species=p["species"], dtype=dtype, field_solver=solver["field_solver"], length=length, G=G, dt=dt, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2], fbr=bcs[3],
                  filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
                  relativistic=solver["relativistic"], engine=engine, deposit=deposit, track_yz=particles,
                  length_y=(box_yz or (0, 0))[0], length_z=(box_yz or (0, 0))[1], steps_per_graph=steps_per_graph)
@@ -289,3 +289,45 @@ def test_multi_cta_field_kernel(G, bcs, solver, engine):
     np.testing.assert_array_equal(E, got["electric_field"][-1])
     np.testing.assert_array_equal(rho, got["charge_density"][-1])
     hp.close()
+
+
+# ------------------------------------------------------------------- per-step electrostatic correction (field_solver != 0)
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("field_solver", [1, 2, 3])
+@pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2)])
+def test_field_solver_correction(bcs, field_solver, engine):
+    """jaxincell/_algorithms.py:69-78 (tests/test_algorithms.py:543-614 of the reference): every step E_x is replaced by the
+    Gauss-FFT / Gauss-Cartesian / Poisson-FFT solve of rho(x_n) deposited on the faces with the post-BC charges."""
+    G, length, T = 24, 0.01, 20
+    p = two_species(2500, 2500, length=length, G=G, seed=13, vth_e=0.3, vth_yz=0.2, drift=5e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    solver = dict(field_solver=field_solver, filter_passes=3, filter_alpha=0.4, filter_strides=(1, 2))
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=bcs[0], pbr=bcs[1],
+                fbl=bcs[2], fbr=bcs[3], solver=solver, keep_particles=engine == "indexed")
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, bcs=bcs, solver=solver, engine=engine, particles=engine == "indexed")
+    assert_parity(got, ref, FIELD_KEYS + (("positions", "velocities") if engine == "indexed" else ()), 1e-5)
+
+
+def test_field_solver_literal_oracle_direct():
+    G, length, T = 12, 0.01, 8
+    p = two_species(60, 60, length=length, G=G, seed=3, vth_e=0.2, vth_yz=0.1, drift=3e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.8)
+    ref = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=dict(field_solver=1))
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, solver=dict(field_solver=1))
+    assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float64, 1e-5), (torch.float32, 2e-3)])
+def test_field_solver_large_grid_binned_fast_path(dtype, rtol):
+    """G = 1024: multi-CTA field kernel + k_gauss over many CTAs + the moment form of the face deposit (bins away from the
+    domain ends), engines against each other and against the oracle."""
+    G, length, T = 1024, 0.05, 10
+    p = two_species(150_000, 150_000, length=length, G=G, seed=5, vth_e=0.05, vth_yz=0.01, drift=6e7, plus_minus=True)
+    dt = cfl_dt(length, G, 1.0)
+    solver = dict(field_solver=1)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=solver, keep_particles=False)
+    b = run_gpu(p, length=length, G=G, dt=dt, T=T, engine="binned", particles=False, solver=solver, dtype=dtype, steps_per_graph=3)
+    assert_parity(b, ref, FIELD_KEYS, rtol)
+    if dtype == torch.float64:
+        a = run_gpu(p, length=length, G=G, dt=dt, T=T, engine="indexed", particles=False, solver=solver)
+        assert_parity(b, a, FIELD_KEYS, 1e-7)

@@ -126,3 +126,17 @@ def test_second_deposit_equals_next_first_deposit():
     E, B, x_m, x_n, x_p, v, qs, ms, qms = out["final_carry"]
     J_first_next = L.current_density(x_m, x_n, x_p, v, qs, out["dx"], dt, out["grid"], out["grid"][0] - out["dx"] / 2, 0, 0)
     assert np.array_equal(J_first_next, out["current_density"][-1])
+
+
+@pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2), (1, 2, 1, 2)])
+@pytest.mark.parametrize("field_solver", [1, 2, 3])
+def test_field_solver_branch_matches_literal(bcs, field_solver):
+    """_algorithms.py:69-78: rho(x_n) on grid + dx/2 with the post-BC charges, then the chosen solve replaces E_x."""
+    G, length = 16, 0.01
+    p = two_species(40, 40, length=length, G=G, seed=3, vth_e=0.05, vth_yz=0.02, drift=6e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    kw = dict(length=length, G=G, dt=dt, total_steps=6, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2], fbr=bcs[3], solver=dict(field_solver=field_solver))
+    a = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], **kw)
+    b = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], **kw)
+    for k in ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities"):
+        np.testing.assert_allclose(b[k], a[k], rtol=0, atol=1e-11 * max(np.abs(a[k]).max(), 1e-300))

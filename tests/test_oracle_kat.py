@@ -331,3 +331,38 @@ def test_constants():
     # tests/test_constants.py -- values are part of the results
     assert (L.epsilon_0, L.mu_0, L.speed_of_light) == (8.85418782e-12, 1.25663706e-6, 2.99792458e8)
     assert (L.elementary_charge, L.mass_electron, L.mass_proton) == (1.60217663e-19, 9.10938371e-31, 1.67262193e-27)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# spectral field solvers -- reference tests/test_fields.py:28-120
+# ---------------------------------------------------------------------------------------------------------------------
+def test_E_from_Gauss_1D_FFT_modes():
+    G, dx = 16, 0.25
+    x = dx * np.arange(G)
+    k = 2 * np.pi * 2 / (G * dx)
+    assert np.all(L.E_from_Gauss_1D_FFT(np.zeros(G), dx) == 0)
+    np.testing.assert_allclose(L.E_from_Gauss_1D_FFT(L.epsilon_0 * np.ones(G), dx), 0, atol=1e-12)  # k = 0 leaks no DC field
+    np.testing.assert_allclose(L.E_from_Gauss_1D_FFT(L.epsilon_0 * np.sin(k * x), dx), -np.cos(k * x) / k, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(L.E_from_Gauss_1D_FFT(3.5 * L.epsilon_0 * np.cos(k * x), dx), 3.5 * np.sin(k * x) / k, rtol=1e-6, atol=1e-12)
+
+
+def test_E_from_Poisson_1D_FFT_modes():
+    G, dx = 16, 0.25
+    x = dx * np.arange(G)
+    k = 2 * np.pi * 2 / (G * dx)
+    assert np.all(L.E_from_Poisson_1D_FFT(np.zeros(G), dx) == 0)
+    for rho, want in ((L.epsilon_0 * np.sin(k * x), -np.cos(k * x) / k), (3.5 * L.epsilon_0 * np.cos(k * x), 3.5 * np.sin(k * x) / k),
+                      (L.epsilon_0 * (7.0 + np.sin(k * x)), -np.cos(k * x) / k)):
+        np.testing.assert_allclose(L.E_from_Poisson_1D_FFT(rho, dx), want, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(L.E_from_Poisson_1D_FFT(L.epsilon_0 * np.sin(k * x), dx), L.E_from_Gauss_1D_FFT(L.epsilon_0 * np.sin(k * x), dx),
+                               rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("G,dx", [(16, 0.25), (17, 0.1), (70, 1e-4), (128, 3e-3)])
+def test_circulant_form_of_the_spectral_solvers(G, dx):
+    """What the CUDA path evaluates (closed_form.solve_Ex: circular convolution with gauss_kernel) is the FFT solve."""
+    from oracle import closed_form as C
+    rho = np.random.default_rng(G).standard_normal(G)
+    for fs in (1, 2, 3):
+        a, b = L.FIELD_SOLVERS[fs](rho, dx), C.solve_Ex(rho, dx, fs)
+        np.testing.assert_allclose(b, a, rtol=0, atol=1e-13 * np.abs(a).max())
