@@ -145,6 +145,23 @@ int jic_profile_steps(jic_context* ctx, int64_t n_steps, double* ms_particle_ker
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 
+/* Initial particles generated ON THE DEVICE with the reference's formulas and jax.random's streams
+ * (jaxincell/_state_initialization.py:51-85 `initialize_species_phase_space`, seeds from `species_seed_pair` :87-96, the
+ * 0.99c clip of :259-260).  One entry per species, in the order the reference concatenates them (electrons, then ions). */
+typedef struct jic_species_sampling {
+  int64_t count;                      /* number_pseudoparticles */
+  int64_t seed_position, seed_velocity; /* axis a uses PRNGKey(seed_position + a + 1) and PRNGKey(seed_velocity + a + 4) */
+  int32_t random_positions[3];        /* random_positions_{x,y,z}: uniform in the box, else linspace(-L/2, L/2, count) */
+  int32_t velocity_plus_minus[3];     /* multiply by (-1)**arange(count) */
+  double perturbation_amplitude[3];
+  double perturbation_wavenumber[3];  /* as in the input: multiplied by 2 pi / box length inside */
+  double vth_over_c[3];
+  double drift_speed[3];
+} jic_species_sampling;
+/* x0, v0: device, real (sum of counts, 3).  threefry_partitionable: 1 = jax >= 0.5 default bit layout, 0 = the original one. */
+int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* species, const double box_size[3],
+                         int32_t threefry_partitionable, void* x0, void* v0, void* stream);
+
 /* Whole-simulation call with HOST buffers (the drop-in for Simulation.run's device part, _simulation.py:169-257):
  * host->device copies of x0, v0 and the external fields, jic_initialize, jic_run, device->host copies of the
  * requested histories and a final synchronise are all inside.  `host_outputs` members point to host memory. */

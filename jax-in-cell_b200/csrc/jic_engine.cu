@@ -14,6 +14,7 @@
 #include "jic_host.cuh"
 #include "jic_kernels.cuh"
 #include "jic_binned.cuh"
+#include "jic_sample.cuh"
 
 namespace jic {
 
@@ -605,6 +606,42 @@ int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* 
 int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
 int jic_profile_steps(jic_context* ctx, int64_t n, double* ms_push, double* ms_fields, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->profile(n, ms_push, ms_fields, (cudaStream_t)st); }
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
+
+int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* sp, const double box[3], int32_t partitionable,
+                         void* x0, void* v0, void* stream) {
+  if (!sp || !box || !x0 || !v0 || n_species < 1) { g_last_error = "jic_sample_particles: null argument"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (dtype != JIC_F64 && dtype != JIC_F32) { g_last_error = "dtype must be JIC_F64 or JIC_F32"; return JIC_ERR_INVALID_ARGUMENT; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_last_error = "no CUDA device: libjic_b200 has no CPU path"; return JIC_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  long long offset = 0;
+  for (int s = 0; s < n_species; ++s) {
+    if (sp[s].count < 0) { g_last_error = "negative species count"; return JIC_ERR_INVALID_ARGUMENT; }
+    SampleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.count = sp[s].count; a.offset = offset;
+    a.seed_position = sp[s].seed_position; a.seed_velocity = sp[s].seed_velocity;
+    a.partitionable = partitionable ? 1 : 0;
+    for (int k = 0; k < 3; ++k) {
+      a.random_positions[k] = sp[s].random_positions[k]; a.plus_minus[k] = sp[s].velocity_plus_minus[k];
+      a.amp[k] = sp[s].perturbation_amplitude[k];
+      a.wavenumber[k] = sp[s].perturbation_wavenumber[k] * 2 * 3.141592653589793 / box[k];  // _state_initialization.py:67
+      a.vth[k] = sp[s].vth_over_c[k] * kC / sqrt(2.0);                                       // :74-76
+      a.drift[k] = sp[s].drift_speed[k];
+      a.box[k] = box[k];
+    }
+    if (a.count > 0) {
+      long long blocks = (a.count + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      if (dtype == JIC_F64) k_sample_species<double><<<(int)blocks, 256, 0, st>>>(a, (double*)x0, (double*)v0);
+      else k_sample_species<float><<<(int)blocks, 256, 0, st>>>(a, (float*)x0, (float*)v0);
+    }
+    offset += a.count;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { g_last_error = format("jic_sample_particles: %s", cudaGetErrorString(ce)); return JIC_ERR_CUDA; }
+  return JIC_OK;
+}
 
 int jic_simulate_host(const jic_params* params, const jic_species* species, const void* x0_host, const void* v0_host,
                       const float* eE_host, const float* eB_host, int64_t n_steps, const jic_outputs* host_out, void* E0_host,

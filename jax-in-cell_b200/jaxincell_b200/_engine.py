@@ -179,6 +179,35 @@ class HotPath:
             pass
 
 
+def sample_particles(species_sampling, box_size, *, dtype=torch.float64, device=None, threefry_partitionable=True):
+    """jic_sample_particles: initial (x0, v0) device tensors from the reference's formulas and jax.random's streams
+    (jaxincell/_state_initialization.py:51-85).  `species_sampling`: dicts with count, seed_position, seed_velocity and per-axis
+    triples random_positions, velocity_plus_minus, perturbation_amplitude, perturbation_wavenumber, vth_over_c, drift_speed."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise JicError("no CUDA device: jaxincell_b200 has no CPU path")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    arr = (_lib.SpeciesSampling * len(species_sampling))()
+    for i, s in enumerate(species_sampling):
+        arr[i].count, arr[i].seed_position, arr[i].seed_velocity = int(s["count"]), int(s["seed_position"]), int(s["seed_velocity"])
+        for a in range(3):
+            arr[i].random_positions[a] = int(bool(s["random_positions"][a]))
+            arr[i].velocity_plus_minus[a] = int(bool(s["velocity_plus_minus"][a]))
+            arr[i].perturbation_amplitude[a] = float(s["perturbation_amplitude"][a])
+            arr[i].perturbation_wavenumber[a] = float(s["perturbation_wavenumber"][a])
+            arr[i].vth_over_c[a] = float(s["vth_over_c"][a])
+            arr[i].drift_speed[a] = float(s["drift_speed"][a])
+    N = int(sum(int(s["count"]) for s in species_sampling))
+    x0 = torch.empty((N, 3), dtype=dtype, device=device)
+    v0 = torch.empty((N, 3), dtype=dtype, device=device)
+    box = (C.c_double * 3)(*[float(b) for b in box_size])
+    with torch.cuda.device(device):
+        _lib.check(lib.jic_sample_particles(_lib.F64 if dtype == torch.float64 else _lib.F32, len(species_sampling), arr, box,
+                                            int(bool(threefry_partitionable)), C.c_void_p(x0.data_ptr()), C.c_void_p(v0.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return x0, v0
+
+
 def simulate_host(*, species, x0, v0, n_steps, ext_E=None, ext_B=None, dtype=np.float64, fields=True, particles=False,
                   initial=False, out=None, **kw):
     """jic_simulate_host: HOST (NumPy) buffers in and out, every host<->device copy inside the call."""

@@ -37,6 +37,13 @@ class Params(C.Structure):
     ]
 
 
+class SpeciesSampling(C.Structure):
+    _fields_ = [("count", C.c_int64), ("seed_position", C.c_int64), ("seed_velocity", C.c_int64),
+                ("random_positions", C.c_int32 * 3), ("velocity_plus_minus", C.c_int32 * 3),
+                ("perturbation_amplitude", C.c_double * 3), ("perturbation_wavenumber", C.c_double * 3),
+                ("vth_over_c", C.c_double * 3), ("drift_speed", C.c_double * 3)]
+
+
 class Outputs(C.Structure):
     _fields_ = [("electric_field", C.c_void_p), ("magnetic_field", C.c_void_p), ("current_density", C.c_void_p),
                 ("charge_density", C.c_void_p), ("positions", C.c_void_p), ("velocities", C.c_void_p)]
@@ -60,6 +67,7 @@ SYMBOLS = [
     ("jic_kinetic_energy", C.c_int, [_P, _P, _P]),
     ("jic_profile_steps", C.c_int, [_P, C.c_int64, _P, _P, _P]),
     ("jic_launch_count", C.c_int64, [_P]),
+    ("jic_sample_particles", C.c_int, [C.c_int32, C.c_int32, C.POINTER(SpeciesSampling), C.POINTER(C.c_double), C.c_int32, _P, _P, _P]),
     ("jic_simulate_host", C.c_int, [C.POINTER(Params), C.POINTER(Species), _P, _P, _P, _P, C.c_int64, C.POINTER(Outputs), _P, _P, _P]),
 ]
 

@@ -3,10 +3,11 @@
 per-step arithmetic all happens in libjic_b200.so.  Host code is NumPy: there is no JAX here, so
 
   * ``input_parameters`` are plain overrides (no autodiff through the path -- out of scope per BASELINE.json);
-  * random initial particles come from ``numpy.random.default_rng`` with the reference's seed schedule
-    (_state_initialization.py:87-96), NOT from ``jax.random`` -- same distributions, different streams.  Bit-level parity with the
-    reference needs explicit ``initial_positions`` / ``initial_velocities`` per species, which the reference also accepts
-    (_parameters/_species_definitions.py:57-58);
+  * random initial particles are generated on the device by ``jic_sample_particles`` (csrc/jic_sample.cuh): the reference's
+    formulas and seed schedule (_state_initialization.py:51-96) on a restatement of ``jax.random``'s Threefry streams
+    (``rng="threefry"``, the default; ``threefry_partitionable`` picks jax's bit layout, True = jax >= 0.5).  ``rng="numpy"``
+    draws them on the host from ``numpy.random.default_rng`` instead (same distributions, different streams).  Explicit
+    ``initial_positions`` / ``initial_velocities`` per species override either (_parameters/_species_definitions.py:57-58);
   * ``time_evolution_algorithm = 1`` (Crank-Nicolson) raises: it is not part of this path.  ``field_solver = 1`` (the per-step
     Gauss correction of _algorithms.py:69-78) runs in the library (k_gauss).
 
@@ -46,7 +47,7 @@ DOMAIN_DEFAULTS = dict(total_steps=350, timestep_over_spatialstep_times_c=1.0, n
 SOLVER_DEFAULTS = dict(print_info=True, field_solver=0, relativistic=False, time_evolution_algorithm=0,
                        max_number_of_Picard_iterations_implicit_CN=20, number_of_particle_substeps_implicit_CN=2,
                        tolerance_Picard_iterations_implicit_CN=1e-6, filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4),
-                       seed=1701, engine="auto", particle_history=True, dtype="float64")
+                       seed=1701, engine="auto", particle_history=True, dtype="float64", rng="threefry", threefry_partitionable=True)
 EXTERNAL_DEFAULTS = dict(external_electric_field_amplitude=0.0, external_electric_field_wavenumber=0.0,
                          external_magnetic_field_amplitude=0.0, external_magnetic_field_wavenumber=0.0,
                          external_electric_field_function=None, external_magnetic_field_function=None)
@@ -168,6 +169,7 @@ class Simulation:
         s["filter_strides"] = tuple(s["filter_strides"])
         assert s["field_solver"] in (0, 1), "Invalid field solver."
         assert s["time_evolution_algorithm"] in (0, 1), "Invalid time evolution algorithm."
+        assert s.get("rng", "threefry") in ("threefry", "numpy"), "rng must be 'threefry' (device, jax.random streams) or 'numpy'."
         assert type(s["filter_passes"]) == int and s["filter_passes"] >= 0, "Number of passes of the digital filter must be a non-negative integer."
         assert 0 < s["filter_alpha"] < 1, "Filter strength must be a float between 0 and 1."
         assert all(type(v) == int and v > 0 for v in s["filter_strides"]), "Filter strides must be a tuple of positive integers."
@@ -207,8 +209,10 @@ class Simulation:
 
     @staticmethod
     def initialize_particle_state(species_parameters, dom, solver, state):
-        """_state_initialization.py:51-286 with numpy.random.default_rng streams."""
+        """_state_initialization.py:51-286.  Random draws: device Threefry (jic_sample_particles) or numpy.random.default_rng."""
         box, G = state["box_size"], int(dom["number_grid_points"])
+        threefry = solver.get("rng", "threefry") == "threefry"
+        sampling, given_any = [], []
         pos, vel, wts, sidx, table = [], [], [], [], []
         charge_l, mass_l, qm_l = [], [], []
         ref = None
@@ -222,7 +226,11 @@ class Simulation:
                     sp_seed = sp["seed_position"]
                 n = sp["number_pseudoparticles"]
                 x = np.empty((n, 3)); v = np.empty((n, 3))
-                for a, ax in enumerate(AXES):
+                sampling.append(dict(count=n, seed_position=sp_seed, seed_velocity=sv_seed,
+                                     **{k: [sp[f"{k}_{ax}"] for ax in AXES] for k in
+                                        ("random_positions", "velocity_plus_minus", "perturbation_amplitude", "perturbation_wavenumber",
+                                         "vth_over_c", "drift_speed")}))
+                for a, ax in enumerate(AXES if not threefry else ()):
                     if sp[f"random_positions_{ax}"]:
                         xa = np.random.default_rng(sp_seed + a + 1).uniform(-box[a] / 2, box[a] / 2, n)
                     else:
@@ -238,6 +246,7 @@ class Simulation:
                         given = np.asarray(sp[key], dtype=float)
                         assert given.shape == (n, 3), f"{key} for {kind}{i} must have shape {(n, 3)}. Got {given.shape}."
                         arr[...] = given
+                        given_any.append((len(pos), key))
                 mass = mass_electron if kind == "electrons" else sp["mass_over_proton_mass"] * mass_proton
                 charge = sp["charge_over_elementary_charge"] * elementary_charge
                 if kind == "electrons" and i == 0:
@@ -251,6 +260,19 @@ class Simulation:
                 pos.append(x); vel.append(v); wts.append(np.full((n, 1), w)); sidx.append(np.full(n, len(table), dtype=np.int32))
                 table.append(dict(count=n, q=charge * w, m=mass * w, qm=charge / mass))
                 charge_l.append(charge); mass_l.append(mass); qm_l.append(charge / mass)
+        if threefry:
+            # one device call for all species; explicit initial_positions / initial_velocities then replace their blocks
+            from ._engine import sample_particles
+            dx0, dv0 = sample_particles(sampling, box, threefry_partitionable=bool(solver.get("threefry_partitionable", True)))
+            hx, hv = dx0.cpu().numpy(), dv0.cpu().numpy()
+            o = 0
+            for k, (x, v) in enumerate(zip(pos, vel)):
+                n = len(x)
+                if (k, "initial_positions") not in given_any:
+                    x[...] = hx[o:o + n]
+                if (k, "initial_velocities") not in given_any:
+                    v[...] = hv[o:o + n]
+                o += n
         positions, velocities = np.concatenate(pos), np.concatenate(vel)
         weights, species_integer_index = np.concatenate(wts), np.concatenate(sidx)
         lim = 0.99 * speed_of_light

@@ -48,7 +48,7 @@ def test_species_cross_references_and_validation():
 
 
 def test_particle_state_shapes_weights_and_seed_schedule():
-    sim = Simulation(SMALL)
+    sim = Simulation({**SMALL, "solver_parameters": {"print_info": False, "rng": "numpy"}})  # host streams: runs without a GPU
     st = sim.build_domain_state(sim.domain_parameters)
     np.testing.assert_allclose(st["dt"], 0.9 * st["dx"] / S.speed_of_light)
     np.testing.assert_allclose(st["grid"][0], -0.005 + st["dx"] / 2)
