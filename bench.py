@@ -273,6 +273,7 @@ def main():
     hp = HotPath(species=w["species"], dtype=dtype, length=w["length"], G=w["G"], dt=w["dt"], engine=engine, deposit=args.deposit)
     if world > 1:
         hp.comm_init_from_torch()
+    reduction = hp.comm_mode()
     x0, v0 = make_particles(w, torch, device, dtype, 1701 + rank, args.order)
     hp.set_external_fields(None, None)
     hp.initialize(x0, v0)
@@ -363,6 +364,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"synthetic two-beam plasma (SURVEY 8d config 5): G={G}, {N} macro-particles per GPU, CFL 1, periodic, "
                                    f"filter 5/0.5/(1,2,4), x order {args.order}", "engine": engine, "particles_per_gpu": N, "grid": G,
+                       "grid_reduction": {"single": "none (one rank)", "nccl": "NCCL all-reduce of the raw grid before the field kernel",
+                                          "fused": "fused into the field kernel: peers' raw grids read over NVLink (CUDA IPC), summed in rank order"}[reduction],
                        "l2": "particle state (>= 3.2 GB per GPU) is far larger than L2; no flush needed",
                        "untimed_steps_before_timing": W + K},
             "gpu_launches": launches,

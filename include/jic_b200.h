@@ -113,10 +113,15 @@ int jic_create(const jic_params* params, const jic_species* species, jic_context
 int jic_destroy(jic_context* ctx);
 
 /* Multi-GPU: particles are sharded across ranks, fields replicated; one all-reduce of the raw [Jx,Jy,Jz,rho] grid per
- * step.  Rank 0 creates an id (128 bytes), the host exchanges it (torch.distributed / MPI / files), every rank calls
+ * step (NCCL, or fused into the field kernel over peer memory -- see jic_comm_mode).  Rank 0 creates an id (128 bytes), the host exchanges it (torch.distributed / MPI / files), every rank calls
  * jic_comm_init before jic_initialize.  No reference counterpart (the reference is single-device). */
 int jic_comm_unique_id(void* id_128_bytes);
 int jic_comm_init(jic_context* ctx, const void* id_128_bytes, int rank, int world_size);
+/* How the per-step reduction of the raw grid runs: 0 = single rank, 1 = NCCL all-reduce in front of the field kernel,
+ * 2 = fused into the field kernel (every rank reads the other ranks' raw grids over NVLink through CUDA-IPC mappings and sums
+ * them in rank order while it loads its window; chosen by jic_comm_init when all ranks are processes of one host and every
+ * mapping succeeds; JIC_P2P=0 in the environment forces 1). */
+int jic_comm_mode(const jic_context* ctx);
 
 /* External fields, float32 (G,3) as the reference stores them (_state_initialization.py:382-392); NULL = zeros. */
 int jic_set_external_fields(jic_context* ctx, const float* external_E, const float* external_B, void* stream);

@@ -16,6 +16,8 @@ constexpr double kEps0 = 8.85418782e-12;   // jaxincell/_constants.py:1
 constexpr double kMu0 = 1.25663706e-6;     // :2
 constexpr double kC = 2.99792458e8;        // :3
 
+constexpr int JIC_MAX_PEERS = 8;  // GPUs of one NVSwitch box
+
 // Row stride (in reals) of the padded total-field table the gather reads: Ex,Ey,Ez,Bx,By,Bz,pad,pad.
 constexpr int kFieldRow = 8;
 // Row stride of the raw deposition grid: Jx,Jy,Jz,rho.

@@ -3,6 +3,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <unistd.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +28,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   std::string error;
@@ -46,9 +49,10 @@ static NcclApi& nccl_api() {
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.error = "libnccl is missing symbols";
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.CommDestroy) api.error = "libnccl is missing symbols";
   });
   return api;
 }
@@ -79,6 +83,16 @@ struct EngineT : Engine {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // fused reduction over peer memory: acc, acc2, the peer flags and the step counter live in ONE allocation (`shared_block`)
+  // that every other rank maps through CUDA IPC
+  unsigned char* shared_block = nullptr;
+  size_t acc_bytes = 0;                    // bytes of one raw grid (G x 5 reals, rounded up to 256)
+  unsigned* peer_flags_local = nullptr;
+  unsigned long long* fused_seq = nullptr;
+  int* dev_error = nullptr;
+  void* peer_block[JIC_MAX_PEERS] = {};    // mapped shared_block of every rank (own entry = shared_block)
+  bool p2p = false;
+  int* barrier_word = nullptr;
   // captured time loops, keyed by the number of steps (the kernels read the output pointers from RunControl at run time)
   std::map<int, cudaGraphExec_t> graphs;
   bool shared_grid = false;
@@ -141,12 +155,21 @@ struct EngineT : Engine {
     } else {
       if ((rc = bins.create(*this, dp, prm, n_sm))) return rc;
     }
-    if ((rc = alloc(&acc, G * (kAccRow + 1))) || (rc = alloc(&F, (G + 3) * kFieldRow))) return rc;
+    {
+      acc_bytes = (G * (kAccRow + 1) * sizeof(R) + 255) & ~(size_t)255;
+      if ((rc = alloc(&shared_block, 2 * acc_bytes + 512))) return rc;
+      acc = (R*)shared_block; acc2 = (R*)(shared_block + acc_bytes);
+      peer_flags_local = (unsigned*)(shared_block + 2 * acc_bytes);
+      fused_seq = (unsigned long long*)(shared_block + 2 * acc_bytes + 256);
+      dev_error = (int*)(shared_block + 2 * acc_bytes + 256 + 8);
+      barrier_word = (int*)(shared_block + 2 * acc_bytes + 256 + 16);
+    }
+    if ((rc = alloc(&F, (G + 3) * kFieldRow))) return rc;
     if ((rc = alloc(&E, G * 3)) || (rc = alloc(&B, G * 3)) || (rc = alloc(&E_int, G * 3)) || (rc = alloc(&B_int, G * 3))) return rc;
     if ((rc = alloc(&J, G * 3)) || (rc = alloc(&rho, G)) || (rc = alloc(&extE, G * 3)) || (rc = alloc(&extB, G * 3))) return rc;
     if ((rc = alloc(&s0, G * kAccRow)) || (rc = alloc(&s1, G * kAccRow)) || (rc = alloc(&E0, G * 3)) || (rc = alloc(&B0, G * 3))) return rc;
     if ((rc = alloc(&ctl, 1))) return rc;
-    if ((rc = alloc(&acc2, G * (kAccRow + 1))) || (rc = alloc(&E2, G * 3)) || (rc = alloc(&B2, G * 3)) || (rc = alloc(&mc_done, 1))) return rc;
+    if ((rc = alloc(&E2, G * 3)) || (rc = alloc(&B2, G * 3)) || (rc = alloc(&mc_done, 1))) return rc;
     if (dp.stag) {
       // per-step electrostatic correction (_algorithms.py:69-78): circulant kernel of the spectral solvers, built once
       if ((rc = alloc(&gauss_h, G)) || (rc = alloc(&ExC, G))) return rc;
@@ -211,11 +234,82 @@ struct EngineT : Engine {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
-    if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
-    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, acc, acc2, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
+    if (p2p) {
+      // peers may still be reading this rank's raw grid in their last field kernel: meet them before unmapping / freeing
+      nccl_barrier(nullptr);
+      cudaDeviceSynchronize();
+      for (int r = 0; r < world; ++r) if (r != rank && peer_block[r]) cudaIpcCloseMemHandle(peer_block[r]);
+    }
+    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
+    if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
   }
+
+  int nccl_barrier(cudaStream_t st) {
+    if (world <= 1 || !comm) return JIC_OK;
+    ncclResult_t r = nccl_api().AllReduce(barrier_word, barrier_word, 1, ncclInt, ncclSum, comm, st);
+    return r == ncclSuccess ? JIC_OK : JIC_ERR_NCCL;
+  }
+
+  // Fused reduction set-up: every rank exports its shared block through CUDA IPC, the handles travel by NCCL all-gather, every
+  // rank maps the others.  All ranks must agree (same host, distinct processes, every mapping succeeded); otherwise the NCCL
+  // all-reduce stays.  JIC_P2P=0 forces the NCCL path.
+  struct PeerInfo { cudaIpcMemHandle_t handle; unsigned long long host; long long pid; int ok; int pad; };
+
+  int setup_p2p() {
+    NcclApi& api = nccl_api();
+    p2p = false;
+    if (world > JIC_MAX_PEERS) return JIC_OK;
+    PeerInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    const char* env = getenv("JIC_P2P");
+    mine.ok = !(env && env[0] == '0') && cudaIpcGetMemHandle(&mine.handle, shared_block) == cudaSuccess;
+    cudaGetLastError();
+    char host[256] = {0};
+    gethostname(host, sizeof(host) - 1);
+    unsigned long long h = 1469598103934665603ull;
+    for (const char* c = host; *c; ++c) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+    mine.host = h; mine.pid = (long long)getpid();
+    PeerInfo* d_all = nullptr;
+    JIC_CUDA(cudaMalloc((void**)&d_all, sizeof(PeerInfo) * world));
+    JIC_CUDA(cudaMemcpy(d_all + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    ncclResult_t r = api.AllGather(d_all + rank, d_all, sizeof(PeerInfo), ncclChar, comm, nullptr);
+    std::vector<PeerInfo> all(world);
+    cudaError_t ce = cudaMemcpy(all.data(), d_all, sizeof(PeerInfo) * world, cudaMemcpyDeviceToHost);  // (synchronises the null stream)
+    cudaFree(d_all);
+    if (r != ncclSuccess || ce != cudaSuccess) return fail(JIC_ERR_NCCL, "all-gather of the IPC handles failed");
+    int ok = 1;
+    for (int q = 0; q < world; ++q) {
+      if (!all[q].ok || all[q].host != mine.host) ok = 0;
+      for (int q2 = 0; q2 < q; ++q2) if (all[q].pid == all[q2].pid) ok = 0;  // IPC handles cannot be opened by their own process
+    }
+    for (int q = 0; q < world; ++q) peer_block[q] = nullptr;
+    if (ok) {
+      for (int q = 0; q < world && ok; ++q) {
+        if (q == rank) { peer_block[q] = shared_block; continue; }
+        if (cudaIpcOpenMemHandle(&peer_block[q], all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { peer_block[q] = nullptr; ok = 0; cudaGetLastError(); }
+      }
+    }
+    // agreement: the fused path is used only if EVERY rank mapped every peer
+    int* d_ok = nullptr;
+    JIC_CUDA(cudaMalloc((void**)&d_ok, sizeof(int)));
+    JIC_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    r = api.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, nullptr);
+    int agreed = 0;
+    ce = cudaMemcpy(&agreed, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_ok);
+    if (r != ncclSuccess || ce != cudaSuccess) agreed = 0;
+    if (!agreed) {
+      for (int q = 0; q < world; ++q) if (q != rank && peer_block[q]) { cudaIpcCloseMemHandle(peer_block[q]); peer_block[q] = nullptr; }
+      return JIC_OK;
+    }
+    p2p = true;
+    return JIC_OK;
+  }
+
+  bool fused() const { return p2p && mc && !dp.stag; }
+  int comm_mode() const override { return world <= 1 ? 0 : (fused() ? 2 : 1); }
 
   int comm_init(const void* id, int rank_, int world_) override {
     if (world_ <= 1) { rank = 0; world = 1; return JIC_OK; }
@@ -227,7 +321,7 @@ struct EngineT : Engine {
     ncclResult_t r = api.CommInitRank(&comm, world_, uid, rank_);
     if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
     rank = rank_; world = world_;
-    return JIC_OK;
+    return setup_p2p();
   }
 
   int set_external(const float* eE, const float* eB, cudaStream_t st) override {
@@ -256,13 +350,14 @@ struct EngineT : Engine {
   double* E_of(int p) const { return (mc && p) ? E2 : E; }
   double* B_of(int p) const { return (mc && p) ? B2 : B; }
 
-  int allreduce(cudaStream_t st, int p) {
+  int allreduce(cudaStream_t st, int p, bool force = false) {
     if (world <= 1) return JIC_OK;
+    if (fused() && !force) return JIC_OK;  // the field kernel sums the peers' grids itself
     NcclApi& api = nccl_api();
     R* buf = acc_of(p);
     ncclResult_t r = api.AllReduce(buf, buf, (size_t)dp.G * (kAccRow + dp.stag), sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, st);
     if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
-    launches += 1;
+    if (!force || !fused()) launches += 1;
     return JIC_OK;
   }
 
@@ -282,6 +377,8 @@ struct EngineT : Engine {
 
   int initialize(const void* x0, const void* v0, cudaStream_t st) override {
     if (!x0 || !v0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
+    // fused mode: peers may still be reading this rank's raw grid in the last field kernel of a previous run
+    if (p2p && nccl_barrier(st)) return fail(JIC_ERR_NCCL, "barrier before initialize failed");
     JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));
     JIC_CUDA(cudaMemsetAsync(acc2, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));
     JIC_CUDA(cudaMemsetAsync(mc_done, 0, sizeof(unsigned), st));
@@ -295,7 +392,7 @@ struct EngineT : Engine {
       if (rc) return rc;
     }
     JIC_CUDA(cudaGetLastError());
-    int rc = allreduce(st, 0);
+    int rc = allreduce(st, 0, true);  // start-up always goes through NCCL
     if (rc) return rc;
     k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));  // init mode is always the single-CTA kernel
     launches += 1;
@@ -337,6 +434,15 @@ struct EngineT : Engine {
     a.E_int = E_int; a.B_int = B_int; a.J = J; a.rho = rho; a.extE = extE; a.extB = extB; a.F = F;
     a.record = 1; a.ctl = ctl; a.done = mc_done;
     a.ExC = dp.stag ? ExC : nullptr;
+    a.world = 1; a.rank = rank; a.seq = fused_seq; a.error = dev_error;
+    if (fused()) {
+      a.world = world;
+      const size_t flags_off = 2 * acc_bytes, acc_off = p ? acc_bytes : 0;
+      for (int q = 0; q < world; ++q) {
+        a.peer_acc[q] = (const R*)((unsigned char*)peer_block[q] + acc_off);
+        a.peer_flags[q] = (unsigned*)((unsigned char*)peer_block[q] + flags_off);
+      }
+    }
     return a;
   }
 
@@ -462,6 +568,12 @@ struct EngineT : Engine {
     if (prm.engine == JIC_ENGINE_BINNED && (out.positions || out.velocities))
       return fail(JIC_ERR_UNSUPPORTED, "particle histories need the INDEXED engine");
     if (out.positions && !prm.track_yz) return fail(JIC_ERR_INVALID_ARGUMENT, "positions history needs track_yz=1");
+    if (fused() && steps_run > 0) {
+      int derr = 0;
+      JIC_CUDA(cudaMemcpyAsync(&derr, dev_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+      JIC_CUDA(cudaStreamSynchronize(st));
+      if (derr == 3) return fail(JIC_ERR_BAD_STATE, "fused reduction: a peer rank did not reach the step within the spin limit");
+    }
     if (prm.engine == JIC_ENGINE_BINNED && steps_run > 0) {
       // the store reports exhausted head-room through a sticky device flag: look at it before queueing more work
       int rc = bins.check_error(*this, st);
@@ -487,7 +599,7 @@ struct EngineT : Engine {
   }
 
   long long count_launches_per_step() const {
-    long long k = 2 + (world > 1 ? 1 : 0) + dp.stag;
+    long long k = 2 + ((world > 1 && !fused()) ? 1 : 0) + dp.stag;
     if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
     return k;
   }
@@ -606,6 +718,7 @@ int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* 
 int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
 int jic_profile_steps(jic_context* ctx, int64_t n, double* ms_push, double* ms_fields, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->profile(n, ms_push, ms_fields, (cudaStream_t)st); }
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
+int jic_comm_mode(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->comm_mode() : 0; }
 
 int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* sp, const double box[3], int32_t partitionable,
                          void* x0, void* v0, void* stream) {

@@ -44,6 +44,7 @@ struct Engine {
   virtual int dtype() const = 0;
   virtual long long n_particles() const = 0;
   virtual int n_grid() const = 0;
+  virtual int comm_mode() const = 0;
 };
 
 

@@ -398,7 +398,36 @@ struct FieldArgsMC {
   int record;
   RunControl* ctl;
   unsigned* done;  // CTAs finished (the last one advances ctl->step / hist_row and resets it)
+  // N GPUs, fused reduction: instead of an NCCL all-reduce in front of this kernel, every rank reads the raw
+  // grids of all ranks straight from their memory over NVLink (peer mappings of the same buffer) while it loads its window, and
+  // sums them in rank order -- the same order on every rank, so E and B stay bit-identical everywhere.
+  int world, rank;                         // world <= 1: not fused
+  const R* peer_acc[JIC_MAX_PEERS];        // acc_cur of every rank (own entry = local pointer)
+  unsigned* peer_flags[JIC_MAX_PEERS];     // flag array of every rank; entry [r] is written by rank r
+  unsigned long long* seq;                 // fused steps completed so far (local; identical on all ranks)
+  int* error;                              // sticky: 3 = a peer did not arrive within the spin limit
 };
+
+constexpr long long kPeerSpinLimit = 4000000000ll;  // clock64 ticks (~2 s): a missing peer must not hang the GPU
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_peer(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 
 constexpr int kFieldsMcThreads = 512;
 
@@ -419,13 +448,43 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
   const bool edgeL = !periodic && idx0 >= 0, edgeR = !periodic && idxL <= W - 1;  // the window reaches the domain edge
   const long long row = a.ctl->hist_row;
 
+  // ---- N GPUs, fused: tell every rank that this rank's push is complete (it precedes this kernel in stream order), then
+  //      wait for the same word from every rank.  One flag per (writer, reader) pair holding the step number, so nothing is
+  //      ever reset.  Passing this point also proves that every rank has finished its PREVIOUS field kernel, i.e. nobody
+  //      still reads the buffer this kernel is about to zero (acc_next).
+  const bool fused = a.world > 1;
+  if (fused) {
+    const unsigned want = (unsigned)(*a.seq) + 1u;
+    if (blockIdx.x == 0 && tid < a.world) st_release_sys(a.peer_flags[tid] + a.rank, want);
+    if (tid < a.world) {
+      const unsigned* f = a.peer_flags[a.rank] + tid;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(f) - want) < 0) {
+        if (clock64() - t0 > kPeerSpinLimit) { atomicExch(a.error, 3); break; }
+      }
+    }
+    __syncthreads();
+  }
   // ---- raw grid window -> shared memory (periodic: wrapped; outside a non-periodic domain: unused)
   for (int li = tid; li < W; li += nt) {
     int g = lo - H + li;
     if (periodic) g = g < 0 ? g + G : (g >= G ? g - G : g);
     const bool in = g >= 0 && g < G;
+    if (!fused) {
 #pragma unroll
-    for (int c = 0; c < kAccRow; ++c) cur[c * W + li] = in ? (double)a.acc_cur[g * kAccRow + c] : 0.0;
+      for (int c = 0; c < kAccRow; ++c) cur[c * W + li] = in ? (double)a.acc_cur[g * kAccRow + c] : 0.0;
+    } else {
+      double sum[kAccRow] = {0.0, 0.0, 0.0, 0.0};
+      if (in) {
+        for (int r = 0; r < a.world; ++r) {  // rank order: identical rounding on every rank
+          const R* src = a.peer_acc[r] + g * kAccRow;
+#pragma unroll
+          for (int c = 0; c < kAccRow; ++c) sum[c] += (double)(r == a.rank ? src[c] : ld_peer(src + c));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kAccRow; ++c) cur[c * W + li] = sum[c];
+    }
   }
   // the other raw buffer was consumed by the previous step: zero our slice of it for the next push
   for (int k = tid; k < (hi - lo) * kAccRow; k += nt) a.acc_next[lo * kAccRow + k] = R(0);
@@ -574,6 +633,7 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
     if (k == gridDim.x - 1) {
       a.ctl->hist_row = row + 1;
       a.ctl->step += 1;
+      if (fused) *a.seq += 1ull;
       *a.done = 0u;
     }
   }

@@ -164,6 +164,10 @@ class HotPath:
         self._chk(self.lib.jic_profile_steps(self.ctx, int(n_steps), C.byref(a), C.byref(b), self._stream()))
         return a.value, b.value
 
+    def comm_mode(self):
+        """"single" | "nccl" (all-reduce in front of the field kernel) | "fused" (peer-memory reduction inside the field kernel)."""
+        return ("single", "nccl", "fused")[int(self.lib.jic_comm_mode(self.ctx))]
+
     def launch_count(self):
         return int(self.lib.jic_launch_count(self.ctx))
 

@@ -58,6 +58,7 @@ SYMBOLS = [
     ("jic_destroy", C.c_int, [_P]),
     ("jic_comm_unique_id", C.c_int, [_P]),
     ("jic_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
+    ("jic_comm_mode", C.c_int, [_P]),
     ("jic_set_external_fields", C.c_int, [_P, _P, _P, _P]),
     ("jic_initialize", C.c_int, [_P, _P, _P, _P]),
     ("jic_run", C.c_int, [_P, C.c_int64, C.POINTER(Outputs), _P]),
