@@ -89,7 +89,14 @@ typedef struct jic_params {
   int32_t field_solver;   /* per-step electrostatic correction of jaxincell/_algorithms.py:69-78 (the `field_solver` argument of
                            * Boris_step): 0 = none, 1 = E_from_Gauss_1D_FFT, 2 = E_from_Gauss_1D_Cartesian, 3 = E_from_Poisson_1D_FFT
                            * (_fields.py:9-81).  E_x is replaced every step by the solve of rho(x_n) deposited on the faces. */
-  int32_t reserved[7];    /* must be zero */
+  int32_t time_evolution_algorithm; /* solver_parameters["time_evolution_algorithm"]: 0 = explicit Boris_step (the hot path),
+                           * 1 = implicit Crank-Nicolson CN_step (jaxincell/_algorithms.py:100-241): Picard iterations over Faraday,
+                           * a sub-stepped push and Ampere with J - <J>.  Periodic S2 gather / deposit, no filter, no external
+                           * fields, non-relativistic, like the reference.  Particle arrays are kept in input order. */
+  int32_t cn_substeps;    /* number_of_particle_substeps_implicit_CN (>= 1) */
+  int32_t cn_max_iterations; /* max_number_of_Picard_iterations_implicit_CN (>= 1) */
+  double cn_tolerance;    /* tolerance_Picard_iterations_implicit_CN */
+  int32_t reserved[2];    /* must be zero */
 } jic_params;
 
 /* Where jic_run writes the per-step outputs (jaxincell/_algorithms.py:93, stacked at _simulation.py:256-257).
@@ -147,6 +154,8 @@ int jic_kinetic_energy(jic_context* ctx, double* kinetic_energy, void* stream);
  * (all-reduce + field kernel) of every step with CUDA events on `stream`; returns the summed milliseconds of each.
  * Synchronises the stream. */
 int jic_profile_steps(jic_context* ctx, int64_t n_steps, double* ms_particle_kernels, double* ms_grid_kernels, void* stream);
+/* Crank-Nicolson only: Picard iterations of the last completed step and of all steps so far.  Synchronises the stream. */
+int jic_get_picard_iterations(jic_context* ctx, int64_t* last_step, int64_t* total, void* stream);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 

@@ -17,6 +17,7 @@
 #include "jic_kernels.cuh"
 #include "jic_binned.cuh"
 #include "jic_sample.cuh"
+#include "jic_cn.cuh"
 
 namespace jic {
 
@@ -102,6 +103,13 @@ struct EngineT : Engine {
   int field_smem_comps = 0;
   size_t field_smem_bytes = 0;
   BinnedStore<R> bins;  // BINNED engine state (unused for INDEXED)
+  // implicit Crank-Nicolson stepper (time_evolution_algorithm = 1)
+  bool cn = false;
+  CnState<R> cn_s[2] = {};          // double-buffered particle state, swapped every step (`par`)
+  R* cn_stag = nullptr;             // staggered positions of the previous Picard iteration, (substeps, N)
+  double *cn_Eg = nullptr, *cn_Bnext = nullptr, *cn_Eavg = nullptr, *cn_Bavg = nullptr;
+  CnControl* cn_ctl = nullptr;
+  uint8_t* cn_alive = nullptr;      // 0 = absorbed by the start-up half step (charge 0 for the whole run)
 
   int dtype() const override { return prm.dtype; }
   long long n_particles() const override { return dp.N; }
@@ -136,7 +144,7 @@ struct EngineT : Engine {
     dp.pbl = prm.particle_bc_left; dp.pbr = prm.particle_bc_right; dp.fbl = prm.field_bc_left; dp.fbr = prm.field_bc_right;
     dp.relativistic = prm.relativistic;
     dp.track_yz = prm.track_yz;
-    dp.stag = prm.field_solver != 0 ? 1 : 0;
+    dp.stag = (prm.field_solver != 0 && prm.time_evolution_algorithm != 1) ? 1 : 0;  // (CN_step has no field_solver branch)
     const double Ly = prm.length_y > 0 ? prm.length_y : prm.length, Lz = prm.length_z > 0 ? prm.length_z : prm.length;
     dp.L = (R)prm.length; dp.Ly = (R)Ly; dp.Lz = (R)Lz;
     dp.half_L = (R)(prm.length / 2); dp.half_Ly = (R)(Ly / 2); dp.half_Lz = (R)(Lz / 2);
@@ -148,7 +156,15 @@ struct EngineT : Engine {
     dp.park_right = (R)(prm.grid_last + 3 * prm.dx);
     const size_t N = (size_t)n, G = (size_t)prm.n_grid;
     int rc;
-    if (prm.engine == JIC_ENGINE_INDEXED) {
+    cn = prm.time_evolution_algorithm == 1;
+    if (cn) {
+      for (int k = 0; k < 2; ++k)
+        if ((rc = alloc(&cn_s[k].x, N)) || (rc = alloc(&cn_s[k].y, N)) || (rc = alloc(&cn_s[k].z, N)) || (rc = alloc(&cn_s[k].vx, N)) ||
+            (rc = alloc(&cn_s[k].vy, N)) || (rc = alloc(&cn_s[k].vz, N)))
+          return rc;
+      if ((rc = alloc(&cn_stag, N * (size_t)prm.cn_substeps)) || (rc = alloc(&v_init, 3 * N)) || (rc = alloc(&cn_ctl, 1)) || (rc = alloc(&cn_alive, N))) return rc;
+      if ((rc = alloc(&cn_Eg, G * 3)) || (rc = alloc(&cn_Bnext, G * 3)) || (rc = alloc(&cn_Eavg, G * 3)) || (rc = alloc(&cn_Bavg, G * 3))) return rc;
+    } else if (prm.engine == JIC_ENGINE_INDEXED) {
       if ((rc = alloc(&xh, N)) || (rc = alloc(&vx, N)) || (rc = alloc(&vy, N)) || (rc = alloc(&vz, N))) return rc;
       if (prm.track_yz && ((rc = alloc(&yh, N)) || (rc = alloc(&zh, N)))) return rc;
       if ((rc = alloc(&v_init, 3 * N))) return rc;
@@ -189,6 +205,7 @@ struct EngineT : Engine {
       }
       const char* env = getenv("JIC_FIELDS_MC");  // "0" forces the single-CTA kernel
       mc = false;
+      if (cn) env = "0";  // the CN stepper has its own single-CTA field kernel
       // (one periodic and one non-periodic field boundary couples the two ends of the domain through the curl ghosts,
       //  _boundary_conditions.py:148-207: that case stays on the single-CTA kernel)
       const bool mixed = (prm.field_bc_left == JIC_BC_PERIODIC) != (prm.field_bc_right == JIC_BC_PERIODIC);
@@ -240,7 +257,8 @@ struct EngineT : Engine {
       cudaDeviceSynchronize();
       for (int r = 0; r < world; ++r) if (r != rank && peer_block[r]) cudaIpcCloseMemHandle(peer_block[r]);
     }
-    void* ptrs[] = {xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
+    for (int k = 0; k < 2; ++k) { void* q[] = {cn_s[k].x, cn_s[k].y, cn_s[k].z, cn_s[k].vx, cn_s[k].vy, cn_s[k].vz}; for (void* p : q) if (p) cudaFree(p); }
+    void* ptrs[] = {cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
     if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
@@ -308,7 +326,7 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
-  bool fused() const { return p2p && mc && !dp.stag; }
+  bool fused() const { return p2p && mc && !dp.stag && !cn; }
   int comm_mode() const override { return world <= 1 ? 0 : (fused() ? 2 : 1); }
 
   int comm_init(const void* id, int rank_, int world_) override {
@@ -384,6 +402,7 @@ struct EngineT : Engine {
     JIC_CUDA(cudaMemsetAsync(mc_done, 0, sizeof(unsigned), st));
     JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
     par = 0;
+    if (cn) return initialize_cn((const R*)x0, (const R*)v0, st);
     if (prm.engine == JIC_ENGINE_INDEXED) {
       k_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x0, (const R*)v0, xh, yh, zh, vx, vy, vz, v_init, acc);
       launches += 1;
@@ -399,6 +418,61 @@ struct EngineT : Engine {
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.plan(*this, dp, st))) return rc;
     JIC_CUDA(cudaGetLastError());
     initialized = true;
+    return JIC_OK;
+  }
+
+  // ---- Crank-Nicolson (csrc/jic_cn.cuh) ---------------------------------------------------------------------------
+  CnFieldArgs<R> cn_field_args(int it, bool prepare_only) const {
+    CnFieldArgs<R> a;
+    memset(&a, 0, sizeof(a));
+    a.G = dp.G; a.fbl = dp.fbl; a.fbr = dp.fbr; a.it = it; a.max_iter = prm.cn_max_iterations; a.prepare_only = prepare_only ? 1 : 0;
+    a.dx = prm.dx; a.dt = prm.dt; a.tol = prm.cn_tolerance;
+    a.acc = acc; a.En = E; a.Bn = B; a.Eg = cn_Eg; a.Bnext = cn_Bnext; a.Eavg = cn_Eavg; a.Bavg = cn_Bavg; a.J = J; a.rho = rho;
+    a.cn = cn_ctl; a.ctl = ctl;
+    return a;
+  }
+
+  int initialize_cn(const R* x0, const R* v0, cudaStream_t st) {
+    JIC_CUDA(cudaMemsetAsync(cn_ctl, 0, sizeof(CnControl), st));
+    k_cn_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, x0, v0, cn_s[0], v_init, cn_alive, acc);
+    launches += 1;
+    JIC_CUDA(cudaGetLastError());
+    int rc = allreduce(st, 0, true);
+    if (rc) return rc;
+    // rho0 -> filtered -> E_x by the Gauss prefix sum (_state_initialization.py:371-378); the kernel then goes on to a leap-frog
+    // half step that the CN carry does not want: take E^0, B^0 back from the copies it made first
+    k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));
+    JIC_CUDA(cudaMemcpyAsync(E, E0, (size_t)dp.G * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    JIC_CUDA(cudaMemcpyAsync(B, B0, (size_t)dp.G * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(0, true));
+    launches += 2;
+    JIC_CUDA(cudaGetLastError());
+    initialized = true;
+    return JIC_OK;
+  }
+
+  // one CN step reading particle buffer `p`: max_iter x (push, all-reduce, fields); iterations after convergence return at once
+  int enqueue_step_cn(cudaStream_t st, int p) {
+    const int g = grid_for(dp.N, 256, 8);
+    for (int it = 0; it < prm.cn_max_iterations; ++it) {
+      k_cn_push<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_stag, prm.cn_substeps, it, cn_Eavg, cn_Bavg, acc, cn_alive, cn_ctl);
+      int rc = allreduce(st, 0, true);
+      if (rc) return rc;
+      k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(it, false));
+      launches += 2;
+    }
+    k_cn_record<R><<<g, 256, 0, st>>>(dp, cn_s[p ^ 1], ctl);
+    launches += 1;
+    return JIC_OK;
+  }
+
+  int picard_iterations(long long* last, long long* total, cudaStream_t st) override {
+    if (!cn) return fail(JIC_ERR_BAD_STATE, "not a Crank-Nicolson context");
+    CnControl h;
+    JIC_CUDA(cudaMemcpyAsync(&h, cn_ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    JIC_CUDA(cudaStreamSynchronize(st));
+    if (last) *last = h.last_iters;
+    if (total) *total = h.total_iters;
     return JIC_OK;
   }
 
@@ -481,6 +555,7 @@ struct EngineT : Engine {
 
   // one step reading the ping-pong buffers `p` (always 0 without the multi-CTA field kernel)
   int enqueue_step(cudaStream_t st, int p) {
+    if (cn) return enqueue_step_cn(st, p);
     int rc = enqueue_push(st, p);
     return rc ? rc : enqueue_fields(st, p);
   }
@@ -504,11 +579,11 @@ struct EngineT : Engine {
     int rc = JIC_OK;
     for (long long s = 0; s < n && rc == JIC_OK; ++s) {
       cudaEventRecord(ev[3 * s], st);
-      rc = enqueue_push(st, par);
+      rc = cn ? enqueue_step_cn(st, par) : enqueue_push(st, par);
       cudaEventRecord(ev[3 * s + 1], st);
-      if (rc == JIC_OK) rc = enqueue_fields(st, par);
+      if (rc == JIC_OK && !cn) rc = enqueue_fields(st, par);
       cudaEventRecord(ev[3 * s + 2], st);
-      if (mc) par ^= 1;
+      if (mc || cn) par ^= 1;
     }
     cudaError_t ce = cudaStreamSynchronize(st);
     double a = 0, b = 0;
@@ -537,7 +612,7 @@ struct EngineT : Engine {
     cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     int rc = JIC_OK;
     if (e == cudaSuccess) {
-      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, mc ? (par ^ (s & 1)) : 0);
+      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, (mc || cn) ? (par ^ (s & 1)) : 0);
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
@@ -565,16 +640,16 @@ struct EngineT : Engine {
     jic_outputs out;
     memset(&out, 0, sizeof(out));
     if (outp) out = *outp;
-    if (prm.engine == JIC_ENGINE_BINNED && (out.positions || out.velocities))
+    if (!cn && prm.engine == JIC_ENGINE_BINNED && (out.positions || out.velocities))
       return fail(JIC_ERR_UNSUPPORTED, "particle histories need the INDEXED engine");
-    if (out.positions && !prm.track_yz) return fail(JIC_ERR_INVALID_ARGUMENT, "positions history needs track_yz=1");
+    if (!cn && out.positions && !prm.track_yz) return fail(JIC_ERR_INVALID_ARGUMENT, "positions history needs track_yz=1");
     if (fused() && steps_run > 0) {
       int derr = 0;
       JIC_CUDA(cudaMemcpyAsync(&derr, dev_error, sizeof(int), cudaMemcpyDeviceToHost, st));
       JIC_CUDA(cudaStreamSynchronize(st));
       if (derr == 3) return fail(JIC_ERR_BAD_STATE, "fused reduction: a peer rank did not reach the step within the spin limit");
     }
-    if (prm.engine == JIC_ENGINE_BINNED && steps_run > 0) {
+    if (!cn && prm.engine == JIC_ENGINE_BINNED && steps_run > 0) {
       // the store reports exhausted head-room through a sticky device flag: look at it before queueing more work
       int rc = bins.check_error(*this, st);
       if (rc) return rc;
@@ -593,12 +668,13 @@ struct EngineT : Engine {
       JIC_CUDA(cudaGraphLaunch(ex, st));
       launches += per_step * steps;
       done += steps;
-      if (mc) par ^= steps & 1;
+      if (mc || cn) par ^= steps & 1;
     }
     return JIC_OK;
   }
 
   long long count_launches_per_step() const {
+    if (cn) return 1 + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
     long long k = 2 + ((world > 1 && !fused()) ? 1 : 0) + dp.stag;
     if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
     return k;
@@ -606,8 +682,8 @@ struct EngineT : Engine {
 
   int get_fields(void* Eo, void* Bo, void* Jo, void* rhoo, cudaStream_t st) override {
     const long long n3 = (long long)dp.G * 3;
-    if (Eo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(E_int, (R*)Eo, n3);
-    if (Bo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(B_int, (R*)Bo, n3);
+    if (Eo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(cn ? E : E_int, (R*)Eo, n3);  // (CN keeps E, B at integer time)
+    if (Bo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(cn ? B : B_int, (R*)Bo, n3);
     if (Jo) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(J, (R*)Jo, n3);
     if (rhoo) k_convert<double, R><<<(dp.G + 255) / 256, 256, 0, st>>>(rho, (R*)rhoo, dp.G);
     JIC_CUDA(cudaGetLastError());
@@ -619,7 +695,7 @@ struct EngineT : Engine {
     if (E0o) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(E0, (R*)E0o, n3);
     if (B0o) k_convert<double, R><<<(int)((n3 + 255) / 256), 256, 0, st>>>(B0, (R*)B0o, n3);
     if (vinit) {
-      if (prm.engine != JIC_ENGINE_INDEXED) return fail(JIC_ERR_UNSUPPORTED, "initial_velocities need the INDEXED engine");
+      if (!cn && prm.engine != JIC_ENGINE_INDEXED) return fail(JIC_ERR_UNSUPPORTED, "initial_velocities need the INDEXED engine");
       JIC_CUDA(cudaMemcpyAsync(vinit, v_init, (size_t)dp.N * 3 * sizeof(R), cudaMemcpyDeviceToDevice, st));
     }
     JIC_CUDA(cudaGetLastError());
@@ -627,6 +703,14 @@ struct EngineT : Engine {
   }
 
   int get_particles(void* x, void* v, uint8_t* alive, cudaStream_t st) override {
+    if (cn) {  // x_n, v_n in input order
+      DevParams<R> d = dp;
+      d.track_yz = 1;
+      const CnState<R>& s = cn_s[par];
+      k_export_particles<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(d, s.x, s.y, s.z, s.vx, s.vy, s.vz, (R*)x, (R*)v, alive);
+      JIC_CUDA(cudaGetLastError());
+      return JIC_OK;
+    }
     if (prm.engine == JIC_ENGINE_BINNED) return bins.export_particles(*this, dp, (R*)x, (R*)v, alive, st);
     k_export_particles<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, xh, yh, zh, vx, vy, vz, (R*)x, (R*)v, alive);
     JIC_CUDA(cudaGetLastError());
@@ -635,6 +719,11 @@ struct EngineT : Engine {
 
   int kinetic(double* out, cudaStream_t st) override {
     JIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (cn) {
+      k_kinetic<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[par].vx, cn_s[par].vy, cn_s[par].vz, out);
+      JIC_CUDA(cudaGetLastError());
+      return JIC_OK;
+    }
     if (prm.engine == JIC_ENGINE_BINNED) return bins.kinetic(*this, dp, out, st);
     k_kinetic<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, vx, vy, vz, out);
     JIC_CUDA(cudaGetLastError());
@@ -655,7 +744,10 @@ static int validate(const jic_params* p, const jic_species* sp, std::string& why
   if (p->filter_passes < 0 || p->n_filter_strides < 0 || p->n_filter_strides > JIC_MAX_STRIDES) { why = "bad filter parameters"; return JIC_ERR_INVALID_ARGUMENT; }
   for (int i = 0; i < p->n_filter_strides; ++i) if (p->filter_strides[i] <= 0) { why = "filter strides must be positive"; return JIC_ERR_INVALID_ARGUMENT; }
   if (p->field_solver < 0 || p->field_solver > 3) { why = "field_solver must be 0 (none), 1 (Gauss FFT), 2 (Gauss Cartesian) or 3 (Poisson FFT)"; return JIC_ERR_INVALID_ARGUMENT; }
-  for (int i = 0; i < 7; ++i) if (p->reserved[i]) { why = "reserved fields must be zero"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->time_evolution_algorithm != 0 && p->time_evolution_algorithm != 1) { why = "time_evolution_algorithm must be 0 (Boris) or 1 (Crank-Nicolson)"; return JIC_ERR_INVALID_ARGUMENT; }
+  if (p->time_evolution_algorithm == 1 && (p->cn_substeps < 1 || p->cn_max_iterations < 1 || !(p->cn_tolerance >= 0))) {
+    why = "Crank-Nicolson needs cn_substeps >= 1, cn_max_iterations >= 1, cn_tolerance >= 0"; return JIC_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < 2; ++i) if (p->reserved[i]) { why = "reserved fields must be zero"; return JIC_ERR_INVALID_ARGUMENT; }
   return JIC_OK;
 }
 
@@ -718,6 +810,14 @@ int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* 
 int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
 int jic_profile_steps(jic_context* ctx, int64_t n, double* ms_push, double* ms_fields, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->profile(n, ms_push, ms_fields, (cudaStream_t)st); }
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
+int jic_get_picard_iterations(jic_context* ctx, int64_t* last, int64_t* total, void* st) {
+  CTX_OR_FAIL(ctx);
+  long long a = 0, b = 0;
+  int rc = ctx->eng->picard_iterations(&a, &b, (cudaStream_t)st);
+  if (last) *last = a;
+  if (total) *total = b;
+  return rc;
+}
 int jic_comm_mode(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->comm_mode() : 0; }
 
 int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* sp, const double box[3], int32_t partitionable,

@@ -45,6 +45,7 @@ struct Engine {
   virtual long long n_particles() const = 0;
   virtual int n_grid() const = 0;
   virtual int comm_mode() const = 0;
+  virtual int picard_iterations(long long* last, long long* total, cudaStream_t st) = 0;
 };
 
 

@@ -16,7 +16,8 @@ _HIST = ("electric_field", "magnetic_field", "current_density", "charge_density"
 
 def make_params(*, length, G, dt, n_species, length_y=0.0, length_z=0.0, pbl=0, pbr=0, fbl=0, fbr=0, filter_passes=5,
                 filter_alpha=0.5, filter_strides=(1, 2, 4), relativistic=False, dtype=torch.float64, engine="indexed",
-                track_yz=False, deposit="auto", steps_per_graph=0, device=-1, field_solver=0):
+                track_yz=False, deposit="auto", steps_per_graph=0, device=-1, field_solver=0,
+                time_evolution_algorithm=0, cn_substeps=2, cn_max_iterations=20, cn_tolerance=1e-6):
     """Fill a jic_params exactly as build_domain_state does (jaxincell/_state_initialization.py:27-49)."""
     p = Params()
     p.struct_bytes = C.sizeof(Params)
@@ -40,6 +41,9 @@ def make_params(*, length, G, dt, n_species, length_y=0.0, length_z=0.0, pbl=0, 
     p.relativistic, p.track_yz = int(bool(relativistic)), int(bool(track_yz))
     p.deposit, p.steps_per_graph = _DEPOSITS[deposit], int(steps_per_graph)
     p.field_solver = int(field_solver)  # Boris_step's `field_solver` argument (jaxincell/_algorithms.py:20,69-78)
+    # CN_step (jaxincell/_algorithms.py:100-241); defaults of _parameters/_solver_parameters.py:15-17
+    p.time_evolution_algorithm, p.cn_substeps, p.cn_max_iterations = int(time_evolution_algorithm), int(cn_substeps), int(cn_max_iterations)
+    p.cn_tolerance = float(cn_tolerance)
     return p, grid
 
 
@@ -162,6 +166,12 @@ class HotPath:
         """(ms in the particle kernels, ms in all-reduce + field kernel) summed over n_steps real steps (CUDA events)."""
         a, b = C.c_double(0.0), C.c_double(0.0)
         self._chk(self.lib.jic_profile_steps(self.ctx, int(n_steps), C.byref(a), C.byref(b), self._stream()))
+        return a.value, b.value
+
+    def picard_iterations(self):
+        """Crank-Nicolson: (Picard iterations of the last step, of all steps so far)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._chk(self.lib.jic_get_picard_iterations(self.ctx, C.byref(a), C.byref(b), self._stream()))
         return a.value, b.value
 
     def comm_mode(self):

@@ -33,7 +33,8 @@ class Params(C.Structure):
         ("filter_passes", C.c_int32), ("n_filter_strides", C.c_int32), ("filter_strides", C.c_int32 * JIC_MAX_STRIDES),
         ("filter_alpha", C.c_double),
         ("relativistic", C.c_int32), ("track_yz", C.c_int32), ("deposit", C.c_int32), ("steps_per_graph", C.c_int32),
-        ("field_solver", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("field_solver", C.c_int32), ("time_evolution_algorithm", C.c_int32), ("cn_substeps", C.c_int32), ("cn_max_iterations", C.c_int32),
+        ("cn_tolerance", C.c_double), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -67,6 +68,7 @@ SYMBOLS = [
     ("jic_get_particles", C.c_int, [_P, _P, _P, _P, _P]),
     ("jic_kinetic_energy", C.c_int, [_P, _P, _P]),
     ("jic_profile_steps", C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    ("jic_get_picard_iterations", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
     ("jic_launch_count", C.c_int64, [_P]),
     ("jic_sample_particles", C.c_int, [C.c_int32, C.c_int32, C.POINTER(SpeciesSampling), C.POINTER(C.c_double), C.c_int32, _P, _P, _P]),
     ("jic_simulate_host", C.c_int, [C.POINTER(Params), C.POINTER(Species), _P, _P, _P, _P, C.c_int64, C.POINTER(Outputs), _P, _P, _P]),

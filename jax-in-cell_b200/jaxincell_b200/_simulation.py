@@ -8,8 +8,8 @@ per-step arithmetic all happens in libjic_b200.so.  Host code is NumPy: there is
     (``rng="threefry"``, the default; ``threefry_partitionable`` picks jax's bit layout, True = jax >= 0.5).  ``rng="numpy"``
     draws them on the host from ``numpy.random.default_rng`` instead (same distributions, different streams).  Explicit
     ``initial_positions`` / ``initial_velocities`` per species override either (_parameters/_species_definitions.py:57-58);
-  * ``time_evolution_algorithm = 1`` (Crank-Nicolson) raises: it is not part of this path.  ``field_solver = 1`` (the per-step
-    Gauss correction of _algorithms.py:69-78) runs in the library (k_gauss).
+  * ``field_solver = 1`` (the per-step Gauss correction of _algorithms.py:69-78) and ``time_evolution_algorithm = 1`` (the implicit
+    Crank-Nicolson stepper, _algorithms.py:100-241) both run in the library (k_gauss; csrc/jic_cn.cuh).
 
 Extra, optional ``solver_parameters`` understood here only: ``engine`` ("auto" | "indexed" | "binned"), ``particle_history``
 (default True, like the reference; False drops the (T,N,3) histories and lets large runs use the binned engine) and ``dtype``
@@ -288,8 +288,6 @@ class Simulation:
         from ._engine import simulate_host
         sec = self._sections(input_parameters)
         dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
-        if solver["time_evolution_algorithm"] != 0:
-            raise JicError("only the explicit Boris path (time_evolution_algorithm=0) is implemented")
         state = self.build_domain_state(dom)
         ps = self.initialize_particle_state(sec["species_parameters"], dom, solver, state)
         G, T = int(dom["number_grid_points"]), int(dom["total_steps"])
@@ -309,7 +307,11 @@ class Simulation:
                             length=state["box_size"][0], length_y=state["box_size"][1], length_z=state["box_size"][2], G=G, dt=state["dt"],
                             pbl=dom["particle_BC_left"], pbr=dom["particle_BC_right"], fbl=dom["field_BC_left"], fbr=dom["field_BC_right"],
                             filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
-                            relativistic=bool(solver["relativistic"]), track_yz=history, field_solver=int(solver["field_solver"]))
+                            relativistic=bool(solver["relativistic"]), track_yz=history, field_solver=int(solver["field_solver"]),
+                            time_evolution_algorithm=int(solver["time_evolution_algorithm"]),
+                            cn_substeps=int(solver["number_of_particle_substeps_implicit_CN"]),
+                            cn_max_iterations=int(solver["max_number_of_Picard_iterations_implicit_CN"]),
+                            cn_tolerance=float(solver["tolerance_Picard_iterations_implicit_CN"]))
         e0 = next(iter(sec["species_parameters"]["electrons"].values()))
         we = ps["weights"][0, 0]
         plasma_frequency = (np.sqrt(e0["number_pseudoparticles"] * we * ps["charge_electrons"] ** 2) / np.sqrt(mass_electron)

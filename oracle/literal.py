@@ -149,19 +149,20 @@ def fields_to_particles_grid(x_n, field, dx, grid, grid_start, bc_left, bc_right
 
 
 def rotation(dt, B, vsub, q_m):
-    """Boris rotation of one velocity.  _particles.py:85-93."""
+    """Boris rotation of one velocity (3,) -- or of (N,3) velocities at once with q_m (N,1).  _particles.py:85-93."""
     B = np.asarray(B, dtype=np.float64)
     vsub = np.asarray(vsub, dtype=np.float64)
     Rvec = vsub + 0.5 * dt * q_m * np.cross(vsub, B)
     Bvec = 0.5 * q_m * dt * B
-    return (np.cross(Rvec, Bvec) + np.dot(Rvec, Bvec) * Bvec + Rvec) / (1 + np.dot(Bvec, Bvec))
+    dot = lambda a, b: np.sum(a * b, axis=-1, keepdims=a.ndim > 1)
+    return (np.cross(Rvec, Bvec) + dot(Rvec, Bvec) * Bvec + Rvec) / (1 + dot(Bvec, Bvec))
 
 
 def boris_step(dt, xs_half, vs, q_ms, E_at_x, B_at_x):
     """Non-relativistic Boris push for (N,3) arrays; q_ms is (N,1).  _particles.py:116-127."""
     q_ms = np.asarray(q_ms, dtype=np.float64).reshape(-1, 1)
     v_minus = vs + q_ms * E_at_x * dt / 2
-    v_rot = np.stack([rotation(dt, B_at_x[p], v_minus[p], q_ms[p, 0]) for p in range(len(vs))]) if len(vs) else v_minus
+    v_rot = rotation(dt, np.asarray(B_at_x, dtype=np.float64), v_minus, q_ms) if len(vs) else v_minus
     v_new = v_rot + q_ms * E_at_x * dt / 2
     return xs_half + dt * v_new, v_new
 
@@ -476,4 +477,108 @@ def run(x0, v0, qs, ms, q_ms, *, length, G, dt, total_steps, box_yz=None, pbl=0,
             hist[k].append(np.array(a, copy=True))
     out = {k: np.stack(v_) for k, v_ in hist.items()}
     out.update(grid=grid, dx=dx, dt=dt, initial_velocities=v, fields=(E, B), final_carry=carry)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# implicit Crank-Nicolson stepper -- jaxincell/_algorithms.py:100-241, _sources.py:10-40,240-282, _particles.py:47-65
+# (already O(1) per particle in the reference: vectorised here, not looped)
+# ----------------------------------------------------------------------------------------------------
+def get_S2_weights_and_indices_periodic_CN(x, dx, grid_start, grid_size):
+    """Nearest node k = round((x - grid_start)/dx) (half to even, like jnp.round), nodes k-1,k,k+1 wrapped.  _sources.py:10-40."""
+    x_norm = (np.asarray(x, dtype=np.float64) - grid_start) / dx
+    k = np.round(x_norm).astype(np.int64)
+    indices = np.stack([k - 1, k, k + 1], axis=-1) % grid_size
+    d = x_norm - k
+    weights = np.stack([0.5 * (0.5 - d) ** 2, 0.75 - d ** 2, 0.5 * (0.5 + d) ** 2], axis=-1)
+    return indices, weights
+
+
+def fields_to_particles_periodic_CN(xs, field, dx, grid_start):
+    """_particles.py:47-65 for all particles: dot(weights, field[indices])."""
+    idx, w = get_S2_weights_and_indices_periodic_CN(xs[:, 0], dx, grid_start, len(field))
+    return np.einsum("pk,pkc->pc", w, np.asarray(field)[idx])
+
+
+def current_density_periodic_CN(xs_n, vs_n, qs, dx, grid_start, grid_size):
+    """J = (q/dx) v S(x) scattered with wrapped indices.  _sources.py:240-282."""
+    idx, w = get_S2_weights_and_indices_periodic_CN(xs_n[:, 0], dx, grid_start, grid_size)
+    J = np.zeros((grid_size, 3))
+    for c in range(3):
+        a = vs_n[:, c] * (qs / dx)
+        J[:, c] = np.bincount(idx.ravel(), weights=(w * a[:, None]).ravel(), minlength=grid_size)
+    return J
+
+
+def CN_step(carry, solver, dx, dt, grid, box_size, pbl, pbr, fbl, fbr, num_substeps):
+    """One implicit step: Picard iteration over (Faraday with E^{n+1/2}, sub-stepped particle push, Ampere with J - <J>).
+    Returns (carry, step_data, n_iterations).  _algorithms.py:100-241."""
+    E_field, B_field, positions, velocities, qs, ms, q_ms = carry
+    E_start = grid[0] + dx / 2  # :110
+    B_start = grid[0] - dx / 2  # :111
+    G = len(grid)
+    tol = solver["tolerance_Picard_iterations_implicit_CN"]
+    max_iter = solver["max_number_of_Picard_iterations_implicit_CN"]
+    dtau = dt / num_substeps
+    c_sq = speed_of_light ** 2
+    pos_stag = np.repeat(positions[None], num_substeps, axis=0)  # :121
+    E_guess = E_field  # picard_init[1]
+    # picard_init (:205): the values the loop returns when it never runs
+    E_calc, B_next, pos_final, vel_final, J_iter = E_field, B_field, positions + dt * velocities, velocities, np.zeros_like(E_field)
+    delta_E, i = np.inf, 0
+    while delta_E > tol and i < max_iter:  # :213-215
+        E_avg = 0.5 * (E_field + E_guess)  # :133
+        B_next = B_field - dt * curlE(E_avg, B_field, dx, dt, fbl, fbr)  # :136-137
+        B_avg = 0.5 * (B_next + B_field)  # :142
+        pos_sub, vel_sub, q_sub, m_sub, qm_sub = positions, velocities, qs, ms, q_ms  # :185 (pos_fix, vel_fix, the outer charges)
+        J_acc = np.zeros((G, 3))
+        new_stag = np.empty_like(pos_stag)
+        for s_ in range(num_substeps):  # :148-184
+            stag_prev = pos_stag[s_]
+            E_mid = fields_to_particles_periodic_CN(stag_prev, E_avg, dx, E_start)
+            B_mid = fields_to_particles_periodic_CN(stag_prev, B_avg, dx, B_start)
+            _, vel_new = boris_step(dtau, stag_prev, vel_sub, q_ms, E_mid, B_mid)  # :157 (the OUTER q/m)
+            vel_mid = 0.5 * (vel_sub + vel_new)
+            pos_new = pos_sub + vel_mid * dtau
+            pos_new, vel_mid, q_new, m_new, qm_new = set_BC_particles(pos_new, vel_mid, q_sub, m_sub, qm_sub, dx, grid, *box_size, pbl, pbr)
+            new_stag[s_] = set_BC_positions(pos_new - 0.5 * dtau * vel_mid, dx, grid, *box_size, pbl, pbr)
+            J_acc += current_density_periodic_CN(stag_prev, vel_mid, qs, dx, E_start, G) * dtau  # :176-181 (the OUTER charges)
+            pos_sub, vel_sub, q_sub, m_sub, qm_sub = pos_new, vel_new, q_new, m_new, qm_new
+        pos_stag = new_stag
+        pos_final, vel_final = pos_sub, vel_sub
+        J_iter = J_acc / dt  # :190
+        mean_J = J_iter.mean(axis=0)
+        E_calc = E_field + dt * (c_sq * curlB(B_avg, E_field, dx, dt, fbl, fbr) - (1 / epsilon_0) * (J_iter - mean_J))  # :197-198
+        delta_E = np.abs(np.max(E_calc - E_guess)) / (np.max(np.abs(E_calc)) + 1e-12)  # :224
+        E_guess = E_calc
+        i += 1
+    rho = calculate_charge_density(pos_final, qs, dx, grid, pbl, pbr, 0, 0.5, (1, 2, 4), fbl, fbr)  # :236-238
+    carry = (E_calc, B_next, pos_final, vel_final, qs, ms, q_ms)
+    return carry, (pos_final, vel_final, E_calc, B_next, J_iter, rho), i
+
+
+def run_CN(x0, v0, qs, ms, q_ms, *, length, G, dt, total_steps, box_yz=None, pbl=0, pbr=0, fbl=0, fbr=0, solver=None):
+    """time_evolution_algorithm = 1: _simulation.py:216-257 with the CN carry (positions stay x0, velocities are the post-BC ones)."""
+    solver = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "max_number_of_Picard_iterations_implicit_CN": 20,
+              "number_of_particle_substeps_implicit_CN": 2, "tolerance_Picard_iterations_implicit_CN": 1e-6, **(solver or {})}
+    dx = length / G
+    grid = np.linspace(-length / 2 + dx / 2, length / 2 - dx / 2, G)
+    Ly, Lz = box_yz if box_yz is not None else (length, length)
+    box = (length, Ly, Lz)
+    x0 = np.asarray(x0, dtype=np.float64); v0 = np.asarray(v0, dtype=np.float64)
+    qs = np.asarray(qs, dtype=np.float64).reshape(-1); ms = np.asarray(ms, dtype=np.float64).reshape(-1)
+    q_ms = np.asarray(q_ms, dtype=np.float64).reshape(-1)
+    E, B = initial_fields(x0, qs, dx, grid, pbl, pbr, solver, fbl, fbr)
+    _, v, q1, m1, qm1 = set_BC_particles(x0 + (dt / 2) * v0, v0, qs, ms, q_ms, dx, grid, *box, pbl, pbr)
+    carry = (E, B, x0, v, q1, m1, qm1)
+    keys = ("positions", "velocities", "electric_field", "magnetic_field", "current_density", "charge_density")
+    hist = {k: [] for k in keys}
+    iters = []
+    for _ in range(total_steps):
+        carry, data, n_it = CN_step(carry, solver, dx, dt, grid, box, pbl, pbr, fbl, fbr, solver["number_of_particle_substeps_implicit_CN"])
+        iters.append(n_it)
+        for k, a in zip(keys, data):
+            hist[k].append(np.array(a, copy=True))
+    out = {k: np.stack(v_) for k, v_ in hist.items()}
+    out.update(grid=grid, dx=dx, dt=dt, initial_velocities=v, fields=(E, B), picard_iterations=np.array(iters))
     return out

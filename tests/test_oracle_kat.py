@@ -366,3 +366,54 @@ def test_circulant_form_of_the_spectral_solvers(G, dx):
     for fs in (1, 2, 3):
         a, b = L.FIELD_SOLVERS[fs](rho, dx), C.solve_Ex(rho, dx, fs)
         np.testing.assert_allclose(b, a, rtol=0, atol=1e-13 * np.abs(a).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# periodic S2 helpers of the Crank-Nicolson stepper -- reference tests/test_sources.py:25-76,331-372, tests/test_particles.py:162-218
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("x,weights", [(0.0, [0.125, 0.75, 0.125]), (0.5, [0.0, 0.5, 0.5]), (-0.25, [0.28125, 0.6875, 0.03125]),
+                                       (4.9, [0.18, 0.74, 0.08])])
+def test_S2_weights_and_indices_periodic_CN(x, weights):
+    idx, w = L.get_S2_weights_and_indices_periodic_CN(np.array([x]), 1.0, 0.0, 5)
+    assert idx[0].tolist() == [4, 0, 1]
+    assert_allclose(w[0], weights, rtol=1e-12, atol=1e-15)
+    assert_allclose(w.sum(), 1.0)
+
+
+def test_current_density_periodic_CN_accumulates_wrapped_particles():
+    J = L.current_density_periodic_CN(np.array([[0.0, 0, 0]]), np.array([[1.0, 2.0, -3.0]]), np.array([2.0]), 1.0, 0.0, 5)
+    want = np.zeros((5, 3)); want[4] = [0.25, 0.5, -0.75]; want[0] = [1.5, 3.0, -4.5]; want[1] = [0.25, 0.5, -0.75]
+    assert_allclose(J, want)
+    J = L.current_density_periodic_CN(np.array([[0.0, 0, 0], [5.0, 0, 0]]), np.array([[1.0, 2.0, -3.0], [4.0, -2.0, 0.5]]), np.array([2.0, 1.0]),
+                                      1.0, 0.0, 5)
+    tot = np.array([2.0, 4.0, -6.0]) + np.array([4.0, -2.0, 0.5])
+    want = np.zeros((5, 3)); want[4] = 0.125 * tot; want[0] = 0.75 * tot; want[1] = 0.125 * tot
+    assert_allclose(J, want)
+
+
+def test_fields_to_particles_periodic_CN():
+    field = np.array([[0.0, 0.0, 0.0], [1.0, 10.0, -1.0], [2.0, 20.0, -2.0], [3.0, 30.0, -3.0], [4.0, 40.0, -4.0]])
+    for x in (0.0, -0.25, 4.9, 5.0):
+        idx, w = L.get_S2_weights_and_indices_periodic_CN(np.array([x]), 1.0, 0.0, 5)
+        assert_allclose(L.fields_to_particles_periodic_CN(np.array([[x, 0.0, 0.0]]), field, 1.0, 0.0)[0], w[0] @ field[idx[0]], rtol=1e-12)
+    const = np.tile(np.array([2.0, -3.0, 5.0]), (5, 1))
+    assert_allclose(L.fields_to_particles_periodic_CN(np.array([[4.75, 0.0, 0.0]]), const, 1.0, 0.0)[0], const[0], rtol=1e-12)
+    half = L.fields_to_particles_periodic_CN(np.array([[2.0 + 0.25, 0.0, 0.0]]), field, 0.5, 2.0)[0]
+    assert_allclose(half, 0.5 * field[0] + 0.5 * field[1], rtol=1e-12)
+
+
+def test_CN_step_picard_stopping_conditions_and_energy():
+    """reference tests/test_algorithms.py:616-680 (stopping rules) + what the scheme is for: energy conservation."""
+    from plasma import cfl_dt, two_species
+    G, length = 16, 0.01
+    p = two_species(300, 300, length=length, G=G, seed=3, vth_e=0.05, vth_yz=0.02, drift=3e7, plus_minus=True, gpdl=0.02)
+    dt = cfl_dt(length, G, 0.3)
+    kw = dict(length=length, G=G, dt=dt, total_steps=4)
+    run = lambda **s: L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], solver=s, **kw)
+    assert run(tolerance_Picard_iterations_implicit_CN=1e9, max_number_of_Picard_iterations_implicit_CN=5)["picard_iterations"].tolist() == [1] * 4
+    assert run(tolerance_Picard_iterations_implicit_CN=1e-30, max_number_of_Picard_iterations_implicit_CN=3)["picard_iterations"].tolist() == [3] * 4
+    out = run(tolerance_Picard_iterations_implicit_CN=1e-10, max_number_of_Picard_iterations_implicit_CN=30, number_of_particle_substeps_implicit_CN=3)
+    assert 1 < out["picard_iterations"].max() < 30
+    from oracle import closed_form as C
+    e = C.energies(out, p["m"], out["dx"])["total_energy"]
+    assert abs(e[-1] / e[0] - 1) < 1e-6
