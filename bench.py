@@ -145,6 +145,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(dtype, engine, n_particles):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one push launch from the committed ncu capture (profiles/), scaled to this
+    run's particle count (the kernel streams every particle once, so its traffic is linear in N); None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "r01_push_traffic.json")
+    if engine != "binned" or not os.path.exists(path):
+        return None
+    rec = json.load(open(path)).get(dtype)
+    if not rec:
+        return None
+    return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * (n_particles / rec["particles"])
+
+
 def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000):
     """Oracle port (NumPy closed form) on the host cores: particles split over threads, grids summed."""
     import numpy as np
@@ -369,7 +381,9 @@ def main():
                        "l2": "particle state (>= 3.2 GB per GPU) is far larger than L2; no flush needed",
                        "untimed_steps_before_timing": W + K},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(args.dtype, engine, N), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_push_traffic.json)",
+                         "algorithmic_bytes_per_launch": bpp * N,
                          "peak_source": peak_src, "kernel": "k_step (fused gather+push+BC+deposit)" if engine == "indexed" else "k_push_binned",
                          "kernel_ms": ms_push_step, "grid_part_ms": ms_grid_step,
                          "algorithmic_bytes": f"{bpp} B per particle-step x {N} particles per launch"},
