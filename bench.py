@@ -157,8 +157,9 @@ def measured_traffic(dtype, engine, n_particles):
     return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * (n_particles / rec["particles"])
 
 
-def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000):
-    """Oracle port (NumPy closed form) on the host cores: particles split over threads, grids summed."""
+def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000, steps=None, warmup=0):
+    """Oracle port (NumPy closed form) on the host cores: particles split over threads, grids summed.
+    steps=None: run for about `seconds_target`; otherwise `warmup` untimed + exactly `steps` timed steps over the sample."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     from oracle import closed_form as CF
@@ -196,19 +197,26 @@ def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000):
     E = sum(s_.E for s_ in states); B = states[0].B
     J = sum(s_.J for s_ in states)  # start() filtered each chunk's J; the filter is linear
     pool = ThreadPoolExecutor(threads)
-    steps, t0 = 0, time.perf_counter()
-    while True:
+
+    def one_step(E, B, J):
         E, B = LT.field_update1(E, B, dom.dx, dt / 2, J, 0, 0)
         parts = list(pool.map(lambda st: push_deposit(st, E, B), states))
         J = LT.filter_vector_field(sum(p_[0] for p_ in parts), 5, 0.5, (1, 2, 4), 0, 0)
         LT.filter_scalar_field(sum(p_[1] for p_ in parts), 5, 0.5, (1, 2, 4), 0, 0)
         E, B = LT.field_update2(E, B, dom.dx, dt / 2, J, 0, 0)
-        steps += 1
+        return E, B, J
+
+    for _ in range(warmup):
+        E, B, J = one_step(E, B, J)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        E, B, J = one_step(E, B, J)
+        done += 1
         el = time.perf_counter() - t0
-        if el > seconds_target or steps >= 200:
+        if (steps is not None and done >= steps) or (steps is None and (el > seconds_target or done >= 200)):
             break
     pool.shutdown()
-    return n_sample * steps / el, threads, f"{n_sample} particles x {steps} steps, G={G}, NumPy closed-form port of the reference, {threads} threads"
+    return n_sample * done / el, threads, f"{n_sample} particles x {done} steps, G={G}, NumPy closed-form port of the reference, {threads} threads", el / done
 
 
 def real_reference_status():
@@ -230,9 +238,12 @@ def run_reference(args):
         return
     w = workload(args, 1)
     why_not = real_reference_status()
-    rate, cores, sample = cpu_port_rate(w, seconds_target=min(60.0, 4.0 * max(args.steps, 1)))
+    # a "step" of this arm = one PIC step over a bounded sample of the workload (4e5 particles); K and W as given, capped so that the
+    # run ends within a few minutes on any host
+    k = max(1, min(args.steps, 400))
+    rate, cores, sample, s_per_step = cpu_port_rate(w, steps=k, warmup=min(max(args.warmup, 0), 20))
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "steps": k, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic two-beam plasma, G={args.grid}, CFL 1, periodic, filter 5/0.5/(1,2,4) (SURVEY 8d config 5), CPU sample"},
             "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
@@ -394,7 +405,7 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu:
-            rate, cores, sample = cpu_port_rate(w, seconds_target=12.0)
+            rate, cores, sample, _ = cpu_port_rate(w, seconds_target=12.0)
             line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
