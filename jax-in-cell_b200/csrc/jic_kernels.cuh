@@ -408,7 +408,8 @@ struct FieldArgsMC {
   int* error;                              // sticky: 3 = a peer did not arrive within the spin limit
 };
 
-constexpr long long kPeerSpinLimit = 4000000000ll;  // clock64 ticks (~2 s): a missing peer must not hang the GPU
+constexpr long long kPeerSpinLimit = 16000000000ll;  // clock64 ticks (~8 s): a missing peer must not hang the GPU; the error is
+                                                     // sticky, so the steps still queued behind a failure do not wait again
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -418,15 +419,14 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ double ld_peer(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
+// one node of a peer's raw grid (kAccRow = 4 reals, 32- / 16-byte aligned): vector loads, issued back to back by the caller for
+// all peers before the first use so that the NVLink round trips overlap instead of adding up
+__device__ __forceinline__ void ld_peer4(const double* p, double v[4]) {
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2) : "memory");
 }
-__device__ __forceinline__ float ld_peer(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void ld_peer4(const float* p, float v[4]) {
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p) : "memory");
 }
 
 constexpr int kFieldsMcThreads = 512;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
   if (fused) {
     const unsigned want = (unsigned)(*a.seq) + 1u;
     if (blockIdx.x == 0 && tid < a.world) st_release_sys(a.peer_flags[tid] + a.rank, want);
-    if (tid < a.world) {
+    if (tid < a.world && *(volatile int*)a.error != 3) {
       const unsigned* f = a.peer_flags[a.rank] + tid;
       const long long t0 = clock64();
       while ((int)(ld_acquire_sys(f) - want) < 0) {
@@ -476,11 +476,16 @@ __global__ void __launch_bounds__(kFieldsMcThreads) k_fields_mc(const FieldArgsM
     } else {
       double sum[kAccRow] = {0.0, 0.0, 0.0, 0.0};
       if (in) {
-        for (int r = 0; r < a.world; ++r) {  // rank order: identical rounding on every rank
-          const R* src = a.peer_acc[r] + g * kAccRow;
+        R vals[JIC_MAX_PEERS][kAccRow];
 #pragma unroll
-          for (int c = 0; c < kAccRow; ++c) sum[c] += (double)(r == a.rank ? src[c] : ld_peer(src + c));
-        }
+        for (int r = 0; r < JIC_MAX_PEERS; ++r)  // all loads first (own rank included: same path, local memory) ...
+          if (r < a.world) ld_peer4(a.peer_acc[r] + g * kAccRow, vals[r]);
+#pragma unroll
+        for (int r = 0; r < JIC_MAX_PEERS; ++r)  // ... then the sum in rank order: identical rounding on every rank
+          if (r < a.world) {
+#pragma unroll
+            for (int c = 0; c < kAccRow; ++c) sum[c] += (double)vals[r][c];
+          }
       }
 #pragma unroll
       for (int c = 0; c < kAccRow; ++c) cur[c * W + li] = sum[c];
