@@ -394,7 +394,7 @@ struct EngineT : Engine {
   }
 
   int initialize(const void* x0, const void* v0, cudaStream_t st) override {
-    if (!x0 || !v0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
+    if ((!x0 || !v0) && dp.N > 0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
     // fused mode: peers may still be reading this rank's raw grid in the last field kernel of a previous run
     if (p2p && nccl_barrier(st)) return fail(JIC_ERR_NCCL, "barrier before initialize failed");
     JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));

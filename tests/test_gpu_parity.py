@@ -331,3 +331,44 @@ def test_field_solver_large_grid_binned_fast_path(dtype, rtol):
     if dtype == torch.float64:
         a = run_gpu(p, length=length, G=G, dt=dt, T=T, engine="indexed", particles=False, solver=solver)
         assert_parity(b, a, FIELD_KEYS, 1e-7)
+
+
+# ------------------------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+def test_ragged_and_tiny_species(engine):
+    """Species of very different sizes, one of them a single particle, on the smallest grid the library accepts (G = 3), and an
+    EMPTY species block in the middle of the table (count 0: nothing to push, must not disturb the others)."""
+    G, length, T = 3, 0.01, 10
+    p = two_species(1, 37, length=length, G=G, seed=4, vth_e=0.2, vth_yz=0.1, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.7)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=dict(filter_passes=1))
+    sp = [p["species"][0], dict(count=0, q=1.0, m=1.0, qm=1.0), p["species"][1]]
+    got = run_gpu(dict(p, species=sp), length=length, G=G, dt=dt, T=T, engine=engine, particles=engine == "indexed", solver=dict(filter_passes=1))
+    assert_parity(got, ref, FIELD_KEYS + (("positions", "velocities") if engine == "indexed" else ()), 1e-5)
+
+
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+def test_no_particles_at_all(engine):
+    """N = 0: the fields stay zero, nothing crashes."""
+    from jaxincell_b200 import HotPath
+    hp = HotPath(species=[dict(count=0, q=1.0, m=1.0, qm=1.0)], length=0.01, G=16, dt=1e-12, engine=engine)
+    hp.set_external_fields(None, None)
+    hp.initialize(np.zeros((0, 3)), np.zeros((0, 3)))
+    out = hp.run(5)
+    torch.cuda.synchronize()
+    assert all(float(v.abs().max()) == 0.0 for v in out.values())
+    hp.close()
+
+
+def test_all_particles_in_one_cell_binned():
+    """Maximum collision case of the binned store: every particle of both species starts in the same cell (one bin holds all)."""
+    G, length, T = 32, 0.01, 15
+    p = two_species(5000, 5000, length=length, G=G, seed=6, vth_e=0.1, vth_yz=0.05, gpdl=0.3)
+    dx = length / G
+    p["x0"][:, 0] = 0.25 * dx + 0.5 * dx * (p["x0"][:, 0] / length)   # all inside cell G/2
+    dt = cfl_dt(length, G, 0.9)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, keep_particles=False)
+    got = run_gpu(p, length=length, G=G, dt=dt, T=T, engine="binned", particles=False)
+    assert_parity(got, ref, FIELD_KEYS, 1e-5)
+    x, v, alive = (t.cpu().numpy() for t in got["hp"].particles())
+    assert int(alive.sum()) == 10000

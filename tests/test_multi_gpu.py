@@ -79,3 +79,66 @@ def test_two_gpus_match_single_rank_oracle(engine, G, p2p):
         pr.join(timeout=60)
     want = "ok:fused" if (p2p and G >= 256) else "ok:nccl"
     assert sorted(res) == [(0, want), (1, want)], res
+
+
+def _worker_modes(rank, world, port, mode, q):
+    """field_solver and the Crank-Nicolson stepper on two ranks (both reduce through NCCL)."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from jaxincell_b200 import HotPath, shard_particles, shard_species
+        from oracle import literal as L
+        G, length, T = 300, 0.01, 8
+        p = two_species(6000, 5000, length=length, G=G, seed=21, vth_e=0.05, vth_yz=0.02, drift=5e7, plus_minus=True, gpdl=0.05)
+        dt = cfl_dt(length, G, 0.3)
+        x, v, idx = shard_particles(p["x0"], p["v0"], p["species"], rank, world)
+        kw = dict(field_solver=1, engine="binned") if mode == "field_solver" else dict(time_evolution_algorithm=1, cn_max_iterations=6, cn_tolerance=1e-8)
+        hp = HotPath(species=shard_species(p["species"], rank, world), length=length, G=G, dt=dt, **kw)
+        hp.comm_init_from_torch()
+        assert hp.comm_mode() == "nccl"
+        hp.set_external_fields(None, None)
+        hp.initialize(x, v)
+        out = hp.run(T)
+        torch.cuda.synchronize()
+        E = out["electric_field"]
+        others = [torch.empty_like(E) for _ in range(world)]
+        dist.all_gather(others, E)
+        assert all(torch.equal(o, E) for o in others), "ranks hold different fields"
+        if rank == 0:
+            if mode == "field_solver":
+                ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, keep_particles=False,
+                            solver=dict(field_solver=1))
+            else:
+                ref = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T,
+                               solver=dict(max_number_of_Picard_iterations_implicit_CN=6, tolerance_Picard_iterations_implicit_CN=1e-8))
+            for k in ("electric_field", "magnetic_field", "current_density", "charge_density"):
+                err = np.abs(out[k].cpu().numpy() - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-300)
+                assert err < 1e-5, (k, err)
+        hp.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("mode", ["field_solver", "crank_nicolson"])
+def test_two_gpus_field_solver_and_crank_nicolson(mode):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_modes, args=(r, 2, port, mode, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
