@@ -38,6 +38,8 @@ constexpr int kMinChunk = 1024;    // particles per work item: chosen by k_plan 
 #endif
 constexpr int kMaxChunk = JIC_MAX_CHUNK;
 constexpr int kChunkAlign = 256;   // items start on multiples of this inside a bin (a multiple of the block size)
+constexpr int kSlowChunk = 256;    // work-item size in bins whose particles all take the general path (wall cells, the edge cells
+                                   // of field_solver runs): small, so that this per-particle work spreads over many warps
 constexpr int kBlk = 32;           // slots per block
 constexpr int kBlkElems = 4 * kBlk;  // reals per block
 #ifndef JIC_PUSH_THREADS
@@ -88,6 +90,7 @@ struct BinDev {
   int* ov_bin[2]; R* ov_d[2]; R* ov_vx[2]; R* ov_vy[2]; R* ov_vz[2];
   int* item_bin; int* item_first; int item_cap;
   int n_workers;          // warps of the push kernel (work-queue consumers)
+  int edge;               // cells c < edge or c > G-1-edge take the general path for every particle (0 = none, G = all)
   PlanHeader* hdr;
 };
 
@@ -126,13 +129,23 @@ __device__ __forceinline__ void store_slot(const BinDev<R>& bd, int dst, int b, 
   }
 }
 
+// Called from divergent code: the lanes that are here together and head for the same bin claim their slots with ONE cursor
+// atomic (a wall cell sends thousands of particles through this path into two or three bins).
 template <typename R>
 __device__ __forceinline__ void insert_particle(const BinDev<R>& bd, int dst, int species, R x, R vx, R vy, R vz, const DevParams<R>& p) {
   int c = (int)floor((x - p.gs) * p.inv_dx);
   c = min(max(c, 0), p.G - 1);
   const R d = (x - node_pos(c, p)) * p.inv_dx;
   const int b = species * p.G + c;
-  const unsigned slot = atomicAdd(&bd.cur[dst][b], 1u);
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, b);
+  const int leader = __ffs(peers) - 1;
+  int lane;
+  asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(&bd.cur[dst][b], (unsigned)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const unsigned slot = base + __popc(peers & ((1u << lane) - 1u));
   store_slot(bd, dst, b, slot, d, vx, vy, vz);
 }
 
@@ -150,13 +163,13 @@ __device__ __noinline__ void slow_tail(const DevParams<R>& p, const BinDev<R>& b
     bc_x(x_mid, p);
     const Cloud<R> c_old = make_cloud(x_old, p), c_new = make_cloud(x_new, p), c_mid = make_cloud(x_mid, p);
     const R a = q * p.inv_dx;
-    const GlobalGrid<R> g{acc};
+    const GlobalGrid<R> g{acc, p.G};
     deposit_jx(g, x_old, c_old, c_new, q / p.dt, p);
     deposit_cloud(g, c_mid, p.G, a * v[1], a * v[2], a, true);
     if (p.stag) {  // rho(x_n) on the faces (field_solver != 0), as in k_step
       R x_n = x_old - p.half_dt * vx_old;
       bc_x(x_n, p);
-      deposit_faces(acc + (size_t)p.G * kAccRow, make_cloud_faces(x_n, p), p.G, a);
+      deposit_faces(g, make_cloud_faces(x_n, p), p.G, a);
     }
     insert_particle(bd, dst, species, x_new, v[0], v[1], v[2], p);
   } else {
@@ -268,12 +281,16 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
   long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
   want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
   const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
+  auto chunk_of = [&](int b) -> int {
+    const int c = b % G;
+    return (c < bd.edge || c > G - 1 - bd.edge) ? kSlowChunk : kChunk;
+  };
   int my_items = 0;
-  for (int b = lo; b < hi; ++b) my_items += (cnt_of(b) + kChunk - 1) / kChunk;
+  for (int b = lo; b < hi; ++b) { const int ch = chunk_of(b); my_items += (cnt_of(b) + ch - 1) / ch; }
   int it = block_exclusive_scan<int>(my_items, &tot_i, sh_i);
   for (int b = lo; b < hi; ++b) {
-    const int n = cnt_of(b);
-    for (int k = 0; k < n; k += kChunk) {
+    const int n = cnt_of(b), ch = chunk_of(b);
+    for (int k = 0; k < n; k += ch) {
       if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
       ++it;
     }
@@ -469,8 +486,15 @@ struct BinnedStore {
     bd.cap_total = (bd.cap_total + kBlk - 1) & ~(long long)(kBlk - 1);
     if (bd.cap_total >= (1ll << 40)) return e.fail(JIC_ERR_UNSUPPORTED, "too many particles for one GPU");
     bd.ov_cap = (int)std::min<long long>(std::max<long long>(N / 16, 1 << 16), 1ll << 28);
-    bd.item_cap = (int)std::min<long long>(N / kMinChunk + bd.nb + 16, 1ll << 30);
+    bd.item_cap = (int)std::min<long long>(N / kSlowChunk + bd.nb + 16, 1ll << 30);
     bd.n_workers = n_sm * push_min_blocks<R>() * kPushWarps;
+    {
+      const bool periodic = dp.pbl == JIC_BC_PERIODIC && dp.pbr == JIC_BC_PERIODIC;
+      // periodic: every bin takes the closed form (field_solver runs fix the reference's left-half-cell quirk up in place);
+      // walls: the closed form's stencil (3 nodes for the moments, 3 faces more with field_solver) must stay on the grid
+      bd.edge = periodic ? 0 : (dp.stag ? 3 : 2);
+      if (dp.G < (dp.stag ? 10 : 8)) bd.edge = dp.G;  // tiny grids: the closed form's stencil would wrap onto itself
+    }
     int rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = alloc(e, &bd.rec[k], 4 * (size_t)bd.cap_total))) return rc;
@@ -482,6 +506,18 @@ struct BinnedStore {
     if ((rc = alloc(e, &bd.item_bin, bd.item_cap)) || (rc = alloc(e, &bd.item_first, bd.item_cap)) || (rc = alloc(e, &bd.hdr, 1))) return rc;
     if ((rc = alloc(e, &dense, bd.nb + 1))) return rc;
     (void)prm;
+    {
+      // Shared-memory carve-out: three CTAs of the fp64 kernel (43.3 KB static + 1 KB reserved each) fit the 132 KB configuration,
+      // which is what the driver picks by itself; the remaining 124 KB of L1 matter (measured: 6 % slower with the 164 KB
+      // configuration, 20 % with the maximum).  JIC_PUSH_CARVEOUT=<per cent of 228 KB> overrides for experiments.
+      if (const char* env = getenv("JIC_PUSH_CARVEOUT")) {
+        const int carve = atoi(env);
+        cudaFuncSetAttribute(k_push<R, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_push<R, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_push<R, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_push<R, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      }
+    }
     {
       int dev = 0, max_smem = 0;
       cudaGetDevice(&dev);

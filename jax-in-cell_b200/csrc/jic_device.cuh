@@ -144,18 +144,6 @@ __device__ __forceinline__ Cloud<R> make_cloud_faces(R x, const DevParams<R>& p)
   return cl;
 }
 
-// rho(x_n) on the faces into the fifth raw component, stored behind the (G,4) grid: accS[k] = acc[G * kAccRow + k]
-template <typename R>
-__device__ __forceinline__ void deposit_faces(R* accS, const Cloud<R>& cl, int G, R a) {
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int k = cl.c + j - 1;
-    if (k >= 0 && k < G) atomicAdd(accS + k, cl.w[j] * a);
-  }
-  if (cl.first != R(0)) atomicAdd(accS, cl.first * a);
-  if (cl.last != R(0)) atomicAdd(accS + G - 1, cl.last * a);
-}
-
 __device__ __forceinline__ int mod_pos(int a, int n) {
   int r = a % n;
   return r < 0 ? r + n : r;
@@ -165,7 +153,9 @@ __device__ __forceinline__ int mod_pos(int a, int n) {
 template <typename R>
 struct GlobalGrid {  // straight to the L2-resident raw grid (RED.ADD.F64 / .F32)
   R* acc;
+  int G = 0;  // only needed for add_face (the face component sits behind the (G,4) block)
   __device__ __forceinline__ void add(int node, int comp, R v) const { atomicAdd(acc + node * kAccRow + comp, v); }
+  __device__ __forceinline__ void add_face(int node, R v) const { atomicAdd(acc + (size_t)G * kAccRow + node, v); }
 };
 
 template <typename R>
@@ -193,6 +183,18 @@ __device__ __forceinline__ void deposit_cloud(const Grid& g, const Cloud<R>& cl,
     if (with_j) { g.add(G - 1, 1, cl.last * ay); g.add(G - 1, 2, cl.last * az); }
     g.add(G - 1, 3, cl.last * arho);
   }
+}
+
+// rho(x_n) on the faces into the fifth raw component (field_solver != 0, jaxincell/_algorithms.py:69-72)
+template <typename R, typename Grid>
+__device__ __forceinline__ void deposit_faces(const Grid& g, const Cloud<R>& cl, int G, R a) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int k = cl.c + j - 1;
+    if (k >= 0 && k < G) g.add_face(k, cl.w[j] * a);
+  }
+  if (cl.first != R(0)) g.add_face(0, cl.first * a);
+  if (cl.last != R(0)) g.add_face(G - 1, cl.last * a);
 }
 
 // Charge-conserving J_x: jaxincell/_sources.py:190-207.  Window of min(6,G) nodes starting three nodes left of

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_step(const DevParams<R> p, R* __restric
           // _algorithms.py:70 (bit-identical recomputation of _algorithms.py:60-61 of the previous step), post-BC charge
           R x_n = x_old - p.half_dt * vx_old;
           bc_x(x_n, p);
-          deposit_faces(acc + (size_t)p.G * kAccRow, make_cloud_faces(x_n, p), p.G, a);
+          deposit_faces(GlobalGrid<R>{acc, p.G}, make_cloud_faces(x_n, p), p.G, a);
         }
       }
       xh[i] = x_new;

@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-reading SR_TID in the loop
   const unsigned lt_mask = (1u << lane) - 1u;
   const int G = p.G;
-  const bool periodic = (p.pbl == JIC_BC_PERIODIC) && (p.pbr == JIC_BC_PERIODIC);
   const R cells_per_v = p.dt * p.inv_dx;  // displacement in cells per unit velocity
 
   const R* my_ring = &ring[warp][0][0][0];
@@ -134,10 +133,13 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     const int b = bd.item_bin[item];
     const int first = bd.item_first[item];
     const int s = b / G, c = b - s * G;
-    const int n = min(chunk, bd.cnt[src][b] - first);
+    const bool fast_bin = c >= bd.edge && c <= G - 1 - bd.edge;  // (k_plan makes the items of the other bins small)
+    // STAG on a periodic domain: the three bins from which x_n can land in the left half cell (see the correction in phase C)
+    const bool quirk_bin = STAG && bd.edge == 0 && (c == G - 1 || c <= 1);
+    const R quirk_shift = c == G - 1 ? R(-0.5) : R(c) + R(0.5);
+    const int n = min(fast_bin ? chunk : kSlowChunk, bd.cnt[src][b] - first);
     const int nblk = (n + kBlk - 1) / kBlk, ngroups = (nblk + KB - 1) / KB;
     const R* item_rec = srec + ((bd.off[src][b] + first) >> 5) * (long long)kBlkElems;
-    const bool fast_bin = STAG ? (G >= 10 && c >= 3 && c <= G - 4) : (G >= 8 && (periodic || (c >= 2 && c <= G - 3)));
 
     // lane 0 starts streaming the item at once; the other lanes set up the item-uniform tables meanwhile
     const unsigned gt0 = gt;
@@ -288,6 +290,16 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
           z0 += vz; z1 = fma(vz, tm_, z1); z2 = fma(vz, tm2, z2); zP = fma(vz, Pm, zP); zN = fma(vz, Nm, zN);
           if (STAG) {
             const R t_ = ts[kb];
+            if (quirk_bin) {
+              // The reference does not wrap the face weights of a particle whose x_n lies in the left half cell [-L/2, g_0): faces
+              // -2 and -1 are simply off its grid (make_cloud_faces).  The sums below wrap them onto faces G-2, G-1: take them back.
+              const R xi = t_ + quirk_shift;  // x_n in cells from the left wall
+              if (xi >= R(0) && xi < R(0.5)) {
+                const R a_ = p.sp_q[s] * p.inv_dx;
+                atomicAdd(acc + (size_t)G * kAccRow + (G - 2), -a_ * R(0.5) * (R(0.5) - xi) * (R(0.5) - xi));
+                atomicAdd(acc + (size_t)G * kAccRow + (G - 1), -a_ * (R(0.75) - xi * xi));
+              }
+            }
             const R n_ = (-t_ - R(1)) + fabs(-t_ - R(1)), z_ = t_ + fabs(t_), p_ = (t_ - R(1)) + fabs(t_ - R(1));
             s1 += t_; s2 = fma(t_, t_, s2); sN = fma(n_, n_, sN); sZ = fma(z_, z_, sZ); sP = fma(p_, p_, sP);
           }
