@@ -61,8 +61,8 @@ def main():
         res[fs] = dict(ms_per_step=ms, push_ms=a / 10, grid_ms=b / 10, finite=bool(torch.isfinite(outs["electric_field"][-1]).all()))
         hp.close()
     print(json.dumps({"row": "8f-3 per-step electrostatic correction (binned engine, 5e7 particles, G=4096)", "field_solver": res,
-                      "note": "push_ms includes the face deposit (STAG instantiation); grid_ms includes k_gauss (G^2 circular convolution) on the "
-                              "single-CTA field kernel path"}), flush=True)
+                      "note": "push_ms includes the face deposit (STAG instantiation of k_push); grid_ms includes k_gauss (filter of the face "
+                              "component + G^2 circular convolution) in front of the field kernel"}), flush=True)
     del x0, v0
     torch.cuda.empty_cache()
 
