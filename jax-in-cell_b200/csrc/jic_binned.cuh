@@ -242,13 +242,38 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
   auto cnt_of = [&](int b) -> int { return SMEM ? s_cnt[b] : bd.cnt[written][b]; };
   // 1. close `written`: cnt = min(cursor, capacity); everything beyond sits in its overflow list (bins interleaved over threads)
   long long mine = 0;
-  for (int b = t; b < nb; b += nt) {
-    const long long cap = bd.off[written][b + 1] - bd.off[written][b];
-    const long long att = g_att[b];
-    const int cnt = (int)(att < cap ? att : cap);
-    bd.cnt[written][b] = cnt;
-    if (SMEM) { s_att[b] = (int)att; s_cnt[b] = cnt; }
-    mine += att;
+  {
+    // all loads of a thread's first kBatch bins are issued before the first store (the stores would otherwise fence the loads of
+    // the next iteration: one L2 round trip per bin on the step's critical path)
+    constexpr int kBatch = 8;
+    const long long* __restrict__ g_off = bd.off[written];
+    long long o0[kBatch], o1[kBatch];
+    unsigned at[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int b = t + k * nt;
+      o0[k] = o1[k] = 0; at[k] = 0u;
+      if (b < nb) { o0[k] = g_off[b]; o1[k] = g_off[b + 1]; at[k] = g_att[b]; }
+    }
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int b = t + k * nt;
+      if (b < nb) {
+        const long long cap = o1[k] - o0[k], att = at[k];
+        const int cnt = (int)(att < cap ? att : cap);
+        bd.cnt[written][b] = cnt;
+        if (SMEM) { s_att[b] = (int)att; s_cnt[b] = cnt; }
+        mine += att;
+      }
+    }
+    for (int b = t + kBatch * nt; b < nb; b += nt) {
+      const long long cap = g_off[b + 1] - g_off[b];
+      const long long att = g_att[b];
+      const int cnt = (int)(att < cap ? att : cap);
+      bd.cnt[written][b] = cnt;
+      if (SMEM) { s_att[b] = (int)att; s_cnt[b] = cnt; }
+      mine += att;
+    }
   }
   block_exclusive_scan<long long>(mine, &tot_ll, sh_ll);
   const long long n_total = tot_ll;
@@ -262,37 +287,68 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
     if (f > fmax) f = fmax;
     if (f < 0) { f = 0; if (t == 0 && room < 0) atomicExch(&h->error, 2); }
   }
-  auto cap_of = [&](int b) -> long long {
-    const int s = b / G, c = b - s * G;
-    const long long a0 = att_of(b), al = att_of(s * G + (c == 0 ? G - 1 : c - 1)), ar = att_of(s * G + (c == G - 1 ? 0 : c + 1));
+  // (one integer division per thread: the cell index runs along with the bin index from here on; this kernel is a single CTA on
+  //  the step's critical path and was instruction-bound -- 275 instructions per bin, mostly divisions)
+  const int s_lo = lo / G, c_lo = lo - s_lo * G;
+  constexpr int kKeep = 8;  // capacities kept in registers between the two passes (per <= 8 up to 8192 bins)
+  long long caps[kKeep];
+  auto cap_at = [&](int b, int c) -> long long {
+    const long long a0 = att_of(b), al = att_of(c == 0 ? b + G - 1 : b - 1), ar = att_of(c == G - 1 ? b - (G - 1) : b + 1);
     const long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
     return (cap + kBlk - 1) & ~(long long)(kBlk - 1);  // bins start on block boundaries
   };
   long long cap_sum = 0;
-  for (int b = lo; b < hi; ++b) cap_sum += cap_of(b);
+  {
+    int c = c_lo;
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+      const int b = lo + k;
+      caps[k] = 0;
+      if (b < hi) { caps[k] = cap_at(b, c); cap_sum += caps[k]; }
+      c = c + 1 == G ? 0 : c + 1;
+    }
+    for (int b = lo + kKeep; b < hi; ++b) { cap_sum += cap_at(b, c); c = c + 1 == G ? 0 : c + 1; }
+  }
   long long run = block_exclusive_scan<long long>(cap_sum, &tot_ll, sh_ll);
-  for (int b = lo; b < hi; ++b) {
-    bd.off[next][b] = run;
-    run += cap_of(b);
-    bd.cur[next][b] = 0u;
+  {
+    int c = c_lo;
+#pragma unroll
+    for (int k = 0; k < kKeep; ++k) {
+      const int b = lo + k;
+      if (b < hi) { bd.off[next][b] = run; run += caps[k]; bd.cur[next][b] = 0u; }
+      c = c + 1 == G ? 0 : c + 1;
+    }
+    for (int b = lo + kKeep; b < hi; ++b) { bd.off[next][b] = run; run += cap_at(b, c); bd.cur[next][b] = 0u; c = c + 1 == G ? 0 : c + 1; }
   }
   if (t == 0) bd.off[next][nb] = tot_ll;
   // 3. work items over `written`: about 4 per warp of the push kernel, between kMinChunk and kMaxChunk particles each
   long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
   want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
   const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
-  auto chunk_of = [&](int b) -> int {
-    const int c = b % G;
-    return (c < bd.edge || c > G - 1 - bd.edge) ? kSlowChunk : kChunk;
+  const float inv_chunk = 1.0f / (float)kChunk;
+  static_assert((kSlowChunk & (kSlowChunk - 1)) == 0, "kSlowChunk must be a power of two");
+  auto items_of = [&](int n, int c) -> int {  // ceil(n / chunk of this bin) without an integer division
+    if (c < bd.edge || c > G - 1 - bd.edge) return (n + kSlowChunk - 1) / kSlowChunk;
+    int q = (int)((float)n * inv_chunk);                        // within one of the quotient ...
+    while ((long long)q * kChunk < n) ++q;                      // ... made exact
+    while (q > 0 && (long long)(q - 1) * kChunk >= n) --q;
+    return q;
   };
   int my_items = 0;
-  for (int b = lo; b < hi; ++b) { const int ch = chunk_of(b); my_items += (cnt_of(b) + ch - 1) / ch; }
+  {
+    int c = c_lo;
+    for (int b = lo; b < hi; ++b) { my_items += items_of(cnt_of(b), c); c = c + 1 == G ? 0 : c + 1; }
+  }
   int it = block_exclusive_scan<int>(my_items, &tot_i, sh_i);
-  for (int b = lo; b < hi; ++b) {
-    const int n = cnt_of(b), ch = chunk_of(b);
-    for (int k = 0; k < n; k += ch) {
-      if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
-      ++it;
+  {
+    int c = c_lo;
+    for (int b = lo; b < hi; ++b) {
+      const int n = cnt_of(b), ch = (c < bd.edge || c > G - 1 - bd.edge) ? kSlowChunk : kChunk;
+      for (int k = 0; k < n; k += ch) {
+        if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
+        ++it;
+      }
+      c = c + 1 == G ? 0 : c + 1;
     }
   }
   if (t == 0) {
