@@ -74,11 +74,19 @@ __global__ void __launch_bounds__(256) k_cn_start(const DevParams<R> p, const R*
 }
 
 // One Picard iteration of the particle part: _algorithms.py:148-188.  `it` is the iteration index of this launch.
-template <typename R>
+// SHARED: persistent CTAs deposit into a CTA-private copy of the raw grid in shared memory (flushed once), like k_step.
+template <typename R, bool SHARED>
 __global__ void __launch_bounds__(256) k_cn_push(const DevParams<R> p, CnState<R> cur, CnState<R> nxt, R* __restrict__ stag, int n_sub, int it,
                                                  const double* __restrict__ Eavg, const double* __restrict__ Bavg, R* __restrict__ acc,
                                                  const uint8_t* __restrict__ alive, const CnControl* __restrict__ cn) {
   if (it > 0 && cn->converged) return;
+  extern __shared__ __align__(16) unsigned char cn_smem_raw[];
+  R* sacc = reinterpret_cast<R*>(cn_smem_raw);
+  if (SHARED) {
+    for (int k = threadIdx.x; k < p.G * kAccRow; k += blockDim.x) sacc[k] = R(0);
+    __syncthreads();
+  }
+  R* const dep = SHARED ? sacc : acc;  // where this CTA's atomics go
   const R dtau = p.dt / R(n_sub), half_dtau = R(0.5) * dtau;
   const R e_start = p.g0 + p.half_dx, b_start = p.g0 - p.half_dx;  // :110-111
   const R w_sub = dtau / p.dt;                                       // J_iter = sum_s J_s dtau / dt  (:179,:190)
@@ -122,9 +130,9 @@ __global__ void __launch_bounds__(256) k_cn_push(const DevParams<R> p, CnState<R
       for (int k = 0; k < 3; ++k) {
         const R wk = we[k] * a;
         if (wk != R(0)) {
-          atomicAdd(acc + ie[k] * kAccRow + 0, wk * vmid[0]);
-          atomicAdd(acc + ie[k] * kAccRow + 1, wk * vmid[1]);
-          atomicAdd(acc + ie[k] * kAccRow + 2, wk * vmid[2]);
+          atomicAdd(dep + ie[k] * kAccRow + 0, wk * vmid[0]);
+          atomicAdd(dep + ie[k] * kAccRow + 1, wk * vmid[1]);
+          atomicAdd(dep + ie[k] * kAccRow + 2, wk * vmid[2]);
         }
       }
       vel[0] = vnew[0]; vel[1] = vnew[1]; vel[2] = vnew[2];
@@ -132,8 +140,15 @@ __global__ void __launch_bounds__(256) k_cn_push(const DevParams<R> p, CnState<R
     nxt.x[i] = pos[0]; nxt.y[i] = pos[1]; nxt.z[i] = pos[2];
     nxt.vx[i] = vel[0]; nxt.vy[i] = vel[1]; nxt.vz[i] = vel[2];
     // rho(x_{n+1}) for the step output (:236-238): ordinary S2 cloud with the particle-BC fold, step-start charge, no filter
-    const GlobalGrid<R> grid{acc};
+    const GlobalGrid<R> grid{dep};
     deposit_cloud(grid, make_cloud(pos[0], p), p.G, R(0), R(0), q * p.inv_dx, false);
+  }
+  if (SHARED) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.G * kAccRow; k += blockDim.x) {
+      const R v = sacc[k];
+      if (v != R(0)) atomicAdd(acc + k, v);
+    }
   }
 }
 

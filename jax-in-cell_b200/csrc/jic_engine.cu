@@ -232,6 +232,7 @@ struct EngineT : Engine {
     shared_grid = prm.deposit == JIC_DEPOSIT_SHARED_GRID || (prm.deposit == JIC_DEPOSIT_AUTO && fits && N >= 4 * G);
     if (shared_grid) {
       JIC_CUDA(cudaFuncSetAttribute(k_step<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
+      JIC_CUDA(cudaFuncSetAttribute(k_cn_push<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
     }
     JIC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     JIC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -454,8 +455,12 @@ struct EngineT : Engine {
   // one CN step reading particle buffer `p`: max_iter x (push, all-reduce, fields); iterations after convergence return at once
   int enqueue_step_cn(cudaStream_t st, int p) {
     const int g = grid_for(dp.N, 256, 8);
+    int per_sm = (int)((size_t)200 * 1024 / (shared_bytes + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    const int gs = grid_for(dp.N, 256, per_sm);  // persistent CTAs with a private grid each (deposit = shared)
     for (int it = 0; it < prm.cn_max_iterations; ++it) {
-      k_cn_push<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_stag, prm.cn_substeps, it, cn_Eavg, cn_Bavg, acc, cn_alive, cn_ctl);
+      if (shared_grid) k_cn_push<R, true><<<gs, 256, shared_bytes, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_stag, prm.cn_substeps, it, cn_Eavg, cn_Bavg, acc, cn_alive, cn_ctl);
+      else k_cn_push<R, false><<<g, 256, 0, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_stag, prm.cn_substeps, it, cn_Eavg, cn_Bavg, acc, cn_alive, cn_ctl);
       int rc = allreduce(st, 0, true);
       if (rc) return rc;
       k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(it, false));

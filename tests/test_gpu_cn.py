@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 KEYS = ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities")
 
 
-def run_gpu_cn(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, dtype=torch.float64, steps_per_graph=0, split=None):
+def run_gpu_cn(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, dtype=torch.float64, steps_per_graph=0, split=None, deposit="auto"):
     from jaxincell_b200 import HotPath
     s = {"max_number_of_Picard_iterations_implicit_CN": 20, "number_of_particle_substeps_implicit_CN": 2,
          "tolerance_Picard_iterations_implicit_CN": 1e-6, "filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), **(solver or {})}
@@ -20,7 +20,7 @@ def run_gpu_cn(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, dtype=torc
                  filter_passes=s["filter_passes"], filter_alpha=s["filter_alpha"], filter_strides=s["filter_strides"],
                  time_evolution_algorithm=1, cn_substeps=s["number_of_particle_substeps_implicit_CN"],
                  cn_max_iterations=s["max_number_of_Picard_iterations_implicit_CN"], cn_tolerance=s["tolerance_Picard_iterations_implicit_CN"],
-                 steps_per_graph=steps_per_graph)
+                 steps_per_graph=steps_per_graph, deposit=deposit)
     hp.set_external_fields(None, None)
     hp.initialize(p["x0"], p["v0"])
     iters = []
@@ -44,15 +44,16 @@ def assert_parity(got, ref, rtol, keys=KEYS):
         assert err < rtol, f"{k}: max rel err {err:.3e} >= {rtol}"
 
 
+@pytest.mark.parametrize("deposit", ["global", "shared"])
 @pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2), (1, 2, 1, 2)])
-def test_cn_matches_the_oracle_all_boundaries(bcs):
+def test_cn_matches_the_oracle_all_boundaries(bcs, deposit):
     G, length, T = 24, 0.01, 12
     p = two_species(1500, 1500, length=length, G=G, seed=13, vth_e=0.2, vth_yz=0.1, drift=4e7, plus_minus=True, gpdl=0.008)
     dt = cfl_dt(length, G, 0.3)
     solver = dict(tolerance_Picard_iterations_implicit_CN=1e-9, max_number_of_Picard_iterations_implicit_CN=12, number_of_particle_substeps_implicit_CN=3)
     ref = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2],
                    fbr=bcs[3], solver=solver)
-    got = run_gpu_cn(p, length=length, G=G, dt=dt, T=T, bcs=bcs, solver=solver, steps_per_graph=5, split=7)
+    got = run_gpu_cn(p, length=length, G=G, dt=dt, T=T, bcs=bcs, solver=solver, steps_per_graph=5, split=7, deposit=deposit)
     assert_parity(got, ref, 1e-5)
     np.testing.assert_allclose(got["initial_velocities"], ref["initial_velocities"], rtol=1e-14)
     np.testing.assert_allclose(got["fields"][0], ref["fields"][0], rtol=1e-10, atol=1e-12 * np.abs(ref["fields"][0]).max())
