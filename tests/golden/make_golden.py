@@ -27,6 +27,15 @@ CASES = {
     "absorbing_reflective_nofilter": (dict(n_e=100, n_i=100, seed=8, vth_e=0.08, vth_yz=0.03, gpdl=0.6), 9, 0.01, 1.1, 8, (2, 1, 2, 1), {"filter_passes": 0}, 0.0),
     "weibel_external_B": (dict(n_e=150, n_i=150, seed=9, vth_e=0.01, vth_yz=0.1, gpdl=0.6, ion_vth_scale=1.0), 14, 0.02, 1.0, 8, (0, 0, 0, 0), {"filter_passes": 2, "filter_strides": (1, 3)}, 1.0),
     "relativistic": (dict(n_e=100, n_i=60, seed=10, vth_e=0.3, vth_yz=0.2, gpdl=0.6), 10, 0.01, 0.7, 8, (0, 0, 0, 0), {"relativistic": True}, 0.3),
+    # per-step electrostatic correction (_algorithms.py:69-78) and the implicit stepper (_algorithms.py:100-241)
+    "field_solver_gauss_fft": (dict(n_e=160, n_i=120, seed=11, vth_e=0.05, vth_yz=0.02, drift=6e7, plus_minus=True, gpdl=0.6), 16, 0.01, 0.9, 10, (0, 0, 0, 0), {"field_solver": 1}, 0.0),
+    "field_solver_cartesian_reflective": (dict(n_e=140, n_i=100, seed=12, vth_e=0.08, vth_yz=0.03, gpdl=0.6), 12, 0.01, 0.9, 10, (1, 1, 1, 1), {"field_solver": 2, "filter_passes": 2}, 0.0),
+    "crank_nicolson_periodic": (dict(n_e=160, n_i=120, seed=13, vth_e=0.05, vth_yz=0.02, drift=4e7, plus_minus=True, gpdl=0.03), 16, 0.01, 0.3, 8, (0, 0, 0, 0),
+                                {"time_evolution_algorithm": 1, "max_number_of_Picard_iterations_implicit_CN": 12, "number_of_particle_substeps_implicit_CN": 2,
+                                 "tolerance_Picard_iterations_implicit_CN": 1e-9}, 0.0),
+    "crank_nicolson_absorbing": (dict(n_e=140, n_i=100, seed=14, vth_e=0.2, vth_yz=0.1, gpdl=0.01), 12, 0.01, 0.3, 8, (2, 2, 2, 2),
+                                 {"time_evolution_algorithm": 1, "max_number_of_Picard_iterations_implicit_CN": 5, "number_of_particle_substeps_implicit_CN": 3,
+                                  "tolerance_Picard_iterations_implicit_CN": 1e-30}, 0.0),
 }
 
 
@@ -40,19 +49,34 @@ def build(name):
     ext_E = (ext * 1e3 * rng.standard_normal((G, 3))).astype(np.float32) if ext else None
     ext_B = (ext * 1e-3 * rng.standard_normal((G, 3))).astype(np.float32) if ext else None
     pbl, pbr, fbl, fbr = bcs
-    out = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=pbl, pbr=pbr, fbl=fbl,
-                fbr=fbr, solver=solver, ext_E=ext_E, ext_B=ext_B)
-    sol = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "relativistic": False, **solver}
+    cn = solver.get("time_evolution_algorithm", 0) == 1
+    if cn:
+        out = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=pbl, pbr=pbr, fbl=fbl,
+                       fbr=fbr, solver=solver)
+    else:
+        out = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=pbl, pbr=pbr, fbl=fbl,
+                    fbr=fbr, solver=solver, ext_E=ext_E, ext_B=ext_B)
+    sol = {"filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), "relativistic": False, "field_solver": 0,
+           "time_evolution_algorithm": 0, "max_number_of_Picard_iterations_implicit_CN": 20, "number_of_particle_substeps_implicit_CN": 2,
+           "tolerance_Picard_iterations_implicit_CN": 1e-6, **solver}
+    extra = dict(field_solver=sol["field_solver"], time_evolution_algorithm=sol["time_evolution_algorithm"],
+                 cn_max_iterations=sol["max_number_of_Picard_iterations_implicit_CN"], cn_substeps=sol["number_of_particle_substeps_implicit_CN"],
+                 cn_tolerance=sol["tolerance_Picard_iterations_implicit_CN"])
+    if cn:
+        extra["picard_iterations"] = out["picard_iterations"]
     return dict(x0=p["x0"], v0=p["v0"], q=p["q"], m=p["m"], qm=p["qm"], n_e=n_e, n_i=n_i, length=length, G=G, dt=dt, T=T,
                 bcs=np.array(bcs), filter_passes=sol["filter_passes"], filter_alpha=sol["filter_alpha"],
                 filter_strides=np.array(sol["filter_strides"]), relativistic=int(sol["relativistic"]),
                 ext_E=np.zeros((G, 3), np.float32) if ext_E is None else ext_E, ext_B=np.zeros((G, 3), np.float32) if ext_B is None else ext_B,
                 positions=out["positions"], velocities=out["velocities"], electric_field=out["electric_field"],
                 magnetic_field=out["magnetic_field"], current_density=out["current_density"], charge_density=out["charge_density"],
-                E0=out["fields"][0], B0=out["fields"][1], initial_velocities=out["initial_velocities"])
+                E0=out["fields"][0], B0=out["fields"][1], initial_velocities=out["initial_velocities"], **extra)
 
 
 if __name__ == "__main__":
-    for name in CASES:
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), **build(name))
+    for name in CASES:  # existing files are kept (pass --all to regenerate everything)
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path) and "--all" not in sys.argv:
+            continue
+        np.savez_compressed(path, **build(name))
         print("wrote", name)

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import closed_form as C
+from oracle import literal as L
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
@@ -19,7 +20,13 @@ RTOL_F64 = 1e-5  # BASELINE.json north_star: per-step E, B, J and particle x/v w
 def _load(path):
     g = dict(np.load(path))
     g["solver"] = dict(filter_passes=int(g["filter_passes"]), filter_alpha=float(g["filter_alpha"]),
-                       filter_strides=tuple(int(s) for s in g["filter_strides"]), relativistic=bool(g["relativistic"]))
+                       filter_strides=tuple(int(s) for s in g["filter_strides"]), relativistic=bool(g["relativistic"]),
+                       field_solver=int(g["field_solver"]) if "field_solver" in g else 0)
+    g["cn"] = int(g["time_evolution_algorithm"]) == 1 if "time_evolution_algorithm" in g else False
+    if g["cn"]:
+        g["solver"].update(max_number_of_Picard_iterations_implicit_CN=int(g["cn_max_iterations"]),
+                           number_of_particle_substeps_implicit_CN=int(g["cn_substeps"]),
+                           tolerance_Picard_iterations_implicit_CN=float(g["cn_tolerance"]))
     return g
 
 
@@ -28,15 +35,19 @@ def _relerr(a, b):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 6
+    assert len(FILES) >= 10
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
 def test_closed_form_oracle_reproduces_golden(path):
     g = _load(path)
     pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
-    out = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]),
-                total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"], ext_E=g["ext_E"], ext_B=g["ext_B"])
+    kw = dict(length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"])
+    if g["cn"]:  # (one oracle only for the implicit stepper: this guards it against drift)
+        out = L.run_CN(g["x0"], g["v0"], g["q"], g["m"], g["qm"], **kw)
+        assert out["picard_iterations"].tolist() == g["picard_iterations"].tolist()
+    else:
+        out = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], ext_E=g["ext_E"], ext_B=g["ext_B"], **kw)
     for k in FIELDS + ("positions", "velocities"):
         assert _relerr(out[k], g[k]) < 1e-10, k
     assert _relerr(out["fields"][0], g["E0"]) < 1e-12
@@ -58,17 +69,25 @@ def test_cuda_reproduces_golden(path, engine):
     g = _load(path)
     pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
     s = g["solver"]
+    cn = g["cn"]
+    if cn and engine == "binned":
+        pytest.skip("the Crank-Nicolson stepper has one particle store")
+    ordered = engine == "indexed" or cn  # particle histories / initial velocities in input order
+    extra = dict(time_evolution_algorithm=1, cn_substeps=s["number_of_particle_substeps_implicit_CN"],
+                 cn_max_iterations=s["max_number_of_Picard_iterations_implicit_CN"], cn_tolerance=s["tolerance_Picard_iterations_implicit_CN"]) if cn else {}
     hp = HotPath(species=_species(g), length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
                  filter_passes=s["filter_passes"], filter_alpha=s["filter_alpha"], filter_strides=s["filter_strides"],
-                 relativistic=s["relativistic"], engine=engine, track_yz=engine == "indexed")
+                 relativistic=s["relativistic"], engine=engine, track_yz=engine == "indexed", field_solver=s["field_solver"], **extra)
     hp.set_external_fields(g["ext_E"], g["ext_B"])
     hp.initialize(g["x0"], g["v0"])
-    out = hp.run(int(g["T"]), particles=engine == "indexed")
+    out = hp.run(int(g["T"]), particles=ordered)
     torch.cuda.synchronize()
-    for k in FIELDS + (("positions", "velocities") if engine == "indexed" else ()):
+    for k in FIELDS + (("positions", "velocities") if ordered else ()):
         assert _relerr(out[k].cpu().numpy(), g[k]) < RTOL_F64, (k, engine)
-    E0, B0, vi = hp.initial(velocities=engine == "indexed")
+    E0, B0, vi = hp.initial(velocities=ordered)
     assert _relerr(E0.cpu().numpy(), g["E0"]) < RTOL_F64
-    if engine == "indexed":
+    if ordered:
         assert _relerr(vi.cpu().numpy(), g["initial_velocities"]) < 1e-14
+    if cn:
+        assert hp.picard_iterations()[1] == int(g["picard_iterations"].sum())
     hp.close()
