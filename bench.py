@@ -353,9 +353,7 @@ def main():
         dev_out = hp.alloc_outputs(K)
         barrier()
         t0 = time.perf_counter()
-        dx0 = hx.to(device, non_blocking=True); dv0 = hv.to(device, non_blocking=True)
-        hp.initialize(dx0, dv0)  # (synchronises: the caller may free x0/v0 afterwards)
-        del dx0, dv0
+        hp.initialize_host(hx, hv)  # pinned host -> device in chunks, overlapped with the start-up kernels; synchronises
         t1 = time.perf_counter()
         o2 = hp.run(K, outputs=dev_out)
         for k, h in host_out.items():
@@ -371,8 +369,9 @@ def main():
         e2e = {"value": N * world * K / el, "unit": "particle-steps/s", "h2d_bytes_per_step": int(world * N * 6 * es / K),
                "d2h_bytes_per_step": int(G * 10 * es), "seconds": el,
                "seconds_breakdown_rank0": {"upload_and_start_up": t1 - t0, "steps_and_download": t2 - t1},
-               "what": f"pinned-host->device copy of x0,v0 ({N * 6 * es / 1e9:.1f} GB per GPU, once per run) + initialize (leap-frog start-up, "
-                       f"binning) + {K} steps + device->host copy of the E,B,J,rho histories, on an existing context"}
+               "what": f"pinned-host->device copy of x0,v0 ({N * 6 * es / 1e9:.1f} GB per GPU, once per run, chunked and overlapped with the "
+                       f"leap-frog start-up / binning kernels: HotPath.initialize_host) + {K} steps + device->host copy of the E,B,J,rho "
+                       f"histories, on an existing context"}
         ok2 = bool(torch.isfinite(host_out["electric_field"][-1]).all().item())
         energy_ok = energy_ok and ok2
     hp.close()

@@ -138,6 +138,12 @@ int jic_set_external_fields(jic_context* ctx, const float* external_E, const flo
  * Gauss solve of _state_initialization.py:374-378, and the first current deposit of _algorithms.py:29-32. */
 int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* stream);
 
+/* The same with HOST buffers (pinned memory makes the copies asynchronous): the upload is cut into chunks that alternate between
+ * two device staging buffers and the start-up kernel of a chunk runs while the next chunk is in flight, so the device never
+ * holds a full copy of x0, v0 and the start-up work hides behind the PCIe transfer.  The host buffers must stay valid until the
+ * stream has drained.  JIC_HOST_CHUNK=<particles> overrides the chunk size (default 2^23). */
+int jic_initialize_host(jic_context* ctx, const void* x0_host, const void* v0_host, void* stream);
+
 /* Advance n_steps (the lax.scan of _simulation.py:253 over Boris_step).  Captured as CUDA graphs; no host sync. */
 int jic_run(jic_context* ctx, int64_t n_steps, const jic_outputs* outputs, void* stream);
 

@@ -367,14 +367,16 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
 // ---------------------------------------------------------------------------------------------------------
 template <typename R>
 __global__ void __launch_bounds__(256) k_start_binned(const DevParams<R> p, const BinDev<R> bd, const R* __restrict__ x0, const R* __restrict__ v0,
+                                                      long long i0, long long n,  // x0, v0 hold particles [i0, i0 + n) of the run
                                                       R* __restrict__ st_x, R* __restrict__ st_vx, R* __restrict__ st_vy, R* __restrict__ st_vz,
                                                       int* __restrict__ st_bin, R* __restrict__ acc) {
   const GlobalGrid<R> grid{acc};
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + j;
     const int s = species_of(i, p);
     const R q = p.sp_q[s];
-    const R X0 = x0[3 * i];
-    R v[3] = {v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]};
+    const R X0 = x0[3 * j];
+    R v[3] = {v0[3 * j], v0[3 * j + 1], v0[3 * j + 2]};
     const Cloud<R> c0 = make_cloud(X0, p);
     deposit_cloud(grid, c0, p.G, R(0), R(0), q * p.inv_dx, false);
     R xp = X0 + p.half_dt * v[0];
@@ -597,25 +599,40 @@ struct BinnedStore {
     return (int)(b < 1 ? 1 : b);
   }
 
-  // initial binning: staging (in buffer 1, which is free until the first push) -> histogram -> exact layout -> scatter
-  int start(Engine& e, const DevParams<R>& dp, const R* x0, const R* v0, R* acc, cudaStream_t st) {
+  // initial binning: staging (in buffer 1, which is free until the first push) -> histogram -> exact layout -> scatter.
+  // Three parts, so that a pipelined host upload can feed the first kernel chunk by chunk.
+  int* st_bin = nullptr;
+  int start_begin(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
     cudaMemsetAsync(bd.hdr, 0, sizeof(PlanHeader), st);
     cudaMemsetAsync(bd.cur[0], 0, sizeof(unsigned) * bd.nb, st);
-    int* st_bin = nullptr;
+    st_bin = nullptr;
     cudaError_t ce = cudaMallocAsync((void**)&st_bin, sizeof(int) * (size_t)(dp.N ? dp.N : 1), st);
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("staging allocation: %s", cudaGetErrorString(ce)));
-    const int g = grid_for(dp.N, 256, 8);
+    return JIC_OK;
+  }
+  int start_chunk(Engine& e, const DevParams<R>& dp, const R* x0, const R* v0, long long i0, long long n, R* acc, cudaStream_t st) {
     // buffer 1 is free until the first push: use it as four linear staging arrays
     R* sx = bd.rec[1]; R* svx = sx + bd.cap_total; R* svy = svx + bd.cap_total; R* svz = svy + bd.cap_total;
-    k_start_binned<R><<<g, 256, 0, st>>>(dp, bd, x0, v0, sx, svx, svy, svz, st_bin, acc);
+    k_start_binned<R><<<grid_for(n, 256, 8), 256, 0, st>>>(dp, bd, x0, v0, i0, n, sx, svx, svy, svz, st_bin, acc);
+    e.launches += 1;
+    return JIC_OK;
+  }
+  int start_end(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
+    R* sx = bd.rec[1]; R* svx = sx + bd.cap_total; R* svy = svx + bd.cap_total; R* svz = svy + bd.cap_total;
     k_first_layout<R><<<1, 1024, 0, st>>>(bd);
-    k_scatter_binned<R><<<g, 256, 0, st>>>(dp, bd, sx, svx, svy, svz, st_bin);
+    k_scatter_binned<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, bd, sx, svx, svy, svz, st_bin);
     cudaFreeAsync(st_bin, st);
-    e.launches += 3;
-    ce = cudaGetLastError();
+    st_bin = nullptr;
+    e.launches += 2;
+    cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("binned start: %s", cudaGetErrorString(ce)));
     first_plan = true;
     return JIC_OK;
+  }
+  int start(Engine& e, const DevParams<R>& dp, const R* x0, const R* v0, R* acc, cudaStream_t st) {
+    int rc = start_begin(e, dp, st);
+    if (rc == JIC_OK) rc = start_chunk(e, dp, x0, v0, 0, dp.N, acc, st);
+    return rc ? rc : start_end(e, dp, st);
   }
   bool first_plan = true;
 

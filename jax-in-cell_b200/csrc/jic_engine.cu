@@ -258,6 +258,9 @@ struct EngineT : Engine {
       cudaDeviceSynchronize();
       for (int r = 0; r < world; ++r) if (r != rank && peer_block[r]) cudaIpcCloseMemHandle(peer_block[r]);
     }
+    for (R* b : hstage) if (b) cudaFree(b);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int k = 0; k < 2; ++k) { if (ev_copied[k]) cudaEventDestroy(ev_copied[k]); if (ev_used[k]) cudaEventDestroy(ev_used[k]); }
     for (int k = 0; k < 2; ++k) { void* q[] = {cn_s[k].x, cn_s[k].y, cn_s[k].z, cn_s[k].vx, cn_s[k].vy, cn_s[k].vz}; for (void* p : q) if (p) cudaFree(p); }
     void* ptrs[] = {cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -394,8 +397,72 @@ struct EngineT : Engine {
     return a;
   }
 
-  int initialize(const void* x0, const void* v0, cudaStream_t st) override {
-    if ((!x0 || !v0) && dp.N > 0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
+  // HOST buffers in: the upload is cut into chunks that alternate between two device staging buffers, and the start-up kernel of a
+  // chunk runs while the next chunk is on the wire -- the device never holds a full copy of x0, v0 (4.8 GB at 1e8 particles), and
+  // the start-up kernels hide behind the PCIe transfer.  (CN: plain upload, then initialize.)
+  R* hstage[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long hstage_n = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+
+  int initialize_host(const void* x0h, const void* v0h, cudaStream_t st) override {
+    if ((!x0h || !v0h) && dp.N > 0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
+    if (cn || dp.N == 0) {
+      R *dx = nullptr, *dv = nullptr;
+      const size_t bytes = (size_t)dp.N * 3 * sizeof(R);
+      JIC_CUDA(cudaMalloc((void**)&dx, bytes ? bytes : 1));
+      JIC_CUDA(cudaMalloc((void**)&dv, bytes ? bytes : 1));
+      cudaMemcpyAsync(dx, x0h, bytes, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(dv, v0h, bytes, cudaMemcpyHostToDevice, st);
+      int rc = initialize(dx, dv, st);
+      cudaStreamSynchronize(st);
+      cudaFree(dx); cudaFree(dv);
+      return rc;
+    }
+    long long chunk = 1ll << 23;
+    if (const char* env = getenv("JIC_HOST_CHUNK")) chunk = std::max(1ll, atoll(env));
+    chunk = std::min(chunk, dp.N);
+    if (hstage_n < chunk) {
+      for (R*& b : hstage) { if (b) cudaFree(b); b = nullptr; }
+      for (R*& b : hstage) JIC_CUDA(cudaMalloc((void**)&b, (size_t)chunk * 3 * sizeof(R)));
+      hstage_n = chunk;
+    }
+    if (!copy_stream) {
+      JIC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        JIC_CUDA(cudaEventCreateWithFlags(&ev_copied[k], cudaEventDisableTiming));
+        JIC_CUDA(cudaEventCreateWithFlags(&ev_used[k], cudaEventDisableTiming));
+      }
+    }
+    int rc = initialize_begin(st);
+    if (rc) return rc;
+    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.start_begin(*this, dp, st))) return rc;
+    // the staging buffers may still be read by the previous call's kernels on `st`
+    JIC_CUDA(cudaEventRecord(ev_used[0], st));
+    JIC_CUDA(cudaEventRecord(ev_used[1], st));
+    int k = 0;
+    for (long long i0 = 0; i0 < dp.N; i0 += chunk, k ^= 1) {
+      const long long n = std::min(chunk, dp.N - i0);
+      const size_t bytes = (size_t)n * 3 * sizeof(R);
+      JIC_CUDA(cudaStreamWaitEvent(copy_stream, ev_used[k], 0));
+      JIC_CUDA(cudaMemcpyAsync(hstage[2 * k], (const R*)x0h + 3 * i0, bytes, cudaMemcpyHostToDevice, copy_stream));
+      JIC_CUDA(cudaMemcpyAsync(hstage[2 * k + 1], (const R*)v0h + 3 * i0, bytes, cudaMemcpyHostToDevice, copy_stream));
+      JIC_CUDA(cudaEventRecord(ev_copied[k], copy_stream));
+      JIC_CUDA(cudaStreamWaitEvent(st, ev_copied[k], 0));
+      if (prm.engine == JIC_ENGINE_INDEXED) {
+        k_start<R><<<grid_for(n, 256, 8), 256, 0, st>>>(dp, hstage[2 * k], hstage[2 * k + 1], i0, n, xh, yh, zh, vx, vy, vz, v_init, acc);
+        launches += 1;
+      } else if ((rc = bins.start_chunk(*this, dp, hstage[2 * k], hstage[2 * k + 1], i0, n, acc, st))) {
+        return rc;
+      }
+      JIC_CUDA(cudaEventRecord(ev_used[k], st));
+    }
+    if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.start_end(*this, dp, st))) return rc;
+    JIC_CUDA(cudaGetLastError());
+    return initialize_finish(st);
+  }
+
+  int initialize_begin(cudaStream_t st) {
     // fused mode: peers may still be reading this rank's raw grid in the last field kernel of a previous run
     if (p2p && nccl_barrier(st)) return fail(JIC_ERR_NCCL, "barrier before initialize failed");
     JIC_CUDA(cudaMemsetAsync(acc, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));
@@ -403,15 +470,10 @@ struct EngineT : Engine {
     JIC_CUDA(cudaMemsetAsync(mc_done, 0, sizeof(unsigned), st));
     JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
     par = 0;
-    if (cn) return initialize_cn((const R*)x0, (const R*)v0, st);
-    if (prm.engine == JIC_ENGINE_INDEXED) {
-      k_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x0, (const R*)v0, xh, yh, zh, vx, vy, vz, v_init, acc);
-      launches += 1;
-    } else {
-      int rc = bins.start(*this, dp, (const R*)x0, (const R*)v0, acc, st);
-      if (rc) return rc;
-    }
-    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
+  int initialize_finish(cudaStream_t st) {
     int rc = allreduce(st, 0, true);  // start-up always goes through NCCL
     if (rc) return rc;
     k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));  // init mode is always the single-CTA kernel
@@ -420,6 +482,21 @@ struct EngineT : Engine {
     JIC_CUDA(cudaGetLastError());
     initialized = true;
     return JIC_OK;
+  }
+
+  int initialize(const void* x0, const void* v0, cudaStream_t st) override {
+    if ((!x0 || !v0) && dp.N > 0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
+    int rc = initialize_begin(st);
+    if (rc) return rc;
+    if (cn) return initialize_cn((const R*)x0, (const R*)v0, st);
+    if (prm.engine == JIC_ENGINE_INDEXED) {
+      k_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x0, (const R*)v0, 0, dp.N, xh, yh, zh, vx, vy, vz, v_init, acc);
+      launches += 1;
+    } else if ((rc = bins.start(*this, dp, (const R*)x0, (const R*)v0, acc, st))) {
+      return rc;
+    }
+    JIC_CUDA(cudaGetLastError());
+    return initialize_finish(st);
   }
 
   // ---- Crank-Nicolson (csrc/jic_cn.cuh) ---------------------------------------------------------------------------
@@ -808,6 +885,7 @@ int jic_comm_unique_id(void* id) {
 int jic_comm_init(jic_context* ctx, const void* id, int rank, int world) { CTX_OR_FAIL(ctx); return ctx->eng->comm_init(id, rank, world); }
 int jic_set_external_fields(jic_context* ctx, const float* eE, const float* eB, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->set_external(eE, eB, (cudaStream_t)st); }
 int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize(x0, v0, (cudaStream_t)st); }
+int jic_initialize_host(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize_host(x0, v0, (cudaStream_t)st); }
 int jic_run(jic_context* ctx, int64_t n, const jic_outputs* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->run(n, out, (cudaStream_t)st); }
 int jic_get_fields(jic_context* ctx, void* E, void* B, void* J, void* rho, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_fields(E, B, J, rho, (cudaStream_t)st); }
 int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* v, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_initial(E0, B0, v, (cudaStream_t)st); }
@@ -874,16 +952,11 @@ int jic_simulate_host(const jic_params* params, const jic_species* species, cons
   auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; dev.push_back(p); return p; };
   auto cleanup = [&](int code) { std::string msg = e->error; for (void* p : dev) cudaFree(p); jic_destroy(ctx); if (code) g_last_error = msg; return code; };
   cudaStream_t st = nullptr;
-  void* dx0 = dalloc(N * 3 * rs);
-  void* dv0 = dalloc(N * 3 * rs);
   float *deE = nullptr, *deB = nullptr;
-  if (!dx0 || !dv0) { e->error = "cudaMalloc failed for the particle upload"; return cleanup(JIC_ERR_CUDA); }
-  cudaMemcpyAsync(dx0, x0_host, N * 3 * rs, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dv0, v0_host, N * 3 * rs, cudaMemcpyHostToDevice, st);
   if (eE_host) { deE = (float*)dalloc(G * 3 * 4); cudaMemcpyAsync(deE, eE_host, G * 3 * 4, cudaMemcpyHostToDevice, st); }
   if (eB_host) { deB = (float*)dalloc(G * 3 * 4); cudaMemcpyAsync(deB, eB_host, G * 3 * 4, cudaMemcpyHostToDevice, st); }
   if ((rc = e->set_external(deE, deB, st))) return cleanup(rc);
-  if ((rc = e->initialize(dx0, dv0, st))) return cleanup(rc);
+  if ((rc = e->initialize_host(x0_host, v0_host, st))) return cleanup(rc);  // chunked upload overlapped with the start-up kernels
   jic_outputs d;
   memset(&d, 0, sizeof(d));
   const size_t sizes[6] = {T * G * 3 * rs, T * G * 3 * rs, T * G * 3 * rs, T * G * rs, T * N * 3 * rs, T * N * 3 * rs};

@@ -10,16 +10,18 @@ namespace jic {
 //   jaxincell/_state_initialization.py:374   rho0 from x0 with the ORIGINAL charges
 //   jaxincell/_algorithms.py:29-32    J^0 from (x_{-1/2}, x0, x_{+1/2}, v, q) with the post-BC charges
 // ---------------------------------------------------------------------------------------------------------
+//   x0, v0 hold particles [i0, i0 + n) of the run (the whole run, or one chunk of a pipelined host upload).
 template <typename R>
-__global__ void __launch_bounds__(256) k_start(const DevParams<R> p, const R* __restrict__ x0, const R* __restrict__ v0,
+__global__ void __launch_bounds__(256) k_start(const DevParams<R> p, const R* __restrict__ x0, const R* __restrict__ v0, long long i0, long long n,
                                                R* __restrict__ xh, R* __restrict__ yh, R* __restrict__ zh, R* __restrict__ vx,
                                                R* __restrict__ vy, R* __restrict__ vz, R* __restrict__ v_init, R* __restrict__ acc) {
   const GlobalGrid<R> grid{acc};
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + j;
     const int s = species_of(i, p);
     const R q = p.sp_q[s];
-    const R X0 = x0[3 * i], Y0 = x0[3 * i + 1], Z0 = x0[3 * i + 2];
-    R v[3] = {v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]};
+    const R X0 = x0[3 * j], Y0 = x0[3 * j + 1], Z0 = x0[3 * j + 2];
+    R v[3] = {v0[3 * j], v0[3 * j + 1], v0[3 * j + 2]};
     // rho0 (original charge, raw initial position)
     const Cloud<R> c0 = make_cloud(X0, p);
     deposit_cloud(grid, c0, p.G, R(0), R(0), q * p.inv_dx, false);
@@ -47,8 +49,8 @@ __global__ void __launch_bounds__(256) k_start(const DevParams<R> p, const R* __
     xh[i] = xp;
     vx[i] = v[0]; vy[i] = v[1]; vz[i] = v[2];
     if (p.track_yz) {
-      yh[i] = wrap_transverse(Y0 + p.half_dt * v0[3 * i + 1], p.Ly, p.half_Ly);
-      zh[i] = wrap_transverse(Z0 + p.half_dt * v0[3 * i + 2], p.Lz, p.half_Lz);
+      yh[i] = wrap_transverse(Y0 + p.half_dt * v0[3 * j + 1], p.Ly, p.half_Ly);
+      zh[i] = wrap_transverse(Z0 + p.half_dt * v0[3 * j + 2], p.Lz, p.half_Lz);
     }
     if (v_init) { v_init[3 * i] = v[0]; v_init[3 * i + 1] = v[1]; v_init[3 * i + 2] = v[2]; }
   }

@@ -112,6 +112,19 @@ class HotPath:
         self._chk(self.lib.jic_initialize(self.ctx, self._ptr(x0), self._ptr(v0), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # x0/v0 may be freed by the caller afterwards
 
+    def initialize_host(self, x0, v0):
+        """x0, v0: HOST tensors / arrays (N,3), ideally pinned: jic_initialize_host uploads them in chunks overlapped with the
+        start-up kernels (the device never holds a full copy).  Synchronises before returning."""
+        x0 = torch.as_tensor(x0).to(dtype=self.dtype).contiguous()
+        v0 = torch.as_tensor(v0).to(dtype=self.dtype).contiguous()
+        if x0.is_cuda or v0.is_cuda:
+            raise JicError("initialize_host takes host memory; use initialize() for device tensors")
+        if tuple(x0.shape) != (self.N, 3) or tuple(v0.shape) != (self.N, 3):
+            raise JicError(f"x0/v0 must have shape ({self.N}, 3)")
+        with torch.cuda.device(self.device):
+            self._chk(self.lib.jic_initialize_host(self.ctx, self._ptr(x0), self._ptr(v0), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
     # ---- stepping
     def alloc_outputs(self, n_steps, fields=True, particles=False):
         out = {}

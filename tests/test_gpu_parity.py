@@ -162,6 +162,29 @@ def test_history_rows_and_graph_chunks():
     assert a["hp"].launch_count() >= 2 * 37
 
 
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("chunk", [None, "37", "256"])
+def test_initialize_host_chunked_upload(engine, chunk, monkeypatch):
+    """jic_initialize_host: host buffers uploaded in chunks (alternating staging buffers) while the start-up kernels run; same
+    result as jic_initialize on device tensors, whatever the chunk size."""
+    from jaxincell_b200 import HotPath
+    if chunk:
+        monkeypatch.setenv("JIC_HOST_CHUNK", chunk)
+    G, length, T = 16, 0.01, 10
+    p = two_species(300, 211, length=length, G=G, seed=9, vth_e=0.1, vth_yz=0.05, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=1, pbr=2, fbl=1, fbr=2)
+    hp = HotPath(species=p["species"], length=length, G=G, dt=dt, engine=engine, pbl=1, pbr=2, fbl=1, fbr=2, track_yz=engine == "indexed")
+    hp.set_external_fields(None, None)
+    hx, hv = torch.from_numpy(p["x0"]).pin_memory(), torch.from_numpy(p["v0"]).pin_memory()
+    for _ in range(2):  # twice: the staging buffers and events are reused
+        hp.initialize_host(hx, hv)
+        out = hp.run(T, particles=engine == "indexed")
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    assert_parity(got, ref, FIELD_KEYS + (("positions", "velocities") if engine == "indexed" else ()), 1e-5)
+    hp.close()
+
+
 def test_host_buffer_entry_point():
     """jic_simulate_host: NumPy in, NumPy out, all copies inside (the e2e boundary)."""
     from jaxincell_b200 import simulate_host
