@@ -77,6 +77,13 @@ struct PlanHeader {
   long long n_absorbed;
 };
 
+constexpr int kPlanMaxCtas = 16;
+struct PlanSync {           // k_plan_mc: per-CTA totals and the two counters of its one grid-wide barrier
+  long long cap_total[kPlanMaxCtas];
+  int item_total[kPlanMaxCtas];
+  unsigned arrive, depart;
+};
+
 template <typename R>
 struct BinDev {
   int nb;                 // n_species * G
@@ -90,6 +97,7 @@ struct BinDev {
   int* ov_bin[2]; R* ov_d[2]; R* ov_vx[2]; R* ov_vy[2]; R* ov_vz[2];
   int* item_bin; int* item_first; int item_cap;
   int n_workers;          // warps of the push kernel (work-queue consumers)
+  struct PlanSync* psync; // cross-CTA state of k_plan_mc
   int edge;               // cells c < edge or c > G-1-edge take the general path for every particle (0 = none, G = all)
   PlanHeader* hdr;
 };
@@ -363,6 +371,132 @@ __global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int fi
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K3m  the plan on NC CTAs (same result as k_plan).  The single-CTA version is latency-bound (38 us at 8192 bins) and sits on the
+//      step's critical path next to an 18 us field kernel; here every thread owns `per` contiguous bins (one at 8192 bins),
+//      neighbour populations come straight from the cursors in global memory, every CTA sums all cursors itself (n_total and
+//      the slack factor need no exchange), and the two prefix sums (slot offsets, work items) are two-level: block scan, per-CTA
+//      totals through global memory, ONE grid-wide barrier (all CTAs are co-resident: the GPU is otherwise idle at this point).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPlanMcThreads = 512;
+
+template <typename R>
+__global__ void __launch_bounds__(kPlanMcThreads) k_plan_mc(const BinDev<R> bd, int G, int first_call) {
+  __shared__ long long sh_ll[33];
+  __shared__ int sh_i[33];
+  __shared__ long long tot_ll;
+  __shared__ int tot_i;
+  PlanHeader* h = bd.hdr;
+  PlanSync* ps = bd.psync;
+  const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb, NC = gridDim.x, cta = blockIdx.x;
+  const int written = first_call ? h->flip : (h->flip ^ 1);
+  const int next = written ^ 1;
+  const unsigned* __restrict__ g_att = bd.cur[written];
+  const long long* __restrict__ g_off = bd.off[written];
+  // n_total: every CTA sums all cursors (a few KB from L2)
+  long long mine = 0;
+  for (int b = t; b < nb; b += nt) mine += (long long)g_att[b];
+  block_exclusive_scan<long long>(mine, &tot_ll, sh_ll);
+  const long long n_total = tot_ll;
+  double f = bd.slack;
+  {
+    const double room = (double)bd.cap_total - (double)n_total - 72.0 * nb;
+    const double fmax = n_total > 0 ? room / (3.0 * (double)n_total) : 0.0;
+    if (f > fmax) f = fmax;
+    if (f < 0) { f = 0; if (t == 0 && cta == 0 && room < 0) atomicExch(&h->error, 2); }
+  }
+  long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
+  want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
+  const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
+  const float inv_chunk = 1.0f / (float)kChunk;
+  // own bins: [lo, hi), contiguous over the whole grid of threads
+  const int T = NC * nt, per = (nb + T - 1) / T;
+  const int lo = min((cta * nt + t) * per, nb), hi = min(lo + per, nb);
+  const int s_lo = lo / G, c_lo = lo - s_lo * G;
+  auto is_slow = [&](int c) { return c < bd.edge || c > G - 1 - bd.edge; };
+  auto cap_at = [&](int b, int c) -> long long {
+    const long long a0 = g_att[b], al = g_att[c == 0 ? b + G - 1 : b - 1], ar = g_att[c == G - 1 ? b - (G - 1) : b + 1];
+    const long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
+    return (cap + kBlk - 1) & ~(long long)(kBlk - 1);
+  };
+  auto cnt_at = [&](int b) -> int {
+    const long long cap = g_off[b + 1] - g_off[b], att = g_att[b];
+    return (int)(att < cap ? att : cap);
+  };
+  auto items_of = [&](int n, int c) -> int {
+    if (is_slow(c)) return (n + kSlowChunk - 1) / kSlowChunk;
+    int q = (int)((float)n * inv_chunk);
+    while ((long long)q * kChunk < n) ++q;
+    while (q > 0 && (long long)(q - 1) * kChunk >= n) --q;
+    return q;
+  };
+  long long cap_sum = 0;
+  int item_sum = 0;
+  {
+    int c = c_lo;
+    for (int b = lo; b < hi; ++b) {
+      const int cnt = cnt_at(b);
+      bd.cnt[written][b] = cnt;
+      cap_sum += cap_at(b, c);
+      item_sum += items_of(cnt, c);
+      c = c + 1 == G ? 0 : c + 1;
+    }
+  }
+  long long run = block_exclusive_scan<long long>(cap_sum, &tot_ll, sh_ll);
+  int it = block_exclusive_scan<int>(item_sum, &tot_i, sh_i);
+  // ---- the one grid-wide exchange: per-CTA totals
+  if (t == 0) {
+    ps->cap_total[cta] = tot_ll;
+    ps->item_total[cta] = tot_i;
+    __threadfence();
+    atomicAdd(&ps->arrive, 1u);
+    const long long t0 = clock64();
+    while (*(volatile unsigned*)&ps->arrive < (unsigned)NC) {
+      if (clock64() - t0 > 2000000000ll) { atomicExch(&h->error, 2); break; }  // never hang the GPU on a lost CTA
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  long long all_caps = 0;
+  int all_items = 0;
+  for (int k = 0; k < NC; ++k) {
+    const long long ck = *(volatile long long*)&ps->cap_total[k];
+    const int ik = *(volatile int*)&ps->item_total[k];
+    if (k < cta) { run += ck; it += ik; }
+    all_caps += ck; all_items += ik;
+  }
+  {
+    int c = c_lo;
+    for (int b = lo; b < hi; ++b) {
+      bd.off[next][b] = run;
+      run += cap_at(b, c);
+      bd.cur[next][b] = 0u;
+      const int n = bd.cnt[written][b], ch = is_slow(c) ? kSlowChunk : kChunk;
+      for (int k = 0; k < n; k += ch) {
+        if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
+        ++it;
+      }
+      c = c + 1 == G ? 0 : c + 1;
+    }
+  }
+  if (cta == 0 && t == 0) {
+    bd.off[next][nb] = all_caps;
+    if (all_items > bd.item_cap) atomicExch(&h->error, 2);
+    h->n_items = all_items < bd.item_cap ? all_items : bd.item_cap;
+    h->chunk = kChunk;
+    h->work = 0;
+    h->flip = written;
+    h->ov_n[next] = 0;
+    h->n_stored = n_total;
+  }
+  // every CTA has read the totals: the last one to leave re-arms the barrier for the next launch
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    if (atomicAdd(&ps->depart, 1u) == (unsigned)NC - 1) { ps->arrive = 0u; ps->depart = 0u; __threadfence(); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // start-up: leap-frog start + initial deposits (as k_start) into a linear staging area, then a scatter into bins
 // ---------------------------------------------------------------------------------------------------------
 template <typename R>
@@ -562,7 +696,12 @@ struct BinnedStore {
         return rc;
     }
     if ((rc = alloc(e, &bd.item_bin, bd.item_cap)) || (rc = alloc(e, &bd.item_first, bd.item_cap)) || (rc = alloc(e, &bd.hdr, 1))) return rc;
-    if ((rc = alloc(e, &dense, bd.nb + 1))) return rc;
+    if ((rc = alloc(e, &dense, bd.nb + 1)) || (rc = alloc(e, &bd.psync, 1))) return rc;
+    {
+      const char* env = getenv("JIC_PLAN_MC");  // "0" keeps the single-CTA plan
+      plan_ctas = (env && env[0] == '0') ? 0 : std::min(kPlanMaxCtas, (bd.nb + kPlanMcThreads - 1) / kPlanMcThreads);
+      if (plan_ctas < 2) plan_ctas = 0;
+    }
     (void)prm;
     {
       // Shared-memory carve-out: three CTAs of the fp64 kernel (43.3 KB static + 1 KB reserved each) fit the 132 KB configuration,
@@ -637,9 +776,11 @@ struct BinnedStore {
   bool first_plan = true;
 
   // runs after every push (and after the start-up scatter), concurrently with the field kernel: plan the next push
+  int plan_ctas = 0;  // > 0: k_plan_mc on that many CTAs
   int plan(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
     const size_t sm = (size_t)2 * bd.nb * sizeof(int);
-    if (sm <= plan_smem_max) k_plan<R, true><<<1, 1024, sm, st>>>(bd, dp.G, first_plan ? 1 : 0);
+    if (plan_ctas > 0) k_plan_mc<R><<<plan_ctas, kPlanMcThreads, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
+    else if (sm <= plan_smem_max) k_plan<R, true><<<1, 1024, sm, st>>>(bd, dp.G, first_plan ? 1 : 0);
     else k_plan<R, false><<<1, 1024, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
     first_plan = false;
     e.launches += 1;
