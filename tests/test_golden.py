@@ -1,6 +1,12 @@
-"""Committed golden vectors (tests/golden/*.npz, written by tests/golden/make_golden.py from the literal oracle).
+"""Committed golden vectors, two families with the same keys:
 
-CPU: the O(N) closed-form oracle must reproduce them (guards the oracle against drift).
+  tests/golden/refsrc_<case>.npz -- written by tests/golden/make_reference_golden.py: the REFERENCE'S OWN SOURCE
+      (`jaxincell.Simulation(...).run()`, i.e. its start-up, `Boris_step` / `CN_step`, scan and output dict) executed in the build
+      container on the NumPy stand-in for jax of tests/refshim (jax itself is not installable); the stand-in is pinned by the
+      reference's own unit tests (tests/golden/REFERENCE_SOURCE_RUN.md).  These pin the *composition* of the step.
+  tests/golden/<case>.npz        -- written by tests/golden/make_golden.py from oracle/literal.py (same inputs).
+
+CPU: both oracles must reproduce both families (guards the oracles against drift, and the restatement against the reference).
 GPU: both CUDA engines, through the C ABI, must reproduce them within the north-star tolerance (1e-5 fp64)."""
 import glob
 import os
@@ -35,7 +41,40 @@ def _relerr(a, b):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 10
+    assert len(FILES) >= 20
+    assert sum(os.path.basename(f).startswith("refsrc_") for f in FILES) >= 10
+
+
+REFSRC = [f for f in FILES if os.path.basename(f).startswith("refsrc_")]
+
+
+@pytest.mark.parametrize("path", REFSRC, ids=[os.path.basename(f)[:-4] for f in REFSRC])
+def test_reference_source_vectors_match_the_oracle_made_ones(path):
+    """Same inputs, one file from the reference's source, one from oracle/literal.py: equal to round-off, Picard counts exactly."""
+    r, o = dict(np.load(path)), dict(np.load(path.replace("refsrc_", "")))
+    for k in ("x0", "v0", "q", "m", "qm", "ext_E", "ext_B", "bcs", "filter_strides"):
+        assert np.array_equal(r[k], o[k]), k
+    assert float(r["dt"]) == float(o["dt"])
+    for k in FIELDS + ("positions", "velocities", "E0", "initial_velocities"):
+        assert _relerr(o[k], r[k]) < 1e-10, k
+    if "picard_iterations" in r:
+        assert r["picard_iterations"].tolist() == o["picard_iterations"].tolist()
+
+
+@pytest.mark.parametrize("path", REFSRC, ids=[os.path.basename(f)[:-4] for f in REFSRC])
+def test_literal_oracle_reproduces_reference_source_vectors(path):
+    g = _load(path)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    kw = dict(length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"])
+    if g["cn"]:
+        out = L.run_CN(g["x0"], g["v0"], g["q"], g["m"], g["qm"], **kw)
+        assert out["picard_iterations"].tolist() == g["picard_iterations"].tolist()
+    else:
+        out = L.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], ext_E=g["ext_E"], ext_B=g["ext_B"], **kw)
+    for k in FIELDS + ("positions", "velocities"):
+        assert _relerr(out[k], g[k]) < 1e-10, k
+    assert _relerr(out["fields"][0], g["E0"]) < 1e-10  # the reference solves a dense bidiagonal system, the oracle sums: cancellation of a neutral plasma
+    assert _relerr(out["initial_velocities"], g["initial_velocities"]) < 1e-15
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
@@ -50,7 +89,7 @@ def test_closed_form_oracle_reproduces_golden(path):
         out = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], ext_E=g["ext_E"], ext_B=g["ext_B"], **kw)
     for k in FIELDS + ("positions", "velocities"):
         assert _relerr(out[k], g[k]) < 1e-10, k
-    assert _relerr(out["fields"][0], g["E0"]) < 1e-12
+    assert _relerr(out["fields"][0], g["E0"]) < (1e-10 if "refsrc_" in path else 1e-12)
     assert _relerr(out["initial_velocities"], g["initial_velocities"]) < 1e-15
 
 
