@@ -48,6 +48,10 @@ SOLVER_DEFAULTS = dict(print_info=True, field_solver=0, relativistic=False, time
                        max_number_of_Picard_iterations_implicit_CN=20, number_of_particle_substeps_implicit_CN=2,
                        tolerance_Picard_iterations_implicit_CN=1e-6, filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4),
                        seed=1701, engine="auto", particle_history=True, dtype="float64", rng="threefry", threefry_partitionable=True)
+# _parameters/_source_parameters.py:10-23 -- carried into the output dictionary; no code of the step reads them
+SOURCE_DEFAULTS = dict(source_term_active=0, source_species=1, how_often_source_should_produce_quasiparticles=20,
+                       source_particles_per_second=1e16, location_of_source=0, width_of_source=1, injection_speed_x=1e7,
+                       injection_speed_y=0, injection_speed_z=0)
 EXTERNAL_DEFAULTS = dict(external_electric_field_amplitude=0.0, external_electric_field_wavenumber=0.0,
                          external_magnetic_field_amplitude=0.0, external_magnetic_field_wavenumber=0.0,
                          external_electric_field_function=None, external_magnetic_field_function=None)
@@ -90,12 +94,7 @@ def _clean_species(species_parameters):
             values = {f"{kind}0": values}
         out[kind] = {}
         for i, (label, v) in enumerate(values.items()):
-            sp = {**_species_defaults(kind, i == 0), **v, "user_label": label}
-            if not (isinstance(sp["number_pseudoparticles"], int) and sp["number_pseudoparticles"] > 0):
-                raise AssertionError(f"Number of pseudoparticles for {label} must be a positive integer. Got {sp['number_pseudoparticles']}.")
-            if not sp["grid_points_per_Debye_length"] > 0:
-                raise AssertionError(f"Grid points per Debye length must be positive. Got {sp['grid_points_per_Debye_length']}.")
-            out[kind][f"_{kind}{i}"] = sp
+            out[kind][f"_{kind}{i}"] = {**_species_defaults(kind, i == 0), **v, "user_label": label}
     labels = {k: {sp["user_label"]: canon for canon, sp in out[k].items()} for k in out}
 
     def find(ref):
@@ -125,6 +124,26 @@ def _clean_species(species_parameters):
                                     * np.sqrt(ref["mass_over_proton_mass"] * mass_proton / mass_electron))
                 else:
                     sp[key] = ref[key]
+    # validation after the references are resolved, as in the reference (_species_parameters.py:66-100,213-221)
+    for kind in out:
+        for canon, sp in out[kind].items():
+            if not (type(sp["number_pseudoparticles"]) == int and sp["number_pseudoparticles"] > 0):
+                raise AssertionError(f"Number of pseudoparticles for {canon} must be a positive integer. Got {sp['number_pseudoparticles']}.")
+            if not sp["grid_points_per_Debye_length"] > 0:
+                raise AssertionError(f"Grid points per Debye length must be positive. Got {sp['grid_points_per_Debye_length']}.")
+            if not sp["weight"] >= 0:
+                raise AssertionError(f"Weight must be non-negative. Got {sp['weight']}.")
+            if kind == "ions":
+                if not sp["mass_over_proton_mass"] > 0:
+                    raise AssertionError(f"Mass over proton mass must be positive. Got {sp['mass_over_proton_mass']}.")
+                for a in AXES:
+                    if not sp[f"ion_temperature_over_electron_temperature_{a}"] >= 0:
+                        raise AssertionError(f"Ion temperature over electron temperature {a} must be positive.")
+            for key in [f"{k}_{a}" for k in ("random_positions", "velocity_plus_minus") for a in AXES] + ["seed_position_override"]:
+                if type(sp[key]) != bool:
+                    raise AssertionError(f"{key} must be a boolean. Got {sp[key]}.")
+            if sp["seed_position_override"] and not (type(sp["seed_position"]) == int and sp["seed_position"] > 0):
+                raise AssertionError(f"Seed position must be a positive integer. Got {sp['seed_position']}.")
     return out
 
 
@@ -152,7 +171,7 @@ class Simulation:
         self.domain_parameters = self._clean_domain({**DOMAIN_DEFAULTS, **parameters.get("domain_parameters", {})})
         self.solver_parameters = self._clean_solver({**SOLVER_DEFAULTS, **parameters.get("solver_parameters", {})})
         self.external_field_parameters = {**EXTERNAL_DEFAULTS, **parameters.get("external_field_parameters", {})}
-        self.source_parameters = dict(parameters.get("source_parameters", {}))  # validated nowhere in the step
+        self.source_parameters = {**SOURCE_DEFAULTS, **parameters.get("source_parameters", {})}
         self.species_parameters = _clean_species(parameters.get("species_parameters", {}))
 
     # ---- cleaning -------------------------------------------------------------------------------------------------
@@ -254,8 +273,9 @@ class Simulation:
                     ref = dict(vth_electrons=max(vths) * speed_of_light, vth_electrons_over_c=max(vths), charge_electrons=charge)
                 if ref is None:
                     raise ValueError("Electron reference species must be initialized before ions.")
+                debye_length_per_dx = 1 / sp["grid_points_per_Debye_length"]  # same operation order as the reference: the weight is bit-equal
                 w = (epsilon_0 * mass_electron * speed_of_light ** 2 / ref["charge_electrons"] ** 2 * G ** 2 / box[0] / (2 * n)
-                     * ref["vth_electrons_over_c"] ** 2 * sp["grid_points_per_Debye_length"] ** 2)
+                     * ref["vth_electrons_over_c"] ** 2 / debye_length_per_dx ** 2)
                 w = w if sp["weight"] == 0 else float(sp["weight"])
                 pos.append(x); vel.append(v); wts.append(np.full((n, 1), w)); sidx.append(np.full(n, len(table), dtype=np.int32))
                 table.append(dict(count=n, q=charge * w, m=mass * w, qm=charge / mass))
@@ -281,7 +301,7 @@ class Simulation:
         return dict(positions=positions, velocities=velocities, weights=weights, species_integer_index=species_integer_index,
                     charge_integer_lookup=cl, mass_integer_lookup=ml, charge_mass_integer_lookup=ql,
                     charges=cl[species_integer_index].reshape(-1, 1) * weights, masses=ml[species_integer_index].reshape(-1, 1) * weights,
-                    charge_to_mass_ratios=ql[species_integer_index].reshape(-1, 1), species_table=table, **ref)
+                    charge_to_mass_ratios=ql[species_integer_index].reshape(-1, 1), species_table=table, sampling=sampling, **ref)
 
     # ---- run ------------------------------------------------------------------------------------------------------
     def simulation(self, input_parameters=None):
@@ -312,6 +332,13 @@ class Simulation:
                             cn_substeps=int(solver["number_of_particle_substeps_implicit_CN"]),
                             cn_max_iterations=int(solver["max_number_of_Picard_iterations_implicit_CN"]),
                             cn_tolerance=float(solver["tolerance_Picard_iterations_implicit_CN"]))
+        return self._assemble_output(sec, state, ps, res, ext_E, ext_B)
+
+    @staticmethod
+    def _assemble_output(sec, state, ps, res, ext_E, ext_B):
+        """jaxincell/_simulation.py:260-344: the output dictionary (`res` holds what the library produced)."""
+        dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
+        G, T = int(dom["number_grid_points"]), int(dom["total_steps"])
         e0 = next(iter(sec["species_parameters"]["electrons"].values()))
         we = ps["weights"][0, 0]
         plasma_frequency = (np.sqrt(e0["number_pseudoparticles"] * we * ps["charge_electrons"] ** 2) / np.sqrt(mass_electron)
@@ -334,6 +361,19 @@ class Simulation:
         return {**dom, **ext, **sec["source_parameters"], **solver, **out, "domain_parameters": dom,
                 "species_parameters": sec["species_parameters"], "external_field_parameters": ext,
                 "source_parameters": sec["source_parameters"], "solver_parameters": solver, "parameter_sections": sec}
+
+    def output_keys(self, input_parameters=None):
+        """Key set of the dictionary `run()` returns (host logic only: no particles are pushed)."""
+        sec = self._sections(input_parameters)
+        dom = sec["domain_parameters"]
+        state = self.build_domain_state(dom)
+        n = sum(sp["number_pseudoparticles"] for kind in sec["species_parameters"].values() for sp in kind.values())
+        e0 = next(iter(sec["species_parameters"]["electrons"].values()))
+        ps = dict(masses=None, charges=None, charge_to_mass_ratios=None, positions=None, velocities=None, weights=np.ones((n, 1)),
+                  species_integer_index=None, charge_integer_lookup=None, mass_integer_lookup=None, charge_mass_integer_lookup=None,
+                  vth_electrons=None, vth_electrons_over_c=None, charge_electrons=e0["charge_over_elementary_charge"] * elementary_charge)
+        res = dict.fromkeys(("positions", "velocities", "electric_field", "magnetic_field", "current_density", "charge_density", "fields"))
+        return sorted(self._assemble_output(sec, state, ps, res, None, None))
 
     def run(self, input_parameters=None):
         return self.simulation(input_parameters)

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Host-driver golden values from the REFERENCE'S OWN SOURCE on the NumPy stand-in (tests/refshim):
+
+    python tests/golden/driver/make_reference_driver_golden.py
+
+Runs only where /root/reference exists (the build container).  TEST INFRASTRUCTURE.  For every parameter dict of
+tests/golden/driver/driver_cases.py it builds the reference's `Simulation(parameters)` (jaxincell/_simulation.py:85-92: cleaners, species
+cross references, domain / particle / field state) and records what the host side of the hot path must reproduce:
+
+  * domain state: dx, dt, grid end points, box size (_state_initialization.py:27-49);
+  * per species, in the reference's order: count, resolved vth / drift / amplitudes / flags, the (seed_position, seed_velocity) pair
+    that actually reached `initialize_species_phase_space` (_state_initialization.py:87-96,126-136), weight, charge, mass, q/m
+    (:172-185,259-261);
+  * the assembled particle state: positions / velocities drawn by the reference's formulas (:51-85) on the Threefry restatement
+    (the stand-in's jax.random = oracle/sampling.py), after the 0.99c clip (:263-264);
+  * for RUN_CASE: `Simulation.run()` -> key set of the output dictionary, plasma_frequency, time_array end points (_simulation.py:263-312),
+    and `diagnostics(output)` (_diagnostics.py:8-147) -> energies, dominant frequency, species names; the run's inputs/outputs that
+    `diagnostics` consumes are stored too so that jaxincell_b200.diagnostics can be fed the same arrays.
+
+Output: tests/golden/driver/refsrc_driver.json (scalars, tables) and tests/golden/driver/refsrc_driver_arrays.npz."""
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
+REF = os.environ.get("JIC_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(ROOT, "tests", "refshim"), REF, ROOT, os.path.join(ROOT, "tests"), HERE]
+
+import jax  # noqa: E402  (the stand-in)
+assert "standin" in jax.__version__
+import jaxincell  # noqa: E402
+import jaxincell._state_initialization as SI  # noqa: E402
+from driver_cases import CASES, RUN_CASE  # noqa: E402
+
+AXES = ("x", "y", "z")
+
+
+def f(v):
+    return float(np.asarray(v))
+
+
+def record(name, params):
+    seeds = []
+    inner = SI.initialize_species_phase_space
+
+    def spy(species, seed_position, seed_velocity, number_particles, box_size):
+        seeds.append((int(seed_position), int(seed_velocity), int(number_particles)))
+        return inner(species, seed_position, seed_velocity, number_particles, box_size)
+    SI.initialize_species_phase_space = spy
+    try:
+        sim = jaxincell.Simulation(copy.deepcopy(params))
+    finally:
+        SI.initialize_species_phase_space = inner
+    sp_all = sim.species_parameters
+    species, o = [], 0
+    k = 0
+    for kind in ("electrons", "ions"):
+        for canon, sp in sp_all[kind].items():
+            n = sp["number_pseudoparticles"]
+            species.append(dict(kind=kind, canonical=canon, user_label=sp["user_label"], count=n,
+                                seed_position=seeds[k][0], seed_velocity=seeds[k][1],
+                                weight=f(sim.weights[o, 0]), charge=f(sim.charges[o, 0]), mass=f(sim.masses[o, 0]),
+                                charge_to_mass=f(sim.charge_to_mass_ratios[o, 0]),
+                                grid_points_per_Debye_length=f(sp["grid_points_per_Debye_length"]),
+                                **{f"{key}_{a}": (bool(sp[f"{key}_{a}"]) if isinstance(sp[f"{key}_{a}"], bool) else f(sp[f"{key}_{a}"]))
+                                   for key in ("vth_over_c", "drift_speed", "perturbation_amplitude", "perturbation_wavenumber",
+                                               "random_positions", "velocity_plus_minus") for a in AXES}))
+            assert seeds[k][2] == n
+            o += n
+            k += 1
+    rec = dict(dx=f(sim.dx), dt=f(sim.dt), grid_first=f(sim.grid[0]), grid_last=f(sim.grid[-1]), grid_size=int(len(sim.grid)),
+               box_size=[f(b) for b in sim.box_size], species=species, n_particles=int(o),
+               solver={k: (list(v) if isinstance(v, tuple) else v) for k, v in sim.solver_parameters.items()},
+               domain={k: (f(v) if not isinstance(v, (int, bool)) else v) for k, v in sim.domain_parameters.items()})
+    arrays = {f"{name}__positions": np.asarray(sim.positions, np.float64), f"{name}__velocities": np.asarray(sim.velocities, np.float64),
+              f"{name}__E0": np.asarray(sim.fields[0], np.float64)}
+    return sim, rec, arrays
+
+
+def main():
+    out, arrays = {}, {}
+    for name, params in CASES.items():
+        sim, rec, arr = record(name, params)
+        out[name] = rec
+        arrays.update(arr)
+        print(name, rec["n_particles"], "particles,", len(rec["species"]), "species")
+        if name == RUN_CASE:
+            res = sim.run()
+            rec["output_keys"] = sorted(k for k in res.keys())
+            rec["plasma_frequency"] = f(res["plasma_frequency"])
+            rec["time_array"] = [f(res["time_array"][0]), f(res["time_array"][1]), f(res["time_array"][-1]), int(len(res["time_array"]))]
+            rec["max_initial_vth_electrons"] = f(res["max_initial_vth_electrons"])
+            rec["number_pseudoelectrons"] = int(res["number_pseudoelectrons"])
+            for k in ("positions", "velocities", "electric_field", "magnetic_field", "current_density", "charge_density", "masses", "charges",
+                      "initial_velocities", "external_electric_field", "external_magnetic_field", "grid"):
+                arrays[f"run__{k}"] = np.asarray(res[k])
+            jaxincell.diagnostics(res)  # mutates `res` and returns None (_diagnostics.py:8-147)
+            d = res
+            rec["diagnostics_keys"] = sorted(d.keys())
+            rec["species_names"] = [s["name"] for s in d["species"]]
+            rec["dominant_frequency"] = f(d["dominant_frequency"])
+            for k in ("electric_field_energy", "magnetic_field_energy", "kinetic_energy", "kinetic_energy_electrons", "kinetic_energy_ions",
+                      "total_energy", "electric_field_energy_density", "external_electric_field_energy", "external_magnetic_field_energy"):
+                arrays[f"diag__{k}"] = np.asarray(d[k], np.float64)
+    with open(os.path.join(HERE, "refsrc_driver.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True, default=lambda v: f(v) if np.ndim(v) == 0 else np.asarray(v).tolist())
+    np.savez_compressed(os.path.join(HERE, "refsrc_driver_arrays.npz"), **arrays)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,118 @@ def test_diagnostics_energies_on_a_fabricated_output():
     assert d["total_energy"].shape == (T,)
 
 
+# ---- against the reference's own source (tests/golden/driver: written by make_reference_driver_golden.py on tests/refshim) -----------
+import copy  # noqa: E402
+import json  # noqa: E402
+import os  # noqa: E402
+import sys  # noqa: E402
+
+_DRV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "driver")
+sys.path.insert(0, _DRV)
+from driver_cases import CASES as DRIVER_CASES, RUN_CASE  # noqa: E402
+
+with open(os.path.join(_DRV, "refsrc_driver.json")) as _f:
+    REFSRC = json.load(_f)
+
+
+def _host_state(name, rng="numpy"):
+    par = copy.deepcopy(DRIVER_CASES[name])
+    par.setdefault("solver_parameters", {})["rng"] = rng
+    sim = Simulation(par)
+    st = sim.build_domain_state(sim.domain_parameters)
+    return sim, st
+
+
+@pytest.mark.parametrize("name", sorted(DRIVER_CASES))
+def test_host_state_matches_the_reference_source(name):
+    """Cleaners, species cross references, domain state, seed schedule, weights / charges / masses: equal to what the reference's
+    `Simulation(parameters)` derives from the same dictionary (_simulation.py:85-92, _state_initialization.py:27-49,87-185,259-261)."""
+    ref = REFSRC[name]
+    sim, st = _host_state(name)
+    np.testing.assert_allclose([st["dx"], st["dt"], st["grid"][0], st["grid"][-1]], [ref["dx"], ref["dt"], ref["grid_first"], ref["grid_last"]], rtol=1e-15)
+    assert len(st["grid"]) == ref["grid_size"]
+    np.testing.assert_allclose(st["box_size"], ref["box_size"], rtol=0)
+    for k, v in ref["solver"].items():
+        got = sim.solver_parameters[k]
+        assert (list(got) if isinstance(got, tuple) else got) == v, k
+    for k, v in ref["domain"].items():
+        assert sim.domain_parameters[k] == v, k
+    mine = [(kind, canon, sp) for kind in ("electrons", "ions") for canon, sp in sim.species_parameters[kind].items()]
+    assert [(k, c, sp["user_label"], sp["number_pseudoparticles"]) for k, c, sp in mine] == \
+        [(r["kind"], r["canonical"], r["user_label"], r["count"]) for r in ref["species"]]
+    for (kind, canon, sp), r in zip(mine, ref["species"]):
+        for key in ("vth_over_c", "drift_speed", "perturbation_amplitude", "perturbation_wavenumber"):
+            for a in "xyz":
+                np.testing.assert_allclose(float(sp[f"{key}_{a}"]), r[f"{key}_{a}"], rtol=1e-15, err_msg=f"{canon} {key}_{a}")
+        for key in ("random_positions", "velocity_plus_minus"):
+            for a in "xyz":
+                assert bool(sp[f"{key}_{a}"]) == r[f"{key}_{a}"], (canon, key, a)
+        np.testing.assert_allclose(float(sp["grid_points_per_Debye_length"]), r["grid_points_per_Debye_length"], rtol=1e-15)
+    ps = sim.initialize_particle_state(sim.species_parameters, sim.domain_parameters, sim.solver_parameters, st)
+    assert len(ps["positions"]) == ref["n_particles"]
+    o = 0
+    for r, t, smp in zip(ref["species"], ps["species_table"], ps["sampling"]):
+        np.testing.assert_allclose([ps["weights"][o, 0], t["q"], t["m"], t["qm"]], [r["weight"], r["charge"], r["mass"], r["charge_to_mass"]], rtol=0)
+        assert (smp["seed_position"], smp["seed_velocity"]) == (r["seed_position"], r["seed_velocity"]), r["canonical"]
+        o += r["count"]
+
+
+@pytest.mark.parametrize("name", sorted(DRIVER_CASES))
+def test_initial_particles_of_the_reference_source_equal_the_sampling_oracle(name):
+    """The reference's `initialize_species_phase_space` (_state_initialization.py:51-85) ran on the Threefry restatement
+    (oracle/sampling.py as the stand-in's jax.random); oracle.sampling.sample composes the same draws itself (linspace form,
+    perturbation, drift, (-1)^i, seed offsets +1..3 / +4..6) and the device kernel is tested against it (tests/test_sampling.py)."""
+    from oracle import sampling as OS
+    arrays = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
+    sim, st = _host_state(name)
+    ps = sim.initialize_particle_state(sim.species_parameters, sim.domain_parameters, sim.solver_parameters, st)
+    x, v = OS.sample(ps["sampling"], st["box_size"], partitionable=True)
+    lim = 0.99 * S.speed_of_light
+    v = np.where(np.abs(v) >= lim, np.sign(v) * lim, v)
+    np.testing.assert_allclose(x, arrays[f"{name}__positions"], rtol=1e-15, atol=1e-18)
+    np.testing.assert_allclose(v, arrays[f"{name}__velocities"], rtol=1e-15, atol=1e-9)
+
+
+def test_output_dictionary_keys_of_the_reference_source():
+    """Every key of the reference's output dictionary (_simulation.py:269-344) is produced by the driver (checked on the key list the
+    driver assembles; the values need a GPU run)."""
+    ref = REFSRC[RUN_CASE]
+    sim, st = _host_state(RUN_CASE)
+    assert set(ref["output_keys"]) <= set(sim.output_keys()), sorted(set(ref["output_keys"]) - set(sim.output_keys()))
+
+
+def test_diagnostics_match_the_reference_source():
+    """jaxincell_b200.diagnostics on the arrays of the reference's run == the reference's own `diagnostics` (_diagnostics.py:8-147)."""
+    ref = REFSRC[RUN_CASE]
+    a = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
+    out = {k[len("run__"):]: a[k] for k in a.files if k.startswith("run__")}
+    out.update(total_steps=ref["domain"]["total_steps"], dt=ref["dt"], dx=ref["dx"], plasma_frequency=ref["plasma_frequency"])
+    d = diagnostics(out)
+    assert [s["name"] for s in d["species"]] == ref["species_names"]
+    np.testing.assert_allclose(d["dominant_frequency"], ref["dominant_frequency"], rtol=1e-12)
+    for k in a.files:
+        if k.startswith("diag__"):
+            np.testing.assert_allclose(d[k[len("diag__"):]], a[k], rtol=1e-12, err_msg=k)
+    missing = set(ref["diagnostics_keys"]) - set(d) - set(ref["output_keys"])
+    assert not missing, sorted(missing)
+
+
+@pytest.mark.gpu
+def test_run_of_the_reference_source_is_reproduced_end_to_end():
+    """`Simulation(parameters).run()` here vs the reference's own `Simulation(parameters).run()` (on the stand-in) for the same parameter
+    dictionary: initial particles from the device Threefry sampler, 40 steps at CFL 4.5 (multi-cell jumps), every history."""
+    ref = REFSRC[RUN_CASE]
+    a = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
+    out = Simulation(copy.deepcopy(DRIVER_CASES[RUN_CASE])).run()
+    assert set(ref["output_keys"]) <= set(out)
+    np.testing.assert_allclose(out["plasma_frequency"], ref["plasma_frequency"], rtol=1e-14)
+    np.testing.assert_allclose([out["time_array"][0], out["time_array"][1], out["time_array"][-1]], ref["time_array"][:3], rtol=1e-14)
+    np.testing.assert_allclose(out["initial_positions"], a[f"{RUN_CASE}__positions"], rtol=0, atol=1e-15 * 0.01)
+    for k in ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities"):
+        err = np.abs(np.asarray(out[k]) - a[f"run__{k}"]).max() / max(np.abs(a[f"run__{k}"]).max(), 1e-300)
+        assert err < 1e-5, (k, err)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_output_contract_and_determinism():
