@@ -8,10 +8,11 @@ including its O(N*G) "every particle touches every node" formulation, so that it
 known-answer vectors of the reference's own unit tests (tests/test_oracle_kat.py) and then used to validate
 the O(N) closed form in ``oracle/closed_form.py`` and the CUDA kernels.
 
-Parity status: PINNED COMPOSITIONALLY.  JAX is not installable in the build image, so the reference cannot
-be executed; every function here is pinned by the hand-computed vectors in the reference's tests
-(SURVEY.md section 8c).  The composed step has no golden vector in the reference (its tests only assert
-shapes/finiteness), so the composition follows ``jaxincell/_algorithms.py:17-95`` line by line.
+Parity status: PINNED -- callees by the hand-computed vectors of the reference's own unit tests (tests/test_oracle_kat.py,
+SURVEY.md section 8c); the composed step / start-up / scan by running the reference's own source files on a NumPy stand-in for
+jax (tests/refshim, itself pinned by 183 of the reference's 188 unit tests): tests/golden/refsrc_*.npz, reproduced here to
+<= 2e-13 relative (tests/test_golden.py, tests/golden/REFERENCE_SOURCE_RUN.md).  Not pinned: XLA's floating-point evaluation
+order (JAX is not installable in the build image), a round-off effect.
 
 All ``file:line`` citations are relative to the reference checkout (``jaxincell/...``).
 """

@@ -74,7 +74,11 @@ def reference_parameters(case):
     kw, G, length, cfl, T, bcs, solver, ext = MG.CASES[case]
     kw = dict(kw)
     n_e, n_i = kw.pop("n_e"), kw.pop("n_i")
+    box_yz = kw.pop("box_yz", None)
     p = two_species(n_e, n_i, length=length, G=G, **kw)
+    if box_yz is not None:
+        p["x0"][:, 1] *= box_yz[0] / length
+        p["x0"][:, 2] *= box_yz[1] / length
     rng = np.random.default_rng(99)
     ext_E = (ext * 1e3 * rng.standard_normal((G, 3))).astype(np.float32) if ext else None
     ext_B = (ext * 1e-3 * rng.standard_normal((G, 3))).astype(np.float32) if ext else None
@@ -97,6 +101,8 @@ def reference_parameters(case):
         },
         "external_field_parameters": {},
     }
+    if box_yz is not None:
+        params["domain_parameters"].update(length_y=box_yz[0], length_z=box_yz[1])
     if ext:
         params["external_field_parameters"] = {"external_electric_field": {"E": ext_E}, "external_magnetic_field": {"B": ext_B}}
     return params, p, field_solver, (ext_E, ext_B)
@@ -167,6 +173,8 @@ def run_case(jaxincell, case):
     assert np.allclose(a(sim.masses)[:, 0], p["m"], rtol=1e-15, atol=0) and np.allclose(a(sim.charge_to_mass_ratios)[:, 0], p["qm"], rtol=1e-15, atol=0)
     if picard is not None:
         rec["picard_iterations"] = np.array(picard)
+    if float(dom.get("length_y", 0)):
+        rec["box_yz"] = np.array([dom["length_y"], dom["length_z"]])
     return rec
 
 
@@ -210,8 +218,12 @@ def main():
     report += ["## Composed runs: reference `Simulation.run()` vs `oracle/literal.py` (max |difference| / max |reference|)", "",
                "| case | E | B | J | rho | x | v | Picard counts |", "|---|---|---|---|---|---|---|---|"]
     for case in MG.CASES:
-        rec = run_case(jaxincell, case)
-        np.savez_compressed(os.path.join(HERE, f"refsrc_{case}.npz"), **rec)
+        path = os.path.join(HERE, f"refsrc_{case}.npz")
+        if os.path.exists(path) and "--all" not in sys.argv:  # existing files are kept (pass --all to regenerate everything)
+            rec = dict(np.load(path))
+        else:
+            rec = run_case(jaxincell, case)
+            np.savez_compressed(path, **rec)
         old = np.load(os.path.join(HERE, case + ".npz"))
         row = []
         for k in ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities"):

@@ -29,6 +29,7 @@ def _load(path):
                        filter_strides=tuple(int(s) for s in g["filter_strides"]), relativistic=bool(g["relativistic"]),
                        field_solver=int(g["field_solver"]) if "field_solver" in g else 0)
     g["cn"] = int(g["time_evolution_algorithm"]) == 1 if "time_evolution_algorithm" in g else False
+    g["box_yz"] = tuple(float(b) for b in g["box_yz"]) if "box_yz" in g else None
     if g["cn"]:
         g["solver"].update(max_number_of_Picard_iterations_implicit_CN=int(g["cn_max_iterations"]),
                            number_of_particle_substeps_implicit_CN=int(g["cn_substeps"]),
@@ -65,7 +66,7 @@ def test_reference_source_vectors_match_the_oracle_made_ones(path):
 def test_literal_oracle_reproduces_reference_source_vectors(path):
     g = _load(path)
     pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
-    kw = dict(length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"])
+    kw = dict(length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"], box_yz=g["box_yz"])
     if g["cn"]:
         out = L.run_CN(g["x0"], g["v0"], g["q"], g["m"], g["qm"], **kw)
         assert out["picard_iterations"].tolist() == g["picard_iterations"].tolist()
@@ -81,7 +82,7 @@ def test_literal_oracle_reproduces_reference_source_vectors(path):
 def test_closed_form_oracle_reproduces_golden(path):
     g = _load(path)
     pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
-    kw = dict(length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"])
+    kw = dict(length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), total_steps=int(g["T"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=g["solver"], box_yz=g["box_yz"])
     if g["cn"]:  # (one oracle only for the implicit stepper: this guards it against drift)
         out = L.run_CN(g["x0"], g["v0"], g["q"], g["m"], g["qm"], **kw)
         assert out["picard_iterations"].tolist() == g["picard_iterations"].tolist()
@@ -93,6 +94,14 @@ def test_closed_form_oracle_reproduces_golden(path):
     assert _relerr(out["initial_velocities"], g["initial_velocities"]) < 1e-15
 
 
+# The GPU legs of the vectors added after the round's GPU budget was spent (every refsrc_* file and the five newest cases) live in
+# tests/test_zz_refsrc_gpu.py, which sorts last: the driver runs `pytest -x`, and a surprise there must not hide the rest of the suite.
+GPU_VERIFIED = ("two_stream_periodic", "large_cfl_jumps", "reflective_absorbing", "absorbing_reflective_nofilter", "weibel_external_B",
+                "relativistic", "field_solver_gauss_fft", "field_solver_cartesian_reflective", "crank_nicolson_periodic", "crank_nicolson_absorbing")
+GPU_FILES = [f for f in FILES if os.path.basename(f)[:-4] in GPU_VERIFIED]
+GPU_FILES_LATE = [f for f in FILES if f not in GPU_FILES]
+
+
 def _species(g):
     ne, ni = int(g["n_e"]), int(g["n_i"])
     return [dict(count=ne, q=float(g["q"][0]), m=float(g["m"][0]), qm=float(g["qm"][0])),
@@ -101,8 +110,12 @@ def _species(g):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("engine", ["indexed", "binned"])
-@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+@pytest.mark.parametrize("path", GPU_FILES, ids=[os.path.basename(f)[:-4] for f in GPU_FILES])
 def test_cuda_reproduces_golden(path, engine):
+    cuda_reproduces_golden(path, engine)
+
+
+def cuda_reproduces_golden(path, engine):
     import torch
     from jaxincell_b200 import HotPath
     g = _load(path)
@@ -114,6 +127,8 @@ def test_cuda_reproduces_golden(path, engine):
     ordered = engine == "indexed" or cn  # particle histories / initial velocities in input order
     extra = dict(time_evolution_algorithm=1, cn_substeps=s["number_of_particle_substeps_implicit_CN"],
                  cn_max_iterations=s["max_number_of_Picard_iterations_implicit_CN"], cn_tolerance=s["tolerance_Picard_iterations_implicit_CN"]) if cn else {}
+    if g["box_yz"] is not None:
+        extra.update(length_y=g["box_yz"][0], length_z=g["box_yz"][1])
     hp = HotPath(species=_species(g), length=float(g["length"]), G=int(g["G"]), dt=float(g["dt"]), pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
                  filter_passes=s["filter_passes"], filter_alpha=s["filter_alpha"], filter_strides=s["filter_strides"],
                  relativistic=s["relativistic"], engine=engine, track_yz=engine == "indexed", field_solver=s["field_solver"], **extra)
