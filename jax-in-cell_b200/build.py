@@ -56,5 +56,28 @@ def build(force=False, verbose=False, out=None, defines=None):
     return out
 
 
+def build_ffi(out=None):
+    """libjic_b200_ffi.so: the XLA FFI handlers of csrc/jic_xla_ffi.cc over libjic_b200.so.  Needs jax (for jax.ffi.include_dir());
+    without it the source reduces to a stub and this function refuses to build a library that could not register anything."""
+    try:
+        import jax.ffi
+        xla_include = jax.ffi.include_dir()
+    except ImportError as e:
+        raise RuntimeError("jax is not installed: the XLA FFI headers (jax.ffi.include_dir()) are unavailable") from e
+    build()
+    out = out or os.path.join(HERE, "jaxincell_b200", "libjic_b200_ffi.so")
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I", xla_include, "-I", os.path.join(cuda_home, "include"),
+           os.path.join(CSRC, "jic_xla_ffi.cc"), "-L", os.path.dirname(OUT), "-l:libjic_b200.so", "-L", os.path.join(cuda_home, "lib64"),
+           "-lcudart", "-Wl,-rpath,$ORIGIN", "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--ffi" in sys.argv:
+        print(build_ffi())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

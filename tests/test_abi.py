@@ -72,3 +72,33 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+# ---- the jax.ffi glue (csrc/jic_xla_ffi.cc): cannot run here (no jax / XLA headers), but it must at least parse and type-check ----
+FFI_SRC = os.path.join(ROOT, "jax-in-cell_b200", "csrc", "jic_xla_ffi.cc")
+CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+
+
+def test_xla_ffi_glue_is_a_stub_without_the_xla_headers(tmp_path):
+    so = str(tmp_path / "ffi_stub.so")
+    subprocess.run(["g++", "-std=c++17", "-shared", "-fPIC", "-I", CUDA_INC, FFI_SRC, "-o", so], check=True)
+    assert C.CDLL(so).jic_xla_ffi_available() == 0
+
+
+def test_xla_ffi_glue_type_checks():
+    """Against tests/ffi_mock (a compile-check mock of the names the glue uses, NOT XLA): the handler's 38 parameters must match the
+    order and types of its binding, and every C-ABI call must match include/jic_b200.h."""
+    res = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "ffi_mock"), "-I", CUDA_INC, FFI_SRC],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
+def test_jax_ffi_binding_fails_loudly_without_jax():
+    from jaxincell_b200 import JicError, _jax_ffi
+    try:
+        import jax  # noqa: F401
+        pytest.skip("jax present")
+    except ImportError:
+        pass
+    with pytest.raises(JicError, match="needs jax"):
+        _jax_ffi.register()
