@@ -248,6 +248,12 @@ struct EngineT : Engine {
   }
 
   ~EngineT() override {
+    // a context may be destroyed from a thread whose current device is another one (several devices in one process):
+    // drain and free on the context's own device, then give the caller its device back
+    int caller_device = -1;
+    cudaGetDevice(&caller_device);
+    if (caller_device != device) cudaSetDevice(device);
+    cudaDeviceSynchronize();
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -266,6 +272,7 @@ struct EngineT : Engine {
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
     if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
+    if (caller_device >= 0 && caller_device != device) cudaSetDevice(caller_device);
   }
 
   int nccl_barrier(cudaStream_t st) {
@@ -865,8 +872,7 @@ int jic_create(const jic_params* params, const jic_species* species, jic_context
 
 int jic_destroy(jic_context* ctx) {
   if (!ctx) return JIC_OK;
-  cudaDeviceSynchronize();
-  delete ctx->eng;
+  delete ctx->eng;  // synchronises the context's device first
   delete ctx;
   return JIC_OK;
 }
@@ -874,6 +880,7 @@ int jic_destroy(jic_context* ctx) {
 int jic_comm_unique_id(void* id) {
   NcclApi& api = nccl_api();
   if (!api.error.empty()) { g_last_error = api.error; return JIC_ERR_NCCL; }
+  if (!id) { g_last_error = "jic_comm_unique_id: null buffer"; return JIC_ERR_INVALID_ARGUMENT; }
   ncclUniqueId uid;
   if (api.GetUniqueId(&uid) != ncclSuccess) { g_last_error = "ncclGetUniqueId failed"; return JIC_ERR_NCCL; }
   memcpy(id, &uid, sizeof(uid));
@@ -953,8 +960,10 @@ int jic_simulate_host(const jic_params* params, const jic_species* species, cons
   auto cleanup = [&](int code) { std::string msg = e->error; for (void* p : dev) cudaFree(p); jic_destroy(ctx); if (code) g_last_error = msg; return code; };
   cudaStream_t st = nullptr;
   float *deE = nullptr, *deB = nullptr;
-  if (eE_host) { deE = (float*)dalloc(G * 3 * 4); cudaMemcpyAsync(deE, eE_host, G * 3 * 4, cudaMemcpyHostToDevice, st); }
-  if (eB_host) { deB = (float*)dalloc(G * 3 * 4); cudaMemcpyAsync(deB, eB_host, G * 3 * 4, cudaMemcpyHostToDevice, st); }
+  if (eE_host && !(deE = (float*)dalloc(G * 3 * 4))) { e->error = "cudaMalloc failed for the external electric field"; return cleanup(JIC_ERR_CUDA); }
+  if (eB_host && !(deB = (float*)dalloc(G * 3 * 4))) { e->error = "cudaMalloc failed for the external magnetic field"; return cleanup(JIC_ERR_CUDA); }
+  if (deE) cudaMemcpyAsync(deE, eE_host, G * 3 * 4, cudaMemcpyHostToDevice, st);
+  if (deB) cudaMemcpyAsync(deB, eB_host, G * 3 * 4, cudaMemcpyHostToDevice, st);
   if ((rc = e->set_external(deE, deB, st))) return cleanup(rc);
   if ((rc = e->initialize_host(x0_host, v0_host, st))) return cleanup(rc);  // chunked upload overlapped with the start-up kernels
   jic_outputs d;
@@ -971,6 +980,7 @@ int jic_simulate_host(const jic_params* params, const jic_species* species, cons
     void* dE0 = E0_host ? dalloc(G * 3 * rs) : nullptr;
     void* dB0 = B0_host ? dalloc(G * 3 * rs) : nullptr;
     void* dvi = vinit_host ? dalloc(N * 3 * rs) : nullptr;
+    if ((E0_host && !dE0) || (B0_host && !dB0) || (vinit_host && !dvi)) { e->error = "cudaMalloc failed for the initial-state buffers"; return cleanup(JIC_ERR_CUDA); }
     if ((rc = e->get_initial(dE0, dB0, dvi, st))) return cleanup(rc);
     if (dE0) cudaMemcpyAsync(E0_host, dE0, G * 3 * rs, cudaMemcpyDeviceToHost, st);
     if (dB0) cudaMemcpyAsync(B0_host, dB0, G * 3 * rs, cudaMemcpyDeviceToHost, st);
