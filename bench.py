@@ -157,15 +157,10 @@ def measured_traffic(dtype, engine, n_particles):
     return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * (n_particles / rec["particles"])
 
 
-def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000, steps=None, warmup=0):
-    """Oracle port (NumPy closed form) on the host cores: particles split over threads, grids summed.
-    steps=None: run for about `seconds_target`; otherwise `warmup` untimed + exactly `steps` timed steps over the sample."""
-    import numpy as np
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import closed_form as CF
-    threads = threads or os.cpu_count() or 1
+def sample_plasma(w, n_sample, np):
+    """A bounded sample of the bench workload for the CPU legs: same geometry and distributions, charges rescaled to the same density."""
     rng = np.random.default_rng(1701)
-    L, G, dt = w["length"], w["G"], w["dt"]
+    L = w["length"]
     n_e = n_i = n_sample // 2
     x0 = np.zeros((n_sample, 3)); v0 = np.zeros((n_sample, 3))
     x0[:, 0] = rng.uniform(-L / 2, L / 2, n_sample)
@@ -177,6 +172,42 @@ def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000, steps=
     q = np.concatenate([np.full(n_e, sp[0]["q"] * scale), np.full(n_i, sp[1]["q"] * scale)])
     m = np.concatenate([np.full(n_e, sp[0]["m"] * scale), np.full(n_i, sp[1]["m"] * scale)])
     qm = np.concatenate([np.full(n_e, sp[0]["qm"]), np.full(n_i, sp[1]["qm"])])
+    return x0, v0, q, m, qm
+
+
+def cpu_port_rate(w, seconds_target=15.0, threads=None, n_sample=4_000_000, steps=None, warmup=0):
+    """The compiled oracle (oracle/c/jic_oracle.c: C + OpenMP restatement of the reference's step, one thread per host core, thread-private
+    grids summed) over a bounded sample of the workload.  steps=None: as many steps as fit about `seconds_target`; otherwise `warmup`
+    untimed + exactly `steps` timed steps.  Falls back to the NumPy port when the C oracle cannot be built or loaded."""
+    import numpy as np
+    try:
+        from oracle import c_port as CP
+        CP.load()
+    except Exception as e:  # noqa: BLE001  (no gcc / no prebuilt library on this host)
+        rate, cores, sample, s_per_step = cpu_numpy_port_rate(w, seconds_target, threads, min(n_sample, 400_000), steps, warmup)
+        return rate, cores, sample + f" (C oracle unavailable: {type(e).__name__})", s_per_step
+    threads = threads or len(os.sched_getaffinity(0)) or 1
+    x0, v0, q, m, qm = sample_plasma(w, n_sample, np)
+    kw = dict(length=w["length"], G=w["G"], dt=w["dt"], keep_particles=False, threads=threads,
+              solver=dict(filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4)))
+    if steps is None:  # calibrate on 2 steps, then fill the time budget
+        probe = CP.run(x0, v0, q, m, qm, total_steps=2, **kw)["step_seconds"]
+        warmup, steps = 1, int(max(3, min(400, seconds_target / max(float(probe[-1]), 1e-6))))
+    secs = CP.run(x0, v0, q, m, qm, total_steps=warmup + steps, **kw)["step_seconds"][warmup:]
+    el = float(secs.sum())
+    return (n_sample * steps / el, threads,
+            f"{n_sample} particles x {steps} steps, G={w['G']}, C/OpenMP closed-form port of the reference (oracle/c/jic_oracle.c), {threads} threads", el / steps)
+
+
+def cpu_numpy_port_rate(w, seconds_target=15.0, threads=None, n_sample=400_000, steps=None, warmup=0):
+    """Oracle port (NumPy closed form) on the host cores: particles split over threads, grids summed.
+    steps=None: run for about `seconds_target`; otherwise `warmup` untimed + exactly `steps` timed steps over the sample."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import closed_form as CF
+    threads = threads or os.cpu_count() or 1
+    L, G, dt = w["length"], w["G"], w["dt"]
+    x0, v0, q, m, qm = sample_plasma(w, n_sample, np)
     dom = CF.Domain(L, G, dt)
     solver = dict(filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4))
     chunks = np.array_split(np.arange(n_sample), threads)
@@ -238,7 +269,7 @@ def run_reference(args):
         return
     w = workload(args, 1)
     why_not = real_reference_status()
-    # a "step" of this arm = one PIC step over a bounded sample of the workload (4e5 particles); K and W as given, capped so that the
+    # a "step" of this arm = one PIC step over a bounded sample of the workload (4e6 particles); K and W as given, capped so that the
     # run ends within a few minutes on any host
     k = max(1, min(args.steps, 400))
     rate, cores, sample, s_per_step = cpu_port_rate(w, steps=k, warmup=min(max(args.warmup, 0), 20))
@@ -249,7 +280,7 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference itself cannot run here (import jaxincell from baseline/_ref -> " + str(why_not) + "); "
-                    "this is the oracle port (NumPy) of its algorithm on the host cores"}
+                    "this is the oracle port of its algorithm (compiled C + OpenMP restatement, NumPy if no compiler) on the host cores"}
     print(json.dumps(line), flush=True)
 
 
