@@ -52,3 +52,5 @@ CASES = {
 # case run end to end by the reference (output-dict contract, plasma frequency, diagnostics); explicit particles are not needed:
 # the draws come from the Threefry restatement on both sides (oracle/sampling.py under the stand-in, jic_sample_particles on the GPU)
 RUN_CASE = "two_stream_references"
+# every case the reference also RUNS (histories stored); the first one additionally feeds the diagnostics comparison
+RUN_CASES = ("two_stream_references", "beam_four_species", "landau_walls_relativistic")

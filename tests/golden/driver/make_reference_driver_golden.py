@@ -34,7 +34,7 @@ import jax  # noqa: E402  (the stand-in)
 assert "standin" in jax.__version__
 import jaxincell  # noqa: E402
 import jaxincell._state_initialization as SI  # noqa: E402
-from driver_cases import CASES, RUN_CASE  # noqa: E402
+from driver_cases import CASES, RUN_CASE, RUN_CASES  # noqa: E402
 
 AXES = ("x", "y", "z")
 
@@ -88,6 +88,11 @@ def main():
         out[name] = rec
         arrays.update(arr)
         print(name, rec["n_particles"], "particles,", len(rec["species"]), "species")
+        if name in RUN_CASES and name != RUN_CASE:
+            res = sim.run()
+            rec["plasma_frequency"] = f(res["plasma_frequency"])
+            for k in ("positions", "velocities", "electric_field", "magnetic_field", "current_density", "charge_density", "initial_velocities"):
+                arrays[f"{name}__run__{k}"] = np.asarray(res[k])
         if name == RUN_CASE:
             res = sim.run()
             rec["output_keys"] = sorted(k for k in res.keys())

@@ -117,7 +117,7 @@ import sys  # noqa: E402
 
 _DRV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "driver")
 sys.path.insert(0, _DRV)
-from driver_cases import CASES as DRIVER_CASES, RUN_CASE  # noqa: E402
+from driver_cases import CASES as DRIVER_CASES, RUN_CASE, RUN_CASES  # noqa: E402
 
 with open(os.path.join(_DRV, "refsrc_driver.json")) as _f:
     REFSRC = json.load(_f)
@@ -179,6 +179,32 @@ def test_initial_particles_of_the_reference_source_equal_the_sampling_oracle(nam
     v = np.where(np.abs(v) >= lim, np.sign(v) * lim, v)
     np.testing.assert_allclose(x, arrays[f"{name}__positions"], rtol=1e-15, atol=1e-18)
     np.testing.assert_allclose(v, arrays[f"{name}__velocities"], rtol=1e-15, atol=1e-9)
+
+
+def _run_arrays(name):
+    a = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
+    prefix = "run__" if name == RUN_CASE else f"{name}__run__"
+    return a, {k[len(prefix):]: a[k] for k in a.files if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_oracle_reproduces_the_runs_of_the_reference_source(name):
+    """The reference's `Simulation(parameters).run()` (on the stand-in, random particles from its own initialisation) against the
+    closed-form oracle started from the same initial particles with the species table THIS driver derives from the same dictionary:
+    five species with different weights, CFL 3 multi-cell jumps without filter / walls + relativistic / CFL 4.5 two-stream."""
+    a, ref = _run_arrays(name)
+    sim, st = _host_state(name)
+    dom, sol = sim.domain_parameters, sim.solver_parameters
+    ps = sim.initialize_particle_state(sim.species_parameters, dom, sol, st)
+    out = C.run(a[f"{name}__positions"], a[f"{name}__velocities"], ps["charges"][:, 0], ps["masses"][:, 0], ps["charge_to_mass_ratios"][:, 0],
+                length=st["box_size"][0], box_yz=st["box_size"][1:], G=int(dom["number_grid_points"]), dt=st["dt"], total_steps=int(dom["total_steps"]),
+                pbl=dom["particle_BC_left"], pbr=dom["particle_BC_right"], fbl=dom["field_BC_left"], fbr=dom["field_BC_right"],
+                solver=dict(filter_passes=sol["filter_passes"], filter_alpha=sol["filter_alpha"], filter_strides=sol["filter_strides"],
+                            relativistic=sol["relativistic"]))
+    for k in ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities"):
+        err = np.abs(out[k] - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-300)
+        assert err < 1e-9, (k, err)
+    np.testing.assert_allclose(out["initial_velocities"], ref["initial_velocities"], rtol=1e-15)
 
 
 def test_output_dictionary_keys_of_the_reference_source():

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from test_golden import GPU_FILES_LATE, cuda_reproduces_golden
-from test_simulation_driver import _DRV, DRIVER_CASES, REFSRC, RUN_CASE, Simulation
+from test_simulation_driver import DRIVER_CASES, REFSRC, RUN_CASE, RUN_CASES, Simulation, _run_arrays
 
 
 @pytest.mark.gpu
@@ -23,19 +23,23 @@ def test_cuda_reproduces_late_golden(path, engine):
 
 
 @pytest.mark.gpu
-def test_run_of_the_reference_source_is_reproduced_end_to_end():
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_run_of_the_reference_source_is_reproduced_end_to_end(name):
     """`Simulation(parameters).run()` here vs the reference's own `Simulation(parameters).run()` (on the stand-in) for the same parameter
-    dictionary: initial particles from the device Threefry sampler, 40 steps at CFL 4.5 (multi-cell jumps), every history."""
-    ref = REFSRC[RUN_CASE]
-    a = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
-    out = Simulation(copy.deepcopy(DRIVER_CASES[RUN_CASE])).run()
-    assert set(ref["output_keys"]) <= set(out)
+    dictionary -- initial particles from the device Threefry sampler, every history: the two-stream set-up at CFL 4.5 (multi-cell
+    jumps), five species with cross references / seed overrides at CFL 3 without filter, walls + relativistic push."""
+    ref = REFSRC[name]
+    a, run = _run_arrays(name)
+    out = Simulation(copy.deepcopy(DRIVER_CASES[name])).run()
+    if name == RUN_CASE:
+        assert set(ref["output_keys"]) <= set(out)
+        np.testing.assert_allclose([out["time_array"][0], out["time_array"][1], out["time_array"][-1]], ref["time_array"][:3], rtol=1e-14)
     np.testing.assert_allclose(out["plasma_frequency"], ref["plasma_frequency"], rtol=1e-14)
-    np.testing.assert_allclose([out["time_array"][0], out["time_array"][1], out["time_array"][-1]], ref["time_array"][:3], rtol=1e-14)
-    np.testing.assert_allclose(out["initial_positions"], a[f"{RUN_CASE}__positions"], rtol=0, atol=1e-15 * 0.01)
+    box = max(ref["box_size"])
+    np.testing.assert_allclose(out["initial_positions"], a[f"{name}__positions"], rtol=0, atol=1e-15 * box)
     for k in ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities"):
-        err = np.abs(np.asarray(out[k]) - a[f"run__{k}"]).max() / max(np.abs(a[f"run__{k}"]).max(), 1e-300)
-        assert err < 1e-5, (k, err)
+        err = np.abs(np.asarray(out[k]) - run[k]).max() / max(np.abs(run[k]).max(), 1e-300)
+        assert err < 1e-5, (name, k, err)
 
 
 # ---- direct per-step parity at BASELINE.json sizes, against the compiled oracle (oracle/c/jic_oracle.c) ---------------------------------
