@@ -13,6 +13,8 @@ cross references, domain / particle / field state) and records what the host sid
     (:172-185,259-261);
   * the assembled particle state: positions / velocities drawn by the reference's formulas (:51-85) on the Threefry restatement
     (the stand-in's jax.random = oracle/sampling.py), after the 0.99c clip (:263-264);
+  * the same host-state record for the reference's own example inputs `examples/input.toml` and `examples/bump-on-tail.toml` (read from
+    the reference checkout, not copied), checked in this container only, where the checkout exists;
   * for RUN_CASE: `Simulation.run()` -> key set of the output dictionary, plasma_frequency, time_array end points (_simulation.py:263-312),
     and `diagnostics(output)` (_diagnostics.py:8-147) -> energies, dominant frequency, species names; the run's inputs/outputs that
     `diagnostics` consumes are stored too so that jaxincell_b200.diagnostics can be fed the same arrays.
@@ -52,7 +54,7 @@ def record(name, params):
         return inner(species, seed_position, seed_velocity, number_particles, box_size)
     SI.initialize_species_phase_space = spy
     try:
-        sim = jaxincell.Simulation(copy.deepcopy(params))
+        sim = jaxincell.Simulation(copy.deepcopy(params))  # a dict, or the path of a TOML file (_simulation.py:85-90)
     finally:
         SI.initialize_species_phase_space = inner
     sp_all = sim.species_parameters
@@ -81,8 +83,15 @@ def record(name, params):
     return sim, rec, arrays
 
 
+TOML_CASES = ("examples/input.toml", "examples/bump-on-tail.toml")  # the reference's own inputs, read where they lie (never copied)
+
+
 def main():
     out, arrays = {}, {}
+    for rel in TOML_CASES:
+        _, rec, _ = record(rel, os.path.join(REF, rel))
+        out["toml:" + rel] = rec
+        print(rel, rec["n_particles"], "particles,", len(rec["species"]), "species")
     for name, params in CASES.items():
         sim, rec, arr = record(name, params)
         out[name] = rec
