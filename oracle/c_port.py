@@ -33,9 +33,15 @@ def build(force=False):
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     tmp = LIB + f".{os.getpid()}.tmp"
     cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra", SRC, "-o", tmp, "-lm"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("gcc failed:\n" + res.stdout + res.stderr)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        failure = None if res.returncode == 0 else res.stdout + res.stderr
+    except OSError as e:  # no compiler on this host
+        failure = str(e)
+    if failure is not None:
+        if os.path.exists(LIB) and not force:
+            return LIB  # a prebuilt library travelled with the snapshot (copies do not keep mtimes): use it
+        raise RuntimeError("gcc failed:\n" + failure)
     os.replace(tmp, LIB)
     return LIB
 

@@ -43,8 +43,9 @@ CASES = {
         "species_parameters": {
             "electrons": {"number_pseudoparticles": 200, "perturbation_amplitude_x": 0.025, "perturbation_wavenumber_x": 1.02, "vth_over_c_x": 0.35,
                           "vth_over_c_z": 0.1, "drift_speed_x": 0, "velocity_plus_minus_x": False, "random_positions_x": False},
+            # (random x: cold ions on a linspace would sit exactly ON the walls, where one ulp decides between "inside" and "absorbed")
             "ions": {"number_pseudoparticles": 160, "mass_over_proton_mass": 1e9, "vth_over_c_x": 0.0, "vth_over_c_y": 0.0, "vth_over_c_z": 0.0,
-                     "perturbation_amplitude_x": 0.0},
+                     "perturbation_amplitude_x": 0.0, "random_positions_x": True},
         },
     },
 }
