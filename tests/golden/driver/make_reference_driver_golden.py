@@ -83,6 +83,23 @@ def record(name, params):
     return sim, rec, arrays
 
 
+def reference_growth_rate(out):
+    """`energy_gamma_from_output` of the reference's examples/inference_two_stream.py:108-203 (the growth-rate diagnostic BASELINE.md names),
+    executed from the file where it lies: the function and its two window constants are cut out of the script by `ast` (the script
+    itself runs simulations and plots at import) and run on the stand-in."""
+    import ast
+    import jax.numpy as jnp
+    path = os.path.join(REF, "examples", "inference_two_stream.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name == "energy_gamma_from_output")
+            or (isinstance(n, ast.Assign) and any(getattr(t, "id", "").startswith("FIT_FRAC") for t in n.targets))]
+    assert len(keep) == 3, [type(n).__name__ for n in keep]
+    ns = {"jnp": jnp}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    res = ns["energy_gamma_from_output"](out, for_jit=True)
+    return f(res["gamma_amp"]), int(res["i_start"]), int(res["i_end"])
+
+
 TOML_CASES = ("examples/input.toml", "examples/bump-on-tail.toml")  # the reference's own inputs, read where they lie (never copied)
 
 
@@ -112,6 +129,7 @@ def main():
             for k in ("positions", "velocities", "electric_field", "magnetic_field", "current_density", "charge_density", "masses", "charges",
                       "initial_velocities", "external_electric_field", "external_magnetic_field", "grid"):
                 arrays[f"run__{k}"] = np.asarray(res[k])
+            rec["growth_rate"], rec["growth_fit_start"], rec["growth_fit_end"] = reference_growth_rate(res)
             jaxincell.diagnostics(res)  # mutates `res` and returns None (_diagnostics.py:8-147)
             d = res
             rec["diagnostics_keys"] = sorted(d.keys())

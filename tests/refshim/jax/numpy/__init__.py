@@ -97,6 +97,12 @@ class Array(_np.ndarray):
                     key = tuple(int(k) for k in key)
         return super().__getitem__(key)
 
+    def __iter__(self):
+        """Exactly len(self) items (the clamped __getitem__ above never raises IndexError, which is what ends the default iteration)."""
+        if self.ndim == 0:
+            raise TypeError("iteration over a 0-d array")
+        return (self[i] for i in range(self.shape[0]))
+
     # jax arrays are immutable: augmented assignment rebinds the name, item assignment is an error.
     def __iadd__(self, other):
         return self + other

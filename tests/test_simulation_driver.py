@@ -200,6 +200,17 @@ def _run_arrays(name):
     return a, {k[len(prefix):]: a[k] for k in a.files if k.startswith(prefix)}
 
 
+def test_growth_rate_diagnostic_matches_the_reference_source():
+    """oracle.closed_form.growth_rate == `energy_gamma_from_output` of the reference's examples/inference_two_stream.py:108-203, which the
+    generator cut out of that script and ran on the E_x history of the reference's own two-stream run (same window, same fit)."""
+    ref = REFSRC[RUN_CASE]
+    _, run = _run_arrays(RUN_CASE)
+    T = ref["domain"]["total_steps"]
+    assert (ref["growth_fit_start"], ref["growth_fit_end"]) == (int(0.30 * T), int(0.50 * T))
+    got = C.growth_rate(run["electric_field"][:, :, 0], ref["dx"], ref["dt"], T)
+    np.testing.assert_allclose(got, ref["growth_rate"], rtol=1e-9)
+
+
 @pytest.mark.parametrize("name", RUN_CASES)
 def test_oracle_reproduces_the_runs_of_the_reference_source(name):
     """The reference's `Simulation(parameters).run()` (on the stand-in, random particles from its own initialisation) against the
