@@ -110,7 +110,7 @@ static void s2_cloud(const jo_params* p, const double* grid, double x, double q,
 
 /* acc layout: [Jx(G) | Jy(G) | Jz(G) | rho(G) | rho_faces(G)] */
 static void deposit_current(const jo_params* p, const double* grid, double x_old, double x_mid, double x_new, double vy, double vz, double q,
-                            double* acc) {
+                            double* acc, int with_rho) {
   const int G = p->G, W = G < 6 ? G : 6;
   const double dx = p->dx, dt = p->dt, gs = grid[0] - dx / 2;
   const long cell = (long)floor_div(x_old - gs, dx);
@@ -137,6 +137,7 @@ static void deposit_current(const jo_params* p, const double* grid, double x_old
   for (int k = 0; k < 5; ++k) {
     acc[G + node[k]] += val[k] * vy;
     acc[2 * G + node[k]] += val[k] * vz;
+    if (with_rho) acc[3 * G + node[k]] += val[k]; /* rho(x_{n+1}) of the step outputs: the same cloud (_algorithms.py:86-89) */
   }
 }
 
@@ -405,7 +406,7 @@ int jo_run(const jo_params* p, int64_t N, const double* x0, const double* v0, co
       bc_particle(p, grid, xp, vv, &qi, &qmi);
       for (int k = 0; k < 3; ++k) xm[k] = x0[3 * i + k] - (dt / 2) * vv[k];
       bc_positions(p, grid, xm);
-      deposit_current(p, grid, xm[0], x0[3 * i], xp[0], vv[1], vv[2], qi, a);
+      deposit_current(p, grid, xm[0], x0[3 * i], xp[0], vv[1], vv[2], qi, a, 0);
       for (int k = 0; k < 3; ++k) {
         xh[3 * i + k] = xp[k];
         xn[3 * i + k] = x0[3 * i + k];
@@ -461,9 +462,8 @@ int jo_run(const jo_params* p, int64_t N, const double* x0, const double* v0, co
         bc_particle(p, grid, xpp, vn, &qi, &qmi);
         for (int k = 0; k < 3; ++k) xnew[k] = xpp[k] - (dt / 2) * vn[k];
         bc_positions(p, grid, xnew);
-        deposit_current(p, grid, x[0], xnew[0], xpp[0], vn[1], vn[2], qi, a);
+        deposit_current(p, grid, x[0], xnew[0], xpp[0], vn[1], vn[2], qi, a, 1);
         if (p->field_solver) deposit_rho(p, grid, xn[3 * i], qi, 1, a + 4 * G); /* rho(x_n) on the faces, post-BC charge (_algorithms.py:69-72) */
-        deposit_rho(p, grid, xnew[0], qi, 0, a + 3 * G);
         for (int k = 0; k < 3; ++k) {
           xh[3 * i + k] = xpp[k];
           xn[3 * i + k] = xnew[k];
