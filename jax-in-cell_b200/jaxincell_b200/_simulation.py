@@ -2,7 +2,8 @@
 ``diagnostics``.  It mirrors jaxincell/_simulation.py:36-344 (interface, defaults, output keys) on top of the C ABI; the
 per-step arithmetic all happens in libjic_b200.so.  Host code is NumPy: there is no JAX here, so
 
-  * ``input_parameters`` are plain overrides (no autodiff through the path -- out of scope per BASELINE.json);
+  * ``run(input_parameters)`` admits what the reference admits there -- its differentiable parameters, same routing, same errors
+    (jaxincell/_routing.py:160-226) -- but as plain numbers: no autodiff through the path (out of scope per BASELINE.json);
   * random initial particles are generated on the device by ``jic_sample_particles`` (csrc/jic_sample.cuh): the reference's
     formulas and seed schedule (_state_initialization.py:51-96) on a restatement of ``jax.random``'s Threefry streams
     (``rng="threefry"``, the default; ``threefry_partitionable`` picks jax's bit layout, True = jax >= 0.5).  ``rng="numpy"``
@@ -83,15 +84,24 @@ def load_parameters(input_file):
         return tomllib.load(f)
 
 
-def _clean_species(species_parameters):
-    """Canonical labels `_electrons<i>` / `_ions<i>`, defaults, cross references (_species_parameters.py:52-200)."""
-    out = {}
+def _normalize_species_input(species_parameters):
+    """{kind: {user_label: values}} whatever the input shape (_species_parameters.py:52-64): empty -> one default species, flat values ->
+    the default label."""
+    norm = {}
     for kind in ("electrons", "ions"):
         values = dict(species_parameters.get(kind, {}) or {})
         if not values:
             values = {f"{kind}0": {}}
         elif not any(isinstance(v, dict) for v in values.values()):
             values = {f"{kind}0": values}
+        norm[kind] = {label: dict(v) for label, v in values.items()}
+    return norm
+
+
+def _clean_species(species_parameters):
+    """Canonical labels `_electrons<i>` / `_ions<i>`, defaults, cross references (_species_parameters.py:52-200)."""
+    out = {}
+    for kind, values in _normalize_species_input(species_parameters).items():
         out[kind] = {}
         for i, (label, v) in enumerate(values.items()):
             out[kind][f"_{kind}{i}"] = {**_species_defaults(kind, i == 0), **v, "user_label": label}
@@ -147,6 +157,17 @@ def _clean_species(species_parameters):
     return out
 
 
+# what `run(input_parameters)` may override (the reference's DIFFERENTIABLE_* lists: _domain_parameters.py:27-32, _solver_parameters.py:24-26,
+# _species_definitions.py:113-146); everything else is fixed at construction, as in the reference
+RUNTIME_FLAT_KEYS = {"timestep_over_spatialstep_times_c": "domain_parameters", "length": "domain_parameters", "length_y": "domain_parameters",
+                     "length_z": "domain_parameters", "filter_alpha": "solver_parameters"}
+_RUNTIME_SPECIES_COMMON = ("grid_points_per_Debye_length", "weight", "charge_over_elementary_charge",
+                           *(f"{k}_{a}" for k in ("perturbation_amplitude", "perturbation_wavenumber", "vth_over_c", "drift_speed") for a in AXES),
+                           "initial_positions", "initial_velocities")
+RUNTIME_SPECIES_KEYS = {"electrons": _RUNTIME_SPECIES_COMMON,
+                        "ions": _RUNTIME_SPECIES_COMMON + ("mass_over_proton_mass", *(f"ion_temperature_over_electron_temperature_{a}" for a in AXES))}
+
+
 def _seed_pair(seed, kind, rng_index, extra):
     """_state_initialization.py:87-96"""
     if rng_index == 0:
@@ -172,7 +193,8 @@ class Simulation:
         self.solver_parameters = self._clean_solver({**SOLVER_DEFAULTS, **parameters.get("solver_parameters", {})})
         self.external_field_parameters = {**EXTERNAL_DEFAULTS, **parameters.get("external_field_parameters", {})}
         self.source_parameters = {**SOURCE_DEFAULTS, **parameters.get("source_parameters", {})}
-        self.species_parameters = _clean_species(parameters.get("species_parameters", {}))
+        self._species_input = _normalize_species_input(parameters.get("species_parameters", {}))  # unresolved: runtime overrides re-resolve
+        self.species_parameters = _clean_species(self._species_input)
 
     # ---- cleaning -------------------------------------------------------------------------------------------------
     @staticmethod
@@ -194,16 +216,58 @@ class Simulation:
         assert all(type(v) == int and v > 0 for v in s["filter_strides"]), "Filter strides must be a tuple of positive integers."
         return s
 
+    def clean_runtime_input_parameters(self, input_parameters=None):
+        """jaxincell/_routing.py:160-226: only the reference's differentiable parameters may change between runs of one Simulation;
+        species overrides are nested {electrons|ions: {label: {...}}} (canonical or user label; without labels: every species of the
+        type).  Same errors as the reference: TypeError for a non-dict, ValueError naming every offending path."""
+        if input_parameters is None:
+            return {}
+        if not isinstance(input_parameters, dict):
+            raise TypeError("Runtime input_parameters must be a dictionary.")
+        invalid = []
+        for key, value in input_parameters.items():
+            if key in ("electrons", "ions"):
+                if not isinstance(value, dict):
+                    raise TypeError(f"Runtime input_parameters[{key!r}] must be a dictionary.")
+                groups = value.items() if any(isinstance(v, dict) for v in value.values()) else [(None, value)]
+                labels = {lab for canon, sp in self.species_parameters[key].items() for lab in (canon, sp["user_label"])}
+                for label, over in groups:
+                    if not isinstance(over, dict):
+                        raise TypeError(f"Runtime input_parameters for {key} must be species dictionaries or flat values, not a mix.")
+                    for k in over:
+                        if k not in RUNTIME_SPECIES_KEYS[key]:
+                            invalid.append(f"{key}.{k}" if label is None else f"{key}.{label}.{k}")
+                    if label is not None and label not in labels:
+                        raise ValueError(f"Could not find {key} species {label!r}.")
+            elif key not in RUNTIME_FLAT_KEYS:
+                invalid.append(key)
+        if invalid:
+            raise ValueError("Runtime input_parameters can only contain differentiable parameters. Invalid parameter(s): " + ", ".join(invalid))
+        return input_parameters
+
     def _sections(self, input_parameters):
         """Overrides: a key is routed to whichever section declares it; species overrides are nested {electrons|ions: {label: {...}}}."""
         sec = {k: copy.deepcopy(getattr(self, k)) for k in SECTIONS}
         raw_species = None
         for key, val in {**self.input_parameters, **(input_parameters or {})}.items():
             if key in ("electrons", "ions"):
-                raw_species = raw_species or {k: {sp["user_label"]: {kk: vv for kk, vv in sp.items() if kk != "user_label"} for sp in v.values()}
-                                              for k, v in self.species_parameters.items()}
-                for label, over in (val.items() if any(isinstance(v, dict) for v in val.values()) else [(next(iter(raw_species[key])), val)]):
-                    raw_species[key].setdefault(label, {}).update(over)
+                # start from the UNRESOLVED input so that cross references ("_electrons0") follow the overridden values, as in the
+                # reference, which re-resolves them inside _simulation (_simulation.py:163, _species_parameters.py:129-166)
+                raw_species = raw_species or copy.deepcopy(self._species_input)
+                user_labels = list(raw_species[key])
+                canonical = {f"_{key}{i}": lab for i, lab in enumerate(user_labels)}
+                groups = val.items() if any(isinstance(v, dict) for v in val.values()) else [(None, val)]
+                for label, over in groups:
+                    if label is None:
+                        targets = user_labels  # no label: every species of the type (_routing.py:185-186)
+                    elif label in canonical:
+                        targets = [canonical[label]]
+                    elif label in raw_species[key]:
+                        targets = [label]
+                    else:
+                        raise ValueError(f"Could not find {key} species {label!r}.")
+                    for t in targets:
+                        raw_species[key][t].update(over)
                 continue
             for name in ("domain_parameters", "solver_parameters", "external_field_parameters", "source_parameters"):
                 if key in sec[name] or name == "source_parameters":
@@ -306,7 +370,7 @@ class Simulation:
     # ---- run ------------------------------------------------------------------------------------------------------
     def simulation(self, input_parameters=None):
         from ._engine import simulate_host
-        sec = self._sections(input_parameters)
+        sec = self._sections(self.clean_runtime_input_parameters(input_parameters))
         dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
         state = self.build_domain_state(dom)
         ps = self.initialize_particle_state(sec["species_parameters"], dom, solver, state)

@@ -55,3 +55,20 @@ CASES = {
 RUN_CASE = "two_stream_references"
 # every case the reference also RUNS (histories stored); the first one additionally feeds the diagnostics comparison
 RUN_CASES = ("two_stream_references", "beam_four_species", "landau_walls_relativistic")
+
+# runtime overrides passed to `run(input_parameters)` / `clean_runtime_input_parameters` on top of a case (the reference only admits its
+# differentiable parameters there, _routing.py:160-226): the electron thermal speed changes, so the ions' "_electrons0" reference must follow
+RUNTIME_OVERRIDES = {
+    "two_stream_references": {"length": 0.02, "filter_alpha": 0.3, "timestep_over_spatialstep_times_c": 2.0,
+                              "electrons": {"electrons0": {"vth_over_c_x": 0.08, "drift_speed_x": 5e7}},
+                              "ions": {"mass_over_proton_mass": 2.0}},
+    "beam_four_species": {"ions": {"_ions2": {"weight": 1.0e9, "drift_speed_y": -2e4}, "beam_neutralizer": {"vth_over_c_x": 0.002}},
+                          "electrons": {"grid_points_per_Debye_length": 1.5}},
+}
+RUNTIME_INVALID = [  # (case, input, exception, text the message must contain)
+    ("two_stream_references", {"total_steps": 2}, "ValueError", "total_steps"),
+    ("two_stream_references", {"ions": {"ions0": {"number_pseudoparticles": 3}}}, "ValueError", "ions.ions0.number_pseudoparticles"),
+    ("two_stream_references", {"ion_drift_speed_x": 3.0}, "ValueError", "ion_drift_speed_x"),
+    ("two_stream_references", {"electrons": {"nobody": {"vth_over_c_x": 0.1}}}, "ValueError", "nobody"),
+    ("two_stream_references", [("length", 1.0)], "TypeError", "dictionary"),
+]

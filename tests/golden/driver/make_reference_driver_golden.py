@@ -36,7 +36,7 @@ import jax  # noqa: E402  (the stand-in)
 assert "standin" in jax.__version__
 import jaxincell  # noqa: E402
 import jaxincell._state_initialization as SI  # noqa: E402
-from driver_cases import CASES, RUN_CASE, RUN_CASES  # noqa: E402
+from driver_cases import CASES, RUN_CASE, RUN_CASES, RUNTIME_INVALID, RUNTIME_OVERRIDES  # noqa: E402
 
 AXES = ("x", "y", "z")
 
@@ -100,6 +100,29 @@ def reference_growth_rate(out):
     return f(res["gamma_amp"]), int(res["i_start"]), int(res["i_end"])
 
 
+def runtime_sections(sim, overrides):
+    """What `_simulation` works with after `run(overrides)`: cleaned runtime input merged into the base sections, references re-resolved
+    (jaxincell/_simulation.py:94-117,148-163)."""
+    from jaxincell._parameters._sections import PARAMETER_SECTIONS
+    from jaxincell._parameters._species_parameters import resolve_species_references
+    from jaxincell._routing import build_runtime_parameter_sections
+    cleaned = sim.clean_runtime_input_parameters(copy.deepcopy(overrides))
+    base = {name: getattr(sim, meta["attribute"]) for name, meta in PARAMETER_SECTIONS.items()}
+    sec = build_runtime_parameter_sections(base, cleaned)
+    resolve_species_references(sec["species_parameters"])
+    species = []
+    for kind in ("electrons", "ions"):
+        for canon, sp in sec["species_parameters"][kind].items():
+            rec = dict(kind=kind, canonical=canon, weight=f(sp["weight"]), grid_points_per_Debye_length=f(sp["grid_points_per_Debye_length"]),
+                       charge_over_elementary_charge=f(sp["charge_over_elementary_charge"]),
+                       **{f"{key}_{a}": f(sp[f"{key}_{a}"]) for key in ("vth_over_c", "drift_speed") for a in AXES})
+            if kind == "ions":
+                rec["mass_over_proton_mass"] = f(sp["mass_over_proton_mass"])
+            species.append(rec)
+    return dict(length=f(sec["domain_parameters"]["length"]), cfl=f(sec["domain_parameters"]["timestep_over_spatialstep_times_c"]),
+                filter_alpha=f(sec["solver_parameters"]["filter_alpha"]), species=species)
+
+
 TOML_CASES = ("examples/input.toml", "examples/bump-on-tail.toml")  # the reference's own inputs, read where they lie (never copied)
 
 
@@ -114,6 +137,17 @@ def main():
         out[name] = rec
         arrays.update(arr)
         print(name, rec["n_particles"], "particles,", len(rec["species"]), "species")
+        if name in RUNTIME_OVERRIDES:
+            rec["runtime_overrides"] = runtime_sections(sim, RUNTIME_OVERRIDES[name])
+        rec["runtime_invalid"] = []
+        for case, bad, exc, text in RUNTIME_INVALID:
+            if case == name:
+                try:
+                    sim.clean_runtime_input_parameters(copy.deepcopy(bad))
+                    rec["runtime_invalid"].append(["no error", ""])
+                except Exception as e:  # noqa: BLE001
+                    assert type(e).__name__ == exc and text in str(e), (bad, type(e).__name__, str(e))
+                    rec["runtime_invalid"].append([type(e).__name__, str(e)])
         if name in RUN_CASES and name != RUN_CASE:
             res = sim.run()
             rec["plasma_frequency"] = f(res["plasma_frequency"])

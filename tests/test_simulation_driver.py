@@ -117,7 +117,7 @@ import sys  # noqa: E402
 
 _DRV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "driver")
 sys.path.insert(0, _DRV)
-from driver_cases import CASES as DRIVER_CASES, RUN_CASE, RUN_CASES  # noqa: E402
+from driver_cases import CASES as DRIVER_CASES, RUN_CASE, RUN_CASES, RUNTIME_INVALID, RUNTIME_OVERRIDES  # noqa: E402
 
 with open(os.path.join(_DRV, "refsrc_driver.json")) as _f:
     REFSRC = json.load(_f)
@@ -198,6 +198,38 @@ def _run_arrays(name):
     a = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
     prefix = "run__" if name == RUN_CASE else f"{name}__run__"
     return a, {k[len(prefix):]: a[k] for k in a.files if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("name", sorted(RUNTIME_OVERRIDES))
+def test_runtime_overrides_resolve_like_the_reference_source(name):
+    """`run(input_parameters)`: the sections the step works with after the overrides, against the reference's
+    clean_runtime_input_parameters + build_runtime_parameter_sections + resolve_species_references (recorded by the generator).
+    A changed electron thermal speed must reach the ions that reference "_electrons0"; a flat species value reaches every species of
+    the type; canonical and user labels both address a species."""
+    ref = REFSRC[name]["runtime_overrides"]
+    sim, _ = _host_state(name)
+    sec = sim._sections(sim.clean_runtime_input_parameters(copy.deepcopy(RUNTIME_OVERRIDES[name])))
+    np.testing.assert_allclose([sec["domain_parameters"]["length"], sec["domain_parameters"]["timestep_over_spatialstep_times_c"],
+                                sec["solver_parameters"]["filter_alpha"]], [ref["length"], ref["cfl"], ref["filter_alpha"]], rtol=0)
+    mine = [(kind, canon, sp) for kind in ("electrons", "ions") for canon, sp in sec["species_parameters"][kind].items()]
+    assert [(k, c) for k, c, _ in mine] == [(r["kind"], r["canonical"]) for r in ref["species"]]
+    for (kind, canon, sp), r in zip(mine, ref["species"]):
+        for key in r:
+            if key in ("kind", "canonical"):
+                continue
+            np.testing.assert_allclose(float(sp[key]), r[key], rtol=1e-15, err_msg=f"{canon}.{key}")
+
+
+def test_runtime_input_errors_match_the_reference_source():
+    """Same exception types, and the offending path named, as the reference's clean_runtime_input_parameters (_routing.py:160-226)."""
+    recorded = {name: list(REFSRC[name]["runtime_invalid"]) for name in REFSRC if REFSRC[name].get("runtime_invalid")}
+    for case, bad, exc, text in RUNTIME_INVALID:
+        ref_exc, ref_msg = recorded[case].pop(0)
+        assert ref_exc == exc and text in ref_msg
+        sim, _ = _host_state(case)
+        with pytest.raises({"ValueError": ValueError, "TypeError": TypeError}[exc]) as err:
+            sim.clean_runtime_input_parameters(copy.deepcopy(bad))
+        assert text in str(err.value)
 
 
 def test_growth_rate_diagnostic_matches_the_reference_source():
