@@ -196,6 +196,53 @@ class Simulation:
         self._species_input = _normalize_species_input(parameters.get("species_parameters", {}))  # unresolved: runtime overrides re-resolve
         self.species_parameters = _clean_species(self._species_input)
 
+    # ---- state attributes of the reference's Simulation object (jaxincell/_simulation.py:438-492): dx, dt, grid, box_size,
+    #      positions, velocities, weights, charges, masses, ..., fields, external_*_field -- computed on first use, cached per parameter set
+    _DOMAIN_ATTRS = ("dx", "dt", "grid", "box_size")
+    _PARTICLE_ATTRS = ("positions", "velocities", "weights", "charges", "masses", "charge_to_mass_ratios", "species_integer_index",
+                       "charge_integer_lookup", "mass_integer_lookup", "charge_mass_integer_lookup", "vth_electrons", "vth_electrons_over_c",
+                       "charge_electrons")
+    _FIELD_ATTRS = ("fields", "external_electric_field", "external_magnetic_field")
+
+    def __getattr__(self, name):  # only reached for names that are not regular attributes
+        if name in Simulation._DOMAIN_ATTRS:
+            return self.build_domain_state(self.domain_parameters)[name]
+        if name in Simulation._PARTICLE_ATTRS:
+            return self._state()["particles"][name]
+        if name in Simulation._FIELD_ATTRS:
+            return self._state(fields=True)[name]
+        raise AttributeError(name)
+
+    def _state(self, fields=False):
+        """Particle state (host arrays; random draws come from the device unless rng='numpy') and, on request, the initial fields:
+        E_x from Gauss's law on the filtered initial charge (_state_initialization.py:365-398), computed by the library."""
+        key = repr((self.domain_parameters, self.solver_parameters, self.species_parameters, sorted(self.external_field_parameters)))
+        cache = self.__dict__.get("_state_cache")
+        if cache is None or cache["key"] != key:
+            dom, solver = self.domain_parameters, self.solver_parameters
+            st = self.build_domain_state(dom)
+            cache = self.__dict__["_state_cache"] = dict(key=key, domain=st, particles=self.initialize_particle_state(self.species_parameters, dom, solver, st))
+        if fields and "fields" not in cache:
+            from ._engine import HotPath
+            dom, solver, st, ps = self.domain_parameters, self.solver_parameters, cache["domain"], cache["particles"]
+            G = int(dom["number_grid_points"])
+            ext = self.external_field_parameters
+            eE, eB = ext.get("external_electric_field"), ext.get("external_magnetic_field")
+            cache["external_electric_field"] = np.asarray(eE["E"], np.float32) if isinstance(eE, dict) and "E" in eE else np.zeros((G, 3), np.float32)
+            cache["external_magnetic_field"] = np.asarray(eB["B"], np.float32) if isinstance(eB, dict) and "B" in eB else np.zeros((G, 3), np.float32)
+            hp = HotPath(species=ps["species_table"], length=st["box_size"][0], length_y=st["box_size"][1], length_z=st["box_size"][2], G=G,
+                         dt=st["dt"], pbl=dom["particle_BC_left"], pbr=dom["particle_BC_right"], fbl=dom["field_BC_left"], fbr=dom["field_BC_right"],
+                         filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
+                         engine="indexed")
+            try:
+                hp.set_external_fields(None, None)
+                hp.initialize(ps["positions"], ps["velocities"])
+                E0, B0, _ = hp.initial(velocities=False)
+                cache["fields"] = (E0.cpu().numpy(), B0.cpu().numpy())
+            finally:
+                hp.close()
+        return cache
+
     # ---- cleaning -------------------------------------------------------------------------------------------------
     @staticmethod
     def _clean_domain(d):

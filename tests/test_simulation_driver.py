@@ -232,6 +232,28 @@ def test_runtime_input_errors_match_the_reference_source():
         assert text in str(err.value)
 
 
+@pytest.mark.parametrize("name", sorted(DRIVER_CASES))
+def test_state_attributes_of_the_simulation_object(name):
+    """The reference's Simulation exposes its initial state as attributes (jaxincell/_simulation.py:438-492; used e.g. by its
+    tests/test_simulation.py:640-700): dx, dt, grid, box_size, positions, velocities, weights, charges, masses, q/m."""
+    ref = REFSRC[name]
+    sim, st = _host_state(name)
+    assert sim.dx == ref["dx"] and sim.dt == ref["dt"] and list(sim.box_size) == ref["box_size"]
+    assert sim.grid.shape == (ref["grid_size"],) and sim.grid[0] == ref["grid_first"]
+    N = ref["n_particles"]
+    assert sim.positions.shape == (N, 3) and sim.velocities.shape == (N, 3)
+    for attr in ("weights", "charges", "masses", "charge_to_mass_ratios"):
+        assert getattr(sim, attr).shape == (N, 1), attr
+    o = 0
+    for r in ref["species"]:
+        assert (sim.weights[o, 0], sim.charges[o, 0], sim.masses[o, 0], sim.charge_to_mass_ratios[o, 0]) == \
+            (r["weight"], r["charge"], r["mass"], r["charge_to_mass"])
+        o += r["count"]
+    assert sim.positions is sim.positions  # cached
+    with pytest.raises(AttributeError):
+        sim.no_such_attribute
+
+
 def test_growth_rate_diagnostic_matches_the_reference_source():
     """oracle.closed_form.growth_rate == `energy_gamma_from_output` of the reference's examples/inference_two_stream.py:108-203, which the
     generator cut out of that script and ran on the E_x history of the reference's own two-stream run (same window, same fit)."""

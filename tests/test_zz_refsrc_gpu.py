@@ -42,6 +42,29 @@ def test_run_of_the_reference_source_is_reproduced_end_to_end(name):
         assert err < 1e-5, (name, k, err)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_initial_fields_attribute_matches_the_reference_source(name):
+    """`Simulation(parameters).fields` (E_x from Gauss's law on the filtered initial charge, _state_initialization.py:365-378) with the
+    reference's own initial particles injected through `initial_positions` / `initial_velocities`."""
+    a, _ = _run_arrays(name)
+    par = copy.deepcopy(DRIVER_CASES[name])
+    o = 0
+    for kind in ("electrons", "ions"):
+        group = par["species_parameters"][kind]
+        group = group if any(isinstance(v, dict) for v in group.values()) else {None: group}
+        for sp in group.values():
+            n = sp["number_pseudoparticles"]
+            sp["initial_positions"] = a[f"{name}__positions"][o:o + n]
+            sp["initial_velocities"] = a[f"{name}__velocities"][o:o + n]
+            o += n
+    sim = Simulation(par)
+    E0, B0 = sim.fields
+    ref = a[f"{name}__E0"]
+    assert np.abs(E0 - ref).max() < 1e-9 * np.abs(ref).max()
+    assert not B0.any() and sim.external_electric_field.shape == ref.shape
+
+
 # ---- direct per-step parity at BASELINE.json sizes, against the compiled oracle (oracle/c/jic_oracle.c) ---------------------------------
 def _full_size_case(n_e, n_i, G, length, cfl, seed, vth, drift, plus_minus, ion_mass=1.0):
     from oracle import literal as L
