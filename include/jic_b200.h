@@ -144,6 +144,15 @@ int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* strea
  * stream has drained.  JIC_HOST_CHUNK=<particles> overrides the chunk size (default 2^23). */
 int jic_initialize_host(jic_context* ctx, const void* x0_host, const void* v0_host, void* stream);
 
+/* Step granularity: load the reference's scan carry instead of starting from t = 0.  The carry of jaxincell/_simulation.py:228-231 /
+ * _algorithms.py:23-24 is (E^n, B^n, x_{n-1/2}, x_n, x_{n+1/2}, v_n, q, m, q/m): E, B real (G,3) at integer time, the four particle
+ * arrays real (N,3) in the order of the species table.  Charges are the species values of jic_create; particles the reference has
+ * absorbed carry q = 0 and sit parked outside the box, which is how this library recognises them too.  After the call
+ * jic_run(ctx, 1, outputs) is exactly one Boris_step (_algorithms.py:17-95): `outputs` rows are its step_data, and the new carry is
+ * (jic_get_fields E, B; the x_{n+1/2} passed in; outputs->positions; jic_get_particles x_half, v).  INDEXED engine, explicit stepper. */
+int jic_load_carry(jic_context* ctx, const void* E, const void* B, const void* x_minus_half, const void* x_n, const void* x_plus_half,
+                   const void* v_n, void* stream);
+
 /* Advance n_steps (the lax.scan of _simulation.py:253 over Boris_step).  Captured as CUDA graphs; no host sync. */
 int jic_run(jic_context* ctx, int64_t n_steps, const jic_outputs* outputs, void* stream);
 

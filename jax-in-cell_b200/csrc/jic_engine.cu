@@ -18,6 +18,7 @@
 #include "jic_binned.cuh"
 #include "jic_sample.cuh"
 #include "jic_cn.cuh"
+#include "jic_carry.cuh"
 
 namespace jic {
 
@@ -506,6 +507,24 @@ struct EngineT : Engine {
     return initialize_finish(st);
   }
 
+  // The reference's scan carry instead of (x0, v0): csrc/jic_carry.cuh.  Same sequence as initialize(): zero the raw grid, one particle
+  // kernel that deposits the carry's current, the reduction over ranks, k_fields in init mode (filter) -- then the carry's own E, B.
+  int load_carry(const void* E_in, const void* B_in, const void* x_minus, const void* x_n, const void* x_plus, const void* v_n, cudaStream_t st) override {
+    if (cn) return fail(JIC_ERR_UNSUPPORTED, "jic_load_carry: the Crank-Nicolson carry is (E, B, x, v); start it with jic_initialize");
+    if (prm.engine != JIC_ENGINE_INDEXED) return fail(JIC_ERR_UNSUPPORTED, "jic_load_carry needs the INDEXED engine (particle order is part of the carry)");
+    if (!E_in || !B_in || ((!x_minus || !x_n || !x_plus || !v_n) && dp.N > 0)) return fail(JIC_ERR_INVALID_ARGUMENT, "jic_load_carry: null argument");
+    int rc = initialize_begin(st);
+    if (rc) return rc;
+    k_load_carry<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x_minus, (const R*)x_n, (const R*)x_plus, (const R*)v_n, xh, yh, zh, vx, vy, vz, v_init, acc);
+    launches += 1;
+    JIC_CUDA(cudaGetLastError());
+    if ((rc = initialize_finish(st))) return rc;
+    k_carry_fields<R><<<1, 1024, 0, st>>>(field_args(true, false), (const R*)E_in, (const R*)B_in);
+    launches += 1;
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
   // ---- Crank-Nicolson (csrc/jic_cn.cuh) ---------------------------------------------------------------------------
   CnFieldArgs<R> cn_field_args(int it, bool prepare_only) const {
     CnFieldArgs<R> a;
@@ -893,6 +912,10 @@ int jic_comm_init(jic_context* ctx, const void* id, int rank, int world) { CTX_O
 int jic_set_external_fields(jic_context* ctx, const float* eE, const float* eB, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->set_external(eE, eB, (cudaStream_t)st); }
 int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize(x0, v0, (cudaStream_t)st); }
 int jic_initialize_host(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize_host(x0, v0, (cudaStream_t)st); }
+int jic_load_carry(jic_context* ctx, const void* E, const void* B, const void* x_minus, const void* x_n, const void* x_plus, const void* v_n, void* st) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->load_carry(E, B, x_minus, x_n, x_plus, v_n, (cudaStream_t)st);
+}
 int jic_run(jic_context* ctx, int64_t n, const jic_outputs* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->run(n, out, (cudaStream_t)st); }
 int jic_get_fields(jic_context* ctx, void* E, void* B, void* J, void* rho, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_fields(E, B, J, rho, (cudaStream_t)st); }
 int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* v, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_initial(E0, B0, v, (cudaStream_t)st); }

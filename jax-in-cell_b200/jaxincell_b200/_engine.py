@@ -112,6 +112,18 @@ class HotPath:
         self._chk(self.lib.jic_initialize(self.ctx, self._ptr(x0), self._ptr(v0), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # x0/v0 may be freed by the caller afterwards
 
+    def load_carry(self, E, B, x_minus_half, x_n, x_plus_half, v_n):
+        """jic_load_carry: the reference's scan carry (jaxincell/_simulation.py:228-231) instead of (x0, v0); `run(1)` is then exactly one
+        Boris_step.  E, B (G,3); the particle arrays (N,3) in species-table order.  INDEXED engine."""
+        E, B = self._dev(E), self._dev(B)
+        parts = [self._dev(a) for a in (x_minus_half, x_n, x_plus_half, v_n)]
+        if tuple(E.shape) != (self.G, 3) or tuple(B.shape) != (self.G, 3):
+            raise JicError(f"E/B must have shape ({self.G}, 3)")
+        if any(tuple(a.shape) != (self.N, 3) for a in parts):
+            raise JicError(f"particle arrays of the carry must have shape ({self.N}, 3)")
+        self._chk(self.lib.jic_load_carry(self.ctx, self._ptr(E), self._ptr(B), *[self._ptr(a) for a in parts], self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()  # the inputs may be freed by the caller afterwards
+
     def initialize_host(self, x0, v0):
         """x0, v0: HOST tensors / arrays (N,3), ideally pinned: jic_initialize_host uploads them in chunks overlapped with the
         start-up kernels (the device never holds a full copy).  Synchronises before returning."""

@@ -371,3 +371,18 @@ def test_large_run_without_particle_history_uses_the_binned_engine():
     assert np.abs(rho_sum - out["charges"].sum()).max() < 1e-9 * np.abs(out["charges"]).sum()
     with pytest.raises(JicError):
         diagnostics(out)
+
+
+def test_species_blocks_of_a_carry():
+    """Boris_step recovers the library's species table from the carry's (q, m, q/m) arrays (jaxincell_b200/_algorithms.py)."""
+    from jaxincell_b200._algorithms import species_blocks
+    q = np.array([-2.0, -2.0, 0.0, 3.0, 3.0, 0.0, 0.0]).reshape(-1, 1)
+    m = np.array([1.0, 1.0, 1.0, 5.0, 5.0, 7.0, 7.0]).reshape(-1, 1)
+    qm = np.array([-2.0, -2.0, 0.0, 0.6, 0.6, 0.0, 0.0]).reshape(-1, 1)
+    blocks = species_blocks(q, m, qm)
+    assert [(b["count"], b["q"], b["m"], b["qm"]) for b in blocks] == [(3, -2.0, 1.0, -2.0), (2, 3.0, 5.0, 0.6), (2, 0.0, 7.0, 0.0)]
+    assert species_blocks(np.zeros(0), np.zeros(0), np.zeros(0))[0]["count"] == 0
+    with pytest.raises(JicError):
+        species_blocks(np.array([1.0, 2.0]), np.array([1.0, 1.0]), np.array([1.0, 2.0]))   # two charges inside one mass block
+    with pytest.raises(JicError):
+        species_blocks(np.ones(20), np.arange(20.0), np.ones(20))                          # more blocks than the library takes

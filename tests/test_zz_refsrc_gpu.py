@@ -117,3 +117,44 @@ def test_binned_engine_against_the_compiled_oracle_at_scale(name, n_e, n_i, G, c
             continue
         assert np.abs(got - ref[k]).max() / scale < 1e-5, (name, k)
     hp.close()
+
+
+# ---- step granularity: Boris_step(carry, ...) with the reference's signature (jic_load_carry + one step) ----------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("bcs,relativistic,field_solver", [((0, 0, 0, 0), False, 0), ((1, 2, 1, 2), False, 0), ((2, 1, 2, 1), True, 0),
+                                                           ((0, 0, 0, 0), False, 2)])
+def test_boris_step_operator_continues_a_carry_like_the_literal_oracle(bcs, relativistic, field_solver):
+    """The literal oracle (pinned to the reference's own Boris_step by the refsrc vectors) runs 6 steps and hands over its carry
+    (E, B, x_{n-1/2}, x_n, x_{n+1/2}, v, q, m, q/m) -- absorbed particles included; jaxincell_b200.Boris_step continues it for 4 steps, one
+    call per step, feeding its own carry back.  step_data and the carry must match the oracle's continuation."""
+    from jaxincell_b200 import Boris_step
+    from jaxincell_b200._algorithms import release_contexts
+    from oracle import literal as L
+    from plasma import cfl_dt, two_species
+    G, length = 14, 0.01
+    pbl, pbr, fbl, fbr = bcs
+    p = two_species(180, 140, length=length, G=G, seed=77 + sum(bcs), vth_e=0.1, vth_yz=0.04, drift=2e7, plus_minus=True, gpdl=0.6)
+    dt = cfl_dt(length, G, 0.9)
+    solver = dict(filter_passes=3, filter_alpha=0.5, filter_strides=(1, 2), relativistic=relativistic, field_solver=field_solver)
+    rng = np.random.default_rng(3)
+    ext = {"external_electric_field": (1e3 * rng.standard_normal((G, 3))).astype(np.float32),
+           "external_magnetic_field": (1e-3 * rng.standard_normal((G, 3))).astype(np.float32)}
+    kw = dict(length=length, G=G, dt=dt, pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=solver, ext_E=ext["external_electric_field"],
+              ext_B=ext["external_magnetic_field"])
+    first = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], total_steps=6, **kw)
+    full = L.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], total_steps=10, **kw)
+    carry = first["final_carry"]
+    dx, grid, box = length / G, first["grid"], (length, length, length)
+    try:
+        for t in range(6, 10):
+            carry, (x1, v1, E1, B1, J1, rho1) = Boris_step(carry, t, solver, ext, dx, dt, grid, box, pbl, pbr, fbl, fbr, field_solver)
+            for got, key in ((x1, "positions"), (v1, "velocities"), (E1, "electric_field"), (B1, "magnetic_field"), (J1, "current_density"),
+                             (rho1, "charge_density")):
+                ref = full[key][t]
+                assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-300), (t, key)
+        ref_carry = full["final_carry"]
+        for got, ref, name in zip(carry, ref_carry, ("E", "B", "x_minus", "x", "x_plus", "v", "q", "m", "qm")):
+            got, ref = np.asarray(got, np.float64).reshape(np.shape(ref)), np.asarray(ref, np.float64)
+            assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-300), name
+    finally:
+        release_contexts()
