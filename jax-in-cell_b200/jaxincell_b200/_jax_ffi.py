@@ -20,6 +20,7 @@ from ._lib import JicError, LIB_PATH
 
 FFI_LIB_PATH = os.environ.get("JIC_B200_FFI_LIB") or os.path.join(os.path.dirname(LIB_PATH), "libjic_b200_ffi.so")
 TARGET = "jic_boris_run"
+STEP_TARGET = "jic_boris_step"
 _registered = False
 
 
@@ -39,7 +40,8 @@ def register():
     lib = ctypes.CDLL(FFI_LIB_PATH)
     if not lib.jic_xla_ffi_available():
         raise JicError("libjic_b200_ffi.so was built without the XLA FFI headers")
-    jax.ffi.register_ffi_target(TARGET, jax.ffi.pycapsule(getattr(lib, TARGET)), platform="CUDA")
+    for target in (TARGET, STEP_TARGET):
+        jax.ffi.register_ffi_target(target, jax.ffi.pycapsule(getattr(lib, target)), platform="CUDA")
     _registered = True
 
 
@@ -77,3 +79,34 @@ def boris_run(positions, velocities, external_E, external_B, *, species, n_steps
         species_count=np.asarray(counts, np.int64), species_charge=np.asarray(q, np.float64), species_mass=np.asarray(m, np.float64),
         species_charge_to_mass=np.asarray(qm, np.float64))
     return (x, v, E, B, J, rho), (E0, B0), v_init
+
+
+def boris_step(carry, step_index, solver_parameters, external_field_parameters, dx, dt, grid, box_size, particle_BC_left, particle_BC_right,
+               field_BC_left, field_BC_right, field_solver=0, *, species):
+    """`Boris_step` of the reference (jaxincell/_algorithms.py:17-95) as one custom call: same positional signature, same carry and
+    step_data, so it can replace `step_func` in the reference's own `lax.scan` (_simulation.py:232-253) under `jax.jit`.  The one extra,
+    static argument is the species table [(count, q*w, m*w, q/m), ...] (the carry's per-particle q, m, q/m arrays are traced values and
+    cannot parameterise the kernel).  q and q/m of particles the step absorbed are zeroed from the returned `alive` mask."""
+    import jax
+    import jax.numpy as jnp
+    register()
+    E, B, x_minus, x_n, x_plus, v_n, qs, ms, q_ms = carry
+    N, G, real = x_plus.shape[0], E.shape[0], x_plus.dtype
+    f = lambda *shape: jax.ShapeDtypeStruct(shape, real)  # noqa: E731
+    results = (f(G, 3), f(G, 3), f(G, 3), f(G), f(N, 3), f(N, 3), f(N, 3), jax.ShapeDtypeStruct((N,), jnp.uint8))
+    counts, q, m, qm = zip(*species)
+    grid = np.asarray(grid, np.float64)
+    sol = solver_parameters
+    E1, B1, J, rho, x1, x_half, v1, alive = jax.ffi.ffi_call(STEP_TARGET, results)(
+        E, B, x_minus, x_n, x_plus, v_n, jnp.asarray(external_field_parameters["external_electric_field"], jnp.float32),
+        jnp.asarray(external_field_parameters["external_magnetic_field"], jnp.float32),
+        length=np.float64(box_size[0]), length_y=np.float64(box_size[1]), length_z=np.float64(box_size[2]), dx=np.float64(dx), dt=np.float64(dt),
+        grid_first=np.float64(grid[0]), grid_last=np.float64(grid[-1]), particle_bc_left=np.int64(particle_BC_left),
+        particle_bc_right=np.int64(particle_BC_right), field_bc_left=np.int64(field_BC_left), field_bc_right=np.int64(field_BC_right),
+        filter_passes=np.int64(sol["filter_passes"]), filter_alpha=np.float64(sol["filter_alpha"]),
+        filter_strides=np.asarray(sol["filter_strides"], np.int64), relativistic=bool(sol["relativistic"]), field_solver=np.int64(field_solver),
+        species_count=np.asarray(counts, np.int64), species_charge=np.asarray(q, np.float64), species_mass=np.asarray(m, np.float64),
+        species_charge_to_mass=np.asarray(qm, np.float64))
+    keep = (alive != 0).reshape((N,) + (1,) * (qs.ndim - 1))
+    new_carry = (E1, B1, x_plus, x1, x_half, v1, jnp.where(keep, qs, 0), ms, jnp.where(keep, q_ms, 0))
+    return new_carry, (x1, v1, E1, B1, J, rho)

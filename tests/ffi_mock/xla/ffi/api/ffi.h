@@ -18,9 +18,10 @@ struct XLA_FFI_CallFrame;
 
 namespace xla::ffi {
 
-enum class DataType { PRED, S32, S64, F32, F64 };
+enum class DataType { PRED, U8, S32, S64, F32, F64 };
 inline constexpr DataType F32 = DataType::F32;
 inline constexpr DataType F64 = DataType::F64;
+inline constexpr DataType U8 = DataType::U8;
 
 template <class T>
 class Span {
@@ -47,7 +48,7 @@ class AnyBuffer {
 template <DataType dtype>
 class Buffer {
  public:
-  using Native = std::conditional_t<dtype == DataType::F32, float, double>;
+  using Native = std::conditional_t<dtype == DataType::F32, float, std::conditional_t<dtype == DataType::U8, uint8_t, double>>;
   Span<const int64_t> dimensions() const { return {}; }
   Native* typed_data() const { return nullptr; }
   void* untyped_data() const { return nullptr; }
@@ -71,6 +72,8 @@ class Error {
   static Error Success() { return {}; }
   static Error InvalidArgument(std::string) { return {}; }
   static Error Internal(std::string) { return {}; }
+  bool failure() const { return false; }
+  bool success() const { return true; }
 };
 
 template <class T>
