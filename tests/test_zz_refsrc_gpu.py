@@ -121,9 +121,9 @@ def test_binned_engine_against_the_compiled_oracle_at_scale(name, n_e, n_i, G, c
 
 # ---- step granularity: Boris_step(carry, ...) with the reference's signature (jic_load_carry + one step) ----------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("bcs,relativistic,field_solver", [((0, 0, 0, 0), False, 0), ((1, 2, 1, 2), False, 0), ((2, 1, 2, 1), True, 0),
-                                                           ((0, 0, 0, 0), False, 2)])
-def test_boris_step_operator_continues_a_carry_like_the_literal_oracle(bcs, relativistic, field_solver):
+@pytest.mark.parametrize("bcs,relativistic,field_solver,G", [((0, 0, 0, 0), False, 0, 14), ((1, 2, 1, 2), False, 0, 14), ((2, 1, 2, 1), True, 0, 14),
+                                                             ((0, 0, 0, 0), False, 2, 14), ((0, 0, 0, 0), False, 0, 1024)])  # 1024: multi-CTA field kernel
+def test_boris_step_operator_continues_a_carry_like_the_literal_oracle(bcs, relativistic, field_solver, G):
     """The literal oracle (pinned to the reference's own Boris_step by the refsrc vectors) runs 6 steps and hands over its carry
     (E, B, x_{n-1/2}, x_n, x_{n+1/2}, v, q, m, q/m) -- absorbed particles included; jaxincell_b200.Boris_step continues it for 4 steps, one
     call per step, feeding its own carry back.  step_data and the carry must match the oracle's continuation."""
@@ -131,7 +131,7 @@ def test_boris_step_operator_continues_a_carry_like_the_literal_oracle(bcs, rela
     from jaxincell_b200._algorithms import release_contexts
     from oracle import literal as L
     from plasma import cfl_dt, two_species
-    G, length = 14, 0.01
+    length = 0.01
     pbl, pbr, fbl, fbr = bcs
     p = two_species(180, 140, length=length, G=G, seed=77 + sum(bcs), vth_e=0.1, vth_yz=0.04, drift=2e7, plus_minus=True, gpdl=0.6)
     dt = cfl_dt(length, G, 0.9)
