@@ -102,3 +102,59 @@ def test_jax_ffi_binding_fails_loudly_without_jax():
         pass
     with pytest.raises(JicError, match="needs jax"):
         _jax_ffi.register()
+
+
+def test_jax_ffi_wrappers_marshal_the_reference_arguments(monkeypatch):
+    """No jax here: a recording fake of `jax.ffi.ffi_call` checks that the two Python wrappers hand the handlers exactly the operands,
+    result shapes and attribute names that csrc/jic_xla_ffi.cc binds (the names are read from the C++ source)."""
+    import sys
+    import types
+
+    import numpy as np
+    from jaxincell_b200 import _jax_ffi
+
+    calls = []
+
+    def ffi_call(target, results):
+        def call(*operands, **attrs):
+            calls.append((target, results, operands, attrs))
+            return tuple(np.zeros(r.shape, r.dtype) for r in results)
+        return call
+
+    fake = types.ModuleType("jax")
+    fake.ShapeDtypeStruct = lambda shape, dtype: types.SimpleNamespace(shape=tuple(shape), dtype=np.dtype(dtype))
+    fake.ffi = types.SimpleNamespace(ffi_call=ffi_call)
+    fake.numpy = types.ModuleType("jax.numpy")
+    for name in ("asarray", "where", "float32", "uint8"):
+        setattr(fake.numpy, name, getattr(np, name))
+    monkeypatch.setitem(sys.modules, "jax", fake)
+    monkeypatch.setitem(sys.modules, "jax.numpy", fake.numpy)
+    monkeypatch.setattr(_jax_ffi, "_registered", True)
+
+    src = open(FFI_SRC).read()
+
+    def bound_attrs(symbol):
+        body = src[src.index(f"    {symbol}, "):]
+        body = body[:body.index("));") + 3]
+        return re.findall(r'\.Attr<[^>]*>+\("(\w+)"\)', body), body.count(".Arg<"), body.count(".Ret<")
+
+    N, G, T = 7, 5, 3
+    species = [(4, -1.0, 2.0, -0.5), (3, 1.0, 9.0, 0.1)]
+    solver = dict(filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4), relativistic=False, field_solver=0)
+    grid = np.linspace(-0.4, 0.4, G)
+    x = np.zeros((N, 3)); eE = np.zeros((G, 3), np.float32)
+    hist, fields0, v_init = _jax_ffi.boris_run(x, x, eE, eE, species=species, n_steps=T, length=1.0, dx=0.2, dt=1e-10, grid=grid, solver=solver)
+    target, results, operands, attrs = calls[-1]
+    names, n_arg, n_ret = bound_attrs("jic_boris_run")
+    assert target == "jic_boris_run" and list(attrs) == names and len(operands) == n_arg and len(results) == n_ret
+    assert hist[0].shape == (T, N, 3) and hist[2].shape == (T, G, 3) and hist[5].shape == (T, G) and fields0[0].shape == (G, 3) and v_init.shape == (N, 3)
+
+    q = np.array([-1.0] * 4 + [1.0] * 3).reshape(-1, 1)
+    carry = (np.zeros((G, 3)), np.zeros((G, 3)), x, x, x, x, q, np.abs(q), q)
+    ext = {"external_electric_field": eE, "external_magnetic_field": eE}
+    new_carry, step_data = _jax_ffi.boris_step(carry, 0, solver, ext, 0.2, 1e-10, grid, (1.0, 1.0, 1.0), 0, 0, 0, 0, 0, species=species)
+    target, results, operands, attrs = calls[-1]
+    names, n_arg, n_ret = bound_attrs("jic_boris_step")
+    assert target == "jic_boris_step" and list(attrs) == names and len(operands) == n_arg and len(results) == n_ret
+    assert len(new_carry) == 9 and len(step_data) == 6 and new_carry[6].shape == q.shape
+    assert not new_carry[6].any()  # the fake returned alive = 0 everywhere: every charge is zeroed
