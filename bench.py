@@ -276,7 +276,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "particle-steps/sec", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": k, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic two-beam plasma, G={args.grid}, CFL 1, periodic, filter 5/0.5/(1,2,4) (SURVEY 8d config 5), CPU sample"},
+            "config": {"workload": f"synthetic two-beam plasma (SURVEY 8d config 5): G={args.grid}, {args.particles} macro-particles per GPU, CFL 1, periodic, "
+                                   f"filter 5/0.5/(1,2,4), x order {args.order}", "particles_per_gpu": args.particles, "grid": args.grid,
+                       "cpu_sample": "the CPU arm steps a bounded sample of this workload (same geometry, distributions and density): " + sample},
             "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference itself cannot run here (import jaxincell from baseline/_ref -> " + str(why_not) + "); "
