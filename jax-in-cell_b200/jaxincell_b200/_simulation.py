@@ -490,6 +490,12 @@ class Simulation:
         return self.simulation(input_parameters)
 
 
+def simulation(parameters=None, input_parameters=None):
+    """Free-function spelling of the entry point (BASELINE.json calls it `simulation()`; this version of the reference spells it
+    `Simulation(parameters).run(input_parameters)`, jaxincell/_simulation.py:94-121): parameters is a dict or the path of a TOML file."""
+    return Simulation(parameters).run(input_parameters)
+
+
 def diagnostics(output):
     """jaxincell/_diagnostics.py:8-147 in NumPy: species split, energies, dominant frequency.  Mutates and returns `output`."""
     if output.get("positions") is None or output.get("velocities") is None:
