@@ -421,6 +421,8 @@ class Simulation:
         dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
         state = self.build_domain_state(dom)
         ps = self.initialize_particle_state(sec["species_parameters"], dom, solver, state)
+        if solver["print_info"]:  # the reference's start-up summary (_simulation.py:176-183)
+            print(INFORMATION_TEXT.format(*simulation_information(dom, sec["species_parameters"], ext, state, ps)))
         G, T = int(dom["number_grid_points"]), int(dom["total_steps"])
         N = len(ps["positions"])
         dtype = np.float64 if str(solver["dtype"]) in ("float64", "f64") else np.float32
@@ -488,6 +490,43 @@ class Simulation:
 
     def run(self, input_parameters=None):
         return self.simulation(input_parameters)
+
+
+INFORMATION_TEXT = (  # jaxincell/_state_initialization.py:320-336
+    "Length of the simulation box: {} Debye lengths or {} Skin Depths\n"
+    "Density of electrons: {} m^-3\n"
+    "Electron temperature: {} eV\n"
+    "Ion temperature / Electron temperature: {}\n"
+    "Debye length: {} m\n"
+    "Skin depth: {} m\n"
+    "Wavenumber * Debye length: {}\n"
+    "Pseudoparticles per cell: {}\n"
+    "Pseudoparticle weight: {}\n"
+    "Steps at each plasma frequency: {}\n"
+    "Total time: {} / plasma frequency\n"
+    "Number of particles on a Debye cube: {}\n"
+    "Relativistic gamma factor: Maximum {}, Average {}\n"
+    "Charge x External electric field x Debye Length / Temperature: {}\n")
+
+
+def simulation_information(dom, species_parameters, ext, state, ps):
+    """The sixteen numbers of the reference's start-up summary (print_simulation_information, _state_initialization.py:288-357), in the
+    order of INFORMATION_TEXT."""
+    e0 = next(iter(species_parameters["electrons"].values()))
+    i0 = next(iter(species_parameters["ions"].values()))
+    length, dx, dt = state["box_size"][0], state["dx"], state["dt"]
+    T, G, n_e = dom["total_steps"], dom["number_grid_points"], e0["number_pseudoparticles"]
+    weight, q_e, vth = ps["weights"][0, 0], ps["charge_electrons"], ps["vth_electrons"]
+    debye_per_dx = 1 / e0["grid_points_per_Debye_length"]
+    temperature = mass_electron * vth ** 2 / 2 / (-q_e)
+    plasma_frequency = np.sqrt(n_e * weight * q_e ** 2) / np.sqrt(mass_electron) / np.sqrt(epsilon_0) / np.sqrt(length)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gamma = 1 / np.sqrt(1 - np.sum(np.asarray(ps["velocities"]) ** 2, axis=1) / speed_of_light ** 2)
+        field_term = -q_e * ext["external_electric_field_amplitude"] * debye_per_dx * dx / (mass_electron * vth ** 2 / 2)
+    return [length / (debye_per_dx * dx), length / (speed_of_light / plasma_frequency), n_e * weight / length, temperature,
+            i0["ion_temperature_over_electron_temperature_x"], debye_per_dx * dx, speed_of_light / plasma_frequency,
+            e0["perturbation_wavenumber_x"] * debye_per_dx * dx, n_e / G, weight, 1 / (plasma_frequency * dt), dt * plasma_frequency * T,
+            n_e * weight / length * (debye_per_dx * dx) ** 3, np.max(gamma), np.mean(gamma), field_term]
 
 
 def simulation(parameters=None, input_parameters=None):

@@ -57,6 +57,17 @@ def record(name, params):
         sim = jaxincell.Simulation(copy.deepcopy(params))  # a dict, or the path of a TOML file (_simulation.py:85-90)
     finally:
         SI.initialize_species_phase_space = inner
+    # the sixteen numbers of the reference's start-up summary (print_simulation_information -> jax.debug.print), captured at the call
+    info = []
+    inner_print = SI.jprint
+    SI.jprint = lambda fmt, *a, **k: info.append([f(v) for v in a])
+    try:
+        solver_on = dict(sim.solver_parameters, print_info=True)
+        particle_state = {"weights": sim.weights, "charge_electrons": sim.charge_electrons, "vth_electrons": sim.vth_electrons, "velocities": sim.velocities}
+        SI.print_simulation_information(sim.domain_parameters, sim.species_parameters, sim.external_field_parameters, solver_on,
+                                        sim.current_domain_state(), particle_state)
+    finally:
+        SI.jprint = inner_print
     sp_all = sim.species_parameters
     species, o = [], 0
     k = 0
@@ -74,7 +85,7 @@ def record(name, params):
             assert seeds[k][2] == n
             o += n
             k += 1
-    rec = dict(dx=f(sim.dx), dt=f(sim.dt), grid_first=f(sim.grid[0]), grid_last=f(sim.grid[-1]), grid_size=int(len(sim.grid)),
+    rec = dict(information=info[0], dx=f(sim.dx), dt=f(sim.dt), grid_first=f(sim.grid[0]), grid_last=f(sim.grid[-1]), grid_size=int(len(sim.grid)),
                box_size=[f(b) for b in sim.box_size], species=species, n_particles=int(o),
                solver={k: (list(v) if isinstance(v, tuple) else v) for k, v in sim.solver_parameters.items()},
                domain={k: (f(v) if not isinstance(v, (int, bool)) else v) for k, v in sim.domain_parameters.items()})

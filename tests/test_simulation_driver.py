@@ -254,6 +254,21 @@ def test_state_attributes_of_the_simulation_object(name):
         sim.no_such_attribute
 
 
+@pytest.mark.parametrize("name", sorted(DRIVER_CASES))
+def test_start_up_summary_matches_the_reference_source(name, capsys):
+    """The sixteen numbers `print_info` reports (print_simulation_information, _state_initialization.py:288-357), computed from the
+    reference's own initial velocities (the gamma factors depend on the draws)."""
+    ref = REFSRC[name]["information"]
+    arrays = np.load(os.path.join(_DRV, "refsrc_driver_arrays.npz"))
+    sim, st = _host_state(name)
+    ps = sim.initialize_particle_state(sim.species_parameters, sim.domain_parameters, sim.solver_parameters, st)
+    ps["velocities"] = arrays[f"{name}__velocities"]
+    got = S.simulation_information(sim.domain_parameters, sim.species_parameters, sim.external_field_parameters, st, ps)
+    np.testing.assert_allclose(np.array(got, dtype=float), np.array(ref, dtype=float), rtol=1e-13, atol=0)
+    text = S.INFORMATION_TEXT.format(*got)
+    assert text.count("\n") == 14 and "Skin Depths" in text and text.startswith("Length of the simulation box: ")
+
+
 def test_growth_rate_diagnostic_matches_the_reference_source():
     """oracle.closed_form.growth_rate == `energy_gamma_from_output` of the reference's examples/inference_two_stream.py:108-203, which the
     generator cut out of that script and ran on the E_x history of the reference's own two-stream run (same window, same fit)."""
