@@ -189,12 +189,46 @@ class Simulation:
         unknown = set(parameters) - set(SECTIONS)
         if unknown:
             raise AssertionError(f"Unknown parameter sections: {sorted(unknown)}")
-        self.domain_parameters = self._clean_domain({**DOMAIN_DEFAULTS, **parameters.get("domain_parameters", {})})
-        self.solver_parameters = self._clean_solver({**SOLVER_DEFAULTS, **parameters.get("solver_parameters", {})})
-        self.external_field_parameters = {**EXTERNAL_DEFAULTS, **parameters.get("external_field_parameters", {})}
-        self.source_parameters = {**SOURCE_DEFAULTS, **parameters.get("source_parameters", {})}
-        self._species_input = _normalize_species_input(parameters.get("species_parameters", {}))  # unresolved: runtime overrides re-resolve
-        self.species_parameters = _clean_species(self._species_input)
+        for name in SECTIONS:  # the section setters clean and overlay the defaults, as the reference's do
+            setattr(self, name, parameters.get(name, {}))
+
+    # ---- parameter sections as properties: assigning one re-cleans it (defaults overlaid on the NEW dict only) and thereby invalidates
+    #      the cached state, like set_parameter_section of the reference (jaxincell/_simulation.py:494-556)
+    def _set_section(self, name, new):
+        new = copy.deepcopy(dict(new or {}))
+        if name == "domain_parameters":
+            self._domain_parameters = self._clean_domain({**DOMAIN_DEFAULTS, **new})
+        elif name == "solver_parameters":
+            self._solver_parameters = self._clean_solver({**SOLVER_DEFAULTS, **new})
+        elif name == "external_field_parameters":
+            self._external_field_parameters = {**EXTERNAL_DEFAULTS, **new}
+        elif name == "source_parameters":
+            self._source_parameters = {**SOURCE_DEFAULTS, **new}
+        else:
+            self._species_input = _normalize_species_input(new)  # unresolved: runtime overrides re-resolve the cross references
+            self._species_parameters = _clean_species(self._species_input)
+
+    domain_parameters = property(lambda self: self._domain_parameters, lambda self, v: self._set_section("domain_parameters", v))
+    species_parameters = property(lambda self: self._species_parameters, lambda self, v: self._set_section("species_parameters", v))
+    external_field_parameters = property(lambda self: self._external_field_parameters, lambda self, v: self._set_section("external_field_parameters", v))
+    source_parameters = property(lambda self: self._source_parameters, lambda self, v: self._set_section("source_parameters", v))
+    solver_parameters = property(lambda self: self._solver_parameters, lambda self, v: self._set_section("solver_parameters", v))
+
+    @staticmethod
+    def _hash(section):
+        """build_parameter_hash of the reference (_parameters/_utils.py:15-20): changes whenever a value of the section changes."""
+        return "".join(str(k) + str(v) for k, v in section.items())
+
+    domain_hash = property(lambda self: self._hash(self._domain_parameters))
+    species_hash = property(lambda self: str(tuple((kind, tuple(label + self._hash(sp) for label, sp in group.items()))
+                                                     for kind, group in self._species_parameters.items())))
+    external_field_hash = property(lambda self: self._hash(self._external_field_parameters))
+    source_hash = property(lambda self: self._hash(self._source_parameters))
+    solver_hash = property(lambda self: self._hash(self._solver_parameters))
+
+    def current_domain_state(self):
+        """jaxincell/_simulation.py:430-436"""
+        return self.build_domain_state(self.domain_parameters)
 
     # ---- state attributes of the reference's Simulation object (jaxincell/_simulation.py:438-492): dx, dt, grid, box_size,
     #      positions, velocities, weights, charges, masses, ..., fields, external_*_field -- computed on first use, cached per parameter set
@@ -202,7 +236,9 @@ class Simulation:
     _PARTICLE_ATTRS = ("positions", "velocities", "weights", "charges", "masses", "charge_to_mass_ratios", "species_integer_index",
                        "charge_integer_lookup", "mass_integer_lookup", "charge_mass_integer_lookup", "vth_electrons", "vth_electrons_over_c",
                        "charge_electrons")
-    _FIELD_ATTRS = ("fields", "external_electric_field", "external_magnetic_field")
+    _PARTICLE_ATTRS += ("species_index",)
+    _FIELD_ATTRS = ("fields",)
+    _EXTERNAL_ATTRS = {"external_electric_field": ("external_electric_field", "E"), "external_magnetic_field": ("external_magnetic_field", "B")}
 
     def __getattr__(self, name):  # only reached for names that are not regular attributes
         if name in Simulation._DOMAIN_ATTRS:
@@ -211,6 +247,11 @@ class Simulation:
             return self._state()["particles"][name]
         if name in Simulation._FIELD_ATTRS:
             return self._state(fields=True)[name]
+        if name in Simulation._EXTERNAL_ATTRS:  # float32 (G,3), zeros unless the section carries {"E": array} / {"B": array} (_state_initialization.py:380-392)
+            key, comp = Simulation._EXTERNAL_ATTRS[name]
+            given = self.external_field_parameters.get(key)
+            G = int(self.domain_parameters["number_grid_points"])
+            return np.asarray(given[comp], np.float32) if isinstance(given, dict) and comp in given else np.zeros((G, 3), np.float32)
         raise AttributeError(name)
 
     def _state(self, fields=False):
@@ -226,10 +267,6 @@ class Simulation:
             from ._engine import HotPath
             dom, solver, st, ps = self.domain_parameters, self.solver_parameters, cache["domain"], cache["particles"]
             G = int(dom["number_grid_points"])
-            ext = self.external_field_parameters
-            eE, eB = ext.get("external_electric_field"), ext.get("external_magnetic_field")
-            cache["external_electric_field"] = np.asarray(eE["E"], np.float32) if isinstance(eE, dict) and "E" in eE else np.zeros((G, 3), np.float32)
-            cache["external_magnetic_field"] = np.asarray(eB["B"], np.float32) if isinstance(eB, dict) and "B" in eB else np.zeros((G, 3), np.float32)
             hp = HotPath(species=ps["species_table"], length=st["box_size"][0], length_y=st["box_size"][1], length_z=st["box_size"][2], G=G,
                          dt=st["dt"], pbl=dom["particle_BC_left"], pbr=dom["particle_BC_right"], fbl=dom["field_BC_left"], fbr=dom["field_BC_right"],
                          filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
@@ -343,7 +380,7 @@ class Simulation:
         box, G = state["box_size"], int(dom["number_grid_points"])
         threefry = solver.get("rng", "threefry") == "threefry"
         sampling, given_any = [], []
-        pos, vel, wts, sidx, table = [], [], [], [], []
+        pos, vel, wts, sidx, table, names = [], [], [], [], [], []
         charge_l, mass_l, qm_l = [], [], []
         ref = None
         extra = 0
@@ -389,6 +426,7 @@ class Simulation:
                      * ref["vth_electrons_over_c"] ** 2 / debye_length_per_dx ** 2)
                 w = w if sp["weight"] == 0 else float(sp["weight"])
                 pos.append(x); vel.append(v); wts.append(np.full((n, 1), w)); sidx.append(np.full(n, len(table), dtype=np.int32))
+                names.extend([f"{kind}.{canon}"] * n)
                 table.append(dict(count=n, q=charge * w, m=mass * w, qm=charge / mass))
                 charge_l.append(charge); mass_l.append(mass); qm_l.append(charge / mass)
         if threefry:
@@ -412,7 +450,8 @@ class Simulation:
         return dict(positions=positions, velocities=velocities, weights=weights, species_integer_index=species_integer_index,
                     charge_integer_lookup=cl, mass_integer_lookup=ml, charge_mass_integer_lookup=ql,
                     charges=cl[species_integer_index].reshape(-1, 1) * weights, masses=ml[species_integer_index].reshape(-1, 1) * weights,
-                    charge_to_mass_ratios=ql[species_integer_index].reshape(-1, 1), species_table=table, sampling=sampling, **ref)
+                    charge_to_mass_ratios=ql[species_integer_index].reshape(-1, 1), species_table=table, sampling=sampling,
+                    species_index=names, **ref)
 
     # ---- run ------------------------------------------------------------------------------------------------------
     def simulation(self, input_parameters=None):

@@ -401,3 +401,34 @@ def test_species_blocks_of_a_carry():
         species_blocks(np.array([1.0, 2.0]), np.array([1.0, 1.0]), np.array([1.0, 2.0]))   # two charges inside one mass block
     with pytest.raises(JicError):
         species_blocks(np.ones(20), np.arange(20.0), np.ones(20))                          # more blocks than the library takes
+
+
+def test_section_setters_reclean_and_invalidate_state():
+    """Mirrors the reference's tests/test_simulation.py:506-577 (property setters) and :622-660 (current_domain_state): assigning a
+    section re-cleans it with the defaults overlaid on the new dictionary, the matching hash changes, cached state follows."""
+    par = {"domain_parameters": {"total_steps": 2, "number_grid_points": 4},
+           "species_parameters": {"electrons": {"electrons0": {"number_pseudoparticles": 4}}, "ions": {"ions0": {"number_pseudoparticles": 4}}},
+           "solver_parameters": {"print_info": False, "rng": "numpy"}}
+    sim = Simulation(par)
+    hashes = (sim.domain_hash, sim.species_hash, sim.external_field_hash, sim.source_hash, sim.solver_hash)
+    assert sim.grid.shape == (4,) and sim.positions.shape == (8, 3) and len(sim.species_index) == 8
+    sim.domain_parameters = {"total_steps": 2, "number_grid_points": 5, "length": 0.02}
+    assert sim.domain_hash != hashes[0] and sim.grid.shape == (5,) and sim.domain_parameters["length"] == 0.02
+    assert sim.domain_parameters["particle_BC_left"] == 0  # defaults overlaid
+    sim.species_parameters = {"electrons": {"electrons0": {"number_pseudoparticles": 3}}, "ions": {"ions0": {"number_pseudoparticles": 2}}}
+    assert sim.species_hash != hashes[1] and sim.positions.shape == (5, 3) and len(sim.species_index) == 5
+    assert sim.species_index[0] == "electrons._electrons0" and sim.species_index[-1] == "ions._ions0"
+    sim.external_field_parameters = {"external_electric_field_amplitude": 2.0, "external_electric_field_wavenumber": 1.0}
+    assert sim.external_field_hash != hashes[2]
+    assert sim.external_electric_field.shape == (5, 3) and sim.external_magnetic_field.dtype == np.float32
+    sim.source_parameters = {"source_term_active": 1, "source_species": 0}
+    assert sim.source_hash != hashes[3] and sim.source_parameters["injection_speed_x"] == 1e7
+    sim.solver_parameters = {"field_solver": 0, "filter_passes": 0, "filter_alpha": 0.25, "print_info": False, "seed": 123, "rng": "numpy"}
+    assert sim.solver_hash != hashes[4] and sim.solver_parameters["filter_strides"] == (1, 2, 4)
+    assert sim.domain_parameters["number_grid_points"] == 5 and sim.positions.shape == (5, 3)
+    state = sim.current_domain_state()
+    assert state["dx"] == sim.dx and state["dt"] == sim.dt and tuple(state["box_size"]) == tuple(sim.box_size)
+    state["dx"] = -1.0
+    assert sim.dx > 0
+    with pytest.raises(AssertionError):
+        sim.solver_parameters = {"filter_alpha": 2.0}
