@@ -153,6 +153,12 @@ int jic_initialize_host(jic_context* ctx, const void* x0_host, const void* v0_ho
 int jic_load_carry(jic_context* ctx, const void* E, const void* B, const void* x_minus_half, const void* x_n, const void* x_plus_half,
                    const void* v_n, void* stream);
 
+/* The same for the implicit stepper (time_evolution_algorithm = 1): the carry of CN_step is (E^n, B^n, x_n, v_n, q, m, q/m)
+ * (jaxincell/_simulation.py:237-240, _algorithms.py:103-104).  alive[N] (uint8, NULL = all ones) is 0 where the carry's charge is zero
+ * (particles absorbed by the start-up half step: their charge stays zero for the whole run).  jic_run(ctx, 1, outputs) is then one
+ * CN_step; the new carry is (jic_get_fields E, B; outputs->positions; outputs->velocities; q, m, q/m unchanged). */
+int jic_load_carry_cn(jic_context* ctx, const void* E, const void* B, const void* x_n, const void* v_n, const uint8_t* alive, void* stream);
+
 /* Advance n_steps (the lax.scan of _simulation.py:253 over Boris_step).  Captured as CUDA graphs; no host sync. */
 int jic_run(jic_context* ctx, int64_t n_steps, const jic_outputs* outputs, void* stream);
 

@@ -10,6 +10,7 @@
 //   k_carry_fields  E^n, B^n in, then E then B by dt/2 (_fields.py:175-183) and the gather table (_algorithms.py:36-43)
 #pragma once
 #include "jic_kernels.cuh"
+#include "jic_cn.cuh"
 
 namespace jic {
 
@@ -65,6 +66,29 @@ __global__ void __launch_bounds__(1024) k_carry_fields(const FieldArgs<R> a, con
       f[3 + c] = src < 0 ? R(0) : (R)(a.B[src * 3 + c] + a.extB[src * 3 + c]);
     }
     f[6] = R(0); f[7] = R(0);
+  }
+}
+
+// ---- Crank-Nicolson: the carry of CN_step is (E, B, x_n, v_n, q, m, q/m) (jaxincell/_simulation.py:237-240, _algorithms.py:103-104).
+// Particles and fields are copied as they are; `alive_in` (0 = the particle's q is zero in the carry: absorbed by the start-up half
+// step, _simulation.py:217-220) replaces the byte k_cn_start computes.  The averaged tables of the first Picard iteration are then
+// prepared by k_cn_fields exactly as after jic_initialize.
+template <typename R>
+__global__ void __launch_bounds__(256) k_cn_load(const DevParams<R> p, const R* __restrict__ x, const R* __restrict__ v, const uint8_t* __restrict__ alive_in,
+                                                 CnState<R> s, R* __restrict__ v_init, uint8_t* __restrict__ alive) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    s.x[i] = x[3 * i]; s.y[i] = x[3 * i + 1]; s.z[i] = x[3 * i + 2];
+    s.vx[i] = v[3 * i]; s.vy[i] = v[3 * i + 1]; s.vz[i] = v[3 * i + 2];
+    alive[i] = alive_in ? (alive_in[i] != 0) : 1;
+    if (v_init) { v_init[3 * i] = v[3 * i]; v_init[3 * i + 1] = v[3 * i + 1]; v_init[3 * i + 2] = v[3 * i + 2]; }
+  }
+}
+
+template <typename R>
+__global__ void k_carry_copy_fields(const R* __restrict__ E_in, const R* __restrict__ B_in, double* E, double* B, double* E0, double* B0, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double e = (double)E_in[k], b = (double)B_in[k];
+    E[k] = e; B[k] = b; E0[k] = e; B0[k] = b;
   }
 }
 

@@ -509,8 +509,25 @@ struct EngineT : Engine {
 
   // The reference's scan carry instead of (x0, v0): csrc/jic_carry.cuh.  Same sequence as initialize(): zero the raw grid, one particle
   // kernel that deposits the carry's current, the reduction over ranks, k_fields in init mode (filter) -- then the carry's own E, B.
+  // Crank-Nicolson carry (E, B, x_n, v_n) + which particles carry q = 0
+  int load_carry_cn(const void* E_in, const void* B_in, const void* x_n, const void* v_n, const uint8_t* alive_in, cudaStream_t st) override {
+    if (!cn) return fail(JIC_ERR_UNSUPPORTED, "jic_load_carry_cn needs time_evolution_algorithm = 1; the Boris carry goes through jic_load_carry");
+    if (!E_in || !B_in || ((!x_n || !v_n) && dp.N > 0)) return fail(JIC_ERR_INVALID_ARGUMENT, "jic_load_carry_cn: null argument");
+    int rc = initialize_begin(st);
+    if (rc) return rc;
+    JIC_CUDA(cudaMemsetAsync(cn_ctl, 0, sizeof(CnControl), st));
+    k_cn_load<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x_n, (const R*)v_n, alive_in, cn_s[0], v_init, cn_alive);
+    const int n3 = dp.G * 3;
+    k_carry_copy_fields<R><<<(n3 + 255) / 256, 256, 0, st>>>((const R*)E_in, (const R*)B_in, E, B, E0, B0, n3);
+    k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(0, true));
+    launches += 3;
+    JIC_CUDA(cudaGetLastError());
+    initialized = true;
+    return JIC_OK;
+  }
+
   int load_carry(const void* E_in, const void* B_in, const void* x_minus, const void* x_n, const void* x_plus, const void* v_n, cudaStream_t st) override {
-    if (cn) return fail(JIC_ERR_UNSUPPORTED, "jic_load_carry: the Crank-Nicolson carry is (E, B, x, v); start it with jic_initialize");
+    if (cn) return fail(JIC_ERR_UNSUPPORTED, "jic_load_carry: the Crank-Nicolson carry is (E, B, x, v): use jic_load_carry_cn");
     if (prm.engine != JIC_ENGINE_INDEXED) return fail(JIC_ERR_UNSUPPORTED, "jic_load_carry needs the INDEXED engine (particle order is part of the carry)");
     if (!E_in || !B_in || ((!x_minus || !x_n || !x_plus || !v_n) && dp.N > 0)) return fail(JIC_ERR_INVALID_ARGUMENT, "jic_load_carry: null argument");
     int rc = initialize_begin(st);
@@ -912,6 +929,10 @@ int jic_comm_init(jic_context* ctx, const void* id, int rank, int world) { CTX_O
 int jic_set_external_fields(jic_context* ctx, const float* eE, const float* eB, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->set_external(eE, eB, (cudaStream_t)st); }
 int jic_initialize(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize(x0, v0, (cudaStream_t)st); }
 int jic_initialize_host(jic_context* ctx, const void* x0, const void* v0, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->initialize_host(x0, v0, (cudaStream_t)st); }
+int jic_load_carry_cn(jic_context* ctx, const void* E, const void* B, const void* x_n, const void* v_n, const uint8_t* alive, void* st) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->load_carry_cn(E, B, x_n, v_n, alive, (cudaStream_t)st);
+}
 int jic_load_carry(jic_context* ctx, const void* E, const void* B, const void* x_minus, const void* x_n, const void* x_plus, const void* v_n, void* st) {
   CTX_OR_FAIL(ctx);
   return ctx->eng->load_carry(E, B, x_minus, x_n, x_plus, v_n, (cudaStream_t)st);

@@ -36,6 +36,7 @@ struct Engine {
   virtual int set_external(const float* eE, const float* eB, cudaStream_t st) = 0;
   virtual int initialize(const void* x0, const void* v0, cudaStream_t st) = 0;
   virtual int initialize_host(const void* x0_host, const void* v0_host, cudaStream_t st) = 0;
+  virtual int load_carry_cn(const void* E, const void* B, const void* x_n, const void* v_n, const uint8_t* alive, cudaStream_t st) = 0;
   virtual int load_carry(const void* E, const void* B, const void* x_minus, const void* x_n, const void* x_plus, const void* v_n, cudaStream_t st) = 0;
   virtual int run(long long n, const jic_outputs* out, cudaStream_t st) = 0;
   virtual int get_fields(void* E, void* B, void* J, void* rho, cudaStream_t st) = 0;

@@ -5,4 +5,4 @@ from ._lib import JicError, LIB_PATH, load  # noqa: F401
 from ._engine import HotPath, make_params, make_species, sample_particles, simulate_host  # noqa: F401
 from ._parallel import shard_counts, shard_particles, shard_species  # noqa: F401
 from ._simulation import Simulation, diagnostics, load_parameters, simulation  # noqa: F401
-from ._algorithms import Boris_step  # noqa: F401
+from ._algorithms import Boris_step, CN_step  # noqa: F401

@@ -1,4 +1,4 @@
-"""`Boris_step` with the reference's signature and carry (jaxincell/_algorithms.py:17-95), executed by the library:
+"""`Boris_step` and `CN_step` with the reference's signatures and carries (jaxincell/_algorithms.py:17-95, :100-241), executed by the library:
 
     carry, step_data = Boris_step(carry, step_index, solver_parameters, external_field_parameters, dx, dt, grid, box_size,
                                   particle_BC_left, particle_BC_right, field_BC_left, field_BC_right, field_solver)
@@ -92,6 +92,32 @@ def Boris_step(carry, step_index, solver_parameters, external_field_parameters, 
     qms1 = np.where(alive, np.asarray(q_ms, np.float64).reshape(-1), 0.0).reshape(shape)
     new_carry = (E1, B1, np.asarray(x_plus), x1, x_half, v1, qs1, ms, qms1)
     return new_carry, (x1, v1, E1, B1, J1, rho1)
+
+
+def CN_step(carry, step_index, solver_parameters, dx, dt, grid, box_size, particle_BC_left, particle_BC_right, field_BC_left, field_BC_right,
+            num_substeps):
+    """`CN_step` with the reference's signature and carry (jaxincell/_algorithms.py:100-241): carry = (E, B, x_n, v_n, q, m, q/m),
+    step_data = (x_{n+1}, v_{n+1}, E^{n+1}, B^{n+1}, J, rho).  The charges of the carry pass through unchanged, as in the reference."""
+    from ._engine import HotPath
+    E, B, x_n, v_n, qs, ms, q_ms = carry
+    grid = np.asarray(grid, np.float64)
+    G = len(grid)
+    blocks = species_blocks(qs, ms, q_ms)
+    sol = solver_parameters
+    key = ("cn", G, float(dx), float(dt), tuple(float(b) for b in box_size), int(particle_BC_left), int(particle_BC_right), int(field_BC_left),
+           int(field_BC_right), int(num_substeps), int(sol["max_number_of_Picard_iterations_implicit_CN"]),
+           float(sol["tolerance_Picard_iterations_implicit_CN"]), tuple((b["count"], b["q"], b["m"], b["qm"]) for b in blocks))
+    hp = _context(key, lambda: HotPath(species=blocks, length=float(box_size[0]), length_y=float(box_size[1]), length_z=float(box_size[2]), G=G,
+                                       dt=float(dt), pbl=int(particle_BC_left), pbr=int(particle_BC_right), fbl=int(field_BC_left),
+                                       fbr=int(field_BC_right), engine="indexed", track_yz=True, time_evolution_algorithm=1,
+                                       cn_substeps=int(num_substeps), cn_max_iterations=int(sol["max_number_of_Picard_iterations_implicit_CN"]),
+                                       cn_tolerance=float(sol["tolerance_Picard_iterations_implicit_CN"])))
+    hp.set_external_fields(None, None)
+    hp.load_carry_cn(E, B, x_n, v_n, alive=np.asarray(qs, np.float64).reshape(-1) != 0.0)
+    out = hp.run(1, particles=True)
+    E1, B1, J1, rho1 = (out[k][0].cpu().numpy() for k in ("electric_field", "magnetic_field", "current_density", "charge_density"))
+    x1, v1 = out["positions"][0].cpu().numpy(), out["velocities"][0].cpu().numpy()
+    return (E1, B1, x1, v1, qs, ms, q_ms), (x1, v1, E1, B1, J1, rho1)
 
 
 def release_contexts():

@@ -124,6 +124,17 @@ class HotPath:
         self._chk(self.lib.jic_load_carry(self.ctx, self._ptr(E), self._ptr(B), *[self._ptr(a) for a in parts], self._stream()))
         torch.cuda.current_stream(self.device).synchronize()  # the inputs may be freed by the caller afterwards
 
+    def load_carry_cn(self, E, B, x_n, v_n, alive=None):
+        """jic_load_carry_cn: the carry of CN_step (jaxincell/_simulation.py:237-240); `alive` (N,) is False where the carry's charge is 0."""
+        E, B, x_n, v_n = self._dev(E), self._dev(B), self._dev(x_n), self._dev(v_n)
+        a = None if alive is None else self._dev(np.asarray(alive).reshape(-1) != 0, torch.uint8)
+        if tuple(E.shape) != (self.G, 3) or tuple(B.shape) != (self.G, 3) or tuple(x_n.shape) != (self.N, 3) or tuple(v_n.shape) != (self.N, 3):
+            raise JicError(f"the CN carry is E, B ({self.G}, 3) and x, v ({self.N}, 3)")
+        if a is not None and tuple(a.shape) != (self.N,):
+            raise JicError(f"alive must have {self.N} entries")
+        self._chk(self.lib.jic_load_carry_cn(self.ctx, self._ptr(E), self._ptr(B), self._ptr(x_n), self._ptr(v_n), self._ptr(a), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
     def initialize_host(self, x0, v0):
         """x0, v0: HOST tensors / arrays (N,3), ideally pinned: jic_initialize_host uploads them in chunks overlapped with the
         start-up kernels (the device never holds a full copy).  Synchronises before returning."""

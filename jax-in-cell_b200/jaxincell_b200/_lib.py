@@ -63,6 +63,7 @@ SYMBOLS = [
     ("jic_set_external_fields", C.c_int, [_P, _P, _P, _P]),
     ("jic_initialize", C.c_int, [_P, _P, _P, _P]),
     ("jic_initialize_host", C.c_int, [_P, _P, _P, _P]),
+    ("jic_load_carry_cn", C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     ("jic_load_carry", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     ("jic_run", C.c_int, [_P, C.c_int64, C.POINTER(Outputs), _P]),
     ("jic_get_fields", C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -581,5 +581,5 @@ def run_CN(x0, v0, qs, ms, q_ms, *, length, G, dt, total_steps, box_yz=None, pbl
         for k, a in zip(keys, data):
             hist[k].append(np.array(a, copy=True))
     out = {k: np.stack(v_) for k, v_ in hist.items()}
-    out.update(grid=grid, dx=dx, dt=dt, initial_velocities=v, fields=(E, B), picard_iterations=np.array(iters))
+    out.update(grid=grid, dx=dx, dt=dt, initial_velocities=v, fields=(E, B), picard_iterations=np.array(iters), final_carry=carry)
     return out

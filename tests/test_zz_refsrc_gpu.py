@@ -158,3 +158,31 @@ def test_boris_step_operator_continues_a_carry_like_the_literal_oracle(bcs, rela
             assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-300), name
     finally:
         release_contexts()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (2, 2, 2, 2)])
+def test_cn_step_operator_continues_a_carry_like_the_literal_oracle(bcs):
+    """The same for the implicit stepper: the literal oracle's CN carry after 4 steps, continued for 3 steps by jaxincell_b200.CN_step."""
+    from jaxincell_b200 import CN_step
+    from jaxincell_b200._algorithms import release_contexts
+    from oracle import literal as L
+    from plasma import cfl_dt, two_species
+    G, length = 16, 0.01
+    pbl, pbr, fbl, fbr = bcs
+    p = two_species(160, 120, length=length, G=G, seed=90 + sum(bcs), vth_e=0.1 if sum(bcs) else 0.05, vth_yz=0.04, drift=4e7, plus_minus=True, gpdl=0.03)
+    dt = cfl_dt(length, G, 0.3)
+    solver = {"max_number_of_Picard_iterations_implicit_CN": 12, "number_of_particle_substeps_implicit_CN": 2, "tolerance_Picard_iterations_implicit_CN": 1e-9}
+    kw = dict(length=length, G=G, dt=dt, pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=solver)
+    first = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], total_steps=4, **kw)
+    full = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], total_steps=7, **kw)
+    carry = first["final_carry"]
+    dx, grid, box = length / G, first["grid"], (length, length, length)
+    try:
+        for t in range(4, 7):
+            carry, data = CN_step(carry, t, solver, dx, dt, grid, box, pbl, pbr, fbl, fbr, 2)
+            for got, key in zip(data, ("positions", "velocities", "electric_field", "magnetic_field", "current_density", "charge_density")):
+                ref = full[key][t]
+                assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-300), (t, key)
+    finally:
+        release_contexts()
