@@ -184,18 +184,77 @@ class Simulation:
             parameters = {}
         if not isinstance(parameters, dict):
             parameters = load_parameters(parameters)
+        self._ingest(parameters)
+
+    def _ingest(self, parameters):
+        """Constructor and `input_parameters` setter (jaxincell/_simulation.py:346-417, _routing.py:77-132): the `input_parameters` entry is
+        routed into the sections; the reference's differentiable parameters among them stay visible as `sim.input_parameters` and are an
+        overlay on the base sections, everything else becomes part of the base sections.  A flat key no section knows is an error; top
+        level keys that are not sections are ignored, as in the reference."""
         parameters = copy.deepcopy(parameters)
-        self.input_parameters = dict(parameters.pop("input_parameters", {}) or {})
-        unknown = set(parameters) - set(SECTIONS)
-        if unknown:
-            raise AssertionError(f"Unknown parameter sections: {sorted(unknown)}")
+        given = dict(parameters.pop("input_parameters", {}) or {})
+        base = {name: dict(parameters.get(name, {}) or {}) for name in SECTIONS}
+        base["species_parameters"] = _normalize_species_input(base["species_parameters"])
+        overlay = copy.deepcopy(base)
+        exposed, unrouted = {}, []
+        flat_defaults = (("domain_parameters", DOMAIN_DEFAULTS), ("solver_parameters", SOLVER_DEFAULTS),
+                         ("external_field_parameters", EXTERNAL_DEFAULTS), ("source_parameters", SOURCE_DEFAULTS))
+        for key, val in given.items():
+            if key in ("electrons", "ions"):
+                labels = list(base["species_parameters"][key])
+                canonical = {f"_{key}{i}": lab for i, lab in enumerate(labels)}
+                groups = val.items() if any(isinstance(v, dict) for v in val.values()) else [(None, val)]
+                for label, over in groups:
+                    if label is None:
+                        targets = labels
+                    elif label in canonical or label in labels:
+                        targets = [canonical.get(label, label)]
+                    else:  # a new species introduced through input_parameters
+                        base["species_parameters"][key][label] = {}
+                        overlay["species_parameters"][key][label] = {}
+                        targets = [label]
+                    for t in targets:
+                        for k, v in over.items():
+                            overlay["species_parameters"][key][t][k] = v
+                            if k in RUNTIME_SPECIES_KEYS[key]:
+                                exposed.setdefault(key, {}).setdefault(t if label is None else label, {})[k] = v
+                            else:
+                                base["species_parameters"][key][t][k] = v
+                continue
+            section = next((name for name, defaults in flat_defaults if key in defaults), None)
+            if section is None:
+                unrouted.append(key)
+                continue
+            overlay[section][key] = val
+            if key in RUNTIME_FLAT_KEYS:
+                exposed[key] = val
+            else:
+                base[section][key] = val
+        if unrouted:
+            raise ValueError("Initial input_parameters included parameter(s) that could not be routed. Unrouted parameter(s): " + ", ".join(unrouted))
+        self._base_sections = base
+        self._input_parameters = exposed
         for name in SECTIONS:  # the section setters clean and overlay the defaults, as the reference's do
-            setattr(self, name, parameters.get(name, {}))
+            self._set_section(name, overlay[name], remember=False)
+
+    @property
+    def input_parameters(self):
+        """The differentiable parameters that came in through `input_parameters` (_simulation.py:548-550)."""
+        return copy.deepcopy(self._input_parameters)
+
+    @input_parameters.setter
+    def input_parameters(self, new_input_parameters):
+        """Re-route on top of the base sections (_simulation.py:552-558)."""
+        parameters = copy.deepcopy(self._base_sections)
+        parameters["input_parameters"] = new_input_parameters
+        self._ingest(parameters)
 
     # ---- parameter sections as properties: assigning one re-cleans it (defaults overlaid on the NEW dict only) and thereby invalidates
     #      the cached state, like set_parameter_section of the reference (jaxincell/_simulation.py:494-556)
-    def _set_section(self, name, new):
+    def _set_section(self, name, new, remember=True):
         new = copy.deepcopy(dict(new or {}))
+        if remember:  # an assignment from outside replaces the base section (set_parameter_section, _simulation.py:494-506)
+            self._base_sections[name] = _normalize_species_input(new) if name == "species_parameters" else copy.deepcopy(new)
         if name == "domain_parameters":
             self._domain_parameters = self._clean_domain({**DOMAIN_DEFAULTS, **new})
         elif name == "solver_parameters":
@@ -333,7 +392,7 @@ class Simulation:
         """Overrides: a key is routed to whichever section declares it; species overrides are nested {electrons|ions: {label: {...}}}."""
         sec = {k: copy.deepcopy(getattr(self, k)) for k in SECTIONS}
         raw_species = None
-        for key, val in {**self.input_parameters, **(input_parameters or {})}.items():
+        for key, val in (input_parameters or {}).items():  # (what came in at construction is part of the sections already)
             if key in ("electrons", "ions"):
                 # start from the UNRESOLVED input so that cross references ("_electrons0") follow the overridden values, as in the
                 # reference, which re-resolves them inside _simulation (_simulation.py:163, _species_parameters.py:129-166)

@@ -432,3 +432,28 @@ def test_section_setters_reclean_and_invalidate_state():
     assert sim.dx > 0
     with pytest.raises(AssertionError):
         sim.solver_parameters = {"filter_alpha": 2.0}
+
+
+def test_input_parameters_entry_and_setter_route_like_the_reference():
+    """Behaviour observed on the reference's own Simulation (run on tests/refshim; cf. its tests/test_simulation.py:579-620): the
+    `input_parameters` entry is routed into the sections; only the reference's differentiable parameters stay exposed; the setter re-routes
+    on top of the base sections, into which the NON-differentiable ones of earlier inputs were merged for good."""
+    par = {"domain_parameters": {"total_steps": 2, "number_grid_points": 4},
+           "species_parameters": {"electrons": {"electrons0": {"number_pseudoparticles": 4}}, "ions": {"ions0": {"number_pseudoparticles": 4}}},
+           "solver_parameters": {"print_info": False, "rng": "numpy"},
+           "input_parameters": {"length": 0.03, "filter_passes": 2,
+                                "electrons": {"electrons0": {"vth_over_c_x": 0.07, "velocity_plus_minus_x": False}}}}
+    sim = Simulation(par)
+    assert sim.input_parameters == {"electrons": {"electrons0": {"vth_over_c_x": 0.07}}, "length": 0.03}
+    e0 = sim.species_parameters["electrons"]["_electrons0"]
+    assert (sim.domain_parameters["length"], sim.solver_parameters["filter_passes"], e0["vth_over_c_x"], e0["velocity_plus_minus_x"]) == (0.03, 2, 0.07, False)
+    sim.input_parameters = {"length": 0.02, "ions": {"ions0": {"mass_over_proton_mass": 2.0, "number_pseudoparticles": 3}}}
+    assert sim.input_parameters == {"ions": {"ions0": {"mass_over_proton_mass": 2.0}}, "length": 0.02}
+    assert sim.domain_parameters["length"] == 0.02 and sim.solver_parameters["filter_passes"] == 2       # the non-differentiable one stayed
+    assert sim.species_parameters["ions"]["_ions0"]["number_pseudoparticles"] == 3 and sim.positions.shape == (7, 3)
+    assert sim.species_parameters["electrons"]["_electrons0"]["vth_over_c_x"] == 0.05                        # the differentiable one did not
+    assert sim.species_parameters["electrons"]["_electrons0"]["velocity_plus_minus_x"] is False
+    for bad in ({"ion_drift_speed_x": 1.0}, {"nonsense": 1}):
+        with pytest.raises(ValueError, match="could not be routed"):
+            sim.input_parameters = bad
+    Simulation({"nonsense_section": {}})  # top-level keys that are not sections are ignored, as in the reference
