@@ -28,7 +28,7 @@ struct EmuParams {
   double q[8], m[8], qm[8];
 };
 
-int emu_run(const EmuParams* ep, const double* x0, const double* v0, const float* extE_f, const float* extB_f, int T, int reload_at,
+__attribute__((visibility("default"))) int emu_run(const EmuParams* ep, const double* x0, const double* v0, const float* extE_f, const float* extB_f, int T, int reload_at,
             double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv, double* E0_out, double* vinit_out) {
   typedef double R;
   DevParams<R> p;

@@ -33,7 +33,9 @@ class EmuParams(C.Structure):
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libjic_emu.so")
-    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(EMU_DIR, "fake_cuda"), "-I", CSRC,
+    # hidden visibility + -Bsymbolic: the emulated kernels have the mangled names of the real library's launch stubs, and libjic_b200.so may
+    # already be loaded RTLD_GLOBAL in this process -- the emulation must bind to its own definitions
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I", os.path.join(EMU_DIR, "fake_cuda"), "-I", CSRC,
            os.path.join(EMU_DIR, "emulate_indexed.cpp"), "-o", so]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
