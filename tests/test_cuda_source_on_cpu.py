@@ -99,3 +99,39 @@ def test_carry_loader_source_continues_a_run(emu, path, reload_at):
     for k in KEYS:
         assert relerr(reloaded[k], g[k]) < 1e-9, k
         assert relerr(reloaded[k], straight[k]) < 1e-12, k
+
+
+def _random_case(seed):
+    from plasma import cfl_dt, two_species
+    rng = np.random.default_rng(1000 + seed)
+    G = int(rng.choice([3, 4, 5, 6, 7, 9, 16, 33]))
+    length = float(rng.choice([0.01, 1.0]))
+    bcs = tuple(int(b) for b in rng.integers(0, 3, 4))
+    n_e, n_i = int(rng.integers(20, 90)), int(rng.integers(20, 90))
+    p = two_species(n_e, n_i, length=length, G=G, seed=seed, vth_e=float(rng.choice([0.02, 0.1, 0.3])), vth_yz=float(rng.choice([0.0, 0.05])),
+                    drift=float(rng.choice([0.0, 4e7])), plus_minus=bool(rng.integers(0, 2)), gpdl=0.6)
+    passes = int(rng.choice([0, 1, 2, 5, 16, 17, 18, 25]))
+    strides = tuple(int(s) for s in rng.choice([1, 2, 3, 4, 8], size=int(rng.integers(1, 4)), replace=False))
+    box = (length * float(rng.choice([0.3, 1.0, 2.0])), length * float(rng.choice([0.5, 1.0])))
+    ext = float(rng.choice([0.0, 1.0]))
+    return dict(x0=p["x0"] * np.array([1.0, box[0] / length, box[1] / length]), v0=p["v0"], q=p["q"], m=p["m"], qm=p["qm"], n_e=n_e, n_i=n_i, length=length, G=G,
+                dt=cfl_dt(length, G, float(rng.choice([0.5, 0.95, 2.5]))), T=int(rng.integers(3, 9)), bcs=np.array(bcs), filter_passes=passes,
+                filter_alpha=float(rng.choice([0.3, 0.5, 0.8])), filter_strides=np.array(strides), relativistic=int(rng.integers(0, 2)), box_yz=np.array(box),
+                ext_E=(ext * 1e3 * rng.standard_normal((G, 3))).astype(np.float32), ext_B=(ext * 1e-3 * rng.standard_normal((G, 3))).astype(np.float32))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_indexed_engine_source_against_the_oracle_on_random_configurations(emu, seed):
+    """Differential check over corners no fixture holds: every BC combination, grids from 3 cells, filter passes beyond the reference's cap
+    of 17, strides larger than the grid, CFL 2.5 jumps, thin transverse boxes, relativistic or not, with and without external fields."""
+    from oracle import closed_form as C
+    g = _random_case(seed)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    ref = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                box_yz=tuple(g["box_yz"]), ext_E=g["ext_E"], ext_B=g["ext_B"],
+                solver=dict(filter_passes=g["filter_passes"], filter_alpha=g["filter_alpha"], filter_strides=tuple(int(s) for s in g["filter_strides"]),
+                            relativistic=bool(g["relativistic"])))
+    out = run_emulated(emu, g, reload_at=2 if seed % 2 else -1)
+    assert all(np.isfinite(ref[k]).all() for k in KEYS)
+    for k in KEYS:
+        assert relerr(out[k], ref[k]) < 1e-7, (k, {kk: g[kk] for kk in ("G", "bcs", "filter_passes", "filter_strides", "relativistic", "T")})

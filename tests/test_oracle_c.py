@@ -92,3 +92,20 @@ def test_larger_run_against_numpy_and_charge_conservation():
     out = CP.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], solver=dict(filter_passes=0), **kw)
     total = out["charge_density"].sum(axis=1) * (length / G)
     assert np.abs(total - p["q"].sum()).max() < 1e-9 * np.abs(p["q"]).sum()
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_configurations_against_the_closed_form(seed):
+    """The corners of tests/test_cuda_source_on_cpu.py::_random_case (every BC combination, grids from 3 cells, filter passes beyond the
+    cap, strides larger than the grid, CFL 2.5, thin transverse boxes) for the compiled oracle as well."""
+    from test_cuda_source_on_cpu import _random_case
+    g = _random_case(seed)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    kw = dict(length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, box_yz=tuple(g["box_yz"]),
+              ext_E=g["ext_E"], ext_B=g["ext_B"],
+              solver=dict(filter_passes=g["filter_passes"], filter_alpha=g["filter_alpha"], filter_strides=tuple(int(s) for s in g["filter_strides"]),
+                          relativistic=bool(g["relativistic"])))
+    ref = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], **kw)
+    got = CP.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], threads=2, **kw)
+    for k in KEYS:
+        assert relerr(got[k], ref[k]) < 1e-7, k  # (CFL 2.5 cases amplify the rounding of the reduction order)
