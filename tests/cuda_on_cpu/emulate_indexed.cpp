@@ -28,9 +28,11 @@ struct EmuParams {
   double q[8], m[8], qm[8];
 };
 
-__attribute__((visibility("default"))) int emu_run(const EmuParams* ep, const double* x0, const double* v0, const float* extE_f, const float* extB_f, int T, int reload_at,
-            double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv, double* E0_out, double* vinit_out) {
-  typedef double R;
+}  // extern "C"
+
+template <typename R>
+static int run(const EmuParams* ep, const R* x0, const R* v0, const float* extE_f, const float* extB_f, int T, int reload_at,
+               R* hE, R* hB, R* hJ, R* hrho, R* hx, R* hv, double* E0_out, R* vinit_out) {
   DevParams<R> p;
   std::memset(&p, 0, sizeof(p));
   long long N = 0;
@@ -64,7 +66,7 @@ __attribute__((visibility("default"))) int emu_run(const EmuParams* ep, const do
   k_start<R>(p, x0, v0, 0, N, xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(), v_init.data(), acc.data());
   k_fields<R>(field_args(true));
   if (E0_out) std::memcpy(E0_out, E0.data(), sizeof(double) * G * 3);
-  if (vinit_out) std::memcpy(vinit_out, v_init.data(), sizeof(double) * 3 * n);
+  if (vinit_out) std::memcpy(vinit_out, v_init.data(), sizeof(R) * 3 * n);
   std::vector<R> x_minus(3 * n), x_plus(3 * n), x_now(3 * n), v_now(3 * n);
   for (int t = 0; t < T; ++t) {
     if (t == reload_at && t > 0) {
@@ -74,10 +76,10 @@ __attribute__((visibility("default"))) int emu_run(const EmuParams* ep, const do
         v_now[3 * i] = vx[i]; v_now[3 * i + 1] = vy[i]; v_now[3 * i + 2] = vz[i];
         for (int c = 0; c < 3; ++c) x_now[3 * i + c] = hx[((size_t)(t - 1) * n + i) * 3 + c];
       }
-      std::vector<R> E_c(E_int.begin(), E_int.end()), B_c(B_int.begin(), B_int.end());
+      std::vector<R> E_c(E_int.begin(), E_int.end()), B_c(B_int.begin(), B_int.end());  // (the carry travels in R, as through the C ABI)
       // wipe the state that jic_load_carry must rebuild
       std::fill(xh.begin(), xh.end(), 0.0); std::fill(vx.begin(), vx.end(), 0.0); std::fill(vy.begin(), vy.end(), 0.0); std::fill(vz.begin(), vz.end(), 0.0);
-      std::fill(E.begin(), E.end(), 1e300); std::fill(B.begin(), B.end(), 1e300); std::fill(J.begin(), J.end(), 1e300); std::fill(F.begin(), F.end(), 1e300);
+      std::fill(E.begin(), E.end(), 1e300); std::fill(B.begin(), B.end(), 1e300); std::fill(J.begin(), J.end(), 1e300); std::fill(F.begin(), F.end(), R(1e30));
       std::fill(acc.begin(), acc.end(), 0.0);
       const long long row = ctl.hist_row, step = ctl.step;
       k_load_carry<R>(p, x_minus.data(), x_now.data(), x_plus.data(), v_now.data(), xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(),
@@ -94,4 +96,15 @@ __attribute__((visibility("default"))) int emu_run(const EmuParams* ep, const do
   return 0;
 }
 
+extern "C" {
+__attribute__((visibility("default"))) int emu_run(const EmuParams* ep, const double* x0, const double* v0, const float* extE, const float* extB, int T,
+                                                   int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv,
+                                                   double* E0_out, double* vinit_out) {
+  return run<double>(ep, x0, v0, extE, extB, T, reload_at, hE, hB, hJ, hrho, hx, hv, E0_out, vinit_out);
+}
+__attribute__((visibility("default"))) int emu_run_f32(const EmuParams* ep, const float* x0, const float* v0, const float* extE, const float* extB, int T,
+                                                       int reload_at, float* hE, float* hB, float* hJ, float* hrho, float* hx, float* hv,
+                                                       double* E0_out, float* vinit_out) {
+  return run<float>(ep, x0, v0, extE, extB, T, reload_at, hE, hB, hJ, hrho, hx, hv, E0_out, vinit_out);
+}
 }  // extern "C"
