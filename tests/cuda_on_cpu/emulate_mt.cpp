@@ -1,0 +1,189 @@
+// TEST INFRASTRUCTURE ONLY -- the warp-level kernels of the INDEXED engine and of the Crank-Nicolson stepper on the multi-threaded
+// emulation of fake_cuda_mt/cuda_runtime.h, launched in the order csrc/jic_engine.cu launches them:
+//   emu_fs_run   explicit stepper with the per-step electrostatic correction: k_start, k_gauss_kernel, { k_step (face deposit), k_gauss,
+//                k_fields (E_x replaced) } -- optional carry reload through k_load_carry / k_carry_fields
+//   emu_cn_run   implicit stepper: k_cn_start, k_fields(init), k_cn_fields(prepare), { max_iter x (k_cn_push, k_cn_fields), k_cn_record }
+//                -- optional carry reload through k_cn_load / k_carry_copy_fields
+#include <cstring>
+#include <vector>
+
+#include "jic_kernels.cuh"
+#include "jic_cn.cuh"
+#include "jic_carry.cuh"
+
+thread_local EmuDim3 threadIdx;
+EmuDim3 blockIdx;
+EmuDim3One blockDim, gridDim;
+EmuBlock* emu_block = nullptr;
+namespace jic {
+alignas(16) double fsm[1];
+alignas(16) unsigned char smem_raw[1];
+alignas(16) unsigned char cn_smem_raw[1];
+alignas(16) double gsm[2 * 4096];
+}  // namespace jic
+
+using namespace jic;
+typedef double R;
+
+extern "C" {
+struct EmuParams {
+  int G, n_species, pbl, pbr, fbl, fbr, relativistic, field_solver;
+  int filter_passes, n_strides, strides[8];
+  double L, Ly, Lz, dx, dt, grid_first, grid_last, filter_alpha;
+  long long count[8];
+  double q[8], m[8], qm[8];
+};
+}
+
+static DevParams<R> dev_params(const EmuParams* ep, long long* N_out) {
+  DevParams<R> p;
+  std::memset(&p, 0, sizeof(p));
+  long long N = 0;
+  for (int s = 0; s < ep->n_species; ++s) { N += ep->count[s]; p.sp_end[s] = N; p.sp_q[s] = ep->q[s]; p.sp_m[s] = ep->m[s]; p.sp_qm[s] = ep->qm[s]; }
+  p.N = N; p.G = ep->G; p.n_species = ep->n_species;
+  p.pbl = ep->pbl; p.pbr = ep->pbr; p.fbl = ep->fbl; p.fbr = ep->fbr; p.relativistic = ep->relativistic; p.track_yz = 1;
+  p.L = ep->L; p.Ly = ep->Ly; p.Lz = ep->Lz; p.half_L = ep->L / 2; p.half_Ly = ep->Ly / 2; p.half_Lz = ep->Lz / 2;
+  p.dx = ep->dx; p.inv_dx = 1.0 / ep->dx; p.half_dx = ep->dx / 2; p.dt = ep->dt; p.half_dt = ep->dt / 2;
+  p.g0 = ep->grid_first; p.gl = ep->grid_last; p.gs = ep->grid_first - ep->dx / 2;
+  p.park_left = ep->grid_first - 1.5 * ep->dx; p.park_right = ep->grid_last + 3 * ep->dx;
+  *N_out = N;
+  return p;
+}
+
+struct GridState {
+  std::vector<R> acc, F;
+  std::vector<double> E, B, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ExC, h;
+  RunControl ctl;
+  explicit GridState(size_t G) : acc(G * (kAccRow + 1)), F((G + 3) * kFieldRow), E(G * 3), B(G * 3), E_int(G * 3), B_int(G * 3), J(G * 3), rho(G),
+                                 extE(G * 3), extB(G * 3), s0(G * kAccRow), s1(G * kAccRow), E0(G * 3), B0(G * 3), ExC(G), h(G) {
+    std::memset(&ctl, 0, sizeof(ctl));
+  }
+  FieldArgs<R> field_args(const EmuParams* ep, bool init, bool with_ExC) {
+    FieldArgs<R> a;
+    std::memset(&a, 0, sizeof(a));
+    a.G = ep->G; a.fbl = ep->fbl; a.fbr = ep->fbr; a.passes = ep->filter_passes; a.n_strides = ep->n_strides; a.init = init;
+    for (int i = 0; i < ep->n_strides; ++i) a.strides[i] = ep->strides[i];
+    a.alpha = ep->filter_alpha; a.dx = ep->dx; a.dt = ep->dt;
+    a.acc = acc.data(); a.E = E.data(); a.B = B.data(); a.E_int = E_int.data(); a.B_int = B_int.data(); a.J = J.data(); a.rho = rho.data();
+    a.extE = extE.data(); a.extB = extB.data(); a.F = F.data(); a.s0 = s0.data(); a.s1 = s1.data(); a.E0 = E0.data(); a.B0 = B0.data(); a.ctl = &ctl;
+    a.record = init ? 0 : 1; a.smem_comps = 0; a.ExC = (with_ExC && !init) ? ExC.data() : nullptr;
+    return a;
+  }
+};
+
+constexpr unsigned kThreads = 64;  // two warps per block: block reductions and warp loops both have something to do
+
+extern "C" {
+
+__attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const double* x0, const double* v0, int T, int reload_at, double* hE, double* hB,
+                                                      double* hJ, double* hrho, double* hx, double* hv) {
+  long long N;
+  DevParams<R> p = dev_params(ep, &N);
+  p.stag = ep->field_solver != 0;
+  const size_t G = (size_t)ep->G, n = (size_t)N;
+  if (2 * G > sizeof(gsm) / sizeof(double)) return -1;
+  GridState gs(G);
+  std::vector<R> xh(n), yh(n), zh(n), vx(n), vy(n), vz(n), v_init(3 * n), x_minus(3 * n), x_plus(3 * n), x_now(3 * n), v_now(3 * n);
+  const bool stag = p.stag != 0;
+  if (stag) emu_launch((unsigned)((G + 127) / 128), 128, [&] { k_gauss_kernel((int)G, ep->dx, gs.h.data()); });
+  emu_launch(2, kThreads, [&] { k_start<R>(p, x0, v0, 0, N, xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(), v_init.data(), gs.acc.data()); });
+  emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, stag)); });
+  for (int t = 0; t < T; ++t) {
+    if (t == reload_at && t > 0) {
+      for (size_t i = 0; i < n; ++i) {
+        x_plus[3 * i] = xh[i]; x_plus[3 * i + 1] = yh[i]; x_plus[3 * i + 2] = zh[i];
+        v_now[3 * i] = vx[i]; v_now[3 * i + 1] = vy[i]; v_now[3 * i + 2] = vz[i];
+        for (int c = 0; c < 3; ++c) x_now[3 * i + c] = hx[((size_t)(t - 1) * n + i) * 3 + c];
+      }
+      std::vector<R> E_c(gs.E_int.begin(), gs.E_int.end()), B_c(gs.B_int.begin(), gs.B_int.end());
+      std::fill(xh.begin(), xh.end(), 0.0); std::fill(vx.begin(), vx.end(), 0.0); std::fill(vy.begin(), vy.end(), 0.0); std::fill(vz.begin(), vz.end(), 0.0);
+      std::fill(gs.E.begin(), gs.E.end(), 1e300); std::fill(gs.B.begin(), gs.B.end(), 1e300); std::fill(gs.J.begin(), gs.J.end(), 1e300);
+      std::fill(gs.F.begin(), gs.F.end(), 1e300); std::fill(gs.acc.begin(), gs.acc.end(), 0.0);
+      const long long row = gs.ctl.hist_row, step = gs.ctl.step;
+      emu_launch(2, kThreads, [&] { k_load_carry<R>(p, x_minus.data(), x_now.data(), x_plus.data(), v_now.data(), xh.data(), yh.data(), zh.data(), vx.data(),
+                                                     vy.data(), vz.data(), v_init.data(), gs.acc.data()); });
+      emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, stag)); });
+      emu_launch(1, kThreads, [&] { k_carry_fields<R>(gs.field_args(ep, true, stag), E_c.data(), B_c.data()); });
+      gs.ctl.hist_row = row; gs.ctl.step = step;
+    }
+    for (size_t i = 0; i < n; ++i) { x_minus[3 * i] = xh[i]; x_minus[3 * i + 1] = yh[i]; x_minus[3 * i + 2] = zh[i]; }
+    gs.ctl.hist[0] = hE; gs.ctl.hist[1] = hB; gs.ctl.hist[2] = hJ; gs.ctl.hist[3] = hrho; gs.ctl.hist[4] = hx; gs.ctl.hist[5] = hv;
+    emu_launch(3, kThreads, [&] { k_step<R, false>(p, xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(), gs.F.data(), gs.acc.data(), &gs.ctl); });
+    if (stag) {  // EngineT::enqueue_gauss
+      GaussArgs<R> a;
+      std::memset(&a, 0, sizeof(a));
+      a.G = ep->G; a.fbl = ep->fbl; a.fbr = ep->fbr; a.passes = ep->filter_passes; a.n_strides = ep->n_strides; a.mode = ep->field_solver;
+      for (int i = 0; i < ep->n_strides; ++i) a.strides[i] = ep->strides[i];
+      a.alpha = ep->filter_alpha; a.dx = ep->dx; a.accS = gs.acc.data() + G * kAccRow; a.h = gs.h.data(); a.Ex = gs.ExC.data();
+      emu_launch((unsigned)((G + 7) / 8), kThreads, [&] { k_gauss<R>(a); });
+    }
+    emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, false, stag)); });
+  }
+  return 0;
+}
+
+__attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const double* x0, const double* v0, int T, int n_sub, int max_iter, double tol,
+                                                      int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv,
+                                                      long long* picard) {
+  long long N;
+  DevParams<R> p = dev_params(ep, &N);
+  const size_t G = (size_t)ep->G, n = (size_t)N;
+  GridState gs(G);
+  std::vector<R> buf[2][6], stag(n * (size_t)n_sub), v_init(3 * n);
+  CnState<R> cs[2];
+  for (int k = 0; k < 2; ++k) {
+    for (auto& b : buf[k]) b.assign(n, 0.0);
+    cs[k] = CnState<R>{buf[k][0].data(), buf[k][1].data(), buf[k][2].data(), buf[k][3].data(), buf[k][4].data(), buf[k][5].data()};
+  }
+  std::vector<uint8_t> alive(n);
+  std::vector<double> Eg(G * 3), Bnext(G * 3), Eavg(G * 3), Bavg(G * 3);
+  CnControl cn;
+  std::memset(&cn, 0, sizeof(cn));
+  auto cn_args = [&](int it, bool prepare_only) {  // EngineT::cn_field_args
+    CnFieldArgs<R> a;
+    std::memset(&a, 0, sizeof(a));
+    a.G = ep->G; a.fbl = ep->fbl; a.fbr = ep->fbr; a.it = it; a.max_iter = max_iter; a.prepare_only = prepare_only ? 1 : 0;
+    a.dx = ep->dx; a.dt = ep->dt; a.tol = tol;
+    a.acc = gs.acc.data(); a.En = gs.E.data(); a.Bn = gs.B.data(); a.Eg = Eg.data(); a.Bnext = Bnext.data(); a.Eavg = Eavg.data(); a.Bavg = Bavg.data();
+    a.J = gs.J.data(); a.rho = gs.rho.data(); a.cn = &cn; a.ctl = &gs.ctl;
+    return a;
+  };
+  // EngineT::initialize_cn
+  emu_launch(2, kThreads, [&] { k_cn_start<R>(p, x0, v0, cs[0], v_init.data(), alive.data(), gs.acc.data()); });
+  emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, false)); });
+  gs.E = gs.E0; gs.B = gs.B0;
+  emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(0, true)); });
+  int par = 0;
+  for (int t = 0; t < T; ++t) {
+    if (t == reload_at && t > 0) {
+      std::vector<R> x(3 * n), v(3 * n), E_c(gs.E.begin(), gs.E.end()), B_c(gs.B.begin(), gs.B.end());
+      for (size_t i = 0; i < n; ++i) {
+        x[3 * i] = cs[par].x[i]; x[3 * i + 1] = cs[par].y[i]; x[3 * i + 2] = cs[par].z[i];
+        v[3 * i] = cs[par].vx[i]; v[3 * i + 1] = cs[par].vy[i]; v[3 * i + 2] = cs[par].vz[i];
+      }
+      std::vector<uint8_t> alive_in(alive);
+      for (int k = 0; k < 2; ++k) for (auto& b : buf[k]) std::fill(b.begin(), b.end(), 1e300);
+      std::fill(alive.begin(), alive.end(), 7); std::fill(gs.E.begin(), gs.E.end(), 1e300); std::fill(gs.B.begin(), gs.B.end(), 1e300);
+      std::fill(Eg.begin(), Eg.end(), 1e300); std::fill(Eavg.begin(), Eavg.end(), 1e300); std::fill(Bavg.begin(), Bavg.end(), 1e300);
+      std::fill(gs.acc.begin(), gs.acc.end(), 0.0);
+      const CnControl keep = cn;
+      std::memset(&cn, 0, sizeof(cn));
+      par = 0;  // EngineT::load_carry_cn
+      emu_launch(2, kThreads, [&] { k_cn_load<R>(p, x.data(), v.data(), alive_in.data(), cs[0], v_init.data(), alive.data()); });
+      emu_launch(1, kThreads, [&] { k_carry_copy_fields<R>(E_c.data(), B_c.data(), gs.E.data(), gs.B.data(), gs.E0.data(), gs.B0.data(), (int)(G * 3)); });
+      emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(0, true)); });
+      cn.total_iters = keep.total_iters;
+    }
+    gs.ctl.hist[0] = hE; gs.ctl.hist[1] = hB; gs.ctl.hist[2] = hJ; gs.ctl.hist[3] = hrho; gs.ctl.hist[4] = hx; gs.ctl.hist[5] = hv;
+    for (int it = 0; it < max_iter; ++it) {  // EngineT::enqueue_step_cn
+      emu_launch(3, kThreads, [&] { k_cn_push<R, false>(p, cs[par], cs[par ^ 1], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(), alive.data(), &cn); });
+      emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(it, false)); });
+    }
+    emu_launch(2, kThreads, [&] { k_cn_record<R>(p, cs[par ^ 1], &gs.ctl); });
+    if (picard) picard[t] = cn.last_iters;
+    par ^= 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -149,3 +149,91 @@ def test_indexed_engine_source_against_the_oracle_on_random_configurations(emu, 
     assert all(np.isfinite(ref[k]).all() for k in KEYS)
     for k in KEYS:
         assert relerr(out[k], ref[k]) < 1e-7, (k, {kk: g[kk] for kk in ("G", "bcs", "filter_passes", "filter_strides", "relativistic", "T")})
+
+
+# ---- warp-level kernels on the multi-threaded emulation (fake_cuda_mt): k_gauss (field_solver) and the Crank-Nicolson stepper ----------
+@pytest.fixture(scope="module")
+def emu_mt(tmp_path_factory):
+    root = tmp_path_factory.mktemp("emu_mt")
+    src = root / "x" / "csrc"
+    src.mkdir(parents=True)
+    (root / "include").mkdir()
+    (root / "include" / "jic_b200.h").write_text(open(os.path.join(ROOT, "include", "jic_b200.h")).read())
+    for name in ("jic_device.cuh", "jic_kernels.cuh", "jic_cn.cuh", "jic_carry.cuh"):
+        # the one textual change: dynamic shared arrays become plain externs (the harness defines them), so that `__shared__` can mean `static`
+        (src / name).write_text(open(os.path.join(CSRC, name)).read().replace("extern __shared__", "extern"))
+    so = str(root / "libjic_emu_mt.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I",
+           os.path.join(EMU_DIR, "fake_cuda_mt"), "-I", str(src), os.path.join(EMU_DIR, "emulate_mt.cpp"), "-o", so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lib = C.CDLL(so)
+    lib.emu_fs_run.restype = C.c_int
+    lib.emu_fs_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    lib.emu_cn_run.restype = C.c_int
+    lib.emu_cn_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 7
+    return lib
+
+
+def _params_of(g):
+    G = int(g["G"])
+    ne, ni = int(g["n_e"]), int(g["n_i"])
+    p = EmuParams()
+    p.G, p.n_species = G, 2
+    p.pbl, p.pbr, p.fbl, p.fbr = (int(b) for b in g["bcs"])
+    p.relativistic, p.filter_passes, p.filter_alpha = int(g["relativistic"]), int(g["filter_passes"]), float(g["filter_alpha"])
+    p.unused = int(g["field_solver"]) if "field_solver" in g else 0
+    strides = [int(s) for s in g["filter_strides"]]
+    p.n_strides = len(strides)
+    for i, s in enumerate(strides):
+        p.strides[i] = s
+    L = float(g["length"])
+    dx = L / G
+    grid = np.linspace(-L / 2 + dx / 2, L / 2 - dx / 2, G)
+    p.L, p.Ly, p.Lz, p.dx, p.dt, p.grid_first, p.grid_last = L, L, L, dx, float(g["dt"]), float(grid[0]), float(grid[-1])
+    for s, (n, o) in enumerate(((ne, 0), (ni, ne))):
+        p.count[s], p.q[s], p.m[s], p.qm[s] = n, float(g["q"][o]), float(g["m"][o]), float(g["qm"][o])
+    return p
+
+
+def _histories(g):
+    G, T, N = int(g["G"]), int(g["T"]), len(g["x0"])
+    return dict(electric_field=np.zeros((T, G, 3)), magnetic_field=np.zeros((T, G, 3)), current_density=np.zeros((T, G, 3)),
+                charge_density=np.zeros((T, G)), positions=np.zeros((T, N, 3)), velocities=np.zeros((T, N, 3)))
+
+
+FS_GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "refsrc_field_solver_*.npz")))
+CN_GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "refsrc_crank_nicolson_*.npz")))
+
+
+@pytest.mark.parametrize("reload_at", [-1, 3])
+@pytest.mark.parametrize("path", FS_GOLDEN, ids=[os.path.basename(f)[:-4] for f in FS_GOLDEN])
+def test_field_solver_source_on_the_threaded_emulation(emu_mt, path, reload_at):
+    """k_step's face deposit, k_gauss_kernel, k_gauss (warp reductions, several CTAs) and k_fields' E_x replacement -- solvers 1, 2, 3, with
+    and without walls -- against the reference-source vectors; with reload_at the carry loader is exercised on this branch too."""
+    g = dict(np.load(path))
+    out = _histories(g)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
+    assert emu_mt.emu_fs_run(C.byref(_params_of(g)), ptr(x0), ptr(v0), int(g["T"]), reload_at, *[ptr(out[k]) for k in KEYS]) == 0
+    for k in KEYS:
+        assert relerr(out[k], g[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("reload_at", [-1, 3])
+@pytest.mark.parametrize("path", CN_GOLDEN, ids=[os.path.basename(f)[:-4] for f in CN_GOLDEN])
+def test_crank_nicolson_source_on_the_threaded_emulation(emu_mt, path, reload_at):
+    """k_cn_start, k_cn_push, k_cn_fields (block reductions, device-side convergence flag), k_cn_record against the reference-source vectors,
+    Picard iteration counts included; with reload_at the CN carry loader (k_cn_load, k_carry_copy_fields) continues a wiped run."""
+    g = dict(np.load(path))
+    out = _histories(g)
+    T = int(g["T"])
+    picard = np.zeros(T, np.int64)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
+    rc = emu_mt.emu_cn_run(C.byref(_params_of(g)), ptr(x0), ptr(v0), T, int(g["cn_substeps"]), int(g["cn_max_iterations"]), float(g["cn_tolerance"]),
+                           reload_at, *[ptr(out[k]) for k in KEYS], ptr(picard))
+    assert rc == 0
+    for k in KEYS:
+        assert relerr(out[k], g[k]) < 1e-9, k
+    assert picard.tolist() == g["picard_iterations"].tolist()
