@@ -69,6 +69,34 @@ __global__ void __launch_bounds__(1024) k_carry_fields(const FieldArgs<R> a, con
   }
 }
 
+// ---- field_solver != 0, step 0 only.  The step kernels deposit rho(x_n) on the faces from x_n = BCpos(x_{n+1/2} - dt/2 v_n), which is what the
+// reference holds in `positions` from step 1 on (_algorithms.py:60-61 of the previous step) -- but in step 0 `positions` is the raw x_0
+// (_simulation.py:228-231).  The two agree unless the start-up half step took the particle through a PERIODIC wall while the opposite wall
+// is not periodic (the way back is then reflected or absorbed instead of wrapped).  For exactly those particles this kernel, launched
+// once after the start-up kernel, puts q [S(x_0) - S(x_n)] on the faces, so that step 0 ends up with the reference's deposit.  Found by
+// running the CUDA source on the CPU against the reference semantics over random boundary combinations (tests/test_cuda_source_on_cpu.py).
+// (A particle that also gets absorbed during step 0 keeps this correction although the reference drops its charge: second order, ignored.)
+template <typename R>
+__global__ void __launch_bounds__(256) k_start_face_fix(const DevParams<R> p, const R* __restrict__ x0, const R* __restrict__ v0, long long i0, long long n,
+                                                        R* __restrict__ acc) {
+  const GlobalGrid<R> grid{acc, p.G};
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    const R X0 = x0[3 * j];
+    R vx0 = v0[3 * j];
+    R xp = X0 + p.half_dt * vx0;
+    const int flag = bc_x(xp, p);
+    if (flag == 2) continue;  // absorbed by the start-up half step: no charge
+    if (flag == 1) vx0 = -vx0;
+    R xn = xp - p.half_dt * vx0;  // what k_step / k_push take for x_n in step 0
+    bc_x(xn, p);
+    if (fabs(xn - X0) > R(1e-6) * p.dx) {
+      const R a = p.sp_q[species_of(i0 + j, p)] * p.inv_dx;
+      deposit_faces(grid, make_cloud_faces(X0, p), p.G, a);
+      deposit_faces(grid, make_cloud_faces(xn, p), p.G, -a);
+    }
+  }
+}
+
 // ---- Crank-Nicolson: the carry of CN_step is (E, B, x_n, v_n, q, m, q/m) (jaxincell/_simulation.py:237-240, _algorithms.py:103-104).
 // Particles and fields are copied as they are; `alive_in` (0 = the particle's q is zero in the carry: absorbed by the start-up half
 // step, _simulation.py:217-220) replaces the byte k_cn_start computes.  The averaged tables of the first Picard iteration are then

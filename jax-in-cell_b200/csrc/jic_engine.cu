@@ -463,6 +463,7 @@ struct EngineT : Engine {
       } else if ((rc = bins.start_chunk(*this, dp, hstage[2 * k], hstage[2 * k + 1], i0, n, acc, st))) {
         return rc;
       }
+      face_fix(hstage[2 * k], hstage[2 * k + 1], i0, n, st);
       JIC_CUDA(cudaEventRecord(ev_used[k], st));
     }
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.start_end(*this, dp, st))) return rc;
@@ -492,6 +493,18 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
+  // step-0 correction of the face deposit (csrc/jic_carry.cuh: k_start_face_fix); single rank only -- with several ranks the start-up
+  // reduction would count it once per rank, and the combination (field_solver with one periodic and one non-periodic particle wall,
+  // sharded) is left as it was
+  bool needs_face_fix() const {
+    return dp.stag && world == 1 && dp.pbl != dp.pbr && (dp.pbl == JIC_BC_PERIODIC || dp.pbr == JIC_BC_PERIODIC);
+  }
+  void face_fix(const R* x0, const R* v0, long long i0, long long n, cudaStream_t st) {
+    if (!needs_face_fix() || n <= 0) return;
+    k_start_face_fix<R><<<grid_for(n, 256, 8), 256, 0, st>>>(dp, x0, v0, i0, n, acc);
+    launches += 1;
+  }
+
   int initialize(const void* x0, const void* v0, cudaStream_t st) override {
     if ((!x0 || !v0) && dp.N > 0) return fail(JIC_ERR_INVALID_ARGUMENT, "x0/v0 is null");
     int rc = initialize_begin(st);
@@ -503,6 +516,7 @@ struct EngineT : Engine {
     } else if ((rc = bins.start(*this, dp, (const R*)x0, (const R*)v0, acc, st))) {
       return rc;
     }
+    face_fix((const R*)x0, (const R*)v0, 0, dp.N, st);
     JIC_CUDA(cudaGetLastError());
     return initialize_finish(st);
   }

@@ -87,6 +87,8 @@ __attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const
   const bool stag = p.stag != 0;
   if (stag) emu_launch((unsigned)((G + 127) / 128), 128, [&] { k_gauss_kernel((int)G, ep->dx, gs.h.data()); });
   emu_launch(2, kThreads, [&] { k_start<R>(p, x0, v0, 0, N, xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(), v_init.data(), gs.acc.data()); });
+  if (stag && ep->pbl != ep->pbr && (ep->pbl == JIC_BC_PERIODIC || ep->pbr == JIC_BC_PERIODIC))  // EngineT::needs_face_fix (one rank)
+    emu_launch(2, kThreads, [&] { k_start_face_fix<R>(p, x0, v0, 0, N, gs.acc.data()); });
   emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, stag)); });
   for (int t = 0; t < T; ++t) {
     if (t == reload_at && t > 0) {

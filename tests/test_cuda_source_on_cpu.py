@@ -6,6 +6,7 @@ What this proves: the arithmetic and control flow of that source (gather, Boris,
 rows, carry reload) are right, without a GPU.  What it cannot see: races, memory spaces, launch configuration, the binned engine
 (warp-level code).  The GPU tests remain the parity tests proper; this one guards the kernels while no GPU is at hand."""
 import ctypes as C
+import ctypes as C_
 import glob
 import os
 import subprocess
@@ -237,3 +238,24 @@ def test_crank_nicolson_source_on_the_threaded_emulation(emu_mt, path, reload_at
     for k in KEYS:
         assert relerr(out[k], g[k]) < 1e-9, k
     assert picard.tolist() == g["picard_iterations"].tolist()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_field_solver_source_against_the_oracle_on_random_configurations(emu_mt, seed):
+    """The corners of _random_case with a random field_solver on top (grids from 3 cells, every BC combination, CFL 2.5, filter passes beyond
+    the cap), against the closed-form oracle; every other case also reloads its carry after two steps."""
+    from oracle import closed_form as C
+    g = _random_case(500 + seed)
+    g["field_solver"] = 1 + seed % 3
+    g["box_yz"] = np.array([g["length"], g["length"]])
+    g["x0"] = np.clip(g["x0"], -g["length"] / 2, g["length"] / 2)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    ref = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                solver=dict(filter_passes=g["filter_passes"], filter_alpha=g["filter_alpha"], filter_strides=tuple(int(s) for s in g["filter_strides"]),
+                            relativistic=bool(g["relativistic"]), field_solver=g["field_solver"]))
+    out = _histories(g)
+    ptr = lambda a: a.ctypes.data_as(C_.c_void_p)  # noqa: E731
+    x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
+    assert emu_mt.emu_fs_run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), int(g["T"]), 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS]) == 0
+    for k in KEYS:
+        assert relerr(out[k], ref[k]) < 1e-7, (k, {kk: g[kk] for kk in ("G", "bcs", "filter_passes", "filter_strides", "relativistic", "T", "field_solver")})

@@ -186,3 +186,32 @@ def test_cn_step_operator_continues_a_carry_like_the_literal_oracle(bcs):
                 assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-300), (t, key)
     finally:
         release_contexts()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("bcs", [(0, 1, 0, 1), (1, 0, 1, 0), (2, 0, 2, 0), (0, 2, 0, 2)])
+def test_field_solver_with_one_periodic_particle_wall(bcs, engine):
+    """field_solver != 0 deposits rho(x_n) on the faces; in step 0 x_n is the raw x_0, which the step kernels' recomputation misses for
+    particles that the start-up half step sent through a periodic wall opposite a non-periodic one.  k_start_face_fix repairs exactly
+    that (found and checked on the CPU emulation of the source: tests/test_cuda_source_on_cpu.py); here on hardware, both engines."""
+    import torch
+    from jaxincell_b200 import HotPath
+    from oracle import closed_form as C
+    from plasma import cfl_dt, two_species
+    G, length, T = 12, 0.01, 8
+    pbl, pbr, fbl, fbr = bcs
+    p = two_species(400, 300, length=length, G=G, seed=61 + sum(bcs), vth_e=0.3, vth_yz=0.05, gpdl=0.6)
+    dt = cfl_dt(length, G, 0.95)
+    solver = dict(field_solver=1, filter_passes=2, filter_strides=(1, 2))
+    ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, solver=solver)
+    hp = HotPath(species=p["species"], length=length, G=G, dt=dt, pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, engine=engine, track_yz=engine == "indexed",
+                 field_solver=1, filter_passes=2, filter_strides=(1, 2))
+    hp.set_external_fields(None, None)
+    hp.initialize(p["x0"], p["v0"])
+    out = hp.run(T, particles=engine == "indexed")
+    torch.cuda.synchronize()
+    for k in ("electric_field", "magnetic_field", "current_density", "charge_density"):
+        ref_k = ref[k]
+        assert np.abs(out[k].cpu().numpy() - ref_k).max() <= 1e-5 * max(np.abs(ref_k).max(), 1e-300), (k, engine)
+    hp.close()
