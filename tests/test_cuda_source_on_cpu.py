@@ -259,3 +259,36 @@ def test_field_solver_source_against_the_oracle_on_random_configurations(emu_mt,
     assert emu_mt.emu_fs_run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), int(g["T"]), 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS]) == 0
     for k in KEYS:
         assert relerr(out[k], ref[k]) < 1e-7, (k, {kk: g[kk] for kk in ("G", "bcs", "filter_passes", "filter_strides", "relativistic", "T", "field_solver")})
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_crank_nicolson_source_against_the_oracle_on_random_configurations(emu_mt, seed):
+    """The implicit stepper's source over random boundary combinations, grids from 3 cells, 1-3 sub-steps, tight and loose Picard tolerances,
+    against oracle/literal.py (pinned to the reference's CN_step by the refsrc vectors); odd seeds reload the CN carry after two steps."""
+    from oracle import literal as L
+    g = _random_case(900 + seed)
+    rng = np.random.default_rng(seed)
+    n_sub, max_iter, tol = int(rng.integers(1, 4)), int(rng.choice([3, 8, 20])), float(rng.choice([1e-4, 1e-9, 1e-30]))
+    g["dt"] = g["dt"] * 0.3  # (the implicit examples of the reference run at a fraction of the light CFL)
+    g["box_yz"] = np.array([g["length"], g["length"]])
+    g["x0"] = np.clip(g["x0"], -g["length"] / 2, g["length"] / 2)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    ref = L.run_CN(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                   solver={"max_number_of_Picard_iterations_implicit_CN": max_iter, "number_of_particle_substeps_implicit_CN": n_sub,
+                           "tolerance_Picard_iterations_implicit_CN": tol,  # (the filter only enters the initial Gauss solve, _state_initialization.py:371-374)
+                           "filter_passes": g["filter_passes"], "filter_alpha": g["filter_alpha"], "filter_strides": tuple(int(s) for s in g["filter_strides"])})
+    out = _histories(g)
+    T = int(g["T"])
+    picard = np.zeros(T, np.int64)
+    ptr = lambda a: a.ctypes.data_as(C_.c_void_p)  # noqa: E731
+    x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
+    assert emu_mt.emu_cn_run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), T, n_sub, max_iter, tol, 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS],
+                             ptr(picard)) == 0
+    assert all(np.isfinite(ref[k]).all() for k in KEYS)
+    info = {kk: g[kk] for kk in ("G", "bcs", "T")} | dict(n_sub=n_sub, max_iter=max_iter, tol=tol)
+    for k in KEYS:
+        assert relerr(out[k], ref[k]) < 1e-7, (k, info)
+    # the Picard loop ends on `delta > tol`; with tolerances at round-off level the last iteration is decided by the summation order
+    # (tol = 1e-30 means "until the iteration reproduces itself bit for bit": the count is then a property of the rounding, not of the scheme)
+    if tol >= 1e-9:
+        assert np.abs(picard - ref["picard_iterations"]).max() <= (0 if tol >= 1e-4 else 1), info
