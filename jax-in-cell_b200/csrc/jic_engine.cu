@@ -485,6 +485,9 @@ struct EngineT : Engine {
   int initialize_finish(cudaStream_t st) {
     int rc = allreduce(st, 0, true);  // start-up always goes through NCCL
     if (rc) return rc;
+    // the step-0 face correction (face_fix) is not consumed by the start-up field kernel: it stays in the raw grid for step 0, whose
+    // own reduction would count the already reduced sum once per rank -- keep the total on rank 0 only
+    if (world > 1 && rank != 0 && needs_face_fix()) JIC_CUDA(cudaMemsetAsync(acc + (size_t)dp.G * kAccRow, 0, (size_t)dp.G * sizeof(R), st));
     k_fields<R><<<1, 1024, field_smem_bytes, st>>>(field_args(true, false));  // init mode is always the single-CTA kernel
     launches += 1;
     if (prm.engine == JIC_ENGINE_BINNED && (rc = bins.plan(*this, dp, st))) return rc;
@@ -493,11 +496,10 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
-  // step-0 correction of the face deposit (csrc/jic_carry.cuh: k_start_face_fix); single rank only -- with several ranks the start-up
-  // reduction would count it once per rank, and the combination (field_solver with one periodic and one non-periodic particle wall,
-  // sharded) is left as it was
+  // step-0 correction of the face deposit (csrc/jic_carry.cuh: k_start_face_fix): field_solver with one periodic and one non-periodic
+  // particle wall.  Every rank corrects its own particles; initialize_finish keeps the reduced sum on one rank.
   bool needs_face_fix() const {
-    return dp.stag && world == 1 && dp.pbl != dp.pbr && (dp.pbl == JIC_BC_PERIODIC || dp.pbr == JIC_BC_PERIODIC);
+    return dp.stag && dp.pbl != dp.pbr && (dp.pbl == JIC_BC_PERIODIC || dp.pbr == JIC_BC_PERIODIC);
   }
   void face_fix(const R* x0, const R* v0, long long i0, long long n, cudaStream_t st) {
     if (!needs_face_fix() || n <= 0) return;

@@ -5,6 +5,7 @@
 //   emu_cn_run   implicit stepper: k_cn_start, k_fields(init), k_cn_fields(prepare), { max_iter x (k_cn_push, k_cn_fields), k_cn_record }
 //                -- optional carry reload through k_cn_load / k_carry_copy_fields
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "jic_kernels.cuh"
@@ -121,6 +122,73 @@ __attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const
     }
     emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, false, stag)); });
   }
+  return 0;
+}
+
+// Two ranks of the explicit stepper with the per-step electrostatic correction, reduced the way EngineT does it through NCCL: every
+// rank deposits its own particles into its own raw grid, the grids (face component included) are summed before the field kernels, and
+// after the START-UP reduction the face component survives on rank 0 only (EngineT::initialize_finish) -- it holds the step-0
+// correction of k_start_face_fix, which the start-up field kernel does not consume and which step 0's reduction must count once.
+// Field histories of rank 0 are returned; both ranks must end up with identical fields (checked here, -2 otherwise).
+__attribute__((visibility("default"))) int emu_fs_run_two_ranks(const EmuParams* ep0, const EmuParams* ep1, const double* x0_0, const double* v0_0,
+                                                                const double* x0_1, const double* v0_1, int T, int keep_on_all_ranks, double* hE,
+                                                                double* hB, double* hJ, double* hrho) {
+  const EmuParams* eps[2] = {ep0, ep1};
+  const double* x0s[2] = {x0_0, x0_1};
+  const double* v0s[2] = {v0_0, v0_1};
+  const size_t G = (size_t)ep0->G;
+  if (2 * G > sizeof(gsm) / sizeof(double) || ep0->field_solver == 0) return -1;
+  struct Rank {
+    DevParams<R> p;
+    long long N = 0;
+    std::unique_ptr<GridState> gs;
+    std::vector<R> xh, yh, zh, vx, vy, vz, v_init;
+    std::vector<double> E, B, J, rho;
+  } rk[2];
+  const size_t n_red = G * (kAccRow + 1);
+  auto allreduce = [&] {
+    for (size_t k = 0; k < n_red; ++k) { const R s = rk[0].gs->acc[k] + rk[1].gs->acc[k]; rk[0].gs->acc[k] = s; rk[1].gs->acc[k] = s; }
+  };
+  const bool fix = ep0->pbl != ep0->pbr && (ep0->pbl == JIC_BC_PERIODIC || ep0->pbr == JIC_BC_PERIODIC);
+  for (int r = 0; r < 2; ++r) {
+    Rank& k = rk[r];
+    k.p = dev_params(eps[r], &k.N);
+    k.p.stag = 1;
+    k.gs = std::make_unique<GridState>(G);
+    const size_t n = (size_t)k.N;
+    k.xh.resize(n); k.yh.resize(n); k.zh.resize(n); k.vx.resize(n); k.vy.resize(n); k.vz.resize(n); k.v_init.resize(3 * n);
+    k.E.resize((size_t)T * G * 3); k.B.resize((size_t)T * G * 3); k.J.resize((size_t)T * G * 3); k.rho.resize((size_t)T * G);
+    emu_launch((unsigned)((G + 127) / 128), 128, [&] { k_gauss_kernel((int)G, eps[r]->dx, k.gs->h.data()); });
+    emu_launch(2, kThreads, [&] { k_start<R>(k.p, x0s[r], v0s[r], 0, k.N, k.xh.data(), k.yh.data(), k.zh.data(), k.vx.data(), k.vy.data(), k.vz.data(),
+                                             k.v_init.data(), k.gs->acc.data()); });
+    if (fix) emu_launch(2, kThreads, [&] { k_start_face_fix<R>(k.p, x0s[r], v0s[r], 0, k.N, k.gs->acc.data()); });
+  }
+  allreduce();
+  if (fix && !keep_on_all_ranks) std::fill(rk[1].gs->acc.begin() + G * kAccRow, rk[1].gs->acc.end(), R(0));
+  for (int r = 0; r < 2; ++r) emu_launch(1, kThreads, [&] { k_fields<R>(rk[r].gs->field_args(eps[r], true, true)); });
+  for (int t = 0; t < T; ++t) {
+    for (int r = 0; r < 2; ++r) {
+      Rank& k = rk[r];
+      k.gs->ctl.hist[0] = k.E.data(); k.gs->ctl.hist[1] = k.B.data(); k.gs->ctl.hist[2] = k.J.data(); k.gs->ctl.hist[3] = k.rho.data();
+      k.gs->ctl.hist[4] = nullptr; k.gs->ctl.hist[5] = nullptr;
+      emu_launch(3, kThreads, [&] { k_step<R, false>(k.p, k.xh.data(), k.yh.data(), k.zh.data(), k.vx.data(), k.vy.data(), k.vz.data(), k.gs->F.data(),
+                                                     k.gs->acc.data(), &k.gs->ctl); });
+    }
+    allreduce();
+    for (int r = 0; r < 2; ++r) {
+      Rank& k = rk[r];
+      GaussArgs<R> a;
+      std::memset(&a, 0, sizeof(a));
+      a.G = ep0->G; a.fbl = ep0->fbl; a.fbr = ep0->fbr; a.passes = ep0->filter_passes; a.n_strides = ep0->n_strides; a.mode = ep0->field_solver;
+      for (int i = 0; i < ep0->n_strides; ++i) a.strides[i] = ep0->strides[i];
+      a.alpha = ep0->filter_alpha; a.dx = ep0->dx; a.accS = k.gs->acc.data() + G * kAccRow; a.h = k.gs->h.data(); a.Ex = k.gs->ExC.data();
+      emu_launch((unsigned)((G + 7) / 8), kThreads, [&] { k_gauss<R>(a); });
+      emu_launch(1, kThreads, [&] { k_fields<R>(k.gs->field_args(eps[r], false, true)); });
+    }
+  }
+  if (rk[0].E != rk[1].E || rk[0].B != rk[1].B || rk[0].J != rk[1].J || rk[0].rho != rk[1].rho) return -2;
+  std::memcpy(hE, rk[0].E.data(), rk[0].E.size() * sizeof(double)); std::memcpy(hB, rk[0].B.data(), rk[0].B.size() * sizeof(double));
+  std::memcpy(hJ, rk[0].J.data(), rk[0].J.size() * sizeof(double)); std::memcpy(hrho, rk[0].rho.data(), rk[0].rho.size() * sizeof(double));
   return 0;
 }
 

@@ -171,6 +171,8 @@ def emu_mt(tmp_path_factory):
     lib = C.CDLL(so)
     lib.emu_fs_run.restype = C.c_int
     lib.emu_fs_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    lib.emu_fs_run_two_ranks.restype = C.c_int
+    lib.emu_fs_run_two_ranks.argtypes = [C.POINTER(EmuParams)] * 2 + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 4
     lib.emu_cn_run.restype = C.c_int
     lib.emu_cn_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 7
     return lib
@@ -259,6 +261,66 @@ def test_field_solver_source_against_the_oracle_on_random_configurations(emu_mt,
     assert emu_mt.emu_fs_run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), int(g["T"]), 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS]) == 0
     for k in KEYS:
         assert relerr(out[k], ref[k]) < 1e-7, (k, {kk: g[kk] for kk in ("G", "bcs", "filter_passes", "filter_strides", "relativistic", "T", "field_solver")})
+
+
+def _two_rank_case(seed):
+    from plasma import cfl_dt, two_species
+    rng = np.random.default_rng(7000 + seed)
+    G = int(rng.choice([5, 9, 12, 16]))
+    # one periodic and one non-periodic particle wall (the face-fix configuration) twice out of three, anything else otherwise
+    bcs = [(0, 1, 0, 1), (1, 0, 1, 0), (2, 0, 2, 0), (0, 2, 0, 2), (0, 0, 0, 0), (1, 2, 1, 2)][seed % 6]
+    n_e, n_i = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+    length = 0.01
+    p = two_species(n_e, n_i, length=length, G=G, seed=seed, vth_e=0.5, vth_yz=0.05, gpdl=0.6)
+    return dict(x0=p["x0"], v0=p["v0"], q=p["q"], m=p["m"], qm=p["qm"], n_e=n_e, n_i=n_i, length=length, G=G, dt=cfl_dt(length, G, 2.5), T=5,
+                bcs=np.array(bcs), filter_passes=2, filter_alpha=0.5, filter_strides=np.array([1, 2]), relativistic=0, field_solver=1 + seed % 3,
+                species=p["species"])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_field_solver_on_two_emulated_ranks(emu_mt, seed):
+    """EngineT's multi-rank orchestration of the field_solver branch, restated on the emulation with the real kernels: particles sharded by
+    jaxincell_b200.shard_particles, raw grids (face component included) summed before the field kernels, and -- the point -- the step-0
+    face correction of k_start_face_fix, which the start-up reduction has already summed, kept on rank 0 only (EngineT::initialize_finish).
+    Both ranks end with identical fields equal to the single-rank oracle; keeping the reduced correction on every rank (what the engine
+    would do without that memset) is shown to be wrong whenever the correction is non-zero."""
+    import importlib.util
+    from oracle import closed_form as C
+    spec = importlib.util.spec_from_file_location("jic_parallel", os.path.join(ROOT, "jax-in-cell_b200", "jaxincell_b200", "_parallel.py"))
+    par = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(par)
+    g = _two_rank_case(seed)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    ref = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                keep_particles=False, solver=dict(filter_passes=2, filter_alpha=0.5, filter_strides=(1, 2), field_solver=g["field_solver"]))
+    ptr = lambda a: a.ctypes.data_as(C_.c_void_p)  # noqa: E731
+    shards, params = [], []
+    for rank in range(2):
+        x, v, _ = par.shard_particles(g["x0"], g["v0"], g["species"], rank, 2)
+        counts = [s["count"] for s in par.shard_species(g["species"], rank, 2)]
+        local = dict(g, n_e=counts[0], n_i=counts[1], q=np.array([g["q"][0]] * counts[0] + [g["q"][-1]] * counts[1]),
+                     m=np.array([g["m"][0]] * counts[0] + [g["m"][-1]] * counts[1]), qm=np.array([g["qm"][0]] * counts[0] + [g["qm"][-1]] * counts[1]))
+        params.append(_params_of(local))
+        shards.append((np.ascontiguousarray(x, np.float64), np.ascontiguousarray(v, np.float64)))
+    fields = ("electric_field", "magnetic_field", "current_density", "charge_density")
+
+    def run(keep_on_all_ranks):
+        out = {k: v for k, v in _histories(g).items() if k in fields}
+        rc = emu_mt.emu_fs_run_two_ranks(C_.byref(params[0]), C_.byref(params[1]), ptr(shards[0][0]), ptr(shards[0][1]), ptr(shards[1][0]), ptr(shards[1][1]),
+                                         int(g["T"]), keep_on_all_ranks, *[ptr(out[k]) for k in fields])
+        return rc, out
+
+    rc, out = run(0)
+    assert rc == 0
+    for k in fields:
+        assert relerr(out[k], ref[k]) < 1e-7, (k, g["bcs"], g["field_solver"])
+    if pbl != pbr and 0 in (pbl, pbr):
+        rc, wrong = run(1)
+        # (rc == -2: the ranks disagree; otherwise they agree on a wrong E_x)  -- unless no particle needed the correction
+        xp = g["x0"][:, 0] + g["dt"] / 2 * g["v0"][:, 0]
+        crossed_periodic = (xp < -g["length"] / 2) if pbl == 0 else (xp > g["length"] / 2)
+        if crossed_periodic.any():
+            assert rc == -2 or relerr(wrong["electric_field"], ref["electric_field"]) > 1e-6
 
 
 @pytest.mark.parametrize("seed", range(24))

@@ -215,3 +215,65 @@ def test_field_solver_with_one_periodic_particle_wall(bcs, engine):
         ref_k = ref[k]
         assert np.abs(out[k].cpu().numpy() - ref_k).max() <= 1e-5 * max(np.abs(ref_k).max(), 1e-300), (k, engine)
     hp.close()
+
+
+def _worker_face_fix(rank, world, port, bcs, engine, q):
+    """Two ranks on the configuration of the test above: every rank corrects its own particles, the reduced sum stays on rank 0."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from jaxincell_b200 import HotPath, shard_particles, shard_species
+        from oracle import closed_form as C
+        from plasma import cfl_dt, two_species
+        G, length, T = 12, 0.01, 8
+        pbl, pbr, fbl, fbr = bcs
+        p = two_species(400, 300, length=length, G=G, seed=61 + sum(bcs), vth_e=0.3, vth_yz=0.05, gpdl=0.6)
+        dt = cfl_dt(length, G, 0.95)
+        solver = dict(field_solver=1, filter_passes=2, filter_strides=(1, 2))
+        x, v, _ = shard_particles(p["x0"], p["v0"], p["species"], rank, world)
+        hp = HotPath(species=shard_species(p["species"], rank, world), length=length, G=G, dt=dt, pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr, engine=engine,
+                     field_solver=1, filter_passes=2, filter_strides=(1, 2))
+        hp.comm_init_from_torch()
+        hp.set_external_fields(None, None)
+        hp.initialize(x, v)
+        out = hp.run(T)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = C.run(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                        solver=solver, keep_particles=False)
+            for k in ("electric_field", "magnetic_field", "current_density", "charge_density"):
+                err = np.abs(out[k].cpu().numpy() - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-300)
+                assert err < 1e-5, (k, err)
+        hp.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("bcs", [(0, 1, 0, 1), (2, 0, 2, 0)])
+def test_two_gpus_field_solver_with_one_periodic_particle_wall(bcs, engine):
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_face_fix, args=(r, 2, port, bcs, engine, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
