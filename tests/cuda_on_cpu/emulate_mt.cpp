@@ -76,8 +76,12 @@ constexpr unsigned kThreads = 64;  // two warps per block: block reductions and 
 
 extern "C" {
 
-__attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const double* x0, const double* v0, int T, int reload_at, double* hE, double* hB,
-                                                      double* hJ, double* hrho, double* hx, double* hv) {
+}  // extern "C"
+
+// n_chunks > 1: the start-up kernels run chunk by chunk on chunk-local x0/v0 pointers with the global offset i0, as EngineT::initialize_host
+// enqueues them for a pipelined host upload
+static int fs_run(const EmuParams* ep, const double* x0, const double* v0, int T, int reload_at, int n_chunks, double* hE, double* hB, double* hJ,
+                  double* hrho, double* hx, double* hv) {
   long long N;
   DevParams<R> p = dev_params(ep, &N);
   p.stag = ep->field_solver != 0;
@@ -87,9 +91,14 @@ __attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const
   std::vector<R> xh(n), yh(n), zh(n), vx(n), vy(n), vz(n), v_init(3 * n), x_minus(3 * n), x_plus(3 * n), x_now(3 * n), v_now(3 * n);
   const bool stag = p.stag != 0;
   if (stag) emu_launch((unsigned)((G + 127) / 128), 128, [&] { k_gauss_kernel((int)G, ep->dx, gs.h.data()); });
-  emu_launch(2, kThreads, [&] { k_start<R>(p, x0, v0, 0, N, xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(), v_init.data(), gs.acc.data()); });
-  if (stag && ep->pbl != ep->pbr && (ep->pbl == JIC_BC_PERIODIC || ep->pbr == JIC_BC_PERIODIC))  // EngineT::needs_face_fix (one rank)
-    emu_launch(2, kThreads, [&] { k_start_face_fix<R>(p, x0, v0, 0, N, gs.acc.data()); });
+  const bool fix = stag && ep->pbl != ep->pbr && (ep->pbl == JIC_BC_PERIODIC || ep->pbr == JIC_BC_PERIODIC);  // EngineT::needs_face_fix
+  for (int c = 0; c < n_chunks; ++c) {
+    const long long i0 = N * c / n_chunks, cn = N * (c + 1) / n_chunks - i0;
+    std::vector<double> cx(x0 + 3 * i0, x0 + 3 * (i0 + cn)), cv(v0 + 3 * i0, v0 + 3 * (i0 + cn));  // a staging buffer: only this chunk is addressable
+    emu_launch(2, kThreads, [&] { k_start<R>(p, cx.data(), cv.data(), i0, cn, xh.data(), yh.data(), zh.data(), vx.data(), vy.data(), vz.data(), v_init.data(),
+                                             gs.acc.data()); });
+    if (fix && cn > 0) emu_launch(2, kThreads, [&] { k_start_face_fix<R>(p, cx.data(), cv.data(), i0, cn, gs.acc.data()); });
+  }
   emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, stag)); });
   for (int t = 0; t < T; ++t) {
     if (t == reload_at && t > 0) {
@@ -123,6 +132,17 @@ __attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const
     emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, false, stag)); });
   }
   return 0;
+}
+
+extern "C" {
+
+__attribute__((visibility("default"))) int emu_fs_run(const EmuParams* ep, const double* x0, const double* v0, int T, int reload_at, double* hE, double* hB,
+                                                      double* hJ, double* hrho, double* hx, double* hv) {
+  return fs_run(ep, x0, v0, T, reload_at, 1, hE, hB, hJ, hrho, hx, hv);
+}
+__attribute__((visibility("default"))) int emu_fs_run_chunked(const EmuParams* ep, const double* x0, const double* v0, int T, int n_chunks, double* hE,
+                                                              double* hB, double* hJ, double* hrho, double* hx, double* hv) {
+  return fs_run(ep, x0, v0, T, -1, n_chunks, hE, hB, hJ, hrho, hx, hv);
 }
 
 // Two ranks of the explicit stepper with the per-step electrostatic correction, reduced the way EngineT does it through NCCL: every

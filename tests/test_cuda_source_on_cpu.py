@@ -171,6 +171,8 @@ def emu_mt(tmp_path_factory):
     lib = C.CDLL(so)
     lib.emu_fs_run.restype = C.c_int
     lib.emu_fs_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    lib.emu_fs_run_chunked.restype = C.c_int
+    lib.emu_fs_run_chunked.argtypes = lib.emu_fs_run.argtypes
     lib.emu_fs_run_two_ranks.restype = C.c_int
     lib.emu_fs_run_two_ranks.argtypes = [C.POINTER(EmuParams)] * 2 + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 4
     lib.emu_cn_run.restype = C.c_int
@@ -275,6 +277,23 @@ def _two_rank_case(seed):
     return dict(x0=p["x0"], v0=p["v0"], q=p["q"], m=p["m"], qm=p["qm"], n_e=n_e, n_i=n_i, length=length, G=G, dt=cfl_dt(length, G, 2.5), T=5,
                 bcs=np.array(bcs), filter_passes=2, filter_alpha=0.5, filter_strides=np.array([1, 2]), relativistic=0, field_solver=1 + seed % 3,
                 species=p["species"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_start_up_kernels_chunk_by_chunk(emu_mt, seed):
+    """jic_initialize_host enqueues k_start (and k_start_face_fix) once per uploaded chunk, on chunk-local pointers with a global offset:
+    three chunks whose borders fall inside the species blocks give the histories of the oracle (face-fix configurations included)."""
+    from oracle import closed_form as C
+    g = _two_rank_case(seed)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    ref = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                solver=dict(filter_passes=2, filter_alpha=0.5, filter_strides=(1, 2), field_solver=g["field_solver"]))
+    out = _histories(g)
+    ptr = lambda a: a.ctypes.data_as(C_.c_void_p)  # noqa: E731
+    x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
+    assert emu_mt.emu_fs_run_chunked(C_.byref(_params_of(g)), ptr(x0), ptr(v0), int(g["T"]), 3, *[ptr(out[k]) for k in KEYS]) == 0
+    for k in KEYS:
+        assert relerr(out[k], ref[k]) < 1e-7, (k, g["bcs"], g["field_solver"])
 
 
 @pytest.mark.parametrize("seed", range(12))
