@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256) k_start_binned(const DevParams<R> p, cons
     int bin = -1;
     if (qj != R(0)) {
       const Cloud<R> cm = make_cloud(xm, p), cp = make_cloud(xp, p);
-      deposit_jx(grid, xm, cm, cp, qj / p.dt, p);
+      deposit_jx_startup(grid, xm, cm, cp, qj / p.dt, p);
       const R a = qj * p.inv_dx;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {

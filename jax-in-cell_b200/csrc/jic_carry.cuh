@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_load_carry(const DevParams<R> p, const 
       const int s = species_of(i, p);
       const R q = p.sp_q[s], a = q * p.inv_dx;
       const Cloud<R> cm = make_cloud(xm, p), cp = make_cloud(xp, p), c0 = make_cloud(x0, p);
-      deposit_jx(grid, xm, cm, cp, q / p.dt, p);
+      deposit_jx_startup(grid, xm, cm, cp, q / p.dt, p);
       deposit_cloud(grid, c0, p.G, a * v[1], a * v[2], a, true);  // J_y,z = rho(x_n) v_{y,z}; the rho component is not used afterwards
     }
     xh[i] = xp;

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+
 #include "../../include/jic_b200.h"
 
 namespace jic {
@@ -39,6 +41,8 @@ struct DevParams {
   int relativistic;
   int track_yz;
   int stag;        // field_solver != 0: also deposit rho(x_n) on the faces g_k + dx/2 (_algorithms.py:69-72)
+  int park_left_cell;  // cell of park_left as the reference's float `//` gives it (reference_floor_div): the start-up J_x window of a
+                       // particle whose x_{-1/2} was parked while it keeps its charge (_simulation.py:216-225)
   R L, Ly, Lz, half_L, half_Ly, half_Lz;
   R dx, inv_dx, half_dx, dt, half_dt;
   R g0, gl;        // grid[0], grid[-1]
@@ -47,6 +51,15 @@ struct DevParams {
   long long sp_end[JIC_MAX_SPECIES];
   R sp_q[JIC_MAX_SPECIES], sp_m[JIC_MAX_SPECIES], sp_qm[JIC_MAX_SPECIES];
 };
+
+// jnp.floor_divide on floats -- the reference's `//` in cell_no = (x - grid_start) // dx (_sources.py:190): the floor of the exact quotient
+// of the two floats, through the remainder (host side; used for DevParams::park_left_cell)
+inline int reference_floor_div(double a, double b) {
+  const double mod = std::fmod(a, b);
+  double div = (a - mod) / b;
+  if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+  return (int)std::nearbyint(div);
+}
 
 template <typename R>
 __device__ __forceinline__ R floor_mod(R a, R b) {  // XLA / NumPy float `%` for b > 0
@@ -201,9 +214,8 @@ __device__ __forceinline__ void deposit_faces(const Grid& g, const Cloud<R>& cl,
 // the cell of x_old, taken with a periodic roll whatever the BC; J_x[k_j] = -(q/dt) * sum_{i<=j}(w_new - w_old)[k_i].
 // Whatever falls outside the window is dropped, as in the reference.
 template <typename R, typename Grid>
-__device__ __forceinline__ void deposit_jx(const Grid& g, R x_old, const Cloud<R>& c_old, const Cloud<R>& c_new, R q_over_dt,
-                                           const DevParams<R>& p) {
-  const int cell = (int)floor((x_old - p.gs) * p.inv_dx);
+__device__ __forceinline__ void deposit_jx_from_cell(const Grid& g, int cell, const Cloud<R>& c_old, const Cloud<R>& c_new, R q_over_dt,
+                                                     const DevParams<R>& p) {
   const int W = p.G < 6 ? p.G : 6;
   R run = R(0);
   for (int j = 0; j < W; ++j) {
@@ -211,6 +223,21 @@ __device__ __forceinline__ void deposit_jx(const Grid& g, R x_old, const Cloud<R
     run += cloud_at(c_new, k, p.G) - cloud_at(c_old, k, p.G);
     if (run != R(0)) g.add(k, 0, -q_over_dt * run);
   }
+}
+template <typename R, typename Grid>
+__device__ __forceinline__ void deposit_jx(const Grid& g, R x_old, const Cloud<R>& c_old, const Cloud<R>& c_new, R q_over_dt,
+                                           const DevParams<R>& p) {
+  deposit_jx_from_cell(g, (int)floor((x_old - p.gs) * p.inv_dx), c_old, c_new, q_over_dt, p);
+}
+// Start-up only (_simulation.py:216-225): x_{-1/2} = BCpos(x_0 - dt/2 v) can be PARKED at grid[0] - 1.5 dx while the particle keeps its
+// charge (only the forward half step zeroes it).  That position sits exactly on a cell border of the J_x window, so the cell is whatever
+// the reference's float floor-division makes of it -- computed once on the host with the same arithmetic (park_left_cell).  (The right
+// park, grid[-1] + 3 dx, is half a cell away from a border; inside a run a parked x_{n-1/2} always comes with q = 0.)
+template <typename R, typename Grid>
+__device__ __forceinline__ void deposit_jx_startup(const Grid& g, R x_old, const Cloud<R>& c_old, const Cloud<R>& c_new, R q_over_dt,
+                                                   const DevParams<R>& p) {
+  const int cell = x_old == p.park_left ? p.park_left_cell : (int)floor((x_old - p.gs) * p.inv_dx);
+  deposit_jx_from_cell(g, cell, c_old, c_new, q_over_dt, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -154,6 +154,7 @@ struct EngineT : Engine {
     dp.g0 = (R)prm.grid_first; dp.gl = (R)prm.grid_last;
     dp.gs = (R)(prm.grid_first - prm.dx / 2);
     dp.park_left = (R)(prm.grid_first - 1.5 * prm.dx);
+    dp.park_left_cell = reference_floor_div((prm.grid_first - 1.5 * prm.dx) - (prm.grid_first - prm.dx / 2), prm.dx);
     dp.park_right = (R)(prm.grid_last + 3 * prm.dx);
     const size_t N = (size_t)n, G = (size_t)prm.n_grid;
     int rc;

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_start(const DevParams<R> p, const R* __
     bc_x(xm, p);
     if (qj != R(0)) {
       const Cloud<R> cm = make_cloud(xm, p), cp = make_cloud(xp, p);
-      deposit_jx(grid, xm, cm, cp, qj / p.dt, p);
+      deposit_jx_startup(grid, xm, cm, cp, qj / p.dt, p);
       // J_y,z = rho(x_0) v_{y,z}: re-use the x0 cloud (same position, post-BC charge)
 #pragma unroll
       for (int j = 0; j < 3; ++j) {

@@ -44,6 +44,7 @@ static int run(const EmuParams* ep, const R* x0, const R* v0, const float* extE_
   p.dx = ep->dx; p.inv_dx = 1.0 / ep->dx; p.half_dx = ep->dx / 2; p.dt = ep->dt; p.half_dt = ep->dt / 2;
   p.g0 = ep->grid_first; p.gl = ep->grid_last; p.gs = ep->grid_first - ep->dx / 2;
   p.park_left = ep->grid_first - 1.5 * ep->dx; p.park_right = ep->grid_last + 3 * ep->dx;
+  p.park_left_cell = reference_floor_div((ep->grid_first - 1.5 * ep->dx) - (ep->grid_first - ep->dx / 2), ep->dx);
   const size_t G = (size_t)ep->G, n = (size_t)N;
   std::vector<R> xh(n), yh(n), zh(n), vx(n), vy(n), vz(n), v_init(3 * n), acc(G * (kAccRow + 1)), F((G + 3) * kFieldRow);
   std::vector<double> E(G * 3), B(G * 3), E_int(G * 3), B_int(G * 3), J(G * 3), rho(G), extE(G * 3), extB(G * 3), s0(G * kAccRow), s1(G * kAccRow),

@@ -47,6 +47,7 @@ static DevParams<R> dev_params(const EmuParams* ep, long long* N_out) {
   p.dx = ep->dx; p.inv_dx = 1.0 / ep->dx; p.half_dx = ep->dx / 2; p.dt = ep->dt; p.half_dt = ep->dt / 2;
   p.g0 = ep->grid_first; p.gl = ep->grid_last; p.gs = ep->grid_first - ep->dx / 2;
   p.park_left = ep->grid_first - 1.5 * ep->dx; p.park_right = ep->grid_last + 3 * ep->dx;
+  p.park_left_cell = reference_floor_div((ep->grid_first - 1.5 * ep->dx) - (ep->grid_first - ep->dx / 2), ep->dx);
   *N_out = N;
   return p;
 }

@@ -14,6 +14,11 @@ import subprocess
 import numpy as np
 import pytest
 
+
+def FUZZ(n):
+    """Seeds per fuzz test; JIC_FUZZ_SCALE=10 runs ten times as many (a bug hunt, not the default suite)."""
+    return int(n * float(os.environ.get("JIC_FUZZ_SCALE", "1")))
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 EMU_DIR = os.path.join(HERE, "cuda_on_cpu")
@@ -135,7 +140,8 @@ def _random_case(seed):
                 ext_E=(ext * 1e3 * rng.standard_normal((G, 3))).astype(np.float32), ext_B=(ext * 1e-3 * rng.standard_normal((G, 3))).astype(np.float32))
 
 
-@pytest.mark.parametrize("seed", range(40))
+# 68, 213 (and 32 below): G = 3, absorbing left wall, CFL 2.5 -- start-up positions x_{-1/2} parked on a cell border (deposit_jx_startup)
+@pytest.mark.parametrize("seed", sorted(set(range(FUZZ(40))) | {68, 213}))
 def test_indexed_engine_source_against_the_oracle_on_random_configurations(emu, seed):
     """Differential check over corners no fixture holds: every BC combination, grids from 3 cells, filter passes beyond the reference's cap
     of 17, strides larger than the grid, CFL 2.5 jumps, thin transverse boxes, relativistic or not, with and without external fields."""
@@ -244,7 +250,7 @@ def test_crank_nicolson_source_on_the_threaded_emulation(emu_mt, path, reload_at
     assert picard.tolist() == g["picard_iterations"].tolist()
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", sorted(set(range(FUZZ(24))) | {32}))
 def test_field_solver_source_against_the_oracle_on_random_configurations(emu_mt, seed):
     """The corners of _random_case with a random field_solver on top (grids from 3 cells, every BC combination, CFL 2.5, filter passes beyond
     the cap), against the closed-form oracle; every other case also reloads its carry after two steps."""
@@ -296,7 +302,7 @@ def test_start_up_kernels_chunk_by_chunk(emu_mt, seed):
         assert relerr(out[k], ref[k]) < 1e-7, (k, g["bcs"], g["field_solver"])
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(FUZZ(12)))
 def test_field_solver_on_two_emulated_ranks(emu_mt, seed):
     """EngineT's multi-rank orchestration of the field_solver branch, restated on the emulation with the real kernels: particles sharded by
     jaxincell_b200.shard_particles, raw grids (face component included) summed before the field kernels, and -- the point -- the step-0
@@ -342,7 +348,7 @@ def test_field_solver_on_two_emulated_ranks(emu_mt, seed):
             assert rc == -2 or relerr(wrong["electric_field"], ref["electric_field"]) > 1e-6
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(FUZZ(24)))
 def test_crank_nicolson_source_against_the_oracle_on_random_configurations(emu_mt, seed):
     """The implicit stepper's source over random boundary combinations, grids from 3 cells, 1-3 sub-steps, tight and loose Picard tolerances,
     against oracle/literal.py (pinned to the reference's CN_step by the refsrc vectors); odd seeds reload the CN carry after two steps."""

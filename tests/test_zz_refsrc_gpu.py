@@ -277,3 +277,35 @@ def test_two_gpus_field_solver_with_one_periodic_particle_wall(bcs, engine):
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["indexed", "binned"])
+@pytest.mark.parametrize("seed", [68, 213])
+def test_start_up_position_parked_on_a_cell_border(seed, engine):
+    """Absorbing left wall: x_{-1/2} = BCpos(x_0 - dt/2 v) of a particle that keeps its charge is parked at grid[0] - 1.5 dx, exactly on a
+    border of the J_x window; its cell must be what the reference's float `//` gives (deposit_jx_startup, DevParams::park_left_cell).
+    Found by the extended fuzz of the CUDA source on the CPU (tests/test_cuda_source_on_cpu.py, JIC_FUZZ_SCALE=6): the two cases it hit,
+    G = 3 at CFL 2.5 with external fields, relativistic."""
+    import torch
+    from jaxincell_b200 import HotPath
+    from oracle import closed_form as C
+    from test_cuda_source_on_cpu import _random_case
+    g = _random_case(seed)
+    pbl, pbr, fbl, fbr = (int(b) for b in g["bcs"])
+    strides = tuple(int(s) for s in g["filter_strides"])
+    ref = C.run(g["x0"], g["v0"], g["q"], g["m"], g["qm"], length=g["length"], G=g["G"], dt=g["dt"], total_steps=g["T"], pbl=pbl, pbr=pbr, fbl=fbl, fbr=fbr,
+                box_yz=tuple(g["box_yz"]), ext_E=g["ext_E"], ext_B=g["ext_B"], keep_particles=False,
+                solver=dict(filter_passes=g["filter_passes"], filter_alpha=g["filter_alpha"], filter_strides=strides, relativistic=bool(g["relativistic"])))
+    species = [dict(count=g["n_e"], q=float(g["q"][0]), m=float(g["m"][0]), qm=float(g["qm"][0])),
+               dict(count=g["n_i"], q=float(g["q"][-1]), m=float(g["m"][-1]), qm=float(g["qm"][-1]))]
+    hp = HotPath(species=species, length=g["length"], length_y=float(g["box_yz"][0]), length_z=float(g["box_yz"][1]), G=g["G"], dt=g["dt"], pbl=pbl, pbr=pbr,
+                 fbl=fbl, fbr=fbr, engine=engine, track_yz=engine == "indexed", relativistic=bool(g["relativistic"]), filter_passes=g["filter_passes"],
+                 filter_alpha=g["filter_alpha"], filter_strides=strides)
+    hp.set_external_fields(g["ext_E"], g["ext_B"])
+    hp.initialize(g["x0"], g["v0"])
+    out = hp.run(g["T"], particles=False)
+    torch.cuda.synchronize()
+    for k in ("electric_field", "current_density", "charge_density"):
+        assert np.abs(out[k].cpu().numpy() - ref[k]).max() <= 1e-5 * max(np.abs(ref[k]).max(), 1e-300), (k, engine)
+    hp.close()
