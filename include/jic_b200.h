@@ -108,6 +108,9 @@ typedef struct jic_outputs {
   void* charge_density;   /* real (T,G)   */
   void* positions;        /* real (T,N,3), INDEXED engine with track_yz only */
   void* velocities;       /* real (T,N,3), INDEXED engine only */
+  void* kinetic_energy;   /* double (T,n_species): sum over the LOCAL particles of a species of m v^2 / 2 after the step -- the kinetic
+                           * energies of jaxincell/_diagnostics.py:131-138 evaluated on the device, for runs whose (T,N,3) velocity
+                           * history would not fit (any engine; one more pass over the velocities per step when requested) */
 } jic_outputs;
 
 typedef struct jic_context jic_context;
@@ -177,6 +180,12 @@ int jic_kinetic_energy(jic_context* ctx, double* kinetic_energy, void* stream);
 int jic_profile_steps(jic_context* ctx, int64_t n_steps, double* ms_particle_kernels, double* ms_grid_kernels, void* stream);
 /* Crank-Nicolson only: Picard iterations of the last completed step and of all steps so far.  Synchronises the stream. */
 int jic_get_picard_iterations(jic_context* ctx, int64_t* last_step, int64_t* total, void* stream);
+/* Synchronises the stream and reports the sticky device-side error flags of the context: exhausted capacity of the BINNED store
+ * (a bin grew faster than its head-room and the overflow list filled up: particles were dropped) and a peer rank that missed the
+ * fused reduction's barrier.  jic_run only enqueues work, so a caller that reads the histories of a single jic_run must call this
+ * (jic_simulate_host does) -- otherwise the flags are only seen by the NEXT jic_run / jic_get_particles.
+ * The reference has no counterpart: its arrays cannot overflow (jaxincell/_simulation.py:228-257 scans fixed-shape carries). */
+int jic_check_status(jic_context* ctx, void* stream);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 
@@ -196,6 +205,12 @@ typedef struct jic_species_sampling {
 /* x0, v0: device, real (sum of counts, 3).  threefry_partitionable: 1 = jax >= 0.5 default bit layout, 0 = the original one. */
 int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* species, const double box_size[3],
                          int32_t threefry_partitionable, void* x0, void* v0, void* stream);
+/* The same streams, but only particles [first[s], first[s] + local_count[s]) of every species s: what one rank of an index-sharded
+ * run owns.  jax.random's Threefry is counter based -- element i of a draw depends on (key, i, n) only -- so a rank
+ * samples its slice without generating or receiving anybody else's.  x0, v0: device, real (sum of local counts, 3). */
+int jic_sample_particles_slice(int32_t dtype, int32_t n_species, const jic_species_sampling* species, const int64_t* first,
+                               const int64_t* local_count, const double box_size[3], int32_t threefry_partitionable, void* x0, void* v0,
+                               void* stream);
 
 /* Whole-simulation call with HOST buffers (the drop-in for Simulation.run's device part, _simulation.py:169-257):
  * host->device copies of x0, v0 and the external fields, jic_initialize, jic_run, device->host copies of the

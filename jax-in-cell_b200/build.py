@@ -42,10 +42,15 @@ def build(force=False, verbose=False, out=None, defines=None):
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false".replace("=false", ""),
            "-shared", "-Xcompiler", "-fPIC", "-I", nccl_include(), "-o", out, os.path.join(CSRC, "jic_engine.cu"), "-ldl"]
     cmd = [c for c in cmd if c != "--use_fast_math"]  # IEEE arithmetic: parity with the reference matters more than a few percent
-    for macro in ("JIC_PUSH_THREADS", "JIC_PUSH_MINBLOCKS", "JIC_PUSH_MINBLOCKS_F32", "JIC_PUSH_STAGES", "JIC_PUSH_STAGE_BLOCKS", "JIC_MAX_CHUNK"):  # tuning knobs of the binned push kernel
+    for macro in ("JIC_PUSH_THREADS", "JIC_PUSH_MINBLOCKS", "JIC_PUSH_THREADS_F32", "JIC_PUSH_MINBLOCKS_F32", "JIC_PUSH_STAGES", "JIC_PUSH_STAGES_F32", "JIC_PUSH_STAGE_BLOCKS", "JIC_PUSH_RUN", "JIC_TAIL_SPLIT", "JIC_MAX_CHUNK"):  # tuning knobs of the binned push kernel
         val = (defines or {}).get(macro, os.environ.get(macro))
-        if val:
+        if val is not None and val != "":
             cmd.insert(1, f"-D{macro}={int(val)}")
+    for item in filter(None, ((defines or {}).get("EXTRA") or os.environ.get("JIC_EXTRA_DEFINES", "")).split(",")):  # experiments: "A=1,B=2"
+        cmd.insert(1, "-D" + item)
+    maxreg = (defines or {}).get("MAXRREG", os.environ.get("JIC_MAXRREG"))
+    if maxreg:
+        cmd.insert(1, f"-maxrregcount={int(maxreg)}")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

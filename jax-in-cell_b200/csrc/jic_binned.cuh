@@ -1,23 +1,29 @@
 // BINNED particle store (sm_100a): particles live in bins keyed by (species, cell of x_{n+1/2}) and are re-binned by
-// the push kernel itself every step, so that for a whole CTA chunk
-//   * the gather stencil is the same 4 grid rows  -> E(d), B(d) are quadratics in the in-cell offset d with CTA-uniform
-//     coefficients held in registers (no per-particle field loads),
-//   * the deposition stencil is the same 5 nodes  -> J_x, J_y, J_z, rho accumulate in per-thread REGISTERS with static
-//     indices, are reduced with warp shuffles + shared memory, and reach the L2-resident raw grid as 19 atomics per chunk
-//     (instead of ~15 atomics per particle),
+// the push kernel itself every step, so that for a whole work item
+//   * the gather stencil is the same 4 grid rows  -> E(d), B(d) are quadratics in the in-cell offset d with item-uniform
+//     coefficients (no per-particle field loads),
+//   * the deposition stencil is the same 5 nodes  -> J_x, J_y, J_z, rho accumulate as moment sums in REGISTERS and reach the
+//     L2-resident raw grid as 19 atomics per item (instead of ~15 atomics per particle),
 //   * species constants (q w, q/m) are uniform,
 // and a particle is stored as (d, v_x, v_y, v_z): its cell is implicit, d = (x - g_c)/dx in [-1/2, 1/2].
-// Each particle's state crosses HBM once per step (4 reals in, 4 reals out); the out-write goes to the particle's NEW bin
-// (slots claimed through warp-aggregated cursor atomics), which is what keeps the store exactly binned with no sort pass.
+// Each particle's state crosses HBM once per step (4 reals in, 4 reals out).
 //
 // Memory layout: slots are grouped in BLOCKS of 32 (one warp); a block is [d x32][v_x x32][v_y x32][v_z x32], i.e. structure
-// of arrays inside 1 KiB (fp64) records.  Bins start on block boundaries.  A warp therefore reads a bin as a contiguous
-// stream of whole blocks (one 1-D bulk async copy per pipeline stage, any length), every lane's four values sit at
-// immediate offsets 0/256/512/768 B from one address, and re-binned particles of one warp land in runs of consecutive
-// slots that fill whole 32-byte sectors.
+// of arrays inside 1 KiB (fp64) records.  A warp reads a bin as a contiguous stream of whole blocks (one 1-D bulk async copy
+// per pipeline stage) and every lane's four values sit at immediate offsets 0/256/512/768 B from one address.
+//
+// Every logical bin b = species * G + cell owns TWO slot ranges per buffer, indexed 2 b + half:
+//   half 0, the BLOCK range: the particles that STAY in the bin, written by the push kernel in whole 32-slot blocks (runs of
+//     kPushRun blocks per cursor atomic).  The last block a work item writes is partial and a run claimed ahead may stay empty:
+//     unused slots hold d = NaN ("hole").  Readers skip holes for free: every comparison of the fast path's domain test
+//     |t| < 3/2 is false for NaN.  (The initial scatter fills this range slot by slot.)
+//   half 1, the SINGLE range: one slot per claim, dense: the particles that ARRIVE from other bins (movers of the fast path in
+//     batches of up to 32, the general path one by one).
+//   The plan pads the last block of every range with holes, so ranges are read as whole blocks.
+// cnt[] and the cursors count SLOTS (holes included).
 //
 // The arithmetic is that of jaxincell/_algorithms.py:40-66,90-92 (see jic_device.cuh for the per-function citations); the
-// "fast path" below is the closed form of the reference's 6-node windowed prefix sum for a particle that moves by at most
+// "fast path" is the closed form of the reference's 6-node windowed prefix sum for a particle that moves by at most
 // one cell and stays clear of non-periodic walls.  Everything else (multi-cell jumps, wall cells, overflowed bins) takes
 // the exact general code of the INDEXED engine, particle by particle -- the deposit is additive, so paths can be mixed.
 #pragma once
@@ -42,28 +48,58 @@ constexpr int kSlowChunk = 256;    // work-item size in bins whose particles all
                                    // of field_solver runs): small, so that this per-particle work spreads over many warps
 constexpr int kBlk = 32;           // slots per block
 constexpr int kBlkElems = 4 * kBlk;  // reals per block
+// Launch shape of the push kernel.  Measured on B200 (profiles/r02_push_variants.txt): the kernel is latency-bound, so resident
+// warps are what counts; fp64: one CTA of 16 warps per SM at 128 registers (two particles per lane in flight, 20 bytes of spills),
+// fp32: five CTAs of 4 warps at 96 registers.
 #ifndef JIC_PUSH_THREADS
-#define JIC_PUSH_THREADS 128
+#define JIC_PUSH_THREADS 512
 #endif
 #ifndef JIC_PUSH_MINBLOCKS
-#define JIC_PUSH_MINBLOCKS 3
+#define JIC_PUSH_MINBLOCKS 1       // 0: no CTA count in the launch bounds (register budget from -maxrregcount, for experiments)
+#endif
+#ifndef JIC_PUSH_THREADS_F32
+#define JIC_PUSH_THREADS_F32 128
+#endif
+#ifndef JIC_PUSH_MINBLOCKS_F32
+#define JIC_PUSH_MINBLOCKS_F32 5
 #endif
 #ifndef JIC_PUSH_STAGES
-#define JIC_PUSH_STAGES 4          // ring slots per warp (power of two)
+#define JIC_PUSH_STAGES 2          // ring slots per warp (power of two)
+#endif
+#ifndef JIC_PUSH_STAGES_F32
+#define JIC_PUSH_STAGES_F32 4
 #endif
 #ifndef JIC_PUSH_STAGE_BLOCKS
-#define JIC_PUSH_STAGE_BLOCKS 2    // 32-particle blocks per ring slot
-#endif
-constexpr int kPushThreads = JIC_PUSH_THREADS;
-constexpr int kPushMinBlocks = JIC_PUSH_MINBLOCKS;
-#ifndef JIC_PUSH_MINBLOCKS_F32
-#define JIC_PUSH_MINBLOCKS_F32 5   // the fp32 kernel fits 96 registers: 20 warps per SM (measured best of 3..6)
+#define JIC_PUSH_STAGE_BLOCKS 2    // 32-particle blocks per ring slot = particles a lane has in flight
 #endif
 template <typename R>
-constexpr int push_min_blocks() { return sizeof(R) == 8 ? kPushMinBlocks : JIC_PUSH_MINBLOCKS_F32; }
-constexpr int kPushStages = JIC_PUSH_STAGES;
+__host__ __device__ constexpr int push_threads() { return sizeof(R) == 8 ? JIC_PUSH_THREADS : JIC_PUSH_THREADS_F32; }
+template <typename R>
+__host__ __device__ constexpr int push_min_blocks() { return sizeof(R) == 8 ? (JIC_PUSH_MINBLOCKS > 0 ? JIC_PUSH_MINBLOCKS : 1) : JIC_PUSH_MINBLOCKS_F32; }
+template <typename R>
+__host__ __device__ constexpr int push_stages() { return sizeof(R) == 8 ? JIC_PUSH_STAGES : JIC_PUSH_STAGES_F32; }
+template <typename R>
+__host__ __device__ constexpr int push_warps() { return push_threads<R>() / 32; }
+// JIC_PUSH_MINBLOCKS=0: one CTA per SM whose register budget comes from -maxrregcount instead of the launch bounds
+#if JIC_PUSH_MINBLOCKS > 0
+#define JIC_PUSH_BOUNDS(R) __launch_bounds__(push_threads<R>(), push_min_blocks<R>())
+#else
+#define JIC_PUSH_BOUNDS(R) __launch_bounds__(push_threads<R>())
+#endif
 constexpr int kPushStageBlocks = JIC_PUSH_STAGE_BLOCKS;
-constexpr int kPushWarps = kPushThreads / 32;
+#ifndef JIC_PUSH_RUN
+#define JIC_PUSH_RUN 4             // output blocks claimed with one cursor atomic (power of two)
+#endif
+constexpr int kPushRun = JIC_PUSH_RUN;
+#ifndef JIC_TAIL_SPLIT
+#define JIC_TAIL_SPLIT 1           // the last eighth of the work queue is cut into quarter-size items (shorter kernel tail)
+#endif
+
+// worst-case holes one work item leaves in its bin's block range: the rest of its last run, one run claimed ahead that stayed
+// empty, and the pool's partial last block
+constexpr int kHolesPerWriter = (2 * kPushRun + 1) * kBlk;
+// constant part of a block range's capacity: two items more than population / chunk + one block
+constexpr int kBlockRangeConst = 2 * kHolesPerWriter + 32;
 
 struct PlanHeader {
   int flip;            // which buffer is the SOURCE of the next push
@@ -72,8 +108,12 @@ struct PlanHeader {
   int error;           // sticky: 1 = overflow list full, 2 = capacity exhausted
   int chunk;           // particles per work item of the next push
   int work;            // dynamic work queue head (reset by k_plan)
+  int tail_chunk;      // ... of the bins b >= tail_from (the end of the queue: smaller items, shorter kernel tail)
+  int tail_from;
+  int work2;           // work queue head of k_push_general (items of the wall bins)
+  int gen_n;           // entries in the general-path list of this step (reset by k_plan)
   int pad;
-  long long n_stored;  // live particles (bins + overflow list) in the source buffer
+  long long n_stored;  // slots in use (holes included) + overflow entries in the source buffer
   long long n_absorbed;
 };
 
@@ -86,14 +126,17 @@ struct PlanSync {           // k_plan_mc: per-CTA totals and the two counters of
 
 template <typename R>
 struct BinDev {
-  int nb;                 // n_species * G
+  int nb;                 // logical bins: n_species * G; slot ranges are indexed 2 b + half (0 = blocks, 1 = singles)
   long long cap_total;    // slots per buffer
   int ov_cap;             // overflow list capacity
   float slack;            // head-room fraction per neighbour
   R* rec[2];              // blocked particle records of each buffer: 4 * cap_total reals
-  long long* off[2];      // [nb+1] first slot of each bin
-  int* cnt[2];            // [nb]   particles stored in each bin
-  unsigned* cur[2];       // [nb]   write cursors (count every attempt, also the overflowed ones)
+  long long* off[2];      // [2 nb + 1] first slot of each range
+  int* cnt[2];            // [2 nb]     slots in use in each range (a multiple of 32; holes included)
+  unsigned* cur[2];       // [2 nb]     write cursors (count every attempt, also the overflowed ones)
+  unsigned* slow0;        // [nb]       start-up only: particles per bin that will probably leave it in step 0
+  // particles of fast bins that left the closed form's domain in this step (|t_new| >= 3/2): pushed by k_push, finished by k_push_general
+  int* gen_bin; R* gen_d; R* gen_vxold; R* gen_vx; R* gen_vy; R* gen_vz; int gen_cap;
   int* ov_bin[2]; R* ov_d[2]; R* ov_vx[2]; R* ov_vy[2]; R* ov_vz[2];
   int* item_bin; int* item_first; int item_cap;
   int n_workers;          // warps of the push kernel (work-queue consumers)
@@ -112,6 +155,10 @@ __device__ __forceinline__ double rcp_fast(double a) {  // 1/a for a >= 1: MUFU 
 }
 __device__ __forceinline__ float rcp_fast(float a) { return __frcp_rn(a); }
 
+// what the d component of an unused slot holds
+__device__ __forceinline__ double hole_value(double) { return __longlong_as_double(0x7ff8000000000000ll); }
+__device__ __forceinline__ float hole_value(float) { return __int_as_float(0x7fc00000); }
+
 template <typename R>
 __device__ __forceinline__ R node_pos(int c, const DevParams<R>& p) { return p.g0 + R(c) * p.dx; }
 
@@ -119,7 +166,8 @@ __device__ __forceinline__ R node_pos(int c, const DevParams<R>& p) { return p.g
 template <typename R>
 __device__ __forceinline__ R* slot_ptr(R* rec, long long k) { return rec + ((k >> 5) << 7) + (k & 31); }
 
-// Put one particle into bin `b` of the destination buffer (or into its overflow list when the bin is full).
+// Put one particle into slot `slot` of range `b` (= 2 * bin + half) of the destination buffer, or into the buffer's overflow
+// list when the range is full.
 template <typename R>
 __device__ __forceinline__ void store_slot(const BinDev<R>& bd, int dst, int b, unsigned slot, R d, R vx, R vy, R vz) {
   const long long o = bd.off[dst][b];
@@ -144,7 +192,7 @@ __device__ __forceinline__ void insert_particle(const BinDev<R>& bd, int dst, in
   int c = (int)floor((x - p.gs) * p.inv_dx);
   c = min(max(c, 0), p.G - 1);
   const R d = (x - node_pos(c, p)) * p.inv_dx;
-  const int b = species * p.G + c;
+  const int b = 2 * (species * p.G + c) + 1;  // the bin's SINGLE range
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, b);
   const int leader = __ffs(peers) - 1;
@@ -197,8 +245,7 @@ __device__ __forceinline__ R warp_sum(R v) {
 namespace jic {
 
 // ---------------------------------------------------------------------------------------------------------
-// K3  plan (single CTA): close the buffer that was just written, lay out the NEXT destination buffer with head-room
-//     proportional to the population of each bin and its neighbours, build the work-item list, flip.
+// block-wide exclusive prefix sum (used by the plan and the layout kernels)
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ T block_exclusive_scan(T v, T* total, T* smem /* >= 33 */) {
@@ -230,152 +277,19 @@ __device__ T block_exclusive_scan(T v, T* total, T* smem /* >= 33 */) {
   return res;
 }
 
-// SMEM: the per-bin cursor values and counts are staged in shared memory (2 * nb ints), so that global memory is read once
-// and the three phases are not separated by L2 round trips; without it (nb too large) the same code re-reads global memory.
-template <typename R, bool SMEM>
-__global__ void __launch_bounds__(1024) k_plan(const BinDev<R> bd, int G, int first_call) {
-  extern __shared__ int plan_sm[];  // SMEM: [nb] attempts, [nb] counts
-  __shared__ long long sh_ll[33];
-  __shared__ int sh_i[33];
-  __shared__ long long tot_ll;
-  __shared__ int tot_i;
-  PlanHeader* h = bd.hdr;
-  const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb;
-  const int written = first_call ? h->flip : (h->flip ^ 1);  // buffer the last kernel wrote = source of the next push
-  const int next = written ^ 1;                               // destination of the next push
-  const unsigned* __restrict__ g_att = bd.cur[written];
-  int* s_att = plan_sm;
-  int* s_cnt = plan_sm + nb;
-  auto att_of = [&](int b) -> long long { return SMEM ? (long long)(unsigned)s_att[b] : (long long)g_att[b]; };
-  auto cnt_of = [&](int b) -> int { return SMEM ? s_cnt[b] : bd.cnt[written][b]; };
-  // 1. close `written`: cnt = min(cursor, capacity); everything beyond sits in its overflow list (bins interleaved over threads)
-  long long mine = 0;
-  {
-    // all loads of a thread's first kBatch bins are issued before the first store (the stores would otherwise fence the loads of
-    // the next iteration: one L2 round trip per bin on the step's critical path)
-    constexpr int kBatch = 8;
-    const long long* __restrict__ g_off = bd.off[written];
-    long long o0[kBatch], o1[kBatch];
-    unsigned at[kBatch];
-#pragma unroll
-    for (int k = 0; k < kBatch; ++k) {
-      const int b = t + k * nt;
-      o0[k] = o1[k] = 0; at[k] = 0u;
-      if (b < nb) { o0[k] = g_off[b]; o1[k] = g_off[b + 1]; at[k] = g_att[b]; }
-    }
-#pragma unroll
-    for (int k = 0; k < kBatch; ++k) {
-      const int b = t + k * nt;
-      if (b < nb) {
-        const long long cap = o1[k] - o0[k], att = at[k];
-        const int cnt = (int)(att < cap ? att : cap);
-        bd.cnt[written][b] = cnt;
-        if (SMEM) { s_att[b] = (int)att; s_cnt[b] = cnt; }
-        mine += att;
-      }
-    }
-    for (int b = t + kBatch * nt; b < nb; b += nt) {
-      const long long cap = g_off[b + 1] - g_off[b];
-      const long long att = g_att[b];
-      const int cnt = (int)(att < cap ? att : cap);
-      bd.cnt[written][b] = cnt;
-      if (SMEM) { s_att[b] = (int)att; s_cnt[b] = cnt; }
-      mine += att;
-    }
-  }
-  block_exclusive_scan<long long>(mine, &tot_ll, sh_ll);
-  const long long n_total = tot_ll;
-  // 2. capacities of `next`: population + slack * (itself and both neighbours in the same species) + a constant.
-  //    From here on every thread owns a contiguous range of bins (offsets are a running sum).
-  const int per = (nb + nt - 1) / nt, lo = min(t * per, nb), hi = min(lo + per, nb);
-  double f = bd.slack;
-  {
-    const double room = (double)bd.cap_total - (double)n_total - 72.0 * nb;
-    const double fmax = n_total > 0 ? room / (3.0 * (double)n_total) : 0.0;
-    if (f > fmax) f = fmax;
-    if (f < 0) { f = 0; if (t == 0 && room < 0) atomicExch(&h->error, 2); }
-  }
-  // (one integer division per thread: the cell index runs along with the bin index from here on; this kernel is a single CTA on
-  //  the step's critical path and was instruction-bound -- 275 instructions per bin, mostly divisions)
-  const int s_lo = lo / G, c_lo = lo - s_lo * G;
-  constexpr int kKeep = 8;  // capacities kept in registers between the two passes (per <= 8 up to 8192 bins)
-  long long caps[kKeep];
-  auto cap_at = [&](int b, int c) -> long long {
-    const long long a0 = att_of(b), al = att_of(c == 0 ? b + G - 1 : b - 1), ar = att_of(c == G - 1 ? b - (G - 1) : b + 1);
-    const long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
-    return (cap + kBlk - 1) & ~(long long)(kBlk - 1);  // bins start on block boundaries
-  };
-  long long cap_sum = 0;
-  {
-    int c = c_lo;
-#pragma unroll
-    for (int k = 0; k < kKeep; ++k) {
-      const int b = lo + k;
-      caps[k] = 0;
-      if (b < hi) { caps[k] = cap_at(b, c); cap_sum += caps[k]; }
-      c = c + 1 == G ? 0 : c + 1;
-    }
-    for (int b = lo + kKeep; b < hi; ++b) { cap_sum += cap_at(b, c); c = c + 1 == G ? 0 : c + 1; }
-  }
-  long long run = block_exclusive_scan<long long>(cap_sum, &tot_ll, sh_ll);
-  {
-    int c = c_lo;
-#pragma unroll
-    for (int k = 0; k < kKeep; ++k) {
-      const int b = lo + k;
-      if (b < hi) { bd.off[next][b] = run; run += caps[k]; bd.cur[next][b] = 0u; }
-      c = c + 1 == G ? 0 : c + 1;
-    }
-    for (int b = lo + kKeep; b < hi; ++b) { bd.off[next][b] = run; run += cap_at(b, c); bd.cur[next][b] = 0u; c = c + 1 == G ? 0 : c + 1; }
-  }
-  if (t == 0) bd.off[next][nb] = tot_ll;
-  // 3. work items over `written`: about 4 per warp of the push kernel, between kMinChunk and kMaxChunk particles each
-  long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
-  want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
-  const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
-  const float inv_chunk = 1.0f / (float)kChunk;
-  static_assert((kSlowChunk & (kSlowChunk - 1)) == 0, "kSlowChunk must be a power of two");
-  auto items_of = [&](int n, int c) -> int {  // ceil(n / chunk of this bin) without an integer division
-    if (c < bd.edge || c > G - 1 - bd.edge) return (n + kSlowChunk - 1) / kSlowChunk;
-    int q = (int)((float)n * inv_chunk);                        // within one of the quotient ...
-    while ((long long)q * kChunk < n) ++q;                      // ... made exact
-    while (q > 0 && (long long)(q - 1) * kChunk >= n) --q;
-    return q;
-  };
-  int my_items = 0;
-  {
-    int c = c_lo;
-    for (int b = lo; b < hi; ++b) { my_items += items_of(cnt_of(b), c); c = c + 1 == G ? 0 : c + 1; }
-  }
-  int it = block_exclusive_scan<int>(my_items, &tot_i, sh_i);
-  {
-    int c = c_lo;
-    for (int b = lo; b < hi; ++b) {
-      const int n = cnt_of(b), ch = (c < bd.edge || c > G - 1 - bd.edge) ? kSlowChunk : kChunk;
-      for (int k = 0; k < n; k += ch) {
-        if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
-        ++it;
-      }
-      c = c + 1 == G ? 0 : c + 1;
-    }
-  }
-  if (t == 0) {
-    if (tot_i > bd.item_cap) atomicExch(&h->error, 2);
-    h->n_items = tot_i < bd.item_cap ? tot_i : bd.item_cap;
-    h->chunk = kChunk;
-    h->work = 0;
-    h->flip = written;
-    h->ov_n[next] = 0;
-    h->n_stored = n_total;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// K3m  the plan on NC CTAs (same result as k_plan).  The single-CTA version is latency-bound (38 us at 8192 bins) and sits on the
-//      step's critical path next to an 18 us field kernel; here every thread owns `per` contiguous bins (one at 8192 bins),
-//      neighbour populations come straight from the cursors in global memory, every CTA sums all cursors itself (n_total and
-//      the slack factor need no exchange), and the two prefix sums (slot offsets, work items) are two-level: block scan, per-CTA
-//      totals through global memory, ONE grid-wide barrier (all CTAs are co-resident: the GPU is otherwise idle at this point).
+// K3  the plan, on NC CTAs: close the buffer that was just written, lay out the NEXT destination buffer, build the work-item
+//     list, flip.  Every thread owns `per` contiguous logical bins (one at 8192 bins) with both of their ranges; every CTA sums
+//     all cursors itself (the totals and the slack factor need no exchange), and the two prefix sums (slot offsets, work items)
+//     are two-level: block scan, per-CTA totals through global memory, ONE grid-wide barrier (all CTAs are co-resident: the GPU
+//     is otherwise idle at this point).
+//     Capacities of the next buffer, from the attempts (cursor values) of this one -- pop = both ranges of a bin, arr = its
+//     single range (what arrived last step; about as many leave):
+//       block range   pop - arr / 2 + the holes its own work items can leave (kHolesPerWriter each)     [only stayers land here]
+//       single range  arr + slack * (arr of 3 bins + pop)          (the whole population next to a non-periodic wall, where every
+//                     particle takes the general path)
+//     Before step 0 the start-up kernel's count of the particles about to leave each bin stands in for `arr`.
+//     What does not fit lands in the overflow list and is re-inserted one step later.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPlanMcThreads = 512;
 
@@ -388,56 +302,93 @@ __global__ void __launch_bounds__(kPlanMcThreads) k_plan_mc(const BinDev<R> bd, 
   PlanHeader* h = bd.hdr;
   PlanSync* ps = bd.psync;
   const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb, NC = gridDim.x, cta = blockIdx.x;
-  const int written = first_call ? h->flip : (h->flip ^ 1);
-  const int next = written ^ 1;
+  const int written = first_call ? h->flip : (h->flip ^ 1);  // buffer the last kernel wrote = source of the next push
+  const int next = written ^ 1;                               // destination of the next push
   const unsigned* __restrict__ g_att = bd.cur[written];
   const long long* __restrict__ g_off = bd.off[written];
-  // n_total: every CTA sums all cursors (a few KB from L2)
-  long long mine = 0;
-  for (int b = t; b < nb; b += nt) mine += (long long)g_att[b];
+  const bool all_slow = bd.edge >= G;
+  auto is_slow = [&](int c) { return c < bd.edge || c > G - 1 - bd.edge; };
+  auto pop = [&](int b) -> long long { return (long long)g_att[2 * b] + (long long)g_att[2 * b + 1]; };
+  auto left_of = [&](int b) { return (b % G) == 0 ? b + G - 1 : b - 1; };
+  auto right_of = [&](int b) { return (b % G) == G - 1 ? b - (G - 1) : b + 1; };
+  auto leaving = [&](int b) -> long long { return first_call ? (long long)bd.slow0[b] : (long long)g_att[2 * b + 1]; };
+  auto arriving = [&](int b) -> long long {
+    if (!first_call) return (long long)g_att[2 * b + 1];
+    const long long l = bd.slow0[left_of(b)], r = bd.slow0[right_of(b)];
+    return l > r ? l : r;
+  };
+  // totals: every CTA sums over all bins (a few KB from L2)
+  long long mine = 0, mine_leave = 0, mine_arr = 0;
+  for (int b = t; b < nb; b += nt) { mine += pop(b); mine_leave += leaving(b); mine_arr += arriving(b); }
   block_exclusive_scan<long long>(mine, &tot_ll, sh_ll);
   const long long n_total = tot_ll;
-  double f = bd.slack;
-  {
-    const double room = (double)bd.cap_total - (double)n_total - 72.0 * nb;
-    const double fmax = n_total > 0 ? room / (3.0 * (double)n_total) : 0.0;
-    if (f > fmax) f = fmax;
-    if (f < 0) { f = 0; if (t == 0 && cta == 0 && room < 0) atomicExch(&h->error, 2); }
-  }
+  block_exclusive_scan<long long>(mine_leave, &tot_ll, sh_ll);
+  const long long t_leave = tot_ll;
+  block_exclusive_scan<long long>(mine_arr, &tot_ll, sh_ll);
+  const long long t_arr = tot_ll;
   long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
   want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
   const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
-  const float inv_chunk = 1.0f / (float)kChunk;
-  // own bins: [lo, hi), contiguous over the whole grid of threads
+  int kTailChunk = ((kChunk / 4 + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;  // the queue's tail: quarter-size items
+  if (kTailChunk < kMinChunk) kTailChunk = kMinChunk < kChunk ? kMinChunk : kChunk;
+  const int tail_from = JIC_TAIL_SPLIT ? nb - nb / 8 : nb;
+  double f = bd.slack;
+  {
+    double room, per_f;
+    if (all_slow) { room = (double)bd.cap_total - (double)n_total - 96.0 * nb; per_f = 3.0 * (double)n_total; }
+    else {
+      room = (double)bd.cap_total - ((double)n_total - 0.5 * (double)t_leave + (double)kHolesPerWriter * ((double)n_total / kTailChunk + 2.0 * nb) +
+                                     (double)t_arr + 160.0 * nb);
+      per_f = 3.0 * (double)t_arr + (double)n_total;
+    }
+    const double fmax = per_f > 0 ? room / per_f : 0.0;
+    if (f > fmax) f = fmax;
+    if (f < 0) { f = 0; if (t == 0 && cta == 0 && room < 0) atomicExch(&h->error, 2); }
+  }
+  // own logical bins: [lo, hi), contiguous over the whole grid of threads
   const int T = NC * nt, per = (nb + T - 1) / T;
   const int lo = min((cta * nt + t) * per, nb), hi = min(lo + per, nb);
   const int s_lo = lo / G, c_lo = lo - s_lo * G;
-  auto is_slow = [&](int c) { return c < bd.edge || c > G - 1 - bd.edge; };
-  auto cap_at = [&](int b, int c) -> long long {
-    const long long a0 = g_att[b], al = g_att[c == 0 ? b + G - 1 : b - 1], ar = g_att[c == G - 1 ? b - (G - 1) : b + 1];
-    const long long cap = a0 + (long long)(f * (double)(a0 + al + ar)) + 32;
-    return (cap + kBlk - 1) & ~(long long)(kBlk - 1);
+  auto chunk_of = [&](int b, int c) -> int { return is_slow(c) ? kSlowChunk : (b >= tail_from ? kTailChunk : kChunk); };
+  auto caps_of = [&](int b, int c, long long& cb, long long& cs) {
+    const int bl = c == 0 ? b + G - 1 : b - 1, br = c == G - 1 ? b - (G - 1) : b + 1;
+    const long long p0 = pop(b);
+    // block range: written by the bin's own (fast) work items only
+    cb = is_slow(c) ? 0 : p0 - leaving(b) / 2 + (long long)kHolesPerWriter * (p0 / chunk_of(b, c) + 2) + 32;
+    const bool near_wall = bd.edge > 0 && (c <= bd.edge || c >= G - 1 - bd.edge);
+    if (near_wall) {
+      cs = p0 + (long long)(f * (double)(p0 + pop(bl) + pop(br))) + 32;
+    } else {
+      const long long a0 = arriving(b), a3 = a0 + arriving(bl) + arriving(br);
+      cs = a0 + (long long)(f * (double)(a3 + p0)) + 32;
+    }
+    cb = (cb + kBlk - 1) & ~(long long)(kBlk - 1);  // ranges start on block boundaries
+    cs = (cs + kBlk - 1) & ~(long long)(kBlk - 1);
   };
-  auto cnt_at = [&](int b) -> int {
-    const long long cap = g_off[b + 1] - g_off[b], att = g_att[b];
-    return (int)(att < cap ? att : cap);
-  };
-  auto items_of = [&](int n, int c) -> int {
-    if (is_slow(c)) return (n + kSlowChunk - 1) / kSlowChunk;
-    int q = (int)((float)n * inv_chunk);
-    while ((long long)q * kChunk < n) ++q;
-    while (q > 0 && (long long)(q - 1) * kChunk >= n) --q;
-    return q;
-  };
+  // 1. close `written`: slots in use = min(cursor, capacity); everything beyond sits in its overflow list.  A range that was
+  //    filled slot by slot is padded with holes up to a whole block.
   long long cap_sum = 0;
   int item_sum = 0;
   {
     int c = c_lo;
     for (int b = lo; b < hi; ++b) {
-      const int cnt = cnt_at(b);
-      bd.cnt[written][b] = cnt;
-      cap_sum += cap_at(b, c);
-      item_sum += items_of(cnt, c);
+      const int ch = chunk_of(b, c);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = 2 * b + half;
+        const long long o = g_off[i], cap = g_off[i + 1] - o, att = g_att[i];
+        int cnt = (int)(att < cap ? att : cap);
+        if (cnt & (kBlk - 1)) {
+          const int full = (cnt + kBlk - 1) & ~(kBlk - 1);
+          for (int k = cnt; k < full; ++k) slot_ptr(bd.rec[written], o + k)[0] = hole_value(R(0));
+          cnt = full;
+        }
+        bd.cnt[written][i] = cnt;
+        item_sum += (cnt + ch - 1) / ch;
+      }
+      long long cb, cs;
+      caps_of(b, c, cb, cs);
+      cap_sum += cb + cs;
       c = c + 1 == G ? 0 : c + 1;
     }
   }
@@ -464,26 +415,39 @@ __global__ void __launch_bounds__(kPlanMcThreads) k_plan_mc(const BinDev<R> bd, 
     if (k < cta) { run += ck; it += ik; }
     all_caps += ck; all_items += ik;
   }
+  // 2. offsets and cursors of `next`, 3. work items over `written`
   {
     int c = c_lo;
     for (int b = lo; b < hi; ++b) {
-      bd.off[next][b] = run;
-      run += cap_at(b, c);
-      bd.cur[next][b] = 0u;
-      const int n = bd.cnt[written][b], ch = is_slow(c) ? kSlowChunk : kChunk;
-      for (int k = 0; k < n; k += ch) {
-        if (it < bd.item_cap) { bd.item_bin[it] = b; bd.item_first[it] = k; }
-        ++it;
+      long long cb, cs;
+      caps_of(b, c, cb, cs);
+      bd.off[next][2 * b] = run;
+      bd.off[next][2 * b + 1] = run + cb;
+      run += cb + cs;
+      bd.cur[next][2 * b] = 0u;
+      bd.cur[next][2 * b + 1] = 0u;
+      const int ch = chunk_of(b, c);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int n = bd.cnt[written][2 * b + half];
+        for (int k = 0; k < n; k += ch) {
+          if (it < bd.item_cap) { bd.item_bin[it] = 2 * b + half; bd.item_first[it] = k; }
+          ++it;
+        }
       }
       c = c + 1 == G ? 0 : c + 1;
     }
   }
   if (cta == 0 && t == 0) {
-    bd.off[next][nb] = all_caps;
-    if (all_items > bd.item_cap) atomicExch(&h->error, 2);
+    bd.off[next][2 * nb] = all_caps;
+    if (all_items > bd.item_cap || all_caps > bd.cap_total) atomicExch(&h->error, 2);
     h->n_items = all_items < bd.item_cap ? all_items : bd.item_cap;
     h->chunk = kChunk;
+    h->tail_chunk = kTailChunk;
+    h->tail_from = tail_from;
     h->work = 0;
+    h->work2 = 0;
+    h->gen_n = 0;
     h->flip = written;
     h->ov_n[next] = 0;
     h->n_stored = n_total;
@@ -535,7 +499,12 @@ __global__ void __launch_bounds__(256) k_start_binned(const DevParams<R> p, cons
       int c = (int)floor((xp - p.gs) * p.inv_dx);
       c = min(max(c, 0), p.G - 1);
       bin = s * p.G + c;
-      atomicAdd(&bd.cur[0][bin], 1u);  // histogram of the first layout
+      atomicAdd(&bd.cur[0][2 * bin], 1u);  // histogram of the first layout: everything starts in the block ranges, slot by slot
+      // how many will leave the bin in step 0 (the velocity barely changes in one step): sizes the single ranges of the first plan
+      {
+        const R t_new = (xp - node_pos(c, p)) * p.inv_dx + v[0] * p.dt * p.inv_dx;
+        if (!(fabs(t_new) < R(0.5))) atomicAdd(&bd.slow0[bin], 1u);
+      }
     } else {
       atomicAdd((unsigned long long*)&bd.hdr->n_absorbed, 1ull);
     }
@@ -548,7 +517,7 @@ template <typename R>
 __global__ void __launch_bounds__(1024) k_first_layout(const BinDev<R> bd) {
   __shared__ long long sh_ll[1024];
   __shared__ long long tot;
-  const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb;
+  const int t = threadIdx.x, nt = blockDim.x, nb = 2 * bd.nb;  // all ranges (the block ranges are empty)
   const int per = (nb + nt - 1) / nt, lo = min(t * per, nb), hi = min(lo + per, nb);
   long long mine = 0;
   for (int b = lo; b < hi; ++b) mine += ((long long)bd.cur[0][b] + kBlk - 1) & ~(long long)(kBlk - 1);
@@ -571,46 +540,70 @@ __global__ void __launch_bounds__(256) k_scatter_binned(const DevParams<R> p, co
     const int b = st_bin[i];
     if (b < 0) continue;
     const int c = b % p.G;
-    const unsigned slot = atomicAdd(&bd.cur[0][b], 1u);
-    store_slot(bd, 0, b, slot, (st_x[i] - node_pos(c, p)) * p.inv_dx, st_vx[i], st_vy[i], st_vz[i]);
+    const unsigned slot = atomicAdd(&bd.cur[0][2 * b], 1u);
+    store_slot(bd, 0, 2 * b, slot, (st_x[i] - node_pos(c, p)) * p.inv_dx, st_vx[i], st_vy[i], st_vz[i]);
   }
 }
 
-// export / diagnostics over the current source buffer --------------------------------------------------------
+// export / diagnostics over the current source buffer (holes, d = NaN, are skipped) ------------------------------
+// live particles per range: one warp per range
 template <typename R>
-__global__ void __launch_bounds__(1024) k_dense_offsets(const BinDev<R> bd, long long* dense /* nb+1 */) {
+__global__ void __launch_bounds__(256) k_count_live(const BinDev<R> bd, int* live /* 2 nb */) {
+  const int src = bd.hdr->flip;
+  const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int i = w; i < 2 * bd.nb; i += nw) {
+    const long long o = bd.off[src][i];
+    int n = 0;
+    for (int k = lane; k < bd.cnt[src][i]; k += 32) {
+      const R d = slot_ptr(bd.rec[src], o + k)[0];
+      n += d == d ? 1 : 0;
+    }
+    for (int s = 16; s; s >>= 1) n += __shfl_xor_sync(0xffffffffu, n, s);
+    if (lane == 0) live[i] = n;
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(1024) k_dense_offsets(const BinDev<R> bd, const int* live, long long* dense /* 2 nb + 1 */) {
   __shared__ long long sh_ll[1024];
   __shared__ long long tot;
-  const int src = bd.hdr->flip;
-  const int t = threadIdx.x, nt = blockDim.x, nb = bd.nb;
+  const int t = threadIdx.x, nt = blockDim.x, nb = 2 * bd.nb;
   const int per = (nb + nt - 1) / nt, lo = min(t * per, nb), hi = min(lo + per, nb);
   long long mine = 0;
-  for (int b = lo; b < hi; ++b) mine += bd.cnt[src][b];
+  for (int b = lo; b < hi; ++b) mine += live[b];
   long long run = block_exclusive_scan<long long>(mine, &tot, sh_ll);
-  for (int b = lo; b < hi; ++b) { dense[b] = run; run += bd.cnt[src][b]; }
+  for (int b = lo; b < hi; ++b) { dense[b] = run; run += live[b]; }
   if (t == 0) dense[nb] = tot;
 }
 
 template <typename R>
-__global__ void k_export_binned(const DevParams<R> p, const BinDev<R> bd, const long long* dense, R* x_out, R* v_out, uint8_t* alive) {
+__global__ void __launch_bounds__(256) k_export_binned(const DevParams<R> p, const BinDev<R> bd, const long long* dense, R* x_out, R* v_out, uint8_t* alive) {
   const int src = bd.hdr->flip;
-  const long long n_bins = dense[bd.nb];
-  for (int b = blockIdx.x; b < bd.nb; b += gridDim.x) {
-    const int c = b % p.G;
-    const long long o = bd.off[src][b], q0 = dense[b];
-    for (int i = threadIdx.x; i < bd.cnt[src][b]; i += blockDim.x) {
-      const long long k = q0 + i;
-      const R* q = slot_ptr(bd.rec[src], o + i);
-      if (x_out) { x_out[3 * k] = node_pos(c, p) + q[0] * p.dx; x_out[3 * k + 1] = R(0); x_out[3 * k + 2] = R(0); }
-      if (v_out) { v_out[3 * k] = q[kBlk]; v_out[3 * k + 1] = q[2 * kBlk]; v_out[3 * k + 2] = q[3 * kBlk]; }
-      if (alive) alive[k] = 1;
+  const long long n_bins = dense[2 * bd.nb];
+  const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int i = w; i < 2 * bd.nb; i += nw) {  // one warp per range, block after block, live particles ranked by ballot
+    const int c = (i >> 1) % p.G;
+    const long long o = bd.off[src][i];
+    long long k = dense[i];
+    for (int j = lane; j < bd.cnt[src][i]; j += 32) {
+      const R* q = slot_ptr(bd.rec[src], o + j);
+      const R d = q[0];
+      const bool ok = d == d;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const long long kk = k + __popc(m & ((1u << lane) - 1u));
+        if (x_out) { x_out[3 * kk] = node_pos(c, p) + d * p.dx; x_out[3 * kk + 1] = R(0); x_out[3 * kk + 2] = R(0); }
+        if (v_out) { v_out[3 * kk] = q[kBlk]; v_out[3 * kk + 1] = q[2 * kBlk]; v_out[3 * kk + 2] = q[3 * kBlk]; }
+        if (alive) alive[kk] = 1;
+      }
+      k += __popc(m);
     }
   }
   const int n_ov = min(bd.hdr->ov_n[src], bd.ov_cap);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N - n_bins; i += (long long)gridDim.x * blockDim.x) {
     const long long k = n_bins + i;
     if (i < n_ov) {
-      const int c = bd.ov_bin[src][i] % p.G;
+      const int c = (bd.ov_bin[src][i] >> 1) % p.G;
       if (x_out) { x_out[3 * k] = node_pos(c, p) + bd.ov_d[src][i] * p.dx; x_out[3 * k + 1] = R(0); x_out[3 * k + 2] = R(0); }
       if (v_out) { v_out[3 * k] = bd.ov_vx[src][i]; v_out[3 * k + 1] = bd.ov_vy[src][i]; v_out[3 * k + 2] = bd.ov_vz[src][i]; }
       if (alive) alive[k] = 1;
@@ -626,23 +619,57 @@ template <typename R>
 __global__ void k_kinetic_binned(const DevParams<R> p, const BinDev<R> bd, double* out) {
   const int src = bd.hdr->flip;
   double acc = 0.0;
-  for (int b = blockIdx.x; b < bd.nb; b += gridDim.x) {
-    const double m = (double)p.sp_m[b / p.G];
-    const long long o = bd.off[src][b];
-    for (int i = threadIdx.x; i < bd.cnt[src][b]; i += blockDim.x) {
-      const R* q = slot_ptr(bd.rec[src], o + i);
-      const double a = q[kBlk], b_ = q[2 * kBlk], c_ = q[3 * kBlk];
-      acc += 0.5 * m * (a * a + b_ * b_ + c_ * c_);
+  for (int i = blockIdx.x; i < 2 * bd.nb; i += gridDim.x) {
+    const double m = (double)p.sp_m[(i >> 1) / p.G];
+    const long long o = bd.off[src][i];
+    for (int j = threadIdx.x; j < bd.cnt[src][i]; j += blockDim.x) {
+      const R* q = slot_ptr(bd.rec[src], o + j);
+      if (q[0] == q[0]) {
+        const double a = q[kBlk], b_ = q[2 * kBlk], c_ = q[3 * kBlk];
+        acc += 0.5 * m * (a * a + b_ * b_ + c_ * c_);
+      }
     }
   }
   const int n_ov = min(bd.hdr->ov_n[src], bd.ov_cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ov; i += gridDim.x * blockDim.x) {
-    const double m = (double)p.sp_m[bd.ov_bin[src][i] / p.G];
+    const double m = (double)p.sp_m[(bd.ov_bin[src][i] >> 1) / p.G];
     const double a = bd.ov_vx[src][i], b_ = bd.ov_vy[src][i], c_ = bd.ov_vz[src][i];
     acc += 0.5 * m * (a * a + b_ * b_ + c_ * c_);
   }
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// per-species kinetic energy of the buffer the push just WROTE into row hist_row of jic_outputs.kinetic_energy (one warp per range;
+// enqueued after the push kernels and before the plan flips the buffers)
+template <typename R>
+__global__ void __launch_bounds__(256) k_kinetic_hist_binned(const DevParams<R> p, const BinDev<R> bd, const RunControl* ctl) {
+  double* out = (double*)ctl->hist[6];
+  if (!out) return;
+  out += ctl->hist_row * p.n_species;
+  const int dst = bd.hdr->flip ^ 1;
+  const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int i = w; i < 2 * bd.nb; i += nw) {
+    const long long o = bd.off[dst][i], cap = bd.off[dst][i + 1] - o;
+    const long long used = min((long long)bd.cur[dst][i], cap);  // (the plan has not closed this buffer yet: cursors, not counts)
+    const int s = (i >> 1) / p.G;
+    double acc = 0.0;
+    for (long long k = lane; k < used; k += 32) {
+      const R* q = slot_ptr(bd.rec[dst], o + k);
+      if (q[0] == q[0]) {
+        const double a = q[kBlk], b_ = q[2 * kBlk], c_ = q[3 * kBlk];
+        acc += a * a + b_ * b_ + c_ * c_;
+      }
+    }
+    for (int sh = 16; sh; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (lane == 0 && acc != 0.0) atomicAdd(out + s, 0.5 * (double)p.sp_m[s] * acc);
+  }
+  const int n_ov = min(bd.hdr->ov_n[dst], bd.ov_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ov; i += gridDim.x * blockDim.x) {
+    const int s = (bd.ov_bin[dst][i] >> 1) / p.G;
+    const double a = bd.ov_vx[dst][i], b_ = bd.ov_vy[dst][i], c_ = bd.ov_vz[dst][i];
+    atomicAdd(out + s, 0.5 * (double)p.sp_m[s] * (a * a + b_ * b_ + c_ * c_));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -653,9 +680,9 @@ struct BinnedStore {
   BinDev<R> bd;
   std::vector<void*> owned;
   long long* dense = nullptr;
+  int* live = nullptr;
   int n_sm = 148;
   bool built = false;
-  size_t plan_smem_max = 0;
 
   template <typename T>
   int alloc(Engine& e, T** ptr, size_t n) {
@@ -674,12 +701,14 @@ struct BinnedStore {
     const long long N = dp.N;
     bd.nb = dp.n_species * dp.G;
     bd.slack = 0.125f;
-    bd.cap_total = (long long)((double)N * (1.0 + 3.0 * bd.slack)) + 96ll * bd.nb + 1024;
+    // both ranges of every bin (see k_plan_mc).  Typical need: 1.35 N (a tenth of the particles change bins per step); the worst
+    // case, every particle on the general path every step, is 2 N; the holes come on top (kHolesPerWriter per work item).
+    bd.cap_total = (long long)((double)N * (2.25 + (double)kHolesPerWriter / kMinChunk)) + (long long)(5 * kHolesPerWriter + 256) * bd.nb + 4096;
     bd.cap_total = (bd.cap_total + kBlk - 1) & ~(long long)(kBlk - 1);
     if (bd.cap_total >= (1ll << 40)) return e.fail(JIC_ERR_UNSUPPORTED, "too many particles for one GPU");
     bd.ov_cap = (int)std::min<long long>(std::max<long long>(N / 16, 1 << 16), 1ll << 28);
-    bd.item_cap = (int)std::min<long long>(N / kSlowChunk + bd.nb + 16, 1ll << 30);
-    bd.n_workers = n_sm * push_min_blocks<R>() * kPushWarps;
+    bd.item_cap = (int)std::min<long long>(bd.cap_total / kSlowChunk + 2 * bd.nb + 16, 1ll << 30);
+    bd.n_workers = n_sm * push_min_blocks<R>() * push_warps<R>();
     {
       const bool periodic = dp.pbl == JIC_BC_PERIODIC && dp.pbr == JIC_BC_PERIODIC;
       // periodic: every bin takes the closed form (field_solver runs fix the reference's left-half-cell quirk up in place);
@@ -690,38 +719,31 @@ struct BinnedStore {
     int rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = alloc(e, &bd.rec[k], 4 * (size_t)bd.cap_total))) return rc;
-      if ((rc = alloc(e, &bd.off[k], bd.nb + 1)) || (rc = alloc(e, &bd.cnt[k], bd.nb)) || (rc = alloc(e, &bd.cur[k], bd.nb))) return rc;
+      if ((rc = alloc(e, &bd.off[k], 2 * bd.nb + 1)) || (rc = alloc(e, &bd.cnt[k], 2 * bd.nb)) || (rc = alloc(e, &bd.cur[k], 2 * bd.nb))) return rc;
       if ((rc = alloc(e, &bd.ov_bin[k], bd.ov_cap)) || (rc = alloc(e, &bd.ov_d[k], bd.ov_cap)) || (rc = alloc(e, &bd.ov_vx[k], bd.ov_cap)) ||
           (rc = alloc(e, &bd.ov_vy[k], bd.ov_cap)) || (rc = alloc(e, &bd.ov_vz[k], bd.ov_cap)))
         return rc;
     }
     if ((rc = alloc(e, &bd.item_bin, bd.item_cap)) || (rc = alloc(e, &bd.item_first, bd.item_cap)) || (rc = alloc(e, &bd.hdr, 1))) return rc;
-    if ((rc = alloc(e, &dense, bd.nb + 1)) || (rc = alloc(e, &bd.psync, 1))) return rc;
-    {
-      const char* env = getenv("JIC_PLAN_MC");  // "0" keeps the single-CTA plan
-      plan_ctas = (env && env[0] == '0') ? 0 : std::min(kPlanMaxCtas, (bd.nb + kPlanMcThreads - 1) / kPlanMcThreads);
-      if (plan_ctas < 2) plan_ctas = 0;
-    }
+    bd.gen_cap = (int)std::min<long long>(N + 1024, 1ll << 30);  // (a run far above CFL 1 sends every particle through this list)
+    if ((rc = alloc(e, &bd.gen_bin, bd.gen_cap)) || (rc = alloc(e, &bd.gen_d, bd.gen_cap)) || (rc = alloc(e, &bd.gen_vxold, bd.gen_cap)) ||
+        (rc = alloc(e, &bd.gen_vx, bd.gen_cap)) || (rc = alloc(e, &bd.gen_vy, bd.gen_cap)) || (rc = alloc(e, &bd.gen_vz, bd.gen_cap)))
+      return rc;
+    if ((rc = alloc(e, &dense, 2 * bd.nb + 1)) || (rc = alloc(e, &live, 2 * bd.nb)) || (rc = alloc(e, &bd.psync, 1)) || (rc = alloc(e, &bd.slow0, bd.nb))) return rc;
+    plan_ctas = std::max(1, std::min(kPlanMaxCtas, (bd.nb + kPlanMcThreads - 1) / kPlanMcThreads));
     (void)prm;
     {
-      // Shared-memory carve-out: three CTAs of the fp64 kernel (43.3 KB static + 1 KB reserved each) fit the 132 KB configuration,
-      // which is what the driver picks by itself; the remaining 124 KB of L1 matter (measured: 6 % slower with the 164 KB
-      // configuration, 20 % with the maximum).  JIC_PUSH_CARVEOUT=<per cent of 228 KB> overrides for experiments.
-      if (const char* env = getenv("JIC_PUSH_CARVEOUT")) {
-        const int carve = atoi(env);
-        cudaFuncSetAttribute(k_push<R, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(k_push<R, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(k_push<R, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(k_push<R, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      // The push kernel's shared memory (input ring + output staging per warp) is dynamic: more than 48 KB per CTA needs the opt-in.
+      // JIC_PUSH_CARVEOUT=<per cent of 228 KB> overrides the carve-out the driver derives from it, for experiments.
+      const char* env = getenv("JIC_PUSH_CARVEOUT");
+      const int carve = env ? atoi(env) : -1;
+      const void* fns[4] = {(const void*)k_push<R, false, false>, (const void*)k_push<R, true, false>, (const void*)k_push<R, false, true>,
+                            (const void*)k_push<R, true, true>};
+      for (const void* fn : fns) {
+        cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)push_smem_bytes<R>());
+        if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("push kernel: %zu bytes of shared memory per CTA: %s", push_smem_bytes<R>(), cudaGetErrorString(ce)));
+        if (carve >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
       }
-    }
-    {
-      int dev = 0, max_smem = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-      plan_smem_max = max_smem > 4096 ? (size_t)max_smem - 4096 : 0;
-      if ((size_t)2 * bd.nb * sizeof(int) > 48 * 1024 && (size_t)2 * bd.nb * sizeof(int) <= plan_smem_max)
-        cudaFuncSetAttribute(k_plan<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * bd.nb * sizeof(int)));
     }
     built = true;
     return JIC_OK;
@@ -743,7 +765,8 @@ struct BinnedStore {
   int* st_bin = nullptr;
   int start_begin(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
     cudaMemsetAsync(bd.hdr, 0, sizeof(PlanHeader), st);
-    cudaMemsetAsync(bd.cur[0], 0, sizeof(unsigned) * bd.nb, st);
+    cudaMemsetAsync(bd.cur[0], 0, sizeof(unsigned) * 2 * bd.nb, st);
+    cudaMemsetAsync(bd.slow0, 0, sizeof(unsigned) * bd.nb, st);
     st_bin = nullptr;
     cudaError_t ce = cudaMallocAsync((void**)&st_bin, sizeof(int) * (size_t)(dp.N ? dp.N : 1), st);
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("staging allocation: %s", cudaGetErrorString(ce)));
@@ -776,12 +799,9 @@ struct BinnedStore {
   bool first_plan = true;
 
   // runs after every push (and after the start-up scatter), concurrently with the field kernel: plan the next push
-  int plan_ctas = 0;  // > 0: k_plan_mc on that many CTAs
+  int plan_ctas = 1;
   int plan(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
-    const size_t sm = (size_t)2 * bd.nb * sizeof(int);
-    if (plan_ctas > 0) k_plan_mc<R><<<plan_ctas, kPlanMcThreads, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
-    else if (sm <= plan_smem_max) k_plan<R, true><<<1, 1024, sm, st>>>(bd, dp.G, first_plan ? 1 : 0);
-    else k_plan<R, false><<<1, 1024, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
+    k_plan_mc<R><<<plan_ctas, kPlanMcThreads, 0, st>>>(bd, dp.G, first_plan ? 1 : 0);
     first_plan = false;
     e.launches += 1;
     return JIC_OK;
@@ -789,14 +809,18 @@ struct BinnedStore {
 
   int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, cudaStream_t st) {
     const int g = n_sm * push_min_blocks<R>();
+    const size_t sm = push_smem_bytes<R>();
     if (dp.stag) {
-      if (dp.relativistic) k_push<R, true, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
-      else k_push<R, false, true><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+      if (dp.relativistic) k_push<R, true, true><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
+      else k_push<R, false, true><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
     } else {
-      if (dp.relativistic) k_push<R, true, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
-      else k_push<R, false, false><<<g, kPushThreads, 0, st>>>(dp, bd, F, acc);
+      if (dp.relativistic) k_push<R, true, false><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
+      else k_push<R, false, false><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
     }
-    e.launches += 1;
+    // everything off the closed form: wall-bin items, this step's general-path list, last step's overflow list (usually all empty)
+    if (dp.relativistic) k_push_general<R, true><<<n_sm * 4, kGeneralThreads, 0, st>>>(dp, bd, F, acc);
+    else k_push_general<R, false><<<n_sm * 4, kGeneralThreads, 0, st>>>(dp, bd, F, acc);
+    e.launches += 2;
     return JIC_OK;
   }
 
@@ -813,10 +837,17 @@ struct BinnedStore {
   int export_particles(Engine& e, const DevParams<R>& dp, R* x, R* v, uint8_t* alive, cudaStream_t st) {
     int rc = check_error(e, st);
     if (rc) return rc;
-    k_dense_offsets<R><<<1, 1024, 0, st>>>(bd, dense);
+    k_count_live<R><<<n_sm * 4, 256, 0, st>>>(bd, live);
+    k_dense_offsets<R><<<1, 1024, 0, st>>>(bd, live, dense);
     k_export_binned<R><<<n_sm * 4, 256, 0, st>>>(dp, bd, dense, x, v, alive);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("binned export: %s", cudaGetErrorString(ce)));
+    return JIC_OK;
+  }
+
+  int kinetic_hist(Engine& e, const DevParams<R>& dp, const RunControl* ctl, cudaStream_t st) {
+    k_kinetic_hist_binned<R><<<n_sm * 8, 256, 0, st>>>(dp, bd, ctl);
+    e.launches += 1;
     return JIC_OK;
   }
 
@@ -827,7 +858,7 @@ struct BinnedStore {
     return JIC_OK;
   }
 
-  long long extra_launches_per_step() const { return 1; }  // k_plan
+  long long extra_launches_per_step() const { return 2; }  // k_push_general, k_plan
 };
 
 }  // namespace jic

@@ -28,7 +28,7 @@ constexpr int kAccRow = 4;
 struct RunControl {
   long long step;      // steps completed since jic_initialize
   long long hist_row;  // row of the history buffers the next step writes
-  void* hist[6];       // jic_outputs of the current jic_run (E, B, J, rho, positions, velocities); read by the kernels at
+  void* hist[7];       // jic_outputs of the current jic_run (E, B, J, rho, positions, velocities, kinetic energy); read by the kernels at
                        // run time so that one captured graph serves every set of output buffers
 };
 

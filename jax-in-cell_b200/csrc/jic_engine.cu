@@ -603,6 +603,7 @@ struct EngineT : Engine {
       k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(it, false));
       launches += 2;
     }
+    if (ke_hist) enqueue_kinetic_hist(st, p);
     k_cn_record<R><<<g, 256, 0, st>>>(dp, cn_s[p ^ 1], ctl);
     launches += 1;
     return JIC_OK;
@@ -695,10 +696,26 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
+  // jic_outputs.kinetic_energy: per-species kinetic energy of the velocities the push just produced (before the field kernel advances
+  // the history row, and before the plan -- forked inside enqueue_fields -- flips the store's buffers)
+  bool ke_hist = false;
+  int enqueue_kinetic_hist(cudaStream_t st, int p) {
+    if (cn) {
+      k_kinetic_hist<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[p ^ 1].vx, cn_s[p ^ 1].vy, cn_s[p ^ 1].vz, ctl);
+    } else if (prm.engine == JIC_ENGINE_BINNED) {
+      return bins.kinetic_hist(*this, dp, ctl, st);
+    } else {
+      k_kinetic_hist<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, vx, vy, vz, ctl);
+    }
+    launches += 1;
+    return JIC_OK;
+  }
+
   // one step reading the ping-pong buffers `p` (always 0 without the multi-CTA field kernel)
   int enqueue_step(cudaStream_t st, int p) {
     if (cn) return enqueue_step_cn(st, p);
     int rc = enqueue_push(st, p);
+    if (rc == JIC_OK && ke_hist) rc = enqueue_kinetic_hist(st, p);
     return rc ? rc : enqueue_fields(st, p);
   }
 
@@ -714,6 +731,7 @@ struct EngineT : Engine {
     if (!initialized) return fail(JIC_ERR_BAD_STATE, "jic_profile_steps before jic_initialize");
     jic_outputs none;
     memset(&none, 0, sizeof(none));
+    ke_hist = false;
     int rc0 = begin_run(none, st);
     if (rc0) return rc0;
     std::vector<cudaEvent_t> ev(3 * (size_t)n);
@@ -745,7 +763,7 @@ struct EngineT : Engine {
   }
 
   int get_graph(int steps, cudaStream_t st, cudaGraphExec_t* exec) {
-    const int key = steps * 2 + par;  // the buffer pointers baked into the graph depend on the starting parity
+    const int key = (steps * 2 + par) * 2 + (ke_hist ? 1 : 0);  // the buffer pointers baked into the graph depend on the starting parity
     auto it = graphs.find(key);
     if (it != graphs.end()) { *exec = it->second; return JIC_OK; }
     cudaStream_t cs;
@@ -785,18 +803,14 @@ struct EngineT : Engine {
     if (!cn && prm.engine == JIC_ENGINE_BINNED && (out.positions || out.velocities))
       return fail(JIC_ERR_UNSUPPORTED, "particle histories need the INDEXED engine");
     if (!cn && out.positions && !prm.track_yz) return fail(JIC_ERR_INVALID_ARGUMENT, "positions history needs track_yz=1");
-    if (fused() && steps_run > 0) {
-      int derr = 0;
-      JIC_CUDA(cudaMemcpyAsync(&derr, dev_error, sizeof(int), cudaMemcpyDeviceToHost, st));
-      JIC_CUDA(cudaStreamSynchronize(st));
-      if (derr == 3) return fail(JIC_ERR_BAD_STATE, "fused reduction: a peer rank did not reach the step within the spin limit");
-    }
-    if (!cn && prm.engine == JIC_ENGINE_BINNED && steps_run > 0) {
-      // the store reports exhausted head-room through a sticky device flag: look at it before queueing more work
-      int rc = bins.check_error(*this, st);
+    if (steps_run > 0) {
+      // the kernels report trouble through sticky device flags: look at them before queueing more work
+      int rc = check_status(st);
       if (rc) return rc;
     }
     steps_run += n;
+    ke_hist = out.kinetic_energy != nullptr;
+    if (ke_hist) JIC_CUDA(cudaMemsetAsync(out.kinetic_energy, 0, (size_t)n * dp.n_species * sizeof(double), st));
     int rcb = begin_run(out, st);
     if (rcb) return rcb;
     const int chunk = prm.steps_per_graph > 0 ? prm.steps_per_graph : 16;
@@ -815,9 +829,22 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
+  // sticky device-side error flags (synchronises the stream): a peer that missed the fused barrier, exhausted store capacity
+  int check_status(cudaStream_t st) override {
+    if (fused()) {
+      int derr = 0;
+      JIC_CUDA(cudaMemcpyAsync(&derr, dev_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+      JIC_CUDA(cudaStreamSynchronize(st));
+      if (derr == 3) return fail(JIC_ERR_BAD_STATE, "fused reduction: a peer rank did not reach the step within the spin limit");
+    }
+    if (!cn && prm.engine == JIC_ENGINE_BINNED && initialized) return bins.check_error(*this, st);
+    JIC_CUDA(cudaStreamSynchronize(st));
+    return JIC_OK;
+  }
+
   long long count_launches_per_step() const {
-    if (cn) return 1 + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
-    long long k = 2 + ((world > 1 && !fused()) ? 1 : 0) + dp.stag;
+    if (cn) return 1 + (ke_hist ? 1 : 0) + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
+    long long k = 2 + ((world > 1 && !fused()) ? 1 : 0) + dp.stag + (ke_hist ? 1 : 0);
     if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
     return k;
   }
@@ -960,6 +987,7 @@ int jic_get_initial(jic_context* ctx, void* E0, void* B0, void* v, void* st) { C
 int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->get_particles(x, v, alive, (cudaStream_t)st); }
 int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
 int jic_profile_steps(jic_context* ctx, int64_t n, double* ms_push, double* ms_fields, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->profile(n, ms_push, ms_fields, (cudaStream_t)st); }
+int jic_check_status(jic_context* ctx, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->check_status((cudaStream_t)st); }
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
 int jic_get_picard_iterations(jic_context* ctx, int64_t* last, int64_t* total, void* st) {
   CTX_OR_FAIL(ctx);
@@ -971,8 +999,8 @@ int jic_get_picard_iterations(jic_context* ctx, int64_t* last, int64_t* total, v
 }
 int jic_comm_mode(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->comm_mode() : 0; }
 
-int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* sp, const double box[3], int32_t partitionable,
-                         void* x0, void* v0, void* stream) {
+int jic_sample_particles_slice(int32_t dtype, int32_t n_species, const jic_species_sampling* sp, const int64_t* first, const int64_t* local_count,
+                               const double box[3], int32_t partitionable, void* x0, void* v0, void* stream) {
   if (!sp || !box || !x0 || !v0 || n_species < 1) { g_last_error = "jic_sample_particles: null argument"; return JIC_ERR_INVALID_ARGUMENT; }
   if (dtype != JIC_F64 && dtype != JIC_F32) { g_last_error = "dtype must be JIC_F64 or JIC_F32"; return JIC_ERR_INVALID_ARGUMENT; }
   int ndev = 0;
@@ -984,6 +1012,9 @@ int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sam
     SampleArgs a;
     memset(&a, 0, sizeof(a));
     a.count = sp[s].count; a.offset = offset;
+    a.first = first ? first[s] : 0;
+    a.n_local = local_count ? local_count[s] : sp[s].count;
+    if (a.first < 0 || a.n_local < 0 || a.first + a.n_local > a.count) { g_last_error = "jic_sample_particles_slice: slice outside the species"; return JIC_ERR_INVALID_ARGUMENT; }
     a.seed_position = sp[s].seed_position; a.seed_velocity = sp[s].seed_velocity;
     a.partitionable = partitionable ? 1 : 0;
     for (int k = 0; k < 3; ++k) {
@@ -994,17 +1025,22 @@ int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sam
       a.drift[k] = sp[s].drift_speed[k];
       a.box[k] = box[k];
     }
-    if (a.count > 0) {
-      long long blocks = (a.count + 255) / 256;
+    if (a.n_local > 0) {
+      long long blocks = (a.n_local + 255) / 256;
       if (blocks > 148 * 16) blocks = 148 * 16;
       if (dtype == JIC_F64) k_sample_species<double><<<(int)blocks, 256, 0, st>>>(a, (double*)x0, (double*)v0);
       else k_sample_species<float><<<(int)blocks, 256, 0, st>>>(a, (float*)x0, (float*)v0);
     }
-    offset += a.count;
+    offset += a.n_local;
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { g_last_error = format("jic_sample_particles: %s", cudaGetErrorString(ce)); return JIC_ERR_CUDA; }
   return JIC_OK;
+}
+
+int jic_sample_particles(int32_t dtype, int32_t n_species, const jic_species_sampling* sp, const double box[3], int32_t partitionable,
+                         void* x0, void* v0, void* stream) {
+  return jic_sample_particles_slice(dtype, n_species, sp, nullptr, nullptr, box, partitionable, x0, v0, stream);
 }
 
 int jic_simulate_host(const jic_params* params, const jic_species* species, const void* x0_host, const void* v0_host,
@@ -1029,13 +1065,14 @@ int jic_simulate_host(const jic_params* params, const jic_species* species, cons
   if ((rc = e->initialize_host(x0_host, v0_host, st))) return cleanup(rc);  // chunked upload overlapped with the start-up kernels
   jic_outputs d;
   memset(&d, 0, sizeof(d));
-  const size_t sizes[6] = {T * G * 3 * rs, T * G * 3 * rs, T * G * 3 * rs, T * G * rs, T * N * 3 * rs, T * N * 3 * rs};
+  const size_t sizes[7] = {T * G * 3 * rs, T * G * 3 * rs, T * G * 3 * rs, T * G * rs, T * N * 3 * rs, T * N * 3 * rs,
+                           T * (size_t)params->n_species * sizeof(double)};
   void* const* hsrc = host_out ? (void* const*)host_out : nullptr;
   void** dptr = (void**)&d;
-  for (int k = 0; k < 6 && hsrc; ++k)
+  for (int k = 0; k < 7 && hsrc; ++k)
     if (hsrc[k]) { dptr[k] = dalloc(sizes[k]); if (!dptr[k]) { e->error = "cudaMalloc failed for a history buffer"; return cleanup(JIC_ERR_CUDA); } }
   if ((rc = e->run(n_steps, &d, st))) return cleanup(rc);
-  for (int k = 0; k < 6 && hsrc; ++k)
+  for (int k = 0; k < 7 && hsrc; ++k)
     if (hsrc[k]) cudaMemcpyAsync(hsrc[k], dptr[k], sizes[k], cudaMemcpyDeviceToHost, st);
   if (E0_host || B0_host || vinit_host) {
     void* dE0 = E0_host ? dalloc(G * 3 * rs) : nullptr;
@@ -1049,6 +1086,8 @@ int jic_simulate_host(const jic_params* params, const jic_species* species, cons
   }
   cudaError_t ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) { e->error = format("simulate_host: %s", cudaGetErrorString(ce)); return cleanup(JIC_ERR_CUDA); }
+  // a run that dropped particles (store capacity) or summed a partial grid (missing peer) must not come back as a result
+  if ((rc = e->check_status(st))) return cleanup(rc);
   return cleanup(JIC_OK);
 }
 

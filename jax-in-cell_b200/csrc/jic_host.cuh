@@ -43,6 +43,7 @@ struct Engine {
   virtual int get_initial(void* E0, void* B0, void* vinit, cudaStream_t st) = 0;
   virtual int get_particles(void* x, void* v, uint8_t* alive, cudaStream_t st) = 0;
   virtual int kinetic(double* out, cudaStream_t st) = 0;
+  virtual int check_status(cudaStream_t st) = 0;
   virtual int profile(long long n, double* ms_push, double* ms_fields, cudaStream_t st) = 0;
   virtual int dtype() const = 0;
   virtual long long n_particles() const = 0;

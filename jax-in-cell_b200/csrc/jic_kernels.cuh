@@ -734,11 +734,38 @@ __global__ void k_kinetic(const DevParams<R> p, const R* vx, const R* vy, const 
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// per-species kinetic energy of the step into row hist_row of the (T, n_species) history (jic_outputs.kinetic_energy), INDEXED / CN
+// layouts: the species of particle i follows from its index.  Enqueued between the push and the field kernel of a step.
+template <typename R>
+__global__ void __launch_bounds__(256) k_kinetic_hist(const DevParams<R> p, const R* vx, const R* vy, const R* vz, const RunControl* ctl) {
+  double* out = (double*)ctl->hist[6];
+  if (!out) return;
+  out += ctl->hist_row * p.n_species;
+  double acc[JIC_MAX_SPECIES];
+#pragma unroll
+  for (int s = 0; s < JIC_MAX_SPECIES; ++s) acc[s] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    const int s = species_of(i, p);
+    const double a = vx[i], b = vy[i], c = vz[i];
+    const double e = 0.5 * (double)p.sp_m[s] * (a * a + b * b + c * c);
+#pragma unroll
+    for (int k = 0; k < JIC_MAX_SPECIES; ++k) acc[k] += k == s ? e : 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < JIC_MAX_SPECIES; ++s) {
+    if (s < p.n_species) {
+      double v = acc[s];
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out + s, v);
+    }
+  }
+}
+
 // start of a jic_run: row 0 of the caller's history buffers is the first step of this call
 __global__ void k_begin_run(RunControl* ctl, jic_outputs out) {
   ctl->hist_row = 0;
   ctl->hist[0] = out.electric_field; ctl->hist[1] = out.magnetic_field; ctl->hist[2] = out.current_density;
-  ctl->hist[3] = out.charge_density; ctl->hist[4] = out.positions; ctl->hist[5] = out.velocities;
+  ctl->hist[3] = out.charge_density; ctl->hist[4] = out.positions; ctl->hist[5] = out.velocities; ctl->hist[6] = out.kinetic_energy;
 }
 
 template <typename R>

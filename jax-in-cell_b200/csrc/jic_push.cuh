@@ -1,12 +1,11 @@
 // K1  the binned push (sm_100a): gather -> Boris -> move -> deposit -> re-bin in one pass over a (species, cell) bin.
 // Included by jic_binned.cuh (store layout, slow_tail, warp_sum are defined there).
 //
-// Design, each point answering a counter of the first version's ncu profile (profiles/r01_push_binned_64x6_*: 328 thread
-// instructions per particle, 18 % occupancy, warps stalled on their own global loads, a __syncthreads per chunk phase):
+// Design, each point answering a counter of an earlier version's ncu profile (profiles/):
 //
-//  1. WARPS ARE THE WORKERS.  Every warp pulls work items (a run of <= chunk particles of one bin) from the queue on its
-//     own, owns a private shared-memory ring and private mbarriers, and flushes its own deposit: no __syncthreads anywhere
-//     in the kernel, no producer/consumer imbalance inside a CTA.
+//  1. WARPS ARE THE WORKERS.  Every warp pulls work items (a run of <= chunk slots of one bin range) from the queue on its
+//     own, owns a private shared-memory input ring, private mbarriers and private output staging, and flushes its own
+//     deposit: no __syncthreads anywhere in the kernel, no producer/consumer imbalance inside a CTA.
 //
 //  2. PARTICLE LOADS ARE OFF THE INSTRUCTION STREAM.  The store keeps particles in 1 KiB blocks of 32
 //     ([d x32][vx x32][vy x32][vz x32]); lane 0 streams whole blocks into the ring with 1-D bulk async copies
@@ -26,17 +25,38 @@
 //         w(c+1) = ((t+1/2)^2 - N - 3P)/2       C(c+1) = 1 - P/2
 //         w(c+2) = P/2
 //
-//  4. RE-BINNING costs one cursor atomic per warp, destination and block (lanes 0..2 claim for stay / left / right), and
-//     the store of a particle is issued one iteration after its claim so that the atomic's round trip is hidden.
+//  4. RE-BINNING: STAYERS KEEP THEIR LANE, MOVERS ARE DEFERRED (round 2).  Measured with the re-binning compiled out, the
+//     kernel runs at the copy peak (0.97 ms per 1e8 particles, profiles/r02_push_no_rebinning_floor.txt); the round-1
+//     re-binning (a cursor atomic per block and destination, a deferred-store stash, scattered stores) cost 85 of its 229
+//     instructions per particle and 0.34 ms.  Now:
+//       * A particle that stays in its bin (|t_new| < 1/2: nine in ten) never moves between lanes.  A processed block of 32 goes
+//         to the bin's BLOCK range straight from the registers, four 256-byte rows, as soon as its holes are filled.
+//       * The holes that movers (and holes of the input) leave are filled from a POOL of already-processed stayers in shared
+//         memory (at most 63): the lane with the r-th hole pops the r-th entry from the top.  When the pool holds fewer than 32
+//         entries the next block becomes a donor: its stayers are pushed onto the pool (ballot ranks) instead of being written.
+//         Every block written is therefore full; only the last one or two of a work item (the pool's remainder) carry holes
+//         (d = NaN), which every reader skips at no cost -- all comparisons of the domain test |t| < 3/2 are false for NaN.
+//       * Output blocks are claimed in runs of kPushRun blocks with one cursor atomic by lane 0, one run ahead of their use
+//         (the round trip is > 1 us under load); fills and counts are warp-uniform, so every decision is a uniform branch.
+//       * Movers go, with their unshifted offset, into a small ring in shared memory.  Every 32 of them are frozen: their slots
+//         in the neighbours' SINGLE ranges are claimed (two atomics), and they are written when the next 32 are frozen -- ten
+//         blocks later, when the claims have long arrived.
+//     A bulk-copy flush (cp.async.bulk.global.shared::cta) of shared-memory staging blocks was measured first: the proxy fence
+//     it needs compiles to MEMBAR.ALL.CTA, which waits for the pending claims, and staging every particle costs as many
+//     instructions as round 1 did.
 //
 // Arithmetic follows jaxincell/_algorithms.py:40-66,90-92 (see jic_device.cuh for the per-function citations).  Particles
-// that leave the closed form's domain (|t_new| >= 3/2, wall cells of non-periodic runs, full destination bins) take the exact
-// general code (slow_tail).
+// that leave the closed form's domain (|t_new| >= 3/2, wall cells of non-periodic runs, full destination ranges) take the
+// exact general code (slow_tail), which re-inserts them one by one into the destination's SINGLE range.
 #pragma once
+
+#ifndef JIC_EXPERIMENT_NOD
+#define JIC_EXPERIMENT_NOD 0
+#endif
 
 namespace jic {
 
-static_assert((kPushStages & (kPushStages - 1)) == 0, "stage count must be a power of two");
+static_assert((JIC_PUSH_STAGES & (JIC_PUSH_STAGES - 1)) == 0 && (JIC_PUSH_STAGES_F32 & (JIC_PUSH_STAGES_F32 - 1)) == 0, "stage count must be a power of two");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -64,23 +84,34 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                "r"(bar)
                : "memory");
 }
+// +1 / -1 / 0 cells as a real: the three doubles differ in their high word only
+__device__ __forceinline__ double cell_shift(bool right, bool left, double) {
+  return __hiloint2double(right ? 0x3ff00000 : (left ? (int)0xbff00000 : 0), 0);
+}
+__device__ __forceinline__ float cell_shift(bool right, bool left, float) { return right ? 1.f : (left ? -1.f : 0.f); }
 
 template <typename R>
 struct __align__(16) DestSlot {
-  R* base;        // first block of the destination bin
+  R* base;        // first block of the destination range
   unsigned cap;   // its capacity in slots
-  int bin;
+  int bin;        // range index (2 * bin + half)
 };
 
+// one warp's shared memory
+constexpr int kPoolCap = 64;   // processed stayers waiting to fill holes (< 32 triggers a donor block, which adds at most 32)
+constexpr int kMixCap = 128;   // ring of movers: 32 frozen (claimed, not yet written) + up to 63 collecting
 template <typename R>
-__device__ __forceinline__ void store_slot_at(const BinDev<R>& bd, int dst, const DestSlot<R>& ds, unsigned slot, R d, R vx, R vy, R vz) {
-  if (slot < ds.cap) {
-    R* q = ds.base + (size_t)(slot >> 5) * kBlkElems + (slot & 31u);
-    q[0] = d; q[kBlk] = vx; q[2 * kBlk] = vy; q[3 * kBlk] = vz;
-  } else {
-    store_slot(bd, dst, ds.bin, slot, d, vx, vy, vz);  // -> overflow list
-  }
-}
+struct __align__(128) PushWarpSmem {
+  R ring[push_stages<R>()][kPushStageBlocks][kBlkElems];  // input: work-item blocks on their way in
+  R pool[4][kPoolCap];                               // d, v_x, v_y, v_z of pooled stayers (a stack)
+  R mix[4][kMixCap];                                 // t_new (unshifted), v_x, v_y, v_z of movers (a ring)
+  R coef[24];                                        // per component k: [e0, e1, a2lo, a2hi, b0, b1, b2, -]
+  R tot[24];
+  unsigned long long full[push_stages<R>()];
+  DestSlot<R> dest[3];                               // 0: the bin's block range; 1 / 2: the left / right neighbour's single range
+};
+template <typename R>
+constexpr size_t push_smem_bytes() { return sizeof(PushWarpSmem<R>) * push_warps<R>(); }
 
 // STAG (field_solver != 0): additionally rho(x_n) on the FACES c-3..c+2 (jaxincell/_algorithms.py:69-72), x_n = x_{n+1/2} - dt/2 v_n
 // at offset ts from node c.  The face weights are the same B-spline seen from half a cell away, so their knots inside
@@ -91,31 +122,29 @@ __device__ __forceinline__ void store_slot_at(const BinDev<R>& bd, int dst, cons
 // Five more sums per lane, six more node values per item.  Bins next to the domain ends take the general path: there the
 // reference drops the weight of faces -1 and -2 instead of wrapping it (make_cloud_faces).
 template <typename R, bool REL, bool STAG>
-__global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
+__global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
                                                                        const R* __restrict__ F, R* __restrict__ acc) {
-  constexpr int NW = kPushWarps, NS = kPushStages, KB = kPushStageBlocks;
+  constexpr int NS = push_stages<R>(), KB = kPushStageBlocks, RUN = kPushRun;
   constexpr unsigned kBlockBytes = kBlkElems * sizeof(R);
-  __shared__ __align__(128) R ring[NW][NS][KB][kBlkElems];
-  __shared__ __align__(8) unsigned long long full[NW][NS];
-  __shared__ __align__(16) R coef_s[NW][24];  // per component k: [e0, e1, a2lo, a2hi, b0, b1, b2, -]
-  __shared__ DestSlot<R> dest_s[NW][3];
-  __shared__ R tot_s[NW][24];
-  __shared__ __align__(16) R stash[NW][KB][kBlkElems];  // re-binned particles waiting for their claimed slots
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char push_smem_raw[];
 
   PlanHeader* hdr = bd.hdr;
   const int src = hdr->flip, dst = src ^ 1;
   const R* __restrict__ srec = bd.rec[src];
-  const int n_items = hdr->n_items, chunk = hdr->chunk;
+  const int n_items = hdr->n_items, chunk = hdr->chunk, tail_chunk = hdr->tail_chunk, tail_from = hdr->tail_from;
   const int warp = threadIdx.x >> 5;
   int lane;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-reading SR_TID in the loop
   const unsigned lt_mask = (1u << lane) - 1u;
   const int G = p.G;
   const R cells_per_v = p.dt * p.inv_dx;  // displacement in cells per unit velocity
+  const R hole = hole_value(R(0));
 
-  const R* my_ring = &ring[warp][0][0][0];
-  const unsigned ring_u32 = smem_u32(my_ring), bar_u32 = smem_u32(&full[warp][0]);
-  const R* coef = coef_s[warp];
+  PushWarpSmem<R>& sm = reinterpret_cast<PushWarpSmem<R>*>(push_smem_raw)[warp];
+  const R* my_ring = &sm.ring[0][0][0];
+  const unsigned ring_u32 = smem_u32(my_ring), bar_u32 = smem_u32(&sm.full[0]);
+  const R* coef = sm.coef;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) mbar_init(bar_u32 + 8u * s, 1);
@@ -128,18 +157,20 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     // ---- next work item from the queue (dynamic: items differ in size)
     int item = 0;
     if (lane == 0) item = atomicAdd(&hdr->work, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
+    item = __shfl_sync(FULL, item, 0);
     if (item >= n_items) break;
-    const int b = bd.item_bin[item];
+    const int range = bd.item_bin[item];  // 2 * bin + half
     const int first = bd.item_first[item];
+    const int b = range >> 1;
     const int s = b / G, c = b - s * G;
-    const bool fast_bin = c >= bd.edge && c <= G - 1 - bd.edge;  // (k_plan makes the items of the other bins small)
+    if (c < bd.edge || c > G - 1 - bd.edge) continue;  // a wall bin: every particle takes the general path (k_push_general)
+    constexpr bool fast_bin = true;
     // STAG on a periodic domain: the three bins from which x_n can land in the left half cell (see the correction in phase C)
     const bool quirk_bin = STAG && bd.edge == 0 && (c == G - 1 || c <= 1);
     const R quirk_shift = c == G - 1 ? R(-0.5) : R(c) + R(0.5);
-    const int n = min(fast_bin ? chunk : kSlowChunk, bd.cnt[src][b] - first);
-    const int nblk = (n + kBlk - 1) / kBlk, ngroups = (nblk + KB - 1) / KB;
-    const R* item_rec = srec + ((bd.off[src][b] + first) >> 5) * (long long)kBlkElems;
+    const int n = min(fast_bin ? (b >= tail_from ? tail_chunk : chunk) : kSlowChunk, bd.cnt[src][range] - first);  // slots: whole blocks
+    const int nblk = n >> 5, ngroups = (nblk + KB - 1) / KB;
+    const R* item_rec = srec + ((bd.off[src][range] + first) >> 5) * (long long)kBlkElems;
 
     // lane 0 starts streaming the item at once; the other lanes set up the item-uniform tables meanwhile
     const unsigned gt0 = gt;
@@ -160,7 +191,7 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     //   B lives on centres (c-1, c, c+1):
     //     B(d) = 1/8 (b[c-1]+b[c+1]) + 3/4 b[c] + d/2 (b[c+1]-b[c-1]) + d^2 (1/2 (b[c-1]+b[c+1]) - b[c])
     //   Non-relativistic: pre-scaled by (q/m) dt/2.
-    __syncwarp();  // the previous item's readers of coef_s / dest_s / tot_s are done
+    __syncwarp();  // the previous item's readers of coef / dest / tot are done
     if (lane < 24) {
       const int k = lane >> 3, w_ = lane & 7;
       R val = R(0);
@@ -176,19 +207,88 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
         }
         val *= hs;
       }
-      coef_s[warp][lane] = val;
+      sm.coef[lane] = val;
     } else if (lane < 27) {
       const int k = lane - 24;
       const int bk = k == 0 ? b : (k == 1 ? s * G + (c == 0 ? G - 1 : c - 1) : s * G + (c == G - 1 ? 0 : c + 1));
-      const long long o = bd.off[dst][bk];
-      dest_s[warp][k].base = bd.rec[dst] + (o >> 5) * (long long)kBlkElems;
-      dest_s[warp][k].cap = (unsigned)(bd.off[dst][bk + 1] - o);
-      dest_s[warp][k].bin = bk;
+      const int rk = 2 * bk + (k ? 1 : 0);  // own bin: block range; neighbours: single ranges
+      const long long o = bd.off[dst][rk];
+      sm.dest[k].base = bd.rec[dst] + (o >> 5) * (long long)kBlkElems;
+      sm.dest[k].cap = (unsigned)(bd.off[dst][rk + 1] - o);
+      sm.dest[k].bin = rk;
     }
     __syncwarp();
 
-    // lanes 0..2 claim slots for the destinations stay / left / right
-    unsigned* my_cursor = bd.cur[dst] + dest_s[warp][lane < 3 ? lane : 0].bin;
+    // ---- output bookkeeping (all warp-uniform; claims are made by lane 0 and stay pending in its register until broadcast)
+    unsigned pool_n = 0;                 // stayers in the pool
+    unsigned mix_head = 0, mix_tail = 0, mix_frozen = 0;  // movers: ring positions; entries [tail, tail + frozen) have claims
+    unsigned out_i = 0, runs_claimed = 0;  // output blocks written; runs of RUN blocks claimed
+    unsigned claim_run = 0, claim_l = 0, claim_r = 0;     // lane 0: next output run; frozen movers' slots in the left / right range
+    bool run_ok = false;                 // the current run lies inside the block range
+    R* out_ptr = nullptr;                // this lane's slot in the next output block
+    unsigned* const cur0 = bd.cur[dst] + sm.dest[0].bin;
+#if JIC_EXPERIMENT_NOD
+    R* nod_out = bd.rec[dst] + ((bd.off[dst][2 * b] + ((range & 1) ? bd.cnt[src][2 * b] : 0) + first) >> 5) * (long long)kBlkElems;
+    if (lane == 0) atomicAdd(cur0, (unsigned)n);
+#else
+    if (fast_bin) {
+      if (lane == 0) claim_run = atomicAdd(cur0, (unsigned)(RUN * kBlk));
+      runs_claimed = 1;
+    }
+#endif
+    // one full block (holes = NaN in d) -> the next slot of the claimed run.  `later` = upper bound of the particles that can still
+    // be written after this block (pool + unprocessed input): decides whether another run is claimed now, one run ahead.
+    auto emit_block = [&](R o_d, R o_v0, R o_v1, R o_v2, unsigned later) {
+      if ((out_i & (unsigned)(RUN - 1)) == 0u) {
+        const unsigned cl = __shfl_sync(FULL, claim_run, 0);
+        const DestSlot<R> ds = sm.dest[0];
+        run_ok = cl + (unsigned)(RUN * kBlk) <= ds.cap;
+        out_ptr = ds.base + (size_t)(cl >> 5) * kBlkElems + lane;
+        if (later > (unsigned)((RUN - 1) * kBlk)) {
+          if (lane == 0) claim_run = atomicAdd(cur0, (unsigned)(RUN * kBlk));
+          runs_claimed += 1;
+        }
+      }
+      if (run_ok) {
+        out_ptr[0] = o_d; out_ptr[kBlk] = o_v0; out_ptr[2 * kBlk] = o_v1; out_ptr[3 * kBlk] = o_v2;
+      } else if (o_d == o_d) {
+        store_slot(bd, dst, sm.dest[0].bin, 0xffffffffu, o_d, o_v0, o_v1, o_v2);  // -> overflow list (rare)
+      }
+      out_ptr += kBlkElems;
+      out_i += 1;
+    };
+    // movers: write the frozen entries to the slots claimed when they were frozen / freeze the next `cnt` entries
+    auto write_frozen = [&]() {
+      const unsigned e = (mix_tail + (unsigned)lane) & (unsigned)(kMixCap - 1);
+      const R t = sm.mix[0][e], o_v0 = sm.mix[1][e], o_v1 = sm.mix[2][e], o_v2 = sm.mix[3][e];
+      const bool act = (unsigned)lane < mix_frozen;
+      const bool right = act && t > R(0), left = act && !(t > R(0));
+      const unsigned mr = __ballot_sync(FULL, right), ml = __ballot_sync(FULL, left);
+      const unsigned base_r = __shfl_sync(FULL, claim_r, 0), base_l = __shfl_sync(FULL, claim_l, 0);
+      if (act) {
+        const DestSlot<R> ds = sm.dest[right ? 2 : 1];
+        const unsigned slot = (right ? base_r : base_l) + __popc((right ? mr : ml) & lt_mask);
+        const R dn = t - cell_shift(right, left, R(0));
+        if (slot < ds.cap) {
+          R* q = ds.base + (size_t)(slot >> 5) * kBlkElems + (slot & 31u);
+          q[0] = dn; q[kBlk] = o_v0; q[2 * kBlk] = o_v1; q[3 * kBlk] = o_v2;
+        } else {
+          store_slot(bd, dst, ds.bin, 0xffffffffu, dn, o_v0, o_v1, o_v2);
+        }
+      }
+      mix_tail += mix_frozen;
+      mix_frozen = 0;
+    };
+    auto freeze = [&](unsigned cnt) {
+      const unsigned e = (mix_tail + (unsigned)lane) & (unsigned)(kMixCap - 1);
+      const bool right = (unsigned)lane < cnt && sm.mix[0][e] > R(0);
+      const unsigned nr = __popc(__ballot_sync(FULL, right)), nl = cnt - nr;
+      if (lane == 0) {
+        if (nr) claim_r = atomicAdd(bd.cur[dst] + sm.dest[2].bin, nr);
+        if (nl) claim_l = atomicAdd(bd.cur[dst] + sm.dest[1].bin, nl);
+      }
+      mix_frozen = cnt;
+    };
 
     // moment accumulators (see the header): rho/J_y/J_z at the mid offset, J_x from the old and new offsets
     R r1 = 0, r2 = 0, rP = 0, rN = 0;
@@ -196,50 +296,23 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     R z0 = 0, z1 = 0, z2 = 0, zP = 0, zN = 0;
     R a1 = 0, a2 = 0, aP = 0, aN = 0;
     R s1 = 0, s2 = 0, sN = 0, sZ = 0, sP = 0;  // STAG
-    int n_slow = 0;  // warp-uniform: particles of this item that took the general path
-
-    // A particle is STORED one group (KB blocks) after its slot was claimed, so that the cursor atomic's round trip
-    // (> 1 us under load: profiles/r01_push_warpworkers_*) overlaps a whole group's arithmetic instead of stalling the warp.
-    // Until then its new state waits in the lane's own slot of a shared-memory stash (no cross-lane traffic, no conflicts)
-    // and only (destination, rank) and the claimed base stay in registers.  q_meta < 0 = nothing pending.
-    int q_meta[KB];
-    unsigned q_claim[KB];
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) { q_meta[kb] = -1; q_claim[kb] = 0; }
-    R* my_stash = &stash[warp][0][0] + lane;
-    auto retire = [&](int kb) {
-      const int kind = q_meta[kb] < 0 ? 0 : (q_meta[kb] & 3);
-      const unsigned base_slot = __shfl_sync(0xffffffffu, q_claim[kb], kind);
-      const DestSlot<R> ds = dest_s[warp][kind];
-      const unsigned sl_ = base_slot + ((unsigned)q_meta[kb] >> 2);
-      const bool pending = q_meta[kb] >= 0, fits = pending && sl_ < ds.cap;
-      const R* st_ = my_stash + kb * kBlkElems;
-      const R o_d = st_[0], o_v0 = st_[kBlk], o_v1 = st_[2 * kBlk], o_v2 = st_[3 * kBlk];
-      if (fits) {
-        R* q = ds.base + (size_t)(sl_ >> 5) * kBlkElems + (sl_ & 31u);
-        q[0] = o_d; q[kBlk] = o_v0; q[2 * kBlk] = o_v1; q[3 * kBlk] = o_v2;
-      }
-      if (__any_sync(0xffffffffu, pending && !fits)) {
-        if (pending && !fits) store_slot(bd, dst, ds.bin, sl_, o_d, o_v0, o_v1, o_v2);  // -> overflow list
-      }
-    };
+    int n_fast = 0;  // warp-uniform: particles of this item on the closed form
 
     for (int g = 0; g < ngroups; ++g, ++gt) {
       const unsigned slot = gt & (NS - 1);
       mbar_wait(bar_u32 + 8u * slot, (gt / NS) & 1u);
-      const R* stage = my_ring + slot * (KB * kBlkElems);
+      const R* stage_in = my_ring + slot * (KB * kBlkElems);
       // The KB particles of a lane go through the arithmetic TOGETHER (phases A-C are straight-line code over kb, so the
       // compiler interleaves the independent FP64 dependency chains and shares the coefficient loads); the warp-level
-      // bookkeeping (votes, claims, stash) follows per block in phase D.  Blocks past the end of the item run with every lane
-      // invalid: no early exit, the loop body stays one straight line.
+      // bookkeeping follows per block in phase D.  Blocks past the end of the item hold stale data and are masked out.
       R d[KB], v[KB][3], u[KB], tn[KB], tm[KB], vx_old[KB], ts[KB];
-      bool valid[KB], fast[KB], all_fast[KB];
+      bool fast[KB], all_fast[KB];
       // ---- A. take the particles
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        valid[kb] = (g * KB + kb) * kBlk + lane < n;
-        d[kb] = stage[kb * kBlkElems + lane];
-        v[kb][0] = stage[kb * kBlkElems + kBlk + lane]; v[kb][1] = stage[kb * kBlkElems + 2 * kBlk + lane]; v[kb][2] = stage[kb * kBlkElems + 3 * kBlk + lane];
+        d[kb] = stage_in[kb * kBlkElems + lane];
+        v[kb][0] = stage_in[kb * kBlkElems + kBlk + lane]; v[kb][1] = stage_in[kb * kBlkElems + 2 * kBlk + lane]; v[kb][2] = stage_in[kb * kBlkElems + 3 * kBlk + lane];
+        if (KB > 1 && kb > 0 && g * KB + kb >= nblk) d[kb] = hole;  // (the last group of an item with an odd number of blocks)
       }
       __syncwarp();  // every lane has taken its particles: the ring slot can be refilled
       if (lane == 0 && g + NS < ngroups) load_group(g + NS);
@@ -266,100 +339,180 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
           v[kb][1] = fma(fma(R2, B[0], fma(-R0, B[2], fma(Rt, B[1], R1))), inv, E[1]);
           v[kb][2] = fma(fma(R0, B[1], fma(-R1, B[0], fma(Rt, B[2], R2))), inv, E[2]);
         }
-        // offsets from node c in cells: new offset tn, mid offset tm
+        // offsets from node c in cells: new offset tn, mid offset tm.  A hole (d = NaN) fails the domain test by itself.
         u[kb] = v[kb][0] * cells_per_v;
         tn[kb] = d[kb] + u[kb];
         tm[kb] = fma(R(0.5), u[kb], d[kb]);
-        fast[kb] = valid[kb] && fast_bin && (fabs(tn[kb]) < R(1.5));
+        fast[kb] = fast_bin && (fabs(tn[kb]) < R(1.5));
         if (STAG) fast[kb] = fast[kb] && (fabs(ts[kb]) < R(1.5));
       }
-      // ---- C. deposit moments (all_fast: the common case, warp-uniform, no per-lane branches)
+      // ---- C. deposit moments
+      auto moments = [&](int kb) {
+        // truncated powers 4 P(t) = (y + |y|)^2 with y = t - 1/2, 4 N(t) likewise with y = -t - 1/2
+        const R tn_ = tn[kb], tm_ = tm[kb], vy = v[kb][1], vz = v[kb][2];
+        const R pn_ = (tn_ - R(0.5)) + fabs(tn_ - R(0.5)), nn_ = (-tn_ - R(0.5)) + fabs(-tn_ - R(0.5));
+        const R pm_ = (tm_ - R(0.5)) + fabs(tm_ - R(0.5)), nm_ = (-tm_ - R(0.5)) + fabs(-tm_ - R(0.5));
+        const R Pm = pm_ * pm_, Nm = nm_ * nm_, tm2 = tm_ * tm_;
+        a1 += u[kb]; a2 = fma(u[kb], tn_ + d[kb], a2); aP = fma(pn_, pn_, aP); aN = fma(nn_, nn_, aN);
+        r1 += tm_; r2 += tm2; rP += Pm; rN += Nm;
+        y0 += vy; y1 = fma(vy, tm_, y1); y2 = fma(vy, tm2, y2); yP = fma(vy, Pm, yP); yN = fma(vy, Nm, yN);
+        z0 += vz; z1 = fma(vz, tm_, z1); z2 = fma(vz, tm2, z2); zP = fma(vz, Pm, zP); zN = fma(vz, Nm, zN);
+        if (STAG) {
+          const R t_ = ts[kb];
+          if (quirk_bin) {
+            // The reference does not wrap the face weights of a particle whose x_n lies in the left half cell [-L/2, g_0): faces
+            // -2 and -1 are simply off its grid (make_cloud_faces).  The sums below wrap them onto faces G-2, G-1: take them back.
+            const R xi = t_ + quirk_shift;  // x_n in cells from the left wall
+            if (xi >= R(0) && xi < R(0.5)) {
+              const R a_ = p.sp_q[s] * p.inv_dx;
+              atomicAdd(acc + (size_t)G * kAccRow + (G - 2), -a_ * R(0.5) * (R(0.5) - xi) * (R(0.5) - xi));
+              atomicAdd(acc + (size_t)G * kAccRow + (G - 1), -a_ * (R(0.75) - xi * xi));
+            }
+          }
+          const R n_ = (-t_ - R(1)) + fabs(-t_ - R(1)), z_ = t_ + fabs(t_), p_ = (t_ - R(1)) + fabs(t_ - R(1));
+          s1 += t_; s2 = fma(t_, t_, s2); sN = fma(n_, n_, sN); sZ = fma(z_, z_, sZ); sP = fma(p_, p_, sP);
+        }
+      };
+      bool group_fast = true;
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb) all_fast[kb] = __all_sync(0xffffffffu, fast[kb]);
+      for (int kb = 0; kb < KB; ++kb) { all_fast[kb] = __all_sync(FULL, fast[kb]); group_fast = group_fast && all_fast[kb]; }
+      if (group_fast) {  // the common case, warp-uniform: one straight line over the KB particles of a lane
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) moments(kb);
+      } else {
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          if (fast[kb]) moments(kb);
+      }
+#if JIC_EXPERIMENT_NOD
+      // TIMING EXPERIMENT ONLY (wrong physics): every particle keeps its bin and slot -- the cost of the kernel without re-binning
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        if (all_fast[kb] || fast[kb]) {
-          // truncated powers 4 P(t) = (y + |y|)^2 with y = t - 1/2, 4 N(t) likewise with y = -t - 1/2
-          const R tn_ = tn[kb], tm_ = tm[kb], vy = v[kb][1], vz = v[kb][2];
-          const R pn_ = (tn_ - R(0.5)) + fabs(tn_ - R(0.5)), nn_ = (-tn_ - R(0.5)) + fabs(-tn_ - R(0.5));
-          const R pm_ = (tm_ - R(0.5)) + fabs(tm_ - R(0.5)), nm_ = (-tm_ - R(0.5)) + fabs(-tm_ - R(0.5));
-          const R Pm = pm_ * pm_, Nm = nm_ * nm_, tm2 = tm_ * tm_;
-          a1 += u[kb]; a2 = fma(u[kb], tn_ + d[kb], a2); aP = fma(pn_, pn_, aP); aN = fma(nn_, nn_, aN);
-          r1 += tm_; r2 += tm2; rP += Pm; rN += Nm;
-          y0 += vy; y1 = fma(vy, tm_, y1); y2 = fma(vy, tm2, y2); yP = fma(vy, Pm, yP); yN = fma(vy, Nm, yN);
-          z0 += vz; z1 = fma(vz, tm_, z1); z2 = fma(vz, tm2, z2); zP = fma(vz, Pm, zP); zN = fma(vz, Nm, zN);
-          if (STAG) {
-            const R t_ = ts[kb];
-            if (quirk_bin) {
-              // The reference does not wrap the face weights of a particle whose x_n lies in the left half cell [-L/2, g_0): faces
-              // -2 and -1 are simply off its grid (make_cloud_faces).  The sums below wrap them onto faces G-2, G-1: take them back.
-              const R xi = t_ + quirk_shift;  // x_n in cells from the left wall
-              if (xi >= R(0) && xi < R(0.5)) {
-                const R a_ = p.sp_q[s] * p.inv_dx;
-                atomicAdd(acc + (size_t)G * kAccRow + (G - 2), -a_ * R(0.5) * (R(0.5) - xi) * (R(0.5) - xi));
-                atomicAdd(acc + (size_t)G * kAccRow + (G - 1), -a_ * (R(0.75) - xi * xi));
+        if (g * KB + kb < nblk) {
+          R* q = nod_out + (size_t)(g * KB + kb) * kBlkElems + lane;
+          q[0] = d[kb]; q[kBlk] = v[kb][0]; q[2 * kBlk] = v[kb][1]; q[3 * kBlk] = v[kb][2];
+        }
+        n_fast += __popc(__ballot_sync(FULL, fast[kb]));
+      }
+      continue;
+#endif
+      // ---- D. per block: stayers keep their lane; holes are filled from the pool; movers are parked in the ring
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const bool fs = fast[kb];
+        const bool stay = fs && fabs(tn[kb]) < R(0.5);  // (false for a hole: NaN)
+        const unsigned ms = __ballot_sync(FULL, stay);
+        R o_d = tn[kb], o_v0 = v[kb][0], o_v1 = v[kb][1], o_v2 = v[kb][2];
+        if (ms != FULL) {
+          const bool mover = fs && !stay;
+          const unsigned mm = __ballot_sync(FULL, mover);
+          n_fast += __popc(ms | mm);
+          if (mm) {
+            if (mover) {
+              const unsigned e = (mix_head + __popc(mm & lt_mask)) & (unsigned)(kMixCap - 1);
+              sm.mix[0][e] = o_d; sm.mix[1][e] = o_v0; sm.mix[2][e] = o_v1; sm.mix[3][e] = o_v2;
+            }
+            mix_head += __popc(mm);
+          }
+          if (!all_fast[kb]) {
+            // a particle (not a hole) off the closed form: its velocity is final; boundary, deposit and re-insertion are k_push_general's
+            const bool general = !fs && d[kb] == d[kb];
+            const unsigned mg = __ballot_sync(FULL, general);
+            if (mg) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&hdr->gen_n, __popc(mg));
+              base = __shfl_sync(FULL, base, 0);
+              const int k = base + __popc(mg & lt_mask);
+              if (general) {
+                if (k < bd.gen_cap) {
+                  bd.gen_bin[k] = b; bd.gen_d[k] = d[kb]; bd.gen_vxold[k] = STAG ? vx_old[kb] : R(0);
+                  bd.gen_vx[k] = v[kb][0]; bd.gen_vy[k] = v[kb][1]; bd.gen_vz[k] = v[kb][2];
+                } else {
+                  atomicExch(&hdr->error, 1);
+                }
               }
             }
-            const R n_ = (-t_ - R(1)) + fabs(-t_ - R(1)), z_ = t_ + fabs(t_), p_ = (t_ - R(1)) + fabs(t_ - R(1));
-            s1 += t_; s2 = fma(t_, t_, s2); sN = fma(n_, n_, sN); sZ = fma(z_, z_, sZ); sP = fma(p_, p_, sP);
           }
+        } else {
+          n_fast += kBlk;
         }
-      }
-      // ---- D. per block: destination, slot claim, retire the block stashed one group ago, stash the new one
-#pragma unroll
-      for (int kb = 0; kb < KB; ++kb) {
-        // destination: 0 stay, 1 left, 2 right (3 = general path, -1 = no particle)
-        const bool go_r = fast[kb] && tn[kb] >= R(0.5), go_l = fast[kb] && tn[kb] < R(-0.5);
-        R dn = tn[kb];
-        if (go_r) dn -= R(1);
-        if (go_l) dn += R(1);
-        const int kind = fast[kb] ? (go_r ? 2 : (go_l ? 1 : 0)) : (valid[kb] ? 3 : -1);
-        // claim slots in the destination bins: one atomic per warp and destination, consumed one group later
-        const unsigned m1 = __ballot_sync(0xffffffffu, go_l), m2 = __ballot_sync(0xffffffffu, go_r);
-        const unsigned m0 = __ballot_sync(0xffffffffu, fast[kb]) & ~(m1 | m2);
-        const unsigned my_cnt = __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
-        unsigned claim = 0;
-        if (lane < 3 && my_cnt) claim = atomicAdd(my_cursor, my_cnt);
-        const unsigned rank = __popc((go_r ? m2 : (go_l ? m1 : m0)) & lt_mask);
-        retire(kb);
-        {
-          R* st_ = my_stash + kb * kBlkElems;
-          st_[0] = dn; st_[kBlk] = v[kb][0]; st_[2 * kBlk] = v[kb][1]; st_[3 * kBlk] = v[kb][2];
-        }
-        q_meta[kb] = fast[kb] ? (int)((rank << 2) | (unsigned)kind) : -1;
-        q_claim[kb] = claim;
-        if (!all_fast[kb]) {
-          const unsigned ms = __ballot_sync(0xffffffffu, kind == 3);
-          if (ms) {
-            n_slow += __popc(ms);
-            if (kind == 3) slow_tail(p, bd, dst, acc, s, node_pos(c, p) + d[kb] * p.dx, STAG ? vx_old[kb] : R(0), v[kb][0], v[kb][1], v[kb][2]);
+        if (fast_bin) {
+          if (pool_n < (unsigned)kBlk) {
+            // donor block: its stayers go to the pool
+            __syncwarp();
+            if (stay) {
+              const unsigned e = pool_n + __popc(ms & lt_mask);
+              sm.pool[0][e] = o_d; sm.pool[1][e] = o_v0; sm.pool[2][e] = o_v1; sm.pool[3][e] = o_v2;
+            }
+            pool_n += __popc(ms);
+          } else {
+            if (ms != FULL) {  // fill the holes from the top of the pool
+              __syncwarp();
+              if (!stay) {
+                const unsigned e = pool_n - 1u - __popc(~ms & lt_mask);
+                o_d = sm.pool[0][e]; o_v0 = sm.pool[1][e]; o_v1 = sm.pool[2][e]; o_v2 = sm.pool[3][e];
+              }
+              pool_n -= __popc(~ms);
+            }
+            const unsigned done = ((unsigned)(g * KB + kb) + 1u) * (unsigned)kBlk;
+            emit_block(o_d, o_v0, o_v1, o_v2, pool_n + (done < (unsigned)n ? (unsigned)n - done : 0u));
+          }
+          if (mix_head - mix_tail - mix_frozen >= (unsigned)kBlk) {  // 32 more movers: write the frozen ones, freeze these
+            __syncwarp();
+            if (mix_frozen) write_frozen();
+            freeze((unsigned)kBlk);
           }
         }
       }
     }
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) retire(kb);  // the last group of the item
+
+    // ---- close the item's output: the pool's remainder (last block padded with holes), the movers, unused claims
+    if (fast_bin && !JIC_EXPERIMENT_NOD) {
+      __syncwarp();
+      for (unsigned i0 = 0; i0 < pool_n; i0 += (unsigned)kBlk) {
+        const unsigned e = i0 + (unsigned)lane;
+        const bool ok = e < pool_n;
+        const unsigned ec = ok ? e : 0u;
+        const R o_d = ok ? sm.pool[0][ec] : hole;
+        emit_block(o_d, sm.pool[1][ec], sm.pool[2][ec], sm.pool[3][ec], pool_n - min(pool_n, i0 + (unsigned)kBlk));
+      }
+      if (mix_frozen) write_frozen();
+      while (mix_head != mix_tail) {
+        freeze(min((unsigned)kBlk, mix_head - mix_tail));
+        write_frozen();
+      }
+      // claimed but never written: the rest of the current run, and a whole run if the bound that claimed it was not reached
+      if (run_ok)
+        for (unsigned k = out_i & (unsigned)(RUN - 1); k != 0u && k < (unsigned)RUN; ++k) { out_ptr[0] = hole; out_ptr += kBlkElems; }
+      if (runs_claimed * (unsigned)RUN >= out_i + (unsigned)RUN) {
+        const unsigned cl = __shfl_sync(FULL, claim_run, 0);
+        const DestSlot<R> ds = sm.dest[0];
+        if (cl + (unsigned)(RUN * kBlk) <= ds.cap)
+          for (int k = 0; k < RUN; ++k) ds.base[(size_t)((cl >> 5) + k) * kBlkElems + lane] = hole;
+      }
+      __syncwarp();
+    }
 
     // ---- flush: warp totals of the moments -> 19 node values -> atomics on the raw (L2-resident) grid
-    if (n_slow < n) {
+    if (n_fast > 0) {
       R vals[18] = {r1, r2, rP, rN, y0, y1, y2, yP, yN, z0, z1, z2, zP, zN, a1, a2, aP, aN};
 #pragma unroll
       for (int j = 0; j < 18; ++j) {
         const R tsum = warp_sum(vals[j]);
-        if (lane == j) tot_s[warp][j] = tsum;
+        if (lane == j) sm.tot[j] = tsum;
       }
       if (STAG) {
         R sv[5] = {s1, s2, sN, sZ, sP};
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           const R tsum = warp_sum(sv[j]);
-          if (lane == j) tot_s[warp][18 + j] = tsum;
+          if (lane == j) sm.tot[18 + j] = tsum;
         }
       }
       __syncwarp();
       if (STAG && lane >= 19 && lane < 25) {  // rho(x_n) on the faces c-3..c+2 (the truncated-power sums carry a factor 4)
-        const R* tot = tot_s[warp];
-        const R X0 = (R)(n - n_slow), X1 = tot[18], X2 = tot[19], Nm = R(0.25) * tot[20], Z = R(0.25) * tot[21], Pp = R(0.25) * tot[22];
+        const R* tot = sm.tot;
+        const R X0 = (R)n_fast, X1 = tot[18], X2 = tot[19], Nm = R(0.25) * tot[20], Z = R(0.25) * tot[21], Pp = R(0.25) * tot[22];
         const int o = lane - 19;
         R val = o == 0 ? Nm
               : o == 1 ? X2 - R(3) * Nm - Z
@@ -371,8 +524,8 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
         if (val != R(0)) atomicAdd(acc + (size_t)G * kAccRow + mod_pos(c - 3 + o, G), val);
       }
       if (lane < 19) {
-        const R* tot = tot_s[warp];
-        const R cnt = (R)(n - n_slow);
+        const R* tot = sm.tot;
+        const R cnt = (R)n_fast;
         const int j = lane;
         R val;
         int node, comp;
@@ -401,10 +554,64 @@ __global__ void __launch_bounds__(kPushThreads, push_min_blocks<R>()) k_push(con
     }
   }
 
-  // ---- particles that did not fit their bin last step: general path, one by one
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1g  everything off the closed form, one thread per particle with the exact general code (slow_tail): global atomics on the raw
+//      grid, re-insertion into the destination's single range.  Kept out of k_push so that its hot loop has no calls (the call's
+//      register needs came on top of the 18 live accumulators: 203 registers wanted, 168 available, spills in the loop).
+//        (a) the work items of wall bins (non-periodic runs; every bin on tiny grids), straight from the store;
+//        (b) the particles k_push found off the closed form in this step (velocity already final);
+//        (c) the particles that did not fit their range last step (overflow list of the source buffer).
+//      On a periodic run at CFL <= 1 all three are empty and the kernel returns at once.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGeneralThreads = 256;
+static_assert(kGeneralThreads >= kSlowChunk, "one thread per slot of a wall-bin item");
+
+template <typename R, bool REL>
+__global__ void __launch_bounds__(kGeneralThreads) k_push_general(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
+                                                                  const R* __restrict__ F, R* __restrict__ acc) {
+  PlanHeader* hdr = bd.hdr;
+  const int src = hdr->flip, dst = src ^ 1;
+  const int G = p.G;
+  // (a) wall-bin items: CTAs stride over the item list (skipped on periodic runs: no wall bins)
+  if (bd.edge > 0) {
+    const int n_items = hdr->n_items;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int range = bd.item_bin[item];
+      const int b = range >> 1;
+      const int s = b / G, c = b - s * G;
+      if (!(c < bd.edge || c > G - 1 - bd.edge)) continue;
+      const int first = bd.item_first[item];
+      const int n = min(kSlowChunk, bd.cnt[src][range] - first);
+      const int i = threadIdx.x;
+      if (i < n) {
+        const R* q = slot_ptr(bd.rec[src], bd.off[src][range] + first + i);
+        const R d = q[0];
+        if (d == d) {
+          const R x_old = node_pos(c, p) + d * p.dx;
+          R v[3] = {q[kBlk], q[2 * kBlk], q[3 * kBlk]};
+          const R vx_old = v[0];
+          R E[3], B[3];
+          gather_fields(F, x_old, p, E, B);
+          if (REL) boris_velocity_relativistic(v, E, B, p.sp_q[s], p.sp_m[s], p.dt);
+          else boris_velocity(v, E, B, p.sp_qm[s], p.dt);
+          slow_tail(p, bd, dst, acc, s, x_old, vx_old, v[0], v[1], v[2]);
+        }
+      }
+    }
+  }
+  // (b) this step's general-path list
+  const int n_gen = min(hdr->gen_n, bd.gen_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gen; i += gridDim.x * blockDim.x) {
+    const int b = bd.gen_bin[i];
+    const int s = b / G, c = b - s * G;
+    slow_tail(p, bd, dst, acc, s, node_pos(c, p) + bd.gen_d[i] * p.dx, bd.gen_vxold[i], bd.gen_vx[i], bd.gen_vy[i], bd.gen_vz[i]);
+  }
+  // (c) particles that did not fit their range last step
   const int n_ov = min(hdr->ov_n[src], bd.ov_cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ov; i += gridDim.x * blockDim.x) {
-    const int b = bd.ov_bin[src][i];
+    const int b = bd.ov_bin[src][i] >> 1;
     const int s = b / G, c = b - s * G;
     const R x_old = node_pos(c, p) + bd.ov_d[src][i] * p.dx;
     R v[3] = {bd.ov_vx[src][i], bd.ov_vy[src][i], bd.ov_vz[src][i]};

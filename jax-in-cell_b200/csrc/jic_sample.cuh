@@ -52,7 +52,8 @@ __device__ __forceinline__ double jax_normal64(long long seed, long long i, long
 }
 
 struct SampleArgs {
-  long long count, offset;       // particles of this species, first row in the concatenated arrays
+  long long count, offset;       // particles of this species (the length of the reference's draws), first output row
+  long long first, n_local;      // the slice [first, first + n_local) of the species that is generated
   long long seed_position, seed_velocity;
   int random_positions[3], plus_minus[3];
   double amp[3], wavenumber[3];  // perturbation_amplitude, perturbation_wavenumber * 2 pi / box
@@ -64,8 +65,9 @@ struct SampleArgs {
 template <typename R>
 __global__ void __launch_bounds__(256) k_sample_species(const SampleArgs a, R* __restrict__ x0, R* __restrict__ v0) {
   const double lim = 0.99 * kC;  // _state_initialization.py:259-260
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.count; i += (long long)gridDim.x * blockDim.x) {
-    const long long row = 3 * (a.offset + i);
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < a.n_local; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = a.first + j;  // index inside the species' draw
+    const long long row = 3 * (a.offset + j);
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
       const double half = a.box[ax] / 2;

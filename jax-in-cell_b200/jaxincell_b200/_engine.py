@@ -11,7 +11,7 @@ from ._lib import JicError, Outputs, Params, Species
 
 _ENGINES = {"indexed": _lib.ENGINE_INDEXED, "binned": _lib.ENGINE_BINNED}
 _DEPOSITS = {"auto": _lib.DEPOSIT_AUTO, "global": _lib.DEPOSIT_GLOBAL_ATOMICS, "shared": _lib.DEPOSIT_SHARED_GRID}
-_HIST = ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities")
+_HIST = ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities", "kinetic_energy")
 
 
 def make_params(*, length, G, dt, n_species, length_y=0.0, length_z=0.0, pbl=0, pbr=0, fbl=0, fbr=0, filter_passes=5,
@@ -149,9 +149,13 @@ class HotPath:
             torch.cuda.current_stream(self.device).synchronize()
 
     # ---- stepping
-    def alloc_outputs(self, n_steps, fields=True, particles=False):
+    def alloc_outputs(self, n_steps, fields=True, particles=False, kinetic=False):
+        """History tensors for `run`.  kinetic=True: "kinetic_energy" (T, n_species) float64 -- the per-species kinetic energy of every
+        step, reduced on the device (one more pass over the velocities per step), for runs too large for the velocity history."""
         out = {}
         T, G, N = int(n_steps), self.G, self.N
+        if kinetic:
+            out["kinetic_energy"] = torch.zeros((T, self.n_species), dtype=torch.float64, device=self.device)
         if fields:
             for k in _HIST[:3]:
                 out[k] = torch.empty((T, G, 3), dtype=self.dtype, device=self.device)
@@ -161,10 +165,10 @@ class HotPath:
             out["velocities"] = torch.empty((T, N, 3), dtype=self.dtype, device=self.device)
         return out
 
-    def run(self, n_steps, outputs=None, fields=True, particles=False):
+    def run(self, n_steps, outputs=None, fields=True, particles=False, kinetic=False):
         """Advance n_steps; returns the dict of history tensors (allocated here unless `outputs` is given)."""
         if outputs is None:
-            outputs = self.alloc_outputs(n_steps, fields, particles)
+            outputs = self.alloc_outputs(n_steps, fields, particles, kinetic)
         o = Outputs()
         for k in _HIST:
             setattr(o, k, outputs[k].data_ptr() if k in outputs else None)
@@ -198,6 +202,11 @@ class HotPath:
         self._chk(self.lib.jic_kinetic_energy(self.ctx, self._ptr(ke), self._stream()))
         return ke
 
+    def check_status(self):
+        """Synchronise and raise JicError if a kernel set a sticky error flag (store capacity exhausted: particles dropped; a peer
+        rank missed the fused reduction).  `run` only enqueues: call this before trusting the histories of a single `run`."""
+        self._chk(self.lib.jic_check_status(self.ctx, self._stream()))
+
     def profile_steps(self, n_steps):
         """(ms in the particle kernels, ms in all-reduce + field kernel) summed over n_steps real steps (CUDA events)."""
         a, b = C.c_double(0.0), C.c_double(0.0)
@@ -229,10 +238,11 @@ class HotPath:
             pass
 
 
-def sample_particles(species_sampling, box_size, *, dtype=torch.float64, device=None, threefry_partitionable=True):
-    """jic_sample_particles: initial (x0, v0) device tensors from the reference's formulas and jax.random's streams
+def sample_particles(species_sampling, box_size, *, dtype=torch.float64, device=None, threefry_partitionable=True, rank=0, world=1):
+    """jic_sample_particles[_slice]: initial (x0, v0) device tensors from the reference's formulas and jax.random's streams
     (jaxincell/_state_initialization.py:51-85).  `species_sampling`: dicts with count, seed_position, seed_velocity and per-axis
-    triples random_positions, velocity_plus_minus, perturbation_amplitude, perturbation_wavenumber, vth_over_c, drift_speed."""
+    triples random_positions, velocity_plus_minus, perturbation_amplitude, perturbation_wavenumber, vth_over_c, drift_speed.
+    world > 1: only this rank's index slice of every species (`_parallel.shard_counts`), generated in place -- no scatter."""
     lib = _lib.load()
     if not torch.cuda.is_available():
         raise JicError("no CUDA device: jaxincell_b200 has no CPU path")
@@ -247,14 +257,21 @@ def sample_particles(species_sampling, box_size, *, dtype=torch.float64, device=
             arr[i].perturbation_wavenumber[a] = float(s["perturbation_wavenumber"][a])
             arr[i].vth_over_c[a] = float(s["vth_over_c"][a])
             arr[i].drift_speed[a] = float(s["drift_speed"][a])
-    N = int(sum(int(s["count"]) for s in species_sampling))
+    from ._parallel import shard_counts
+    firsts, locals_ = [], []
+    for s in species_sampling:
+        counts = shard_counts(int(s["count"]), world)
+        firsts.append(sum(counts[:rank])); locals_.append(counts[rank])
+    first = (C.c_int64 * len(firsts))(*firsts)
+    local = (C.c_int64 * len(locals_))(*locals_)
+    N = int(sum(locals_))
     x0 = torch.empty((N, 3), dtype=dtype, device=device)
     v0 = torch.empty((N, 3), dtype=dtype, device=device)
     box = (C.c_double * 3)(*[float(b) for b in box_size])
     with torch.cuda.device(device):
-        _lib.check(lib.jic_sample_particles(_lib.F64 if dtype == torch.float64 else _lib.F32, len(species_sampling), arr, box,
-                                            int(bool(threefry_partitionable)), C.c_void_p(x0.data_ptr()), C.c_void_p(v0.data_ptr()),
-                                            C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        _lib.check(lib.jic_sample_particles_slice(_lib.F64 if dtype == torch.float64 else _lib.F32, len(species_sampling), arr, first, local, box,
+                                                  int(bool(threefry_partitionable)), C.c_void_p(x0.data_ptr()), C.c_void_p(v0.data_ptr()),
+                                                  C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
     return x0, v0
 
 
@@ -280,6 +297,8 @@ def simulate_host(*, species, x0, v0, n_steps, ext_E=None, ext_B=None, dtype=np.
     if particles:
         res.setdefault("positions", np.empty((T, N, 3), dtype=dtype))
         res.setdefault("velocities", np.empty((T, N, 3), dtype=dtype))
+    if kw.pop("kinetic", False):
+        res.setdefault("kinetic_energy", np.zeros((T, len(species)), dtype=np.float64))
     o = Outputs()
     for k in _HIST:
         setattr(o, k, res[k].ctypes.data if k in res else None)

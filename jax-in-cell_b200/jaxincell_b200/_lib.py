@@ -47,7 +47,7 @@ class SpeciesSampling(C.Structure):
 
 class Outputs(C.Structure):
     _fields_ = [("electric_field", C.c_void_p), ("magnetic_field", C.c_void_p), ("current_density", C.c_void_p),
-                ("charge_density", C.c_void_p), ("positions", C.c_void_p), ("velocities", C.c_void_p)]
+                ("charge_density", C.c_void_p), ("positions", C.c_void_p), ("velocities", C.c_void_p), ("kinetic_energy", C.c_void_p)]
 
 
 # every symbol include/jic_b200.h declares: (name, restype, argtypes)
@@ -72,8 +72,11 @@ SYMBOLS = [
     ("jic_kinetic_energy", C.c_int, [_P, _P, _P]),
     ("jic_profile_steps", C.c_int, [_P, C.c_int64, _P, _P, _P]),
     ("jic_get_picard_iterations", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
+    ("jic_check_status", C.c_int, [_P, _P]),
     ("jic_launch_count", C.c_int64, [_P]),
     ("jic_sample_particles", C.c_int, [C.c_int32, C.c_int32, C.POINTER(SpeciesSampling), C.POINTER(C.c_double), C.c_int32, _P, _P, _P]),
+    ("jic_sample_particles_slice", C.c_int, [C.c_int32, C.c_int32, C.POINTER(SpeciesSampling), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_double), C.c_int32, _P, _P, _P]),
     ("jic_simulate_host", C.c_int, [C.POINTER(Params), C.POINTER(Species), _P, _P, _P, _P, C.c_int64, C.POINTER(Outputs), _P, _P, _P]),
 ]
 
