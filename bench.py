@@ -7,7 +7,10 @@
 One JSON line on rank 0.  `value` is device-timed (CUDA events around the graph-captured time loop, barrier + sync on
 both sides, max over ranks) with the particles resident in HBM; `e2e` is the same metric through the host-buffer
 entry point (pinned host -> device copies of the initial particles and device -> host copies of the field histories
-inside the timed region).  Weak scaling: every rank owns --particles macro-particles.
+inside the timed region).  Weak scaling (default): every rank owns --particles macro-particles; --scaling strong: the
+ranks share --total-particles.  Before anything is timed, `parity` steps a small plasma of the same shape on the same
+ranks and compares it with the compiled oracle (checker only); `sustained` repeats the timed replay until the clocks
+have settled under the power cap; `roofline.kernel_ms` is taken by the push kernel itself inside the timed replay.
 """
 import argparse
 import json
@@ -148,7 +151,9 @@ def peaks():
 def measured_traffic(dtype, engine, n_particles):
     """dram__bytes_read.sum + dram__bytes_write.sum of one push launch from the committed ncu capture (profiles/), scaled to this
     run's particle count (the kernel streams every particle once, so its traffic is linear in N); None when there is no capture."""
-    path = os.path.join(ROOT, "profiles", "r01_push_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_push_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_push_traffic.json")
     if engine != "binned" or not os.path.exists(path):
         return None
     rec = json.load(open(path)).get(dtype)
@@ -286,6 +291,82 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def parity_check(args, torch, dist, device, rank, world, engine):
+    """N-rank parity where the driver sees it: a small plasma of the bench's shape (same grid, geometry, distributions and filter),
+    index-sharded over the ranks exactly like the timed run, stepped through the same kernels and the same grid reduction; rank 0
+    compares every step's E, B, J, rho with the compiled oracle (checker only) and all ranks compare their final fields bit for bit
+    with rank 0's."""
+    import numpy as np
+    from jaxincell_b200 import HotPath
+    from jaxincell_b200._parallel import shard_particles, shard_species
+    from oracle import c_port as CP
+    n_total, T = args.parity_particles, args.parity_steps
+
+    class A:
+        grid, particles = args.grid, n_total
+    w = workload(A, 1)
+    x0, v0, q, m, qm = sample_plasma(w, n_total, np)
+    ne = n_total // 2
+    species = [dict(count=ne, q=float(q[0]), m=float(m[0]), qm=float(qm[0])), dict(count=n_total - ne, q=float(q[-1]), m=float(m[-1]), qm=float(qm[-1]))]
+    xs, vs, _ = shard_particles(x0, v0, species, rank, world)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    hp = HotPath(species=shard_species(species, rank, world), dtype=dtype, length=w["length"], G=w["G"], dt=w["dt"], engine=engine)
+    if world > 1:
+        hp.comm_init_from_torch()
+    hp.set_external_fields(None, None)
+    hp.initialize(torch.from_numpy(xs).to(device=device, dtype=dtype), torch.from_numpy(vs).to(device=device, dtype=dtype))
+    out = hp.run(T)
+    hp.check_status()
+    mode = hp.comm_mode()
+    keys = ("electric_field", "magnetic_field", "current_density", "charge_density")
+    identical = True
+    if world > 1:
+        for k in keys:
+            ref0 = out[k].clone()
+            dist.broadcast(ref0, src=0)
+            same = torch.tensor([1 if torch.equal(ref0, out[k]) else 0], device=device)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            identical = identical and bool(int(same.item()))
+    res = None
+    if rank == 0:
+        CP.load()
+        ref = CP.run(x0, v0, q, m, qm, length=w["length"], G=w["G"], dt=w["dt"], total_steps=T, keep_particles=False,
+                     threads=len(os.sched_getaffinity(0)) or 1, solver=dict(filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4)))
+        worst, per_key = 0.0, {}
+        for k in keys:
+            a, b = out[k].double().cpu().numpy(), np.asarray(ref[k])
+            # per step (row-wise): max |a - b| over the grid / max |b| over the grid of that step
+            den = np.maximum(np.abs(b).reshape(T, -1).max(axis=1), 1e-300)
+            err = float((np.abs(a - b).reshape(T, -1).max(axis=1) / den).max())
+            per_key[k] = err
+            worst = max(worst, err)
+        tol = 1e-5 if args.dtype == "f64" else 1e-3
+        res = {"ok": bool(worst < tol and identical), "max_rel_err": worst, "per_key": per_key, "tolerance": tol, "ranks_identical": identical,
+               "norm": "per step: max|cuda - oracle| over the grid / max|oracle| over the grid, worst step", "steps": T, "particles": n_total,
+               "ranks": world, "grid_reduction": mode, "checker": "oracle/c/jic_oracle.c (CPU, test infrastructure)"}
+    hp.close()
+    return res
+
+
+def timed_run(hp, torch, dist, world, K, outs, barrier):
+    """K graph-replayed steps bracketed by barrier + synchronize; returns (ms, device-side ms of the push kernel inside the same replay)."""
+    barrier()
+    try:
+        hp.push_kernel_time(reset=True)
+        have_ktime = True
+    except Exception:  # noqa: BLE001  (INDEXED engine or an older library)
+        have_ktime = False
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    hp.run(K, outputs=outs)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kms, kn = hp.push_kernel_time(reset=True) if have_ktime else (0.0, 0)
+    return ms, (kms / kn if kn else None), kn
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,6 +374,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=100_000_000, help="macro-particles PER GPU (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-particles", type=int, default=100_000_000, help="macro-particles over ALL GPUs (--scaling strong)")
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--engine", default=os.environ.get("JIC_BENCH_ENGINE", "auto"))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
@@ -300,10 +383,18 @@ def main():
     ap.add_argument("--deposit", default="auto", choices=["auto", "global", "shared"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-f32", action="store_true")
+    ap.add_argument("--parity-particles", type=int, default=2_000_000)
+    ap.add_argument("--parity-steps", type=int, default=10)
+    ap.add_argument("--sustained-seconds", type=float, default=1.5)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    # the checker / CPU baseline is OpenMP code: its idle threads must sleep, not spin, while the GPU legs are timed
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     import torch
     import torch.distributed as dist
     from jaxincell_b200 import HotPath, JicError
@@ -329,6 +420,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    if args.scaling == "strong":  # fixed total work: every rank owns 1/world of --total-particles
+        args.particles = args.total_particles // world
     w = workload(args, world)
     engine = args.engine
     if engine == "auto":
@@ -337,6 +430,24 @@ def main():
             HotPath(species=[dict(count=8, q=1.0, m=1.0, qm=1.0)], length=1.0, G=8, dt=1e-9, engine="binned").close()
         except JicError:
             engine = "indexed"
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity first (small, same shape, same sharding and reduction): a fast wrong answer is not a result
+    parity = None
+    if not args.no_parity:
+        all_now = os.sched_getaffinity(0)
+        if rank == 0:
+            os.sched_setaffinity(0, all_cpus)  # the checker may use every host core
+        parity = parity_check(args, torch, dist, device, rank, world, engine)
+        if rank == 0:
+            os.sched_setaffinity(0, all_now)
+        barrier()
+
     hp = HotPath(species=w["species"], dtype=dtype, length=w["length"], G=w["G"], dt=w["dt"], engine=engine, deposit=args.deposit)
     if world > 1:
         hp.comm_init_from_torch()
@@ -346,12 +457,6 @@ def main():
     hp.initialize(x0, v0)
     N, G, K, W = hp.N, hp.G, args.steps, max(args.warmup, 3)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     outs = hp.alloc_outputs(K)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -360,25 +465,22 @@ def main():
     hp.run(K, outputs=outs)  # untimed: instantiates the CUDA graphs the timed call replays
     barrier()
     l0 = hp.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     m0 = sampler.mark() if sampler else 0
-    e0.record()
-    hp.run(K, outputs=outs)
-    e1.record()
-    barrier()
+    ms, kernel_ms_graph, kernel_launches = timed_run(hp, torch, dist, world, K, outs, barrier)
     m1 = sampler.mark() if sampler else 0
-    ms = e0.elapsed_time(e1)
     launches = hp.launch_count() - l0
-    # dominant kernel, timed live with CUDA events on its own stream (jic_profile_steps), a few more real steps
+    hp.check_status()
+    # the same kernels outside the graph, CUDA events around the particle kernel(s) and the grid part of every step (kept as a
+    # cross-check of the in-graph figure; its launches are not overlapped, so it reads a little higher)
     n_prof = min(K, 10)
     ms_push, ms_grid = hp.profile_steps(n_prof)
     barrier()
     clocks = sampler.stop(m0, max(m1, m0 + 1)) if sampler else None
-    t = torch.tensor([ms, ms_push / n_prof, ms_grid / n_prof], dtype=torch.float64, device=device)
+    t = torch.tensor([ms, kernel_ms_graph if kernel_ms_graph is not None else ms_push / n_prof, ms_push / n_prof, ms_grid / n_prof],
+                     dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_push_step, ms_grid_step = (float(v) for v in t.cpu())
+    ms, kernel_ms, ms_push_step, ms_grid_step = (float(v) for v in t.cpu())
     value = N * world * K / (ms * 1e-3)
     energy_ok = bool(torch.isfinite(outs["electric_field"][-1]).all().item())
 
@@ -405,6 +507,7 @@ def main():
                 h.copy_(o2[k], non_blocking=True)
             barrier()
             t2 = time.perf_counter()
+        hp.check_status()
         el = t2 - t0
         tt = torch.tensor([el], dtype=torch.float64, device=device)
         if world > 1:
@@ -420,31 +523,107 @@ def main():
                        f"histories, on an existing context; second of two identical passes (the first one creates the staging buffers)"}
         ok2 = bool(torch.isfinite(host_out["electric_field"][-1]).all().item())
         energy_ok = energy_ok and ok2
+        del hx, hv, host_out, dev_out
+    # ---- sustained: the same K-step replay repeated until the board has been under load for a while (power cap, clocks settle)
+    sustained = None
+    if not args.no_sustained:
+        s2 = ClockSampler(local) if rank == 0 else None
+        if s2:
+            s2.start()
+        outs = hp.alloc_outputs(K)
+        hp.run(K, outputs=outs)  # (after the e2e leg re-initialised the context: the same state, graphs already instantiated)
+        reps, t_start = [], time.perf_counter()
+        budget = torch.tensor([0.0], device=device)
+        while True:
+            ms_r, k_r, _ = timed_run(hp, torch, dist, world, K, outs, barrier)
+            tt = torch.tensor([ms_r, k_r if k_r is not None else 0.0], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            reps.append(tuple(float(v) for v in tt.cpu()))
+            budget[0] = 1.0 if (time.perf_counter() - t_start) >= args.sustained_seconds or len(reps) >= 400 else 0.0
+            if world > 1:
+                dist.all_reduce(budget, op=dist.ReduceOp.MAX)
+            if budget.item() > 0:
+                break
+        c2 = s2.stop() if s2 else None
+        tail = sorted(r[0] for r in reps[len(reps) // 2:])  # the second half: after the clocks have settled
+        med = tail[len(tail) // 2]
+        ktail = sorted(r[1] for r in reps[len(reps) // 2:])
+        sustained = {"value": N * world * K / (med * 1e-3), "unit": "particle-steps/s", "ms_per_step": med / K, "kernel_ms": ktail[len(ktail) // 2],
+                     "replays": len(reps), "steps_per_replay": K, "seconds": time.perf_counter() - t_start,
+                     "what": f"median over the second half of {len(reps)} back-to-back replays of the same {K}-step graph loop", "clocks": c2}
+
     hp.close()
+    torch.cuda.empty_cache()
+
+    # ---- the same workload in fp32 (sub-record; the headline stays the reference's own precision)
+    f32 = None
+    if not args.no_f32 and args.dtype == "f64" and engine == "binned":
+        try:
+            hp32 = HotPath(species=w["species"], dtype=torch.float32, length=w["length"], G=w["G"], dt=w["dt"], engine=engine)
+            if world > 1:
+                hp32.comm_init_from_torch()
+            xa, va = make_particles(w, torch, device, torch.float32, 1701 + rank, args.order)
+            hp32.set_external_fields(None, None)
+            hp32.initialize(xa, va)
+            del xa, va
+            o32 = hp32.alloc_outputs(K)
+            hp32.run(W, outputs=hp32.alloc_outputs(W))
+            hp32.run(K, outputs=o32)
+            ms32, k32, _ = timed_run(hp32, torch, dist, world, K, o32, barrier)
+            hp32.check_status()
+            t32 = torch.tensor([ms32, k32 if k32 is not None else 0.0], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+            ms32, k32 = (float(v) for v in t32.cpu())
+            f32 = {"value": N * world * K / (ms32 * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms32 / K, "kernel_ms": k32,
+                   "finite": bool(torch.isfinite(o32["electric_field"][-1]).all().item())}
+            hp32.close()
+        except Exception as e:  # noqa: BLE001
+            f32 = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_src = peaks()
         bpp = BYTES_PER_PARTICLE_STEP[args.dtype]
-        achieved = bpp * N / (ms_push_step * 1e-3) / 1e9
+        achieved = bpp * N / (kernel_ms * 1e-3) / 1e9
+        in_graph = kernel_ms_graph is not None
         line = {
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": f"synthetic two-beam plasma (SURVEY 8d config 5): G={G}, {N} macro-particles per GPU, CFL 1, periodic, "
-                                   f"filter 5/0.5/(1,2,4), x order {args.order}", "engine": engine, "particles_per_gpu": N, "grid": G,
+            "config": {"workload": f"synthetic two-beam plasma (SURVEY 8d config 5): G={G}, {N} macro-particles per GPU"
+                                   + (f" ({N * world} in total, strong scaling)" if args.scaling == "strong" else "")
+                                   + f", CFL 1, periodic, filter 5/0.5/(1,2,4), x order {args.order}", "engine": engine, "particles_per_gpu": N, "grid": G,
                        "grid_reduction": {"single": "none (one rank)", "nccl": "NCCL all-reduce of the raw grid before the field kernel",
                                           "fused": "fused into the field kernel: peers' raw grids read over NVLink (CUDA IPC), summed in rank order"}[reduction],
                        "l2": "particle state (>= 3.2 GB per GPU) is far larger than L2; no flush needed",
-                       "untimed_steps_before_timing": W + K},
+                       "untimed_steps_before_timing": W + K,
+                       "timed_region": f"{K} steps = {ms:.1f} ms: a burst at boost clocks when K is small; see `sustained` for the figure under the power cap"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.dtype, engine, N), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_push_traffic.json)",
+                         "traffic": measured_traffic(args.dtype, engine, N),
+                         "traffic_unit": "bytes per launch; NOT measured by this run: dram__bytes_read + dram__bytes_write of one launch from the committed "
+                                         "ncu capture (profiles/), scaled to this run's particle count",
                          "algorithmic_bytes_per_launch": bpp * N,
                          "peak_source": peak_src, "kernel": "k_step (fused gather+push+BC+deposit)" if engine == "indexed" else "k_push_binned",
-                         "kernel_ms": ms_push_step, "grid_part_ms": ms_grid_step,
+                         "kernel_ms": kernel_ms,
+                         "kernel_ms_source": ("device-side %globaltimer span (first CTA in, last CTA out) of k_push, averaged over the launches INSIDE the timed "
+                                              "graph replay (jic_push_kernel_time)" if in_graph else "CUDA events around the kernel, separate un-graphed pass"),
+                         "grid_part_ms": ms / K - kernel_ms if in_graph else ms_grid_step,
+                         "ungraphed_cross_check": {"kernel_ms": ms_push_step, "grid_part_ms": ms_grid_step,
+                                                   "how": "jic_profile_steps: CUDA events around the particle kernel(s) and the grid part, launches not overlapped"},
                          "algorithmic_bytes": f"{bpp} B per particle-step x {N} particles per launch"},
             "finite": energy_ok,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if sustained is not None:
+            sustained["roofline_frac"] = (bpp * N / (sustained["kernel_ms"] * 1e-3) / 1e9 / peak) if sustained["kernel_ms"] else None
+            line["sustained"] = sustained
+        if f32 is not None:
+            if "value" in f32:
+                f32["roofline_frac"] = (32 * N / (f32["kernel_ms"] * 1e-3) / 1e9 / peak) if f32["kernel_ms"] else None
+            line["extra"] = {"f32": f32}
         if clocks:
             line["clocks"] = clocks
         if e2e:

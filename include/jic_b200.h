@@ -186,6 +186,11 @@ int jic_get_picard_iterations(jic_context* ctx, int64_t* last_step, int64_t* tot
  * (jic_simulate_host does) -- otherwise the flags are only seen by the NEXT jic_run / jic_get_particles.
  * The reference has no counterpart: its arrays cannot overflow (jaxincell/_simulation.py:228-257 scans fixed-shape carries). */
 int jic_check_status(jic_context* ctx, void* stream);
+/* Measurement aid, BINNED engine: device-side duration of the push kernel (k_push), summed over its launches since the last reset.
+ * Every CTA stamps %globaltimer on entry and exit; the span first-in .. last-out of a launch is accumulated on the device, so the
+ * figure is valid for launches inside CUDA-graph replays (the same replays jic_run's throughput is measured on), where events around
+ * single kernels are not available.  Synchronises the stream.  reset != 0 zeroes the sum afterwards. */
+int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, int32_t reset, void* stream);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 

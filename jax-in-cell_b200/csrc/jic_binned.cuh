@@ -807,19 +807,19 @@ struct BinnedStore {
     return JIC_OK;
   }
 
-  int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, cudaStream_t st) {
+  int step(Engine& e, const DevParams<R>& dp, const R* F, R* acc, RunControl* ctl, cudaStream_t st) {
     const int g = n_sm * push_min_blocks<R>();
     const size_t sm = push_smem_bytes<R>();
     if (dp.stag) {
-      if (dp.relativistic) k_push<R, true, true><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
-      else k_push<R, false, true><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
+      if (dp.relativistic) k_push<R, true, true><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc, ctl);
+      else k_push<R, false, true><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc, ctl);
     } else {
-      if (dp.relativistic) k_push<R, true, false><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
-      else k_push<R, false, false><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc);
+      if (dp.relativistic) k_push<R, true, false><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc, ctl);
+      else k_push<R, false, false><<<g, push_threads<R>(), sm, st>>>(dp, bd, F, acc, ctl);
     }
     // everything off the closed form: wall-bin items, this step's general-path list, last step's overflow list (usually all empty)
-    if (dp.relativistic) k_push_general<R, true><<<n_sm * 4, kGeneralThreads, 0, st>>>(dp, bd, F, acc);
-    else k_push_general<R, false><<<n_sm * 4, kGeneralThreads, 0, st>>>(dp, bd, F, acc);
+    if (dp.relativistic) k_push_general<R, true><<<n_sm * 4, kGeneralThreads, 0, st>>>(dp, bd, F, acc, ctl);
+    else k_push_general<R, false><<<n_sm * 4, kGeneralThreads, 0, st>>>(dp, bd, F, acc, ctl);
     e.launches += 2;
     return JIC_OK;
   }

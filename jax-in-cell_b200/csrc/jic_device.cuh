@@ -30,7 +30,16 @@ struct RunControl {
   long long hist_row;  // row of the history buffers the next step writes
   void* hist[7];       // jic_outputs of the current jic_run (E, B, J, rho, positions, velocities, kinetic energy); read by the kernels at
                        // run time so that one captured graph serves every set of output buffers
+  // device-side timing of the binned push kernel (%globaltimer): first CTA in, last CTA out of the current launch; the kernel behind
+  // it folds the difference into the running sum (jic_push_kernel_time) -- valid inside CUDA-graph replays, where events are not
+  unsigned long long push_t0, push_t1, push_ns, push_launches;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <typename R>
 struct DevParams {

@@ -479,6 +479,7 @@ struct EngineT : Engine {
     JIC_CUDA(cudaMemsetAsync(acc2, 0, (size_t)dp.G * (kAccRow + 1) * sizeof(R), st));
     JIC_CUDA(cudaMemsetAsync(mc_done, 0, sizeof(unsigned), st));
     JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
+    JIC_CUDA(cudaMemsetAsync(&ctl->push_t0, 0xFF, sizeof(unsigned long long), st));
     par = 0;
     return JIC_OK;
   }
@@ -634,7 +635,7 @@ struct EngineT : Engine {
       launches += 1;
       return JIC_OK;
     }
-    return bins.step(*this, dp, F, acc, st);
+    return bins.step(*this, dp, F, acc, ctl, st);
   }
 
   // grid part of a step.  BINNED: the plan of the next push only depends on the push that just ran, so it runs on a side
@@ -829,6 +830,19 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
+  // device-timed push kernel: summed %globaltimer span (first CTA in, last CTA out) of the launches since the last reset
+  int push_kernel_time(double* ms_sum, long long* n_launches, int reset, cudaStream_t st) override {
+    RunControl h;
+    JIC_CUDA(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    JIC_CUDA(cudaStreamSynchronize(st));
+    if (ms_sum) *ms_sum = (double)h.push_ns * 1e-6;
+    if (n_launches) *n_launches = (long long)h.push_launches;
+    if (reset) {
+      JIC_CUDA(cudaMemsetAsync(&ctl->push_ns, 0, 2 * sizeof(unsigned long long), st));
+    }
+    return JIC_OK;
+  }
+
   // sticky device-side error flags (synchronises the stream): a peer that missed the fused barrier, exhausted store capacity
   int check_status(cudaStream_t st) override {
     if (fused()) {
@@ -988,6 +1002,13 @@ int jic_get_particles(jic_context* ctx, void* x, void* v, uint8_t* alive, void* 
 int jic_kinetic_energy(jic_context* ctx, double* out, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->kinetic(out, (cudaStream_t)st); }
 int jic_profile_steps(jic_context* ctx, int64_t n, double* ms_push, double* ms_fields, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->profile(n, ms_push, ms_fields, (cudaStream_t)st); }
 int jic_check_status(jic_context* ctx, void* st) { CTX_OR_FAIL(ctx); return ctx->eng->check_status((cudaStream_t)st); }
+int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, int32_t reset, void* st) {
+  CTX_OR_FAIL(ctx);
+  long long n = 0;
+  int rc = ctx->eng->push_kernel_time(ms_sum, &n, reset, (cudaStream_t)st);
+  if (n_launches) *n_launches = n;
+  return rc;
+}
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
 int jic_get_picard_iterations(jic_context* ctx, int64_t* last, int64_t* total, void* st) {
   CTX_OR_FAIL(ctx);

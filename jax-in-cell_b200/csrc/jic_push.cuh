@@ -123,8 +123,9 @@ constexpr size_t push_smem_bytes() { return sizeof(PushWarpSmem<R>) * push_warps
 // reference drops the weight of faces -1 and -2 instead of wrapping it (make_cloud_faces).
 template <typename R, bool REL, bool STAG>
 __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
-                                                                       const R* __restrict__ F, R* __restrict__ acc) {
+                                                                       const R* __restrict__ F, R* __restrict__ acc, RunControl* __restrict__ ctl) {
   constexpr int NS = push_stages<R>(), KB = kPushStageBlocks, RUN = kPushRun;
+  if (threadIdx.x == 0) atomicMin(&ctl->push_t0, global_timer_ns());
   constexpr unsigned kBlockBytes = kBlkElems * sizeof(R);
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char push_smem_raw[];
@@ -554,6 +555,8 @@ __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p
     }
   }
 
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(&ctl->push_t1, global_timer_ns());
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -570,10 +573,14 @@ static_assert(kGeneralThreads >= kSlowChunk, "one thread per slot of a wall-bin 
 
 template <typename R, bool REL>
 __global__ void __launch_bounds__(kGeneralThreads) k_push_general(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
-                                                                  const R* __restrict__ F, R* __restrict__ acc) {
+                                                                  const R* __restrict__ F, R* __restrict__ acc, RunControl* __restrict__ ctl) {
   PlanHeader* hdr = bd.hdr;
   const int src = hdr->flip, dst = src ^ 1;
   const int G = p.G;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // fold the push kernel's device-side duration into the running sum, re-arm the stamps
+    if (ctl->push_t1 > ctl->push_t0) { ctl->push_ns += ctl->push_t1 - ctl->push_t0; ctl->push_launches += 1; }
+    ctl->push_t0 = ~0ull; ctl->push_t1 = 0ull;
+  }
   // (a) wall-bin items: CTAs stride over the item list (skipped on periodic runs: no wall bins)
   if (bd.edge > 0) {
     const int n_items = hdr->n_items;

@@ -213,6 +213,13 @@ class HotPath:
         self._chk(self.lib.jic_profile_steps(self.ctx, int(n_steps), C.byref(a), C.byref(b), self._stream()))
         return a.value, b.value
 
+    def push_kernel_time(self, reset=True):
+        """(summed device-side ms of the binned push kernel, number of launches) since the last reset -- %globaltimer stamps taken
+        by the kernel itself, valid inside graph replays."""
+        a, n = C.c_double(0.0), C.c_int64(0)
+        self._chk(self.lib.jic_push_kernel_time(self.ctx, C.byref(a), C.byref(n), int(bool(reset)), self._stream()))
+        return a.value, n.value
+
     def picard_iterations(self):
         """Crank-Nicolson: (Picard iterations of the last step, of all steps so far)."""
         a, b = C.c_int64(0), C.c_int64(0)

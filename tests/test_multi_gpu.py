@@ -1,5 +1,6 @@
-"""Two ranks, two GPUs, one reduction of the raw grid per step (NCCL all-reduce, or fused into the field kernel over peer memory): fields must match the single-rank oracle and be
-bit-identical across ranks.  Skipped unless the box has >= 2 GPUs (gpurun --gpus 2)."""
+"""2, 4 or 8 ranks, one GPU each, one reduction of the raw grid per step (NCCL all-reduce, or fused into the field kernel over peer
+memory): fields must match the single-rank oracle and be bit-identical across ranks.  Every world size the box has the
+GPUs for runs; the others are skipped (gpurun --gpus 2 / 4 / 8)."""
 import os
 import socket
 
@@ -61,24 +62,27 @@ def _worker(rank, world, port, engine, q, G=64, p2p=True):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("engine,G,p2p", [("indexed", 64, True), ("binned", 64, True), ("binned", 512, True), ("indexed", 300, True),
-                                          ("binned", 512, False)])
-def test_two_gpus_match_single_rank_oracle(engine, G, p2p):
+                                          ("binned", 512, False), ("binned", 4096, True)])
+def test_n_gpus_match_single_rank_oracle(engine, G, p2p, world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world > 2 and (engine, G) not in (("binned", 512), ("binned", 4096)):
+        pytest.skip("the small-grid / INDEXED variants are covered at two ranks")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, engine, q, G, p2p)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, engine, q, G, p2p)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=240) for _ in procs]
     for pr in procs:
         pr.join(timeout=60)
     want = "ok:fused" if (p2p and G >= 256) else "ok:nccl"
-    assert sorted(res) == [(0, want), (1, want)], res
+    assert sorted(res) == [(r, want) for r in range(world)], res
 
 
 def _worker_modes(rank, world, port, mode, q):
@@ -126,19 +130,20 @@ def _worker_modes(rank, world, port, mode, q):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("mode", ["field_solver", "crank_nicolson"])
-def test_two_gpus_field_solver_and_crank_nicolson(mode):
+def test_n_gpus_field_solver_and_crank_nicolson(mode, world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_modes, args=(r, 2, port, mode, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_modes, args=(r, world, port, mode, q)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=240) for _ in procs]
     for pr in procs:
         pr.join(timeout=60)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
