@@ -67,6 +67,7 @@ class HotPath:
         self.species = make_species(species)
         self.N = int(sum(int(s["count"]) for s in species))
         self.G = self.params.n_grid
+        self.n_species = len(species)
         self.ctx = C.c_void_p()
         _lib.check(self.lib.jic_create(C.byref(self.params), self.species, C.byref(self.ctx)))
         self._keep = []
@@ -102,6 +103,9 @@ class HotPath:
     def set_external_fields(self, ext_E=None, ext_B=None):
         e = None if ext_E is None else self._dev(ext_E, torch.float32)
         b = None if ext_B is None else self._dev(ext_B, torch.float32)
+        for name, a in (("ext_E", e), ("ext_B", b)):  # the library reads exactly G * 3 floats from each
+            if a is not None and tuple(a.shape) != (self.G, 3):
+                raise JicError(f"{name} must have shape ({self.G}, 3), got {tuple(a.shape)}")
         self._chk(self.lib.jic_set_external_fields(self.ctx, self._ptr(e), self._ptr(b), self._stream()))
         self._keep = [e, b]
 
@@ -170,9 +174,17 @@ class HotPath:
         if outputs is None:
             outputs = self.alloc_outputs(n_steps, fields, particles, kinetic)
         o = Outputs()
+        T = int(n_steps)
         for k in _HIST:
+            if k in outputs:  # the library writes T rows of the full shape: check before handing over a raw pointer
+                t = outputs[k]
+                want = {"charge_density": (T, self.G), "positions": (T, self.N, 3), "velocities": (T, self.N, 3),
+                        "kinetic_energy": (T, self.n_species)}.get(k, (T, self.G, 3))
+                wdt = torch.float64 if k == "kinetic_energy" else self.dtype
+                if tuple(t.shape) != want or t.dtype != wdt or not t.is_contiguous() or t.device != self.device:
+                    raise JicError(f"output buffer '{k}' must be a contiguous {wdt} tensor of shape {want} on {self.device}")
             setattr(o, k, outputs[k].data_ptr() if k in outputs else None)
-        self._chk(self.lib.jic_run(self.ctx, int(n_steps), C.byref(o), self._stream()))
+        self._chk(self.lib.jic_run(self.ctx, T, C.byref(o), self._stream()))
         return outputs
 
     # ---- state out
@@ -289,6 +301,7 @@ def simulate_host(*, species, x0, v0, n_steps, ext_E=None, ext_B=None, dtype=np.
     tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
     if particles:
         kw.setdefault("track_yz", True)
+    kinetic = bool(kw.pop("kinetic", False))
     params, grid = make_params(n_species=len(species), dtype=tdt, **kw)
     sp = make_species(species)
     N = int(sum(int(s["count"]) for s in species))
@@ -304,17 +317,28 @@ def simulate_host(*, species, x0, v0, n_steps, ext_E=None, ext_B=None, dtype=np.
     if particles:
         res.setdefault("positions", np.empty((T, N, 3), dtype=dtype))
         res.setdefault("velocities", np.empty((T, N, 3), dtype=dtype))
-    if kw.pop("kinetic", False):
+    if kinetic:
         res.setdefault("kinetic_energy", np.zeros((T, len(species)), dtype=np.float64))
     o = Outputs()
     for k in _HIST:
         setattr(o, k, res[k].ctypes.data if k in res else None)
     eE = None if ext_E is None else np.ascontiguousarray(ext_E, dtype=np.float32)
     eB = None if ext_B is None else np.ascontiguousarray(ext_B, dtype=np.float32)
+    for name, a in (("ext_E", eE), ("ext_B", eB)):  # the library reads exactly G * 3 floats from each
+        if a is not None and a.shape != (G, 3):
+            raise JicError(f"{name} must have shape ({G}, 3), got {a.shape}")
+    for k in _HIST:  # caller-provided output buffers: the library writes T rows of the full shape into them
+        if k in res:
+            want = {"charge_density": (T, G), "positions": (T, N, 3), "velocities": (T, N, 3), "kinetic_energy": (T, len(species))}.get(k, (T, G, 3))
+            wdt = np.float64 if k == "kinetic_energy" else np.dtype(dtype)
+            if not isinstance(res[k], np.ndarray) or res[k].shape != want or res[k].dtype != wdt or not res[k].flags["C_CONTIGUOUS"]:
+                raise JicError(f"output buffer '{k}' must be a C-contiguous {np.dtype(wdt).name} array of shape {want}")
     E0 = B0 = vi = None
     if initial:
         E0, B0 = np.empty((G, 3), dtype=dtype), np.empty((G, 3), dtype=dtype)
-        if kw.get("engine", "indexed") == "indexed":  # the binned store does not keep particle order
+        # post-BC initial velocities: kept by the INDEXED store and by the Crank-Nicolson stepper (whatever the engine string says);
+        # the binned store does not keep particle order
+        if kw.get("engine", "indexed") == "indexed" or int(kw.get("time_evolution_algorithm", 0)) == 1:
             vi = np.empty((N, 3), dtype=dtype)
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
     _lib.check(lib.jic_simulate_host(C.byref(params), sp, vp(x0), vp(v0), vp(eE), vp(eB), T, C.byref(o), vp(E0), vp(B0), vp(vi)))

@@ -13,8 +13,17 @@ per-step arithmetic all happens in libjic_b200.so.  Host code is NumPy: there is
     Crank-Nicolson stepper, _algorithms.py:100-241) both run in the library (k_gauss; csrc/jic_cn.cuh).
 
 Extra, optional ``solver_parameters`` understood here only: ``engine`` ("auto" | "indexed" | "binned"), ``particle_history``
-(default True, like the reference; False drops the (T,N,3) histories and lets large runs use the binned engine) and ``dtype``
-("float64" | "float32").
+(default True, like the reference; False drops the (T,N,3) histories and lets large runs use the binned engine), ``dtype``
+("float64" | "float32"), ``device_resident`` ("auto" | True | False) and ``kinetic_energy_history`` (default False).
+
+Large runs (``particle_history=False``; a million particles or more, or several ranks) take the DEVICE-RESIDENT path: like the
+reference, which builds its particles inside the jit on the device (jaxincell/_simulation.py:169-190), the particles are sampled
+on the GPU and handed to the library there -- no host copy of the (N,3) arrays exists unless the output dictionary is asked to
+hold them (N <= ``PARTICLE_ARRAYS_LIMIT``).  Under ``torchrun`` (an initialised ``torch.distributed`` NCCL group) every rank
+samples only its own index slice of every species (Threefry is counter based), pushes it, and the library reduces the grid
+over NVLink every step: fields and energies in the output are global, per-particle arrays (when present) are the rank's slice.
+``kinetic_energy_history=True`` adds a per-species kinetic-energy history reduced on the device (``kinetic_energy_species``,
+(T, n_species)), which ``diagnostics`` uses when the velocity history does not exist.
 """
 from __future__ import annotations
 
@@ -48,7 +57,9 @@ DOMAIN_DEFAULTS = dict(total_steps=350, timestep_over_spatialstep_times_c=1.0, n
 SOLVER_DEFAULTS = dict(print_info=True, field_solver=0, relativistic=False, time_evolution_algorithm=0,
                        max_number_of_Picard_iterations_implicit_CN=20, number_of_particle_substeps_implicit_CN=2,
                        tolerance_Picard_iterations_implicit_CN=1e-6, filter_passes=5, filter_alpha=0.5, filter_strides=(1, 2, 4),
-                       seed=1701, engine="auto", particle_history=True, dtype="float64", rng="threefry", threefry_partitionable=True)
+                       seed=1701, engine="auto", particle_history=True, dtype="float64", rng="threefry", threefry_partitionable=True,
+                       device_resident="auto", kinetic_energy_history=False)
+PARTICLE_ARRAYS_LIMIT = 20_000_000  # device-resident runs above this hold None under the per-particle output keys
 # _parameters/_source_parameters.py:10-23 -- carried into the output dictionary; no code of the step reads them
 SOURCE_DEFAULTS = dict(source_term_active=0, source_species=1, how_often_source_should_produce_quasiparticles=20,
                        source_particles_per_second=1e16, location_of_source=0, width_of_source=1, injection_speed_x=1e7,
@@ -434,10 +445,13 @@ class Simulation:
                     grid=np.linspace(-length / 2 + dx / 2, length / 2 - dx / 2, G))
 
     @staticmethod
-    def initialize_particle_state(species_parameters, dom, solver, state):
-        """_state_initialization.py:51-286.  Random draws: device Threefry (jic_sample_particles) or numpy.random.default_rng."""
+    def initialize_particle_state(species_parameters, dom, solver, state, materialize=True):
+        """_state_initialization.py:51-286.  Random draws: device Threefry (jic_sample_particles) or numpy.random.default_rng.
+        materialize=False (device-resident runs): only the per-species tables; no per-particle host array is built."""
         box, G = state["box_size"], int(dom["number_grid_points"])
         threefry = solver.get("rng", "threefry") == "threefry"
+        if not materialize:
+            return Simulation._species_level_state(species_parameters, dom, solver, state)
         sampling, given_any = [], []
         pos, vel, wts, sidx, table, names = [], [], [], [], [], []
         charge_l, mass_l, qm_l = [], [], []
@@ -512,12 +526,159 @@ class Simulation:
                     charge_to_mass_ratios=ql[species_integer_index].reshape(-1, 1), species_table=table, sampling=sampling,
                     species_index=names, **ref)
 
+    @staticmethod
+    def _species_level_state(species_parameters, dom, solver, state):
+        """The per-species part of initialize_particle_state (same seeds, weights, charges: same code path of the reference,
+        _state_initialization.py:87-96,172-185,242-261) without any per-particle array."""
+        box, G = state["box_size"], int(dom["number_grid_points"])
+        sampling, table, overrides, weights = [], [], {}, []
+        charge_l, mass_l, qm_l = [], [], []
+        ref, extra = None, 0
+        for kind in ("electrons", "ions"):
+            for i, (canon, sp) in enumerate(species_parameters[kind].items()):
+                sp_seed, sv_seed = _seed_pair(int(solver["seed"]), kind, i, extra)
+                if i != 0:
+                    extra += 1
+                if sp["seed_position_override"]:
+                    sp_seed = sp["seed_position"]
+                n = sp["number_pseudoparticles"]
+                sampling.append(dict(count=n, seed_position=sp_seed, seed_velocity=sv_seed,
+                                     **{k: [sp[f"{k}_{ax}"] for ax in AXES] for k in
+                                        ("random_positions", "velocity_plus_minus", "perturbation_amplitude", "perturbation_wavenumber",
+                                         "vth_over_c", "drift_speed")}))
+                for key in ("initial_positions", "initial_velocities"):
+                    if sp[key] is not None:
+                        given = np.asarray(sp[key], dtype=float)
+                        assert given.shape == (n, 3), f"{key} for {kind}{i} must have shape {(n, 3)}. Got {given.shape}."
+                        overrides.setdefault(len(table), {})[key] = given
+                mass = mass_electron if kind == "electrons" else sp["mass_over_proton_mass"] * mass_proton
+                charge = sp["charge_over_elementary_charge"] * elementary_charge
+                if kind == "electrons" and i == 0:
+                    vths = [sp[f"vth_over_c_{ax}"] for ax in AXES]
+                    ref = dict(vth_electrons=max(vths) * speed_of_light, vth_electrons_over_c=max(vths), charge_electrons=charge)
+                if ref is None:
+                    raise ValueError("Electron reference species must be initialized before ions.")
+                debye_length_per_dx = 1 / sp["grid_points_per_Debye_length"]
+                w = (epsilon_0 * mass_electron * speed_of_light ** 2 / ref["charge_electrons"] ** 2 * G ** 2 / box[0] / (2 * n)
+                     * ref["vth_electrons_over_c"] ** 2 / debye_length_per_dx ** 2)
+                w = w if sp["weight"] == 0 else float(sp["weight"])
+                weights.append(w)
+                table.append(dict(count=n, q=charge * w, m=mass * w, qm=charge / mass, name=f"{kind}.{canon}"))
+                charge_l.append(charge); mass_l.append(mass); qm_l.append(charge / mass)
+        return dict(species_table=table, sampling=sampling, overrides=overrides, species_weights=weights,
+                    charge_integer_lookup=np.array(charge_l), mass_integer_lookup=np.array(mass_l),
+                    charge_mass_integer_lookup=np.array(qm_l), **ref)
+
+    @staticmethod
+    def _distributed():
+        """(rank, world) of an initialised torch.distributed group, else (0, 1)."""
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except Exception:  # noqa: BLE001
+            pass
+        return 0, 1
+
+    def _simulation_device(self, sec, state, rank, world):
+        """The run with the particles resident on the device from the first random bit to the last step (module docstring)."""
+        import torch
+        from ._engine import HotPath, sample_particles
+        from ._parallel import shard_counts, shard_species
+        dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
+        ps = self.initialize_particle_state(sec["species_parameters"], dom, solver, state, materialize=False)
+        G, T = int(dom["number_grid_points"]), int(dom["total_steps"])
+        box = state["box_size"]
+        tdt = torch.float64 if str(solver["dtype"]) in ("float64", "f64") else torch.float32
+        if not torch.cuda.is_available():
+            raise JicError("no CUDA device: jaxincell_b200 has no CPU path")
+        device = torch.device("cuda", torch.cuda.current_device())
+        eE = ext.get("external_electric_field"); eB = ext.get("external_magnetic_field")
+        ext_E = np.asarray(eE["E"], np.float32) if isinstance(eE, dict) and "E" in eE else np.zeros((G, 3), np.float32)
+        ext_B = np.asarray(eB["B"], np.float32) if isinstance(eB, dict) and "B" in eB else np.zeros((G, 3), np.float32)
+        if ext_E.shape != (G, 3) or ext_B.shape != (G, 3):
+            raise JicError(f"external fields must have shape ({G}, 3), got {ext_E.shape} and {ext_B.shape}")
+        x0, v0 = sample_particles(ps["sampling"], box, dtype=tdt, device=device,
+                                  threefry_partitionable=bool(solver.get("threefry_partitionable", True)), rank=rank, world=world)
+        o = 0
+        for k, spl in enumerate(ps["sampling"]):  # explicit per-species arrays replace this rank's slice of their block
+            counts = shard_counts(spl["count"], world)
+            lo, n = sum(counts[:rank]), counts[rank]
+            for key, arr in ps["overrides"].get(k, {}).items():
+                t = torch.as_tensor(arr[lo:lo + n]).to(device=device, dtype=tdt)
+                if key == "initial_velocities":
+                    lim = 0.99 * speed_of_light
+                    t = torch.where(t.abs() >= lim, torch.sign(t) * lim, t)
+                (x0 if key == "initial_positions" else v0)[o:o + n] = t
+            o += n
+        engine = solver["engine"] if solver["engine"] in ("indexed", "binned") else "binned"
+        local_table = shard_species(ps["species_table"], rank, world)
+        hp = HotPath(species=local_table, dtype=tdt, device=device, engine=engine,
+                     length=box[0], length_y=box[1], length_z=box[2], G=G, dt=state["dt"],
+                     pbl=dom["particle_BC_left"], pbr=dom["particle_BC_right"], fbl=dom["field_BC_left"], fbr=dom["field_BC_right"],
+                     filter_passes=solver["filter_passes"], filter_alpha=solver["filter_alpha"], filter_strides=solver["filter_strides"],
+                     relativistic=bool(solver["relativistic"]), field_solver=int(solver["field_solver"]),
+                     time_evolution_algorithm=int(solver["time_evolution_algorithm"]),
+                     cn_substeps=int(solver["number_of_particle_substeps_implicit_CN"]),
+                     cn_max_iterations=int(solver["max_number_of_Picard_iterations_implicit_CN"]),
+                     cn_tolerance=float(solver["tolerance_Picard_iterations_implicit_CN"]))
+        try:
+            if world > 1:
+                hp.comm_init_from_torch()
+            hp.set_external_fields(ext_E, ext_B)
+            hp.initialize(x0, v0)
+            keep = hp.N <= PARTICLE_ARRAYS_LIMIT
+            hx0 = x0.cpu().numpy() if keep else None
+            hv0 = v0.cpu().numpy() if keep else None
+            del x0, v0
+            E0, B0, _ = hp.initial(velocities=False)
+            ke = bool(solver.get("kinetic_energy_history", False))
+            out = hp.run(T, kinetic=ke)
+            hp.check_status()
+            res = {k: out[k].cpu().numpy() for k in ("electric_field", "magnetic_field", "current_density", "charge_density")}
+            res["fields"] = (E0.cpu().numpy(), B0.cpu().numpy())
+            if ke:
+                kin = out["kinetic_energy"]
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(kin)
+                res["kinetic_energy_species"] = kin.cpu().numpy()
+        finally:
+            hp.close()
+        # per-particle output arrays: this rank's slice, or None above PARTICLE_ARRAYS_LIMIT
+        if keep:
+            counts = [s_["count"] for s_ in local_table]
+            sidx = np.repeat(np.arange(len(counts), dtype=np.int32), counts)
+            w = np.asarray(ps["species_weights"])[sidx].reshape(-1, 1)
+            ps.update(positions=hx0, velocities=hv0, weights=w, species_integer_index=sidx,
+                      charges=ps["charge_integer_lookup"][sidx].reshape(-1, 1) * w, masses=ps["mass_integer_lookup"][sidx].reshape(-1, 1) * w,
+                      charge_to_mass_ratios=ps["charge_mass_integer_lookup"][sidx].reshape(-1, 1))
+        else:
+            ps.update(positions=None, velocities=None, weights=None, species_integer_index=None, charges=None, masses=None,
+                      charge_to_mass_ratios=None)
+        out_d = self._assemble_output(sec, state, ps, res, ext_E, ext_B)
+        out_d["species_table"] = ps["species_table"]
+        out_d["rank"], out_d["world_size"] = rank, world
+        if "kinetic_energy_species" in res:
+            out_d["kinetic_energy_species"] = res["kinetic_energy_species"]
+        return out_d
+
     # ---- run ------------------------------------------------------------------------------------------------------
     def simulation(self, input_parameters=None):
         from ._engine import simulate_host
         sec = self._sections(self.clean_runtime_input_parameters(input_parameters))
         dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
         state = self.build_domain_state(dom)
+        rank, world = self._distributed()
+        n_all = sum(sp["number_pseudoparticles"] for kind in sec["species_parameters"].values() for sp in kind.values())
+        mode = solver.get("device_resident", "auto")
+        can = (not bool(solver["particle_history"])) and solver.get("rng", "threefry") == "threefry" and solver["engine"] != "indexed"
+        if mode is True and not can:
+            raise JicError("device_resident=True needs particle_history=False, rng='threefry' and engine 'auto' or 'binned'")
+        if world > 1 and not can:
+            raise JicError("a run over several ranks needs particle_history=False, rng='threefry' and engine 'auto' or 'binned'")
+        if can and (mode is True or (mode == "auto" and (n_all >= 1_000_000 or world > 1))):
+            return self._simulation_device(sec, state, rank, world)
         ps = self.initialize_particle_state(sec["species_parameters"], dom, solver, state)
         if solver["print_info"]:  # the reference's start-up summary (_simulation.py:176-183)
             print(INFORMATION_TEXT.format(*simulation_information(dom, sec["species_parameters"], ext, state, ps)))
@@ -527,6 +688,8 @@ class Simulation:
         eE = ext.get("external_electric_field"); eB = ext.get("external_magnetic_field")
         ext_E = np.asarray(eE["E"], np.float32) if isinstance(eE, dict) and "E" in eE else np.zeros((G, 3), np.float32)
         ext_B = np.asarray(eB["B"], np.float32) if isinstance(eB, dict) and "B" in eB else np.zeros((G, 3), np.float32)
+        if ext_E.shape != (G, 3) or ext_B.shape != (G, 3):
+            raise JicError(f"external fields must have shape ({G}, 3), got {ext_E.shape} and {ext_B.shape}")
         history = bool(solver["particle_history"])
         engine = solver["engine"]
         if engine == "auto":
@@ -551,13 +714,16 @@ class Simulation:
         dom, solver, ext = sec["domain_parameters"], sec["solver_parameters"], sec["external_field_parameters"]
         G, T = int(dom["number_grid_points"]), int(dom["total_steps"])
         e0 = next(iter(sec["species_parameters"]["electrons"].values()))
-        we = ps["weights"][0, 0]
+        we = ps["species_weights"][0] if "species_weights" in ps else ps["weights"][0, 0]
         plasma_frequency = (np.sqrt(e0["number_pseudoparticles"] * we * ps["charge_electrons"] ** 2) / np.sqrt(mass_electron)
                             / np.sqrt(epsilon_0) / np.sqrt(state["box_size"][0]))
         out = {  # jaxincell/_simulation.py:269-312
             "positions": res.get("positions"), "velocities": res.get("velocities"), "masses": ps["masses"], "charges": ps["charges"],
             "charge_to_mass_ratios": ps["charge_to_mass_ratios"], "initial_positions": ps["positions"],
-            "initial_velocities": res["initial_velocities"] if "initial_velocities" in res else ps["velocities"],
+            "initial_velocities": (res["initial_velocities"] if "initial_velocities" in res else
+                                   None if ps["velocities"] is None else
+                                   post_bc_initial_velocities(ps["positions"], ps["velocities"], state["dt"], state["box_size"][0],
+                                                              dom["particle_BC_left"], dom["particle_BC_right"])),
             "weights": ps["weights"], "species_integer_index": ps["species_integer_index"],
             "charge_integer_lookup": ps["charge_integer_lookup"], "mass_integer_lookup": ps["mass_integer_lookup"],
             "charge_mass_integer_lookup": ps["charge_mass_integer_lookup"],
@@ -633,10 +799,64 @@ def simulation(parameters=None, input_parameters=None):
     return Simulation(parameters).run(input_parameters)
 
 
+def _field_energies(output):
+    """The field part of jaxincell/_diagnostics.py:98-129 (needs no particles)."""
+    T, dt, dx = int(output["total_steps"]), float(output["dt"]), output["dx"]
+    sig = output["electric_field"][:, len(output["grid"]) // 2, 0]
+    sig = (sig - np.mean(sig)) / np.max(sig)
+    half = T // 2
+    mag = np.abs(np.fft.fft(sig)[:half])
+    freqs = np.fft.fftfreq(T, d=dt)[:half] * 2 * np.pi
+    dominant = np.abs(freqs[np.argmax(mag)])
+    E2 = np.sum(output["electric_field"] ** 2, axis=-1); B2 = np.sum(output["magnetic_field"] ** 2, axis=-1)
+    eE2 = np.sum(np.asarray(output["external_electric_field"], np.float64) ** 2, axis=-1)
+    eB2 = np.sum(np.asarray(output["external_magnetic_field"], np.float64) ** 2, axis=-1)
+    return {
+        "electric_field_energy_density": epsilon_0 / 2 * E2, "electric_field_energy": epsilon_0 / 2 * np.sum(E2, axis=-1) * dx,
+        "magnetic_field_energy_density": 1 / (2 * mu_0) * B2, "magnetic_field_energy": 1 / (2 * mu_0) * np.sum(B2, axis=-1) * dx,
+        "dominant_frequency": dominant,
+        "external_electric_field_energy_density": epsilon_0 / 2 * eE2, "external_electric_field_energy": epsilon_0 / 2 * np.sum(eE2) * dx,
+        "external_magnetic_field_energy_density": 1 / (2 * mu_0) * eB2, "external_magnetic_field_energy": 1 / (2 * mu_0) * np.sum(eB2) * dx,
+    }
+
+
+def _diagnostics_from_energy_history(output):
+    """diagnostics() for a device-resident run: the same energies (jaxincell/_diagnostics.py:98-146), the kinetic ones from the
+    per-species history the library reduced on the device instead of from a (T,N,3) velocity history that was never stored.
+    Electrons = the species with negative charge, ions = the others (the reference's split by the sign of the charge, :31-32)."""
+    ke = np.asarray(output["kinetic_energy_species"], dtype=np.float64)
+    q = np.array([s["q"] for s in output["species_table"]])
+    ke_e, ke_i = ke[:, q < 0].sum(axis=1), ke[:, q >= 0].sum(axis=1)
+    output.update(_field_energies(output))
+    output.update({"kinetic_energy": ke_e + ke_i, "kinetic_energy_electrons": ke_e, "kinetic_energy_ions": ke_i,
+                   "species": [dict(name=s.get("name", f"species_{i}"), charge=float(s["q"]), mass=float(s["m"]), kinetic_energy=ke[:, i])
+                               for i, s in enumerate(output["species_table"])]})
+    output["total_energy"] = (output["electric_field_energy"] + output["external_electric_field_energy"] + output["magnetic_field_energy"]
+                              + output["external_magnetic_field_energy"] + output["kinetic_energy"])
+    return output
+
+
+def post_bc_initial_velocities(x0, v0, dt, length, pbl, pbr):
+    """The reference's output key `initial_velocities` (jaxincell/_simulation.py:217,286): the velocities after set_BC_particles was
+    applied to the start-up half step x0 + dt/2 v0 -- v_x flipped for a particle a reflective wall sent back, zero for an absorbed one
+    (_boundary_conditions.py:32-56).  Used when the library cannot return them (the binned store keeps no particle order)."""
+    x0, v0 = np.asarray(x0), np.array(v0, copy=True)
+    xp = x0[:, 0] + 0.5 * dt * v0[:, 0]
+    for out_side, bc in ((xp < -length / 2, pbl), (xp > length / 2, pbr)):
+        if bc == 1:
+            v0[out_side, 0] = -v0[out_side, 0]
+        elif bc == 2:
+            v0[out_side, :] = 0.0
+    return v0
+
+
 def diagnostics(output):
     """jaxincell/_diagnostics.py:8-147 in NumPy: species split, energies, dominant frequency.  Mutates and returns `output`."""
     if output.get("positions") is None or output.get("velocities") is None:
-        raise JicError("diagnostics() needs the particle histories (solver_parameters['particle_history']=True)")
+        if output.get("kinetic_energy_species") is None:
+            raise JicError("diagnostics() needs the particle histories (solver_parameters['particle_history']=True) or, for runs too "
+                           "large for them, the device-reduced kinetic energies (solver_parameters['kinetic_energy_history']=True)")
+        return _diagnostics_from_energy_history(output)
     q = np.asarray(output["charges"]).reshape(-1); m = np.asarray(output["masses"]).reshape(-1)
     esel, isel = q < 0, q >= 0
     output.update(position_electrons=output["positions"][:, esel, :], velocity_electrons=output["velocities"][:, esel, :],
