@@ -72,6 +72,9 @@ constexpr int kBlkElems = 4 * kBlk;  // reals per block
 #ifndef JIC_PUSH_STAGE_BLOCKS
 #define JIC_PUSH_STAGE_BLOCKS 2    // 32-particle blocks per ring slot = particles a lane has in flight
 #endif
+#ifndef JIC_PUSH_STAGE_BLOCKS_F32
+#define JIC_PUSH_STAGE_BLOCKS_F32 2
+#endif
 template <typename R>
 __host__ __device__ constexpr int push_threads() { return sizeof(R) == 8 ? JIC_PUSH_THREADS : JIC_PUSH_THREADS_F32; }
 template <typename R>
@@ -86,7 +89,8 @@ __host__ __device__ constexpr int push_warps() { return push_threads<R>() / 32; 
 #else
 #define JIC_PUSH_BOUNDS(R) __launch_bounds__(push_threads<R>())
 #endif
-constexpr int kPushStageBlocks = JIC_PUSH_STAGE_BLOCKS;
+template <typename R>
+__host__ __device__ constexpr int push_stage_blocks() { return sizeof(R) == 8 ? JIC_PUSH_STAGE_BLOCKS : JIC_PUSH_STAGE_BLOCKS_F32; }
 #ifndef JIC_PUSH_RUN
 #define JIC_PUSH_RUN 4             // output blocks claimed with one cursor atomic (power of two)
 #endif

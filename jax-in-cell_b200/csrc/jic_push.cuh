@@ -102,7 +102,7 @@ constexpr int kPoolCap = 64;   // processed stayers waiting to fill holes (< 32 
 constexpr int kMixCap = 128;   // ring of movers: 32 frozen (claimed, not yet written) + up to 63 collecting
 template <typename R>
 struct __align__(128) PushWarpSmem {
-  R ring[push_stages<R>()][kPushStageBlocks][kBlkElems];  // input: work-item blocks on their way in
+  R ring[push_stages<R>()][push_stage_blocks<R>()][kBlkElems];  // input: work-item blocks on their way in
   R pool[4][kPoolCap];                               // d, v_x, v_y, v_z of pooled stayers (a stack)
   R mix[4][kMixCap];                                 // t_new (unshifted), v_x, v_y, v_z of movers (a ring)
   R coef[24];                                        // per component k: [e0, e1, a2lo, a2hi, b0, b1, b2, -]
@@ -124,7 +124,7 @@ constexpr size_t push_smem_bytes() { return sizeof(PushWarpSmem<R>) * push_warps
 template <typename R, bool REL, bool STAG>
 __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
                                                                        const R* __restrict__ F, R* __restrict__ acc, RunControl* __restrict__ ctl) {
-  constexpr int NS = push_stages<R>(), KB = kPushStageBlocks, RUN = kPushRun;
+  constexpr int NS = push_stages<R>(), KB = push_stage_blocks<R>(), RUN = kPushRun;
   if (threadIdx.x == 0) atomicMin(&ctl->push_t0, global_timer_ns());
   constexpr unsigned kBlockBytes = kBlkElems * sizeof(R);
   constexpr unsigned FULL = 0xffffffffu;
