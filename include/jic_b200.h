@@ -191,6 +191,11 @@ int jic_check_status(jic_context* ctx, void* stream);
  * figure is valid for launches inside CUDA-graph replays (the same replays jic_run's throughput is measured on), where events around
  * single kernels are not available.  Synchronises the stream.  reset != 0 zeroes the sum afterwards. */
 int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, int32_t reset, void* stream);
+/* Diagnostic aid, BINNED engine: counters of the particle store after the work queued so far (synchronises the stream):
+ * out[0] work items of the next push, out[1] / out[2] entries in the overflow lists of the two buffers, out[3] sticky error flag
+ * (0 ok, 1 overflow or general-path list full, 2 slot capacity exhausted), out[4] entries in the general-path list of the last step,
+ * out[5] slots in use (holes included), out[6] slots per buffer, out[7] particles absorbed so far. */
+int jic_store_stats(jic_context* ctx, int64_t out[8], void* stream);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 

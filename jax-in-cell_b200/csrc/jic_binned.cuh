@@ -116,7 +116,7 @@ struct PlanHeader {
   int tail_from;
   int work2;           // work queue head of k_push_general (items of the wall bins)
   int gen_n;           // entries in the general-path list of this step (reset by k_plan)
-  int pad;
+  int gen_last;        // ... of the step before (diagnostics)
   long long n_stored;  // slots in use (holes included) + overflow entries in the source buffer
   long long n_absorbed;
 };
@@ -451,6 +451,7 @@ __global__ void __launch_bounds__(kPlanMcThreads) k_plan_mc(const BinDev<R> bd, 
     h->tail_from = tail_from;
     h->work = 0;
     h->work2 = 0;
+    h->gen_last = h->gen_n;
     h->gen_n = 0;
     h->flip = written;
     h->ov_n[next] = 0;

@@ -843,6 +843,16 @@ struct EngineT : Engine {
     return JIC_OK;
   }
 
+  int store_stats(long long out[8], cudaStream_t st) override {
+    if (cn || prm.engine != JIC_ENGINE_BINNED) return fail(JIC_ERR_UNSUPPORTED, "jic_store_stats needs the BINNED engine");
+    PlanHeader h;
+    JIC_CUDA(cudaMemcpyAsync(&h, bins.bd.hdr, sizeof(h), cudaMemcpyDeviceToHost, st));
+    JIC_CUDA(cudaStreamSynchronize(st));
+    out[0] = h.n_items; out[1] = h.ov_n[0]; out[2] = h.ov_n[1]; out[3] = h.error; out[4] = h.gen_last; out[5] = h.n_stored;
+    out[6] = bins.bd.cap_total; out[7] = h.n_absorbed;
+    return JIC_OK;
+  }
+
   // sticky device-side error flags (synchronises the stream): a peer that missed the fused barrier, exhausted store capacity
   int check_status(cudaStream_t st) override {
     if (fused()) {
@@ -1007,6 +1017,13 @@ int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, 
   long long n = 0;
   int rc = ctx->eng->push_kernel_time(ms_sum, &n, reset, (cudaStream_t)st);
   if (n_launches) *n_launches = n;
+  return rc;
+}
+int jic_store_stats(jic_context* ctx, int64_t out[8], void* st) {
+  CTX_OR_FAIL(ctx);
+  long long tmp[8] = {0};
+  int rc = ctx->eng->store_stats(tmp, (cudaStream_t)st);
+  for (int i = 0; i < 8 && out; ++i) out[i] = tmp[i];
   return rc;
 }
 int64_t jic_launch_count(const jic_context* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }

@@ -44,6 +44,7 @@ struct Engine {
   virtual int get_particles(void* x, void* v, uint8_t* alive, cudaStream_t st) = 0;
   virtual int kinetic(double* out, cudaStream_t st) = 0;
   virtual int check_status(cudaStream_t st) = 0;
+  virtual int store_stats(long long out[8], cudaStream_t st) = 0;
   virtual int push_kernel_time(double* ms_sum, long long* n_launches, int reset, cudaStream_t st) = 0;
   virtual int profile(long long n, double* ms_push, double* ms_fields, cudaStream_t st) = 0;
   virtual int dtype() const = 0;

@@ -219,6 +219,13 @@ class HotPath:
         rank missed the fused reduction).  `run` only enqueues: call this before trusting the histories of a single `run`."""
         self._chk(self.lib.jic_check_status(self.ctx, self._stream()))
 
+    def store_stats(self):
+        """Counters of the binned particle store (jic_store_stats): dict with items, overflow (per buffer), error, general (entries of
+        the last step's general-path list), slots_used, slots_per_buffer, absorbed."""
+        a = (C.c_int64 * 8)()
+        self._chk(self.lib.jic_store_stats(self.ctx, a, self._stream()))
+        return dict(items=a[0], overflow=(a[1], a[2]), error=a[3], general=a[4], slots_used=a[5], slots_per_buffer=a[6], absorbed=a[7])
+
     def profile_steps(self, n_steps):
         """(ms in the particle kernels, ms in all-reduce + field kernel) summed over n_steps real steps (CUDA events)."""
         a, b = C.c_double(0.0), C.c_double(0.0)

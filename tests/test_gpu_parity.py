@@ -38,7 +38,13 @@ def run_gpu(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, ext_E=None, e
     return res
 
 
+ROW_FLOOR = 1e-3  # a step whose field is below this fraction of the run's maximum is measured against the floor (pure noise otherwise)
+
+
 def assert_parity(got, ref, keys, rtol):
+    """Two norms.  Global: max |cuda - oracle| over the whole history / max |oracle| over the whole history.
+    Per step (row-wise): the same ratio step by step, the denominator floored at ROW_FLOOR of the global maximum -- so that a late blow-up of a
+    small component cannot hide under an early large one.  Both must be below the tolerance."""
     for k in keys:
         scale = np.abs(ref[k]).max()
         if scale == 0:
@@ -46,6 +52,11 @@ def assert_parity(got, ref, keys, rtol):
             continue
         err = np.abs(got[k] - ref[k]).max() / scale
         assert err < rtol, f"{k}: max rel err {err:.3e} >= {rtol}"
+        T = ref[k].shape[0]
+        num = np.abs(got[k] - ref[k]).reshape(T, -1).max(axis=1)
+        den = np.maximum(np.abs(ref[k]).reshape(T, -1).max(axis=1), ROW_FLOOR * scale)
+        row = (num / den).max()
+        assert row < rtol, f"{k}: per-step max rel err {row:.3e} >= {rtol} (step {int((num / den).argmax())})"
 
 
 @pytest.mark.parametrize("deposit", ["global", "shared"])
@@ -340,7 +351,7 @@ def test_field_solver_literal_oracle_direct():
     assert_parity(got, ref, FIELD_KEYS + ("positions", "velocities"), 1e-5)
 
 
-@pytest.mark.parametrize("dtype,rtol", [(torch.float64, 1e-5), (torch.float32, 2e-3)])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float64, 1e-5), (torch.float32, 1e-3)])
 def test_field_solver_large_grid_binned_fast_path(dtype, rtol):
     """G = 1024: multi-CTA field kernel + k_gauss over many CTAs + the moment form of the face deposit (bins away from the
     domain ends), engines against each other and against the oracle."""

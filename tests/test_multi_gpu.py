@@ -147,3 +147,74 @@ def test_n_gpus_field_solver_and_crank_nicolson(mode, world):
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def _worker_bump(rank, world, port, n_total, T, q):
+    """BASELINE config 4 as BASELINE.json states it: the bump-on-tail plasma sharded by index over the ranks."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import bump_on_tail as BT
+        from jaxincell_b200 import HotPath, shard_species
+        from jaxincell_b200._parallel import shard_counts
+        s = BT.setup(n_total)
+        # every rank draws its own slice on its device (one seed per rank: the plasma is statistically the same as the single-GPU one)
+        local = shard_species(s["species"], rank, world)
+        s_local = dict(s, counts=tuple(sp["count"] for sp in local))
+        dev = torch.device("cuda", rank)
+        x0, v0 = BT.particles_torch(s_local, dev, seed=250724 + rank)
+        hp = HotPath(engine="binned", species=local, length=s["length"], G=s["G"], dt=s["dt"], filter_passes=0)
+        hp.comm_init_from_torch()
+        hp.set_external_fields(None, None)
+        hp.initialize(x0, v0)
+        del x0, v0
+        out = hp.run(T)
+        hp.check_status()
+        E = out["electric_field"]
+        ref0 = E.clone()
+        dist.broadcast(ref0, src=0)
+        same = torch.tensor([1 if torch.equal(ref0, E) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        rho_sum = float(out["charge_density"].double().sum(dim=1).abs().max()) * s["dx"]
+        q_scale = sum(sp["count"] * abs(sp["q"]) for sp in s["species"])
+        gamma, mode, window = BT.growth_rate_of_mode(E[:, :, 0].cpu().numpy(), s)
+        st = hp.store_stats()
+        hp.close()
+        q.put((rank, dict(identical=bool(int(same.item())), neutrality=rho_sum / q_scale, gamma=gamma / s["gamma_theory"], mode=mode,
+                          theory_mode=s["mode"], window=window, error=st["error"], comm=world)))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_config4_bump_on_tail_sharded(world):
+    """2e8 macro-particles over 2 / 4 / 8 GPUs (BASELINE config 4): ranks hold bit-identical fields, the plasma stays neutral, and the
+    k = 4.9 omega_pe / c mode grows at the rate of linear theory (0.075 omega_pe, tolerance as in tests/test_full_size.py)."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    sys_path_tests = os.path.dirname(os.path.abspath(__file__))
+    os.environ["PYTHONPATH"] = sys_path_tests + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_bump, args=(r, world, port, 200_000_000, 320, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted((q.get(timeout=540) for _ in procs), key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    for rank, r in res:
+        assert isinstance(r, dict), r
+        assert r["identical"] and r["error"] == 0, r
+        assert r["neutrality"] < 1e-9, r
+        assert abs(r["mode"] - r["theory_mode"]) <= 1, r
+        assert abs(r["gamma"] - 1) < 0.15, r
+    print("bump-on-tail sharded:", res[0][1])
