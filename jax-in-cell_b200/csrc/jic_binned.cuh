@@ -95,6 +95,9 @@ __host__ __device__ constexpr int push_stage_blocks() { return sizeof(R) == 8 ? 
 #define JIC_PUSH_RUN 4             // output blocks claimed with one cursor atomic (power of two)
 #endif
 constexpr int kPushRun = JIC_PUSH_RUN;
+#ifndef JIC_ITEMS_PER_WARP
+#define JIC_ITEMS_PER_WARP 3       // work items per warp of the push kernel the plan aims for (load balance vs per-item overhead and holes)
+#endif
 #ifndef JIC_TAIL_SPLIT
 #define JIC_TAIL_SPLIT 1           // the last eighth of the work queue is cut into quarter-size items (shorter kernel tail)
 #endif
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kPlanMcThreads) k_plan_mc(const BinDev<R> bd, 
   const long long t_leave = tot_ll;
   block_exclusive_scan<long long>(mine_arr, &tot_ll, sh_ll);
   const long long t_arr = tot_ll;
-  long long want = n_total / (4ll * (bd.n_workers > 0 ? bd.n_workers : 1));
+  long long want = n_total / ((long long)JIC_ITEMS_PER_WARP * (bd.n_workers > 0 ? bd.n_workers : 1));
   want = want < kMinChunk ? kMinChunk : (want > kMaxChunk ? kMaxChunk : want);
   const int kChunk = (int)((want + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;
   int kTailChunk = ((kChunk / 4 + kChunkAlign - 1) / kChunkAlign) * kChunkAlign;  // the queue's tail: quarter-size items
