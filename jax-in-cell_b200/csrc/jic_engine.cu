@@ -273,7 +273,7 @@ struct EngineT : Engine {
     void* ptrs[] = {cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
-    if (comm && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
+    if (comm && !comm_shared && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
     if (caller_device >= 0 && caller_device != device) cudaSetDevice(caller_device);
   }
 
@@ -342,15 +342,36 @@ struct EngineT : Engine {
   bool fused() const { return p2p && mc && !dp.stag && !cn; }
   int comm_mode() const override { return world <= 1 ? 0 : (fused() ? 2 : 1); }
 
+  // NCCL communicators are kept for the life of the process and shared by the contexts of one (device, rank, world): creating one
+  // costs 0.3-3 s at 8 ranks, which would otherwise be paid by every Simulation.run().  All ranks take the same path as long as they
+  // create their contexts in the same order (they do: one process per GPU running the same program).  JIC_COMM_CACHE=0 disables it.
+  bool comm_shared = false;
   int comm_init(const void* id, int rank_, int world_) override {
     if (world_ <= 1) { rank = 0; world = 1; return JIC_OK; }
     NcclApi& api = nccl_api();
     if (!api.error.empty()) return fail(JIC_ERR_NCCL, api.error);
-    ncclUniqueId uid;
-    memcpy(&uid, id, sizeof(uid));
     JIC_CUDA(cudaSetDevice(device));
-    ncclResult_t r = api.CommInitRank(&comm, world_, uid, rank_);
-    if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
+    static std::mutex mu;
+    static std::map<long long, ncclComm_t> cache;
+    const char* env = getenv("JIC_COMM_CACHE");
+    const bool use_cache = !(env && env[0] == '0');
+    const long long key = ((long long)world_ << 40) | ((long long)rank_ << 20) | (long long)device;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = cache.find(key);
+      if (use_cache && it != cache.end()) { comm = it->second; comm_shared = true; }
+    }
+    if (!comm) {
+      ncclUniqueId uid;
+      memcpy(&uid, id, sizeof(uid));
+      ncclResult_t r = api.CommInitRank(&comm, world_, uid, rank_);
+      if (r != ncclSuccess) return fail(JIC_ERR_NCCL, format("ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(r) : "?"));
+      if (use_cache) {
+        std::lock_guard<std::mutex> lock(mu);
+        cache[key] = comm;
+        comm_shared = true;
+      }
+    }
     rank = rank_; world = world_;
     return setup_p2p();
   }
