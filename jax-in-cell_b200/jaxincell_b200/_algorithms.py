@@ -80,6 +80,17 @@ def Boris_step(carry, step_index, solver_parameters, external_field_parameters, 
                                        engine="indexed", track_yz=True, field_solver=int(field_solver)))
     if abs(hp.params.dx - float(dx)) > 1e-14 * abs(float(dx)):
         raise JicError("dx is not box_size[0] / len(grid)")
+    # The library marks an absorbed particle by its parked position (outside the box), the reference by q == 0
+    # (_boundary_conditions.py:40-56 does both at once).  The two agree for every carry the reference's own steps produce as long as
+    # a reflected particle cannot overshoot the far wall in one step (CFL < number of cells); a hand-made carry that breaks the
+    # equivalence is refused rather than silently revived or killed.
+    q_flat = np.asarray(qs, np.float64).reshape(-1)
+    xp = np.asarray(x_plus, np.float64).reshape(-1, 3)[:, 0]
+    inside = (xp >= -length / 2) & (xp <= length / 2)
+    if np.any((q_flat == 0.0) & inside):
+        raise JicError("carry holds particles with q == 0 inside the box: the library identifies absorbed particles by their parked position")
+    if np.any((q_flat != 0.0) & ~inside):
+        raise JicError("carry holds charged particles outside the box (a reflection that overshot the far wall: CFL >= number of cells?)")
     hp.set_external_fields(ext_E, ext_B)
     hp.load_carry(E, B, x_minus, x_n, x_plus, v_n)
     out = hp.run(1, particles=True)
