@@ -194,7 +194,9 @@ int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, 
 /* Diagnostic aid, BINNED engine: counters of the particle store after the work queued so far (synchronises the stream):
  * out[0] work items of the next push, out[1] / out[2] entries in the overflow lists of the two buffers, out[3] sticky error flag
  * (0 ok, 1 overflow or general-path list full, 2 slot capacity exhausted), out[4] entries in the general-path list of the last step,
- * out[5] slots in use (holes included), out[6] slots per buffer, out[7] particles absorbed so far. */
+ * out[5] slots in use (holes included), out[6] slots per buffer, out[7] particles absorbed so far.
+ * Crank-Nicolson contexts (no binned store): out[0] = 1 when the context runs the cell-sorted push (csrc/jic_cn_sorted.cuh; contexts of
+ * at least JIC_CN_SORTED_MIN particles, an environment variable read at creation, default 200000), 0 for the unsorted one; the rest 0. */
 int jic_store_stats(jic_context* ctx, int64_t out[8], void* stream);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);

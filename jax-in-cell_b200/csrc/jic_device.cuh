@@ -98,7 +98,9 @@ __device__ __forceinline__ int bc_x(R& x, const DevParams<R>& p) {
 
 template <typename R>
 __device__ __forceinline__ R wrap_transverse(R y, R len, R half_len) {
-  return floor_mod(y + half_len, len) - half_len;
+  const R t = y + half_len;
+  if (t >= R(0) && t < len) return t - half_len;  // (fmod returns its first argument bit for bit on [0, len): skip the slow remainder loop)
+  return floor_mod(t, len) - half_len;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@
 #include "jic_binned.cuh"
 #include "jic_sample.cuh"
 #include "jic_cn.cuh"
+#include "jic_cn_sorted.cuh"
 #include "jic_carry.cuh"
 
 namespace jic {
@@ -111,6 +112,12 @@ struct EngineT : Engine {
   double *cn_Eg = nullptr, *cn_Bnext = nullptr, *cn_Eavg = nullptr, *cn_Bavg = nullptr;
   CnControl* cn_ctl = nullptr;
   uint8_t* cn_alive = nullptr;      // 0 = absorbed by the start-up half step (charge 0 for the whole run)
+  // cell-sorted Crank-Nicolson push (csrc/jic_cn_sorted.cuh): permutation (slot -> input index), species and alive bytes per slot,
+  // their scatter targets, and the counting sort's histogram / offsets
+  bool cn_sorted = false;
+  int *cn_perm = nullptr, *cn_perm2 = nullptr;
+  uint8_t *cn_sp = nullptr, *cn_sp2 = nullptr, *cn_alive2 = nullptr;
+  unsigned *cn_hist = nullptr, *cn_off = nullptr;
 
   int dtype() const override { return prm.dtype; }
   long long n_particles() const override { return dp.N; }
@@ -166,6 +173,18 @@ struct EngineT : Engine {
           return rc;
       if ((rc = alloc(&cn_stag, N * (size_t)prm.cn_substeps)) || (rc = alloc(&v_init, 3 * N)) || (rc = alloc(&cn_ctl, 1)) || (rc = alloc(&cn_alive, N))) return rc;
       if ((rc = alloc(&cn_Eg, G * 3)) || (rc = alloc(&cn_Bnext, G * 3)) || (rc = alloc(&cn_Eavg, G * 3)) || (rc = alloc(&cn_Bavg, G * 3))) return rc;
+      {
+        // large runs: sorted push with warp-aggregated deposit (JIC_CN_SORTED_MIN overrides the particle-count threshold; 0 = always)
+        long long min_n = 200000;
+        if (const char* env = getenv("JIC_CN_SORTED_MIN")) min_n = atoll(env);
+        cn_sorted = (long long)N >= min_n && G >= 8 && N < (1ull << 31);
+        if (cn_sorted) {
+          if ((rc = alloc(&cn_perm, N)) || (rc = alloc(&cn_perm2, N)) || (rc = alloc(&cn_sp, N)) || (rc = alloc(&cn_sp2, N)) ||
+              (rc = alloc(&cn_alive2, N)) || (rc = alloc(&cn_hist, G)) || (rc = alloc(&cn_off, G + 1)))
+            return rc;
+          JIC_CUDA(cudaFuncSetAttribute(k_cn_push_sorted<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cn_sorted_smem_bytes<R>()));
+        }
+      }
     } else if (prm.engine == JIC_ENGINE_INDEXED) {
       if ((rc = alloc(&xh, N)) || (rc = alloc(&vx, N)) || (rc = alloc(&vy, N)) || (rc = alloc(&vz, N))) return rc;
       if (prm.track_yz && ((rc = alloc(&yh, N)) || (rc = alloc(&zh, N)))) return rc;
@@ -270,7 +289,7 @@ struct EngineT : Engine {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (int k = 0; k < 2; ++k) { if (ev_copied[k]) cudaEventDestroy(ev_copied[k]); if (ev_used[k]) cudaEventDestroy(ev_used[k]); }
     for (int k = 0; k < 2; ++k) { void* q[] = {cn_s[k].x, cn_s[k].y, cn_s[k].z, cn_s[k].vx, cn_s[k].vy, cn_s[k].vz}; for (void* p : q) if (p) cudaFree(p); }
-    void* ptrs[] = {cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
+    void* ptrs[] = {cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive2, cn_hist, cn_off, cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
     if (comm && !comm_shared && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
@@ -556,6 +575,7 @@ struct EngineT : Engine {
     if (rc) return rc;
     JIC_CUDA(cudaMemsetAsync(cn_ctl, 0, sizeof(CnControl), st));
     k_cn_load<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, (const R*)x_n, (const R*)v_n, alive_in, cn_s[0], v_init, cn_alive);
+    if (cn_sorted) { k_cn_meta_init<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_perm, cn_sp); launches += 1; }
     const int n3 = dp.G * 3;
     k_carry_copy_fields<R><<<(n3 + 255) / 256, 256, 0, st>>>((const R*)E_in, (const R*)B_in, E, B, E0, B0, n3);
     k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(0, true));
@@ -596,6 +616,7 @@ struct EngineT : Engine {
     JIC_CUDA(cudaMemsetAsync(cn_ctl, 0, sizeof(CnControl), st));
     k_cn_start<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, x0, v0, cn_s[0], v_init, cn_alive, acc);
     launches += 1;
+    if (cn_sorted) { k_cn_meta_init<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_perm, cn_sp); launches += 1; }
     JIC_CUDA(cudaGetLastError());
     int rc = allreduce(st, 0, true);
     if (rc) return rc;
@@ -612,7 +633,40 @@ struct EngineT : Engine {
   }
 
   // one CN step reading particle buffer `p`: max_iter x (push, all-reduce, fields); iterations after convergence return at once
+  // sorted variant: the state of buffer p is scattered, cell by cell, into buffer p ^ 1 (with the permutation and the per-slot bytes),
+  // the Picard iterations read p ^ 1 and write p, so the step ends where it began and `par` does not flip
+  int enqueue_step_cn_sorted(cudaStream_t st, int p) {
+    const int g = grid_for(dp.N, 256, 8);
+    const size_t N = (size_t)dp.N;
+    k_cn_hist<R><<<g, 256, 0, st>>>(dp, cn_s[p].x, cn_hist);
+    k_cn_scan<<<1, 1024, 0, st>>>(dp.G, cn_hist, cn_off);
+    k_cn_scatter<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive, cn_alive2, cn_off, cn_hist);
+    JIC_CUDA(cudaMemsetAsync(cn_hist, 0, sizeof(unsigned) * dp.G, st));  // (the scatter used it as its cursors)
+    JIC_CUDA(cudaMemcpyAsync(cn_perm, cn_perm2, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    JIC_CUDA(cudaMemcpyAsync(cn_sp, cn_sp2, N, cudaMemcpyDeviceToDevice, st));
+    JIC_CUDA(cudaMemcpyAsync(cn_alive, cn_alive2, N, cudaMemcpyDeviceToDevice, st));
+    launches += 3;
+    const int gs = grid_for(dp.N, kCnSortedThreads, 3);
+    for (int it = 0; it < prm.cn_max_iterations; ++it) {
+      k_cn_push_sorted<R><<<gs, kCnSortedThreads, cn_sorted_smem_bytes<R>(), st>>>(dp, cn_s[p ^ 1], cn_s[p], cn_stag, prm.cn_substeps, it, cn_Eavg,
+                                                                                    cn_Bavg, acc, cn_alive, cn_sp, cn_ctl);
+      int rc = allreduce(st, 0, true);
+      if (rc) return rc;
+      k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(it, false));
+      launches += 2;
+    }
+    if (ke_hist) {
+      k_cn_kinetic_sorted<R><<<g, 256, 0, st>>>(dp, cn_s[p].vx, cn_s[p].vy, cn_s[p].vz, cn_sp, nullptr, ctl, 1);
+      launches += 1;
+    }
+    k_cn_record_sorted<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_perm, ctl);
+    launches += 1;
+    JIC_CUDA(cudaGetLastError());
+    return JIC_OK;
+  }
+
   int enqueue_step_cn(cudaStream_t st, int p) {
+    if (cn_sorted) return enqueue_step_cn_sorted(st, p);
     const int g = grid_for(dp.N, 256, 8);
     int per_sm = (int)((size_t)200 * 1024 / (shared_bytes + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
@@ -723,11 +777,11 @@ struct EngineT : Engine {
   bool ke_hist = false;
   int enqueue_kinetic_hist(cudaStream_t st, int p) {
     if (cn) {
-      k_kinetic_hist<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[p ^ 1].vx, cn_s[p ^ 1].vy, cn_s[p ^ 1].vz, ctl);
+      k_kinetic_hist<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[p ^ 1].vx, cn_s[p ^ 1].vy, cn_s[p ^ 1].vz, ctl, 1);
     } else if (prm.engine == JIC_ENGINE_BINNED) {
       return bins.kinetic_hist(*this, dp, ctl, st);
     } else {
-      k_kinetic_hist<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, vx, vy, vz, ctl);
+      k_kinetic_hist<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, vx, vy, vz, ctl, 0);
     }
     launches += 1;
     return JIC_OK;
@@ -765,7 +819,7 @@ struct EngineT : Engine {
       cudaEventRecord(ev[3 * s + 1], st);
       if (rc == JIC_OK && !cn) rc = enqueue_fields(st, par);
       cudaEventRecord(ev[3 * s + 2], st);
-      if (mc || cn) par ^= 1;
+      if (flips()) par ^= 1;
     }
     cudaError_t ce = cudaStreamSynchronize(st);
     double a = 0, b = 0;
@@ -794,7 +848,7 @@ struct EngineT : Engine {
     cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     int rc = JIC_OK;
     if (e == cudaSuccess) {
-      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, (mc || cn) ? (par ^ (s & 1)) : 0);
+      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, flips() ? (par ^ (s & 1)) : (cn ? par : 0));
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
@@ -846,10 +900,13 @@ struct EngineT : Engine {
       JIC_CUDA(cudaGraphLaunch(ex, st));
       launches += per_step * steps;
       done += steps;
-      if (mc || cn) par ^= steps & 1;
+      if (flips()) par ^= steps & 1;
     }
     return JIC_OK;
   }
+  // do consecutive steps alternate between the ping-pong buffers?  (multi-CTA field kernel; unsorted CN state.  The sorted CN step
+  // scatters p -> p ^ 1 and iterates p ^ 1 -> p: it ends where it began.)
+  bool flips() const { return mc || (cn && !cn_sorted); }
 
   // device-timed push kernel: summed %globaltimer span (first CTA in, last CTA out) of the launches since the last reset
   int push_kernel_time(double* ms_sum, long long* n_launches, int reset, cudaStream_t st) override {
@@ -865,7 +922,12 @@ struct EngineT : Engine {
   }
 
   int store_stats(long long out[8], cudaStream_t st) override {
-    if (cn || prm.engine != JIC_ENGINE_BINNED) return fail(JIC_ERR_UNSUPPORTED, "jic_store_stats needs the BINNED engine");
+    if (cn) {  // Crank-Nicolson contexts keep no binned store: out[0] says which push they run
+      for (int i = 0; i < 8; ++i) out[i] = 0;
+      out[0] = cn_sorted ? 1 : 0;
+      return JIC_OK;
+    }
+    if (prm.engine != JIC_ENGINE_BINNED) return fail(JIC_ERR_UNSUPPORTED, "jic_store_stats needs the BINNED engine");
     PlanHeader h;
     JIC_CUDA(cudaMemcpyAsync(&h, bins.bd.hdr, sizeof(h), cudaMemcpyDeviceToHost, st));
     JIC_CUDA(cudaStreamSynchronize(st));
@@ -888,7 +950,7 @@ struct EngineT : Engine {
   }
 
   long long count_launches_per_step() const {
-    if (cn) return 1 + (ke_hist ? 1 : 0) + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
+    if (cn) return 1 + (cn_sorted ? 3 : 0) + (ke_hist ? 1 : 0) + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
     long long k = 2 + ((world > 1 && !fused()) ? 1 : 0) + dp.stag + (ke_hist ? 1 : 0);
     if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
     return k;
@@ -917,6 +979,11 @@ struct EngineT : Engine {
   }
 
   int get_particles(void* x, void* v, uint8_t* alive, cudaStream_t st) override {
+    if (cn && cn_sorted) {  // x_n, v_n back in input order through the permutation
+      k_cn_export_sorted<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[par], cn_perm, (R*)x, (R*)v, alive);
+      JIC_CUDA(cudaGetLastError());
+      return JIC_OK;
+    }
     if (cn) {  // x_n, v_n in input order
       DevParams<R> d = dp;
       d.track_yz = 1;
@@ -933,6 +1000,11 @@ struct EngineT : Engine {
 
   int kinetic(double* out, cudaStream_t st) override {
     JIC_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (cn && cn_sorted) {
+      k_cn_kinetic_sorted<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[par].vx, cn_s[par].vy, cn_s[par].vz, cn_sp, out, nullptr, 0);
+      JIC_CUDA(cudaGetLastError());
+      return JIC_OK;
+    }
     if (cn) {
       k_kinetic<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, cn_s[par].vx, cn_s[par].vy, cn_s[par].vz, out);
       JIC_CUDA(cudaGetLastError());

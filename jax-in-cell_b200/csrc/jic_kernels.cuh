@@ -737,10 +737,10 @@ __global__ void k_kinetic(const DevParams<R> p, const R* vx, const R* vy, const 
 // per-species kinetic energy of the step into row hist_row of the (T, n_species) history (jic_outputs.kinetic_energy), INDEXED / CN
 // layouts: the species of particle i follows from its index.  Enqueued between the push and the field kernel of a step.
 template <typename R>
-__global__ void __launch_bounds__(256) k_kinetic_hist(const DevParams<R> p, const R* vx, const R* vy, const R* vz, const RunControl* ctl) {
+__global__ void __launch_bounds__(256) k_kinetic_hist(const DevParams<R> p, const R* vx, const R* vy, const R* vz, const RunControl* ctl, int row_back) {
   double* out = (double*)ctl->hist[6];
   if (!out) return;
-  out += ctl->hist_row * p.n_species;
+  out += (ctl->hist_row - row_back) * p.n_species;  // (row_back = 1: the Crank-Nicolson field kernel has already advanced the row)
   double acc[JIC_MAX_SPECIES];
 #pragma unroll
   for (int s = 0; s < JIC_MAX_SPECIES; ++s) acc[s] = 0.0;

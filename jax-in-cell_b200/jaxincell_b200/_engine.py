@@ -224,6 +224,8 @@ class HotPath:
         the last step's general-path list), slots_used, slots_per_buffer, absorbed."""
         a = (C.c_int64 * 8)()
         self._chk(self.lib.jic_store_stats(self.ctx, a, self._stream()))
+        if self.params.time_evolution_algorithm == 1:   # no binned store: which Crank-Nicolson push the context runs
+            return dict(cn_sorted=int(a[0]))
         return dict(items=a[0], overflow=(a[1], a[2]), error=a[3], general=a[4], slots_used=a[5], slots_per_buffer=a[6], absorbed=a[7])
 
     def profile_steps(self, n_steps):

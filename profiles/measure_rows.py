@@ -27,13 +27,56 @@ def timed(fn, reps=1):
     return e0.elapsed_time(e1) / reps
 
 
+def crank_nicolson(dev):
+    """Particle-iterations per second of the two Crank-Nicolson pushes on the same particles in the same process: the cell-sorted one
+    (default from 200000 particles up) and the unsorted one (JIC_CN_SORTED_MIN raised above N), and how far their fields are apart."""
+    class A:
+        grid, particles = 4096, 20_000_000
+    w = bench.workload(A, 1)
+    x0, v0 = bench.make_particles(w, torch, dev, torch.float64, 1701, "random")
+    S, max_it = 2, 6
+    fields = {}
+    for name, threshold in (("sorted", "0"), ("unsorted", str(1 << 40))):
+        os.environ["JIC_CN_SORTED_MIN"] = threshold
+        hp = HotPath(species=w["species"], length=w["length"], G=w["G"], dt=0.3 * w["dt"], time_evolution_algorithm=1, cn_substeps=S,
+                     cn_max_iterations=max_it, cn_tolerance=1e-30)
+        hp.set_external_fields(None, None)
+        hp.initialize(x0, v0)
+        outs = hp.alloc_outputs(10)
+        hp.run(10, outputs=outs)
+        fields[name] = outs["electric_field"].clone()
+        it0 = hp.picard_iterations()[1]
+        ms = timed(lambda: hp.run(10, outputs=outs))
+        iters = hp.picard_iterations()[1] - it0
+        N = hp.N
+        bytes_per = (12 + 2 * S) * 8 + 1
+        print(json.dumps({"row": f"8f-4 Crank-Nicolson, {name} push", "cn_sorted": hp.store_stats()["cn_sorted"], "particles": N, "substeps": S,
+                          "picard_iterations": iters, "ms_per_iteration": ms / iters, "particle_iterations_per_s": N * iters / ms * 1e3,
+                          "achieved_GBps": bytes_per * N * iters / ms / 1e6, "peak_GBps": PEAK, "frac": bytes_per * N * iters / ms / 1e6 / PEAK,
+                          "finite": bool(torch.isfinite(outs["electric_field"][-1]).all()),
+                          "note": f"algorithmic bytes per particle and iteration = {bytes_per} (x,v in, x,v out, S staggered positions in and out, "
+                                  "alive byte); the sorted push pays one counting sort of the state per step on top (not counted as algorithmic)"}),
+              flush=True)
+        hp.close()
+    del os.environ["JIC_CN_SORTED_MIN"]
+    a, b = fields["sorted"], fields["unsorted"]
+    print(json.dumps({"row": "8f-4 Crank-Nicolson, sorted vs unsorted push", "steps": 10,
+                      "max_rel_diff_E": float((a - b).abs().max() / b.abs().max())}), flush=True)
+
+
 def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
 
     class A:  # the bench workload (SURVEY 8d config 5)
         grid, particles = 4096, 100_000_000
     w = bench.workload(A, 1)
+
+    if only in (None, "cn"):
+        crank_nicolson(dev)
+    if only == "cn":
+        return
 
     # ---- initial sampling (jic_sample_particles): 48 B written per particle in fp64
     n = 50_000_000
@@ -65,30 +108,6 @@ def main():
                               "component + G^2 circular convolution) in front of the field kernel"}), flush=True)
     del x0, v0
     torch.cuda.empty_cache()
-
-    # ---- Crank-Nicolson: particle-iterations per second
-    A.particles = 20_000_000
-    w = bench.workload(A, 1)
-    x0, v0 = bench.make_particles(w, torch, dev, torch.float64, 1701, "random")
-    S, max_it = 2, 6
-    hp = HotPath(species=w["species"], length=w["length"], G=w["G"], dt=0.3 * w["dt"], time_evolution_algorithm=1, cn_substeps=S,
-                 cn_max_iterations=max_it, cn_tolerance=1e-30)
-    hp.set_external_fields(None, None)
-    hp.initialize(x0, v0)
-    outs = hp.alloc_outputs(10)
-    hp.run(10, outputs=outs)
-    it0 = hp.picard_iterations()[1]
-    ms = timed(lambda: hp.run(10, outputs=outs))
-    iters = hp.picard_iterations()[1] - it0
-    N = hp.N
-    bytes_per = (12 + 2 * S) * 8 + 1
-    print(json.dumps({"row": "8f-4 Crank-Nicolson (k_cn_push + k_cn_fields)", "particles": N, "substeps": S, "picard_iterations": iters,
-                      "ms_per_iteration": ms / iters, "particle_iterations_per_s": N * iters / ms * 1e3,
-                      "achieved_GBps": bytes_per * N * iters / ms / 1e6, "peak_GBps": PEAK, "frac": bytes_per * N * iters / ms / 1e6 / PEAK,
-                      "finite": bool(torch.isfinite(outs["electric_field"][-1]).all()),
-                      "note": f"algorithmic bytes per particle and iteration = {bytes_per} (x,v in, x,v out, S staggered positions in and out, alive byte); "
-                              "deposition by global atomics"}), flush=True)
-    hp.close()
 
 
 if __name__ == "__main__":

@@ -4,12 +4,16 @@
 //                k_fields (E_x replaced) } -- optional carry reload through k_load_carry / k_carry_fields
 //   emu_cn_run   implicit stepper: k_cn_start, k_fields(init), k_cn_fields(prepare), { max_iter x (k_cn_push, k_cn_fields), k_cn_record }
 //                -- optional carry reload through k_cn_load / k_carry_copy_fields
+//   emu_cn_sorted_run   the same with the cell-sorted push of csrc/jic_cn_sorted.cuh, as EngineT::enqueue_step_cn_sorted launches it:
+//                k_cn_meta_init, { k_cn_hist, k_cn_scan, k_cn_scatter, max_iter x (k_cn_push_sorted, k_cn_fields), k_cn_record_sorted };
+//                the reload goes through k_cn_export_sorted (what jic_get_particles runs)
 #include <cstring>
 #include <memory>
 #include <vector>
 
 #include "jic_kernels.cuh"
 #include "jic_cn.cuh"
+#include "jic_cn_sorted.cuh"
 #include "jic_carry.cuh"
 
 thread_local EmuDim3 threadIdx;
@@ -20,6 +24,7 @@ namespace jic {
 alignas(16) double fsm[1];
 alignas(16) unsigned char smem_raw[1];
 alignas(16) unsigned char cn_smem_raw[1];
+alignas(256) unsigned char cn_sorted_smem[(kCnSortedThreads / 32) * kCnWin * kCnWinComps * kCnColStride * sizeof(double)];
 alignas(16) double gsm[2 * 4096];
 }  // namespace jic
 
@@ -213,9 +218,8 @@ __attribute__((visibility("default"))) int emu_fs_run_two_ranks(const EmuParams*
   return 0;
 }
 
-__attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const double* x0, const double* v0, int T, int n_sub, int max_iter, double tol,
-                                                      int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv,
-                                                      long long* picard) {
+static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, const double* v0, int T, int n_sub, int max_iter, double tol,
+                           int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv, long long* picard) {
   long long N;
   DevParams<R> p = dev_params(ep, &N);
   const size_t G = (size_t)ep->G, n = (size_t)N;
@@ -226,7 +230,9 @@ __attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const
     for (auto& b : buf[k]) b.assign(n, 0.0);
     cs[k] = CnState<R>{buf[k][0].data(), buf[k][1].data(), buf[k][2].data(), buf[k][3].data(), buf[k][4].data(), buf[k][5].data()};
   }
-  std::vector<uint8_t> alive(n);
+  std::vector<uint8_t> alive(n), alive2(n), sp(n), sp2(n);
+  std::vector<int> perm(n), perm2(n);
+  std::vector<unsigned> hist(G, 0u), off(G, 0u);
   std::vector<double> Eg(G * 3), Bnext(G * 3), Eavg(G * 3), Bavg(G * 3);
   CnControl cn;
   std::memset(&cn, 0, sizeof(cn));
@@ -241,6 +247,7 @@ __attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const
   };
   // EngineT::initialize_cn
   emu_launch(2, kThreads, [&] { k_cn_start<R>(p, x0, v0, cs[0], v_init.data(), alive.data(), gs.acc.data()); });
+  if (sorted) emu_launch(2, kThreads, [&] { k_cn_meta_init<R>(p, perm.data(), sp.data()); });
   emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, false)); });
   gs.E = gs.E0; gs.B = gs.B0;
   emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(0, true)); });
@@ -248,11 +255,17 @@ __attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const
   for (int t = 0; t < T; ++t) {
     if (t == reload_at && t > 0) {
       std::vector<R> x(3 * n), v(3 * n), E_c(gs.E.begin(), gs.E.end()), B_c(gs.B.begin(), gs.B.end());
-      for (size_t i = 0; i < n; ++i) {
-        x[3 * i] = cs[par].x[i]; x[3 * i + 1] = cs[par].y[i]; x[3 * i + 2] = cs[par].z[i];
-        v[3 * i] = cs[par].vx[i]; v[3 * i + 1] = cs[par].vy[i]; v[3 * i + 2] = cs[par].vz[i];
-      }
       std::vector<uint8_t> alive_in(alive);
+      if (sorted) {  // EngineT::get_particles; the q = 0 bytes back in input order
+        emu_launch(2, kThreads, [&] { k_cn_export_sorted<R>(p, cs[par], perm.data(), x.data(), v.data(), (uint8_t*)nullptr); });
+        for (size_t i = 0; i < n; ++i) alive_in[(size_t)perm[i]] = alive[i];
+        std::fill(perm.begin(), perm.end(), -1); std::fill(sp.begin(), sp.end(), 99);
+      } else {
+        for (size_t i = 0; i < n; ++i) {
+          x[3 * i] = cs[par].x[i]; x[3 * i + 1] = cs[par].y[i]; x[3 * i + 2] = cs[par].z[i];
+          v[3 * i] = cs[par].vx[i]; v[3 * i + 1] = cs[par].vy[i]; v[3 * i + 2] = cs[par].vz[i];
+        }
+      }
       for (int k = 0; k < 2; ++k) for (auto& b : buf[k]) std::fill(b.begin(), b.end(), 1e300);
       std::fill(alive.begin(), alive.end(), 7); std::fill(gs.E.begin(), gs.E.end(), 1e300); std::fill(gs.B.begin(), gs.B.end(), 1e300);
       std::fill(Eg.begin(), Eg.end(), 1e300); std::fill(Eavg.begin(), Eavg.end(), 1e300); std::fill(Bavg.begin(), Bavg.end(), 1e300);
@@ -261,11 +274,28 @@ __attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const
       std::memset(&cn, 0, sizeof(cn));
       par = 0;  // EngineT::load_carry_cn
       emu_launch(2, kThreads, [&] { k_cn_load<R>(p, x.data(), v.data(), alive_in.data(), cs[0], v_init.data(), alive.data()); });
+      if (sorted) emu_launch(2, kThreads, [&] { k_cn_meta_init<R>(p, perm.data(), sp.data()); });
       emu_launch(1, kThreads, [&] { k_carry_copy_fields<R>(E_c.data(), B_c.data(), gs.E.data(), gs.B.data(), gs.E0.data(), gs.B0.data(), (int)(G * 3)); });
       emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(0, true)); });
       cn.total_iters = keep.total_iters;
     }
     gs.ctl.hist[0] = hE; gs.ctl.hist[1] = hB; gs.ctl.hist[2] = hJ; gs.ctl.hist[3] = hrho; gs.ctl.hist[4] = hx; gs.ctl.hist[5] = hv;
+    if (sorted) {  // EngineT::enqueue_step_cn_sorted
+      emu_launch(3, kThreads, [&] { k_cn_hist<R>(p, cs[par].x, hist.data()); });
+      emu_launch(1, kThreads, [&] { k_cn_scan((int)G, hist.data(), off.data()); });
+      emu_launch(3, kThreads, [&] { k_cn_scatter<R>(p, cs[par], cs[par ^ 1], perm.data(), perm2.data(), sp.data(), sp2.data(), alive.data(), alive2.data(),
+                                                    off.data(), hist.data()); });
+      std::fill(hist.begin(), hist.end(), 0u);
+      perm = perm2; sp = sp2; alive = alive2;
+      for (int it = 0; it < max_iter; ++it) {
+        emu_launch(3, kThreads, [&] { k_cn_push_sorted<R>(p, cs[par ^ 1], cs[par], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(),
+                                                                  alive.data(), sp.data(), &cn); });
+        emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(it, false)); });
+      }
+      emu_launch(2, kThreads, [&] { k_cn_record_sorted<R>(p, cs[par], perm.data(), &gs.ctl); });
+      if (picard) picard[t] = cn.last_iters;
+      continue;  // (the step ends in the buffer it began in)
+    }
     for (int it = 0; it < max_iter; ++it) {  // EngineT::enqueue_step_cn
       emu_launch(3, kThreads, [&] { k_cn_push<R, false>(p, cs[par], cs[par ^ 1], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(), alive.data(), &cn); });
       emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(it, false)); });
@@ -275,6 +305,17 @@ __attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const
     par ^= 1;
   }
   return 0;
+}
+
+__attribute__((visibility("default"))) int emu_cn_run(const EmuParams* ep, const double* x0, const double* v0, int T, int n_sub, int max_iter, double tol,
+                                                      int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv,
+                                                      long long* picard) {
+  return emu_cn_run_impl(false, ep, x0, v0, T, n_sub, max_iter, tol, reload_at, hE, hB, hJ, hrho, hx, hv, picard);
+}
+__attribute__((visibility("default"))) int emu_cn_sorted_run(const EmuParams* ep, const double* x0, const double* v0, int T, int n_sub, int max_iter,
+                                                             double tol, int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx,
+                                                             double* hv, long long* picard) {
+  return emu_cn_run_impl(true, ep, x0, v0, T, n_sub, max_iter, tol, reload_at, hE, hB, hJ, hrho, hx, hv, picard);
 }
 
 }  // extern "C"

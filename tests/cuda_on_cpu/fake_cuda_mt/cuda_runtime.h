@@ -3,7 +3,7 @@
 // atomics = compare-and-swap on the bit pattern.  Blocks of a launch run one after the other (kernels that wait for other blocks are out
 // of scope).  The sources are compiled from a copy in which `extern __shared__` was turned into `extern` (the arrays are defined by the
 // harness) so that `__shared__` can mean `static` here: one copy per block, shared by its threads.
-// With it the warp-level kernels of the INDEXED / CN paths (k_gauss, k_cn_fields' block reductions) run on a CPU;
+// With it the warp-level kernels of the INDEXED / CN paths (k_gauss, k_cn_fields' block reductions, the cell-sorted CN push) run on a CPU;
 // tests/test_cuda_source_on_cpu.py compares them with the golden vectors.  Logic only: no memory model, no performance.
 #pragma once
 #include <atomic>
@@ -69,6 +69,32 @@ inline T emu_shuffle(T v, unsigned src_lane) {
 }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int o) { return emu_shuffle(v, (threadIdx.x & 31u) ^ (unsigned)o); }
 template <class T> inline T __shfl_up_sync(unsigned, T v, int o) { const unsigned l = threadIdx.x & 31u; return emu_shuffle(v, l >= (unsigned)o ? l - o : l); }
+
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_shuffle(v, (unsigned)src); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu_block->warp[threadIdx.x >> 5]->arrive_and_wait(); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+// lanes of the warp (all of them take part) that hold the same value / the smallest value of the warp
+template <class F>
+inline void emu_warp_gather(int v, F&& each) {  // every lane publishes v, then sees the values of all lanes of its warp that exist
+  const unsigned w = threadIdx.x >> 5, base = w << 5;
+  emu_block->slot[threadIdx.x] = (unsigned long long)(long long)v;
+  emu_block->warp[w]->arrive_and_wait();
+  for (unsigned l = 0; l < 32 && base + l < blockDim.x; ++l) each(l, (int)(long long)emu_block->slot[base + l]);
+  emu_block->warp[w]->arrive_and_wait();
+}
+inline unsigned __match_any_sync(unsigned, int v) {
+  unsigned m = 0;
+  emu_warp_gather(v, [&](unsigned l, int u) { m |= (u == v ? 1u : 0u) << l; });
+  return m;
+}
+inline int __reduce_min_sync(unsigned, int v) {
+  int r = v;
+  emu_warp_gather(v, [&](unsigned, int u) { r = min(r, u); });
+  return r;
+}
+struct double2 { double x, y; };
+struct float2 { float x, y; };
 
 template <class T, class U>
 inline T emu_atomic_add_bits(T* p, T v) {

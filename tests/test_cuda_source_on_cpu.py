@@ -166,7 +166,7 @@ def emu_mt(tmp_path_factory):
     src.mkdir(parents=True)
     (root / "include").mkdir()
     (root / "include" / "jic_b200.h").write_text(open(os.path.join(ROOT, "include", "jic_b200.h")).read())
-    for name in ("jic_device.cuh", "jic_kernels.cuh", "jic_cn.cuh", "jic_carry.cuh"):
+    for name in ("jic_device.cuh", "jic_kernels.cuh", "jic_cn.cuh", "jic_cn_sorted.cuh", "jic_carry.cuh"):
         # the one textual change: dynamic shared arrays become plain externs (the harness defines them), so that `__shared__` can mean `static`
         (src / name).write_text(open(os.path.join(CSRC, name)).read().replace("extern __shared__", "extern"))
     so = str(root / "libjic_emu_mt.so")
@@ -183,6 +183,8 @@ def emu_mt(tmp_path_factory):
     lib.emu_fs_run_two_ranks.argtypes = [C.POINTER(EmuParams)] * 2 + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 4
     lib.emu_cn_run.restype = C.c_int
     lib.emu_cn_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 7
+    lib.emu_cn_sorted_run.restype = C.c_int
+    lib.emu_cn_sorted_run.argtypes = lib.emu_cn_run.argtypes
     return lib
 
 
@@ -231,19 +233,23 @@ def test_field_solver_source_on_the_threaded_emulation(emu_mt, path, reload_at):
         assert relerr(out[k], g[k]) < 1e-9, k
 
 
+@pytest.mark.parametrize("push", ["unsorted", "sorted"])
 @pytest.mark.parametrize("reload_at", [-1, 3])
 @pytest.mark.parametrize("path", CN_GOLDEN, ids=[os.path.basename(f)[:-4] for f in CN_GOLDEN])
-def test_crank_nicolson_source_on_the_threaded_emulation(emu_mt, path, reload_at):
+def test_crank_nicolson_source_on_the_threaded_emulation(emu_mt, path, reload_at, push):
     """k_cn_start, k_cn_push, k_cn_fields (block reductions, device-side convergence flag), k_cn_record against the reference-source vectors,
-    Picard iteration counts included; with reload_at the CN carry loader (k_cn_load, k_carry_copy_fields) continues a wiped run."""
+    Picard iteration counts included; with reload_at the CN carry loader (k_cn_load, k_carry_copy_fields) continues a wiped run.
+    push = sorted: the large-run variant (csrc/jic_cn_sorted.cuh: counting sort by cell every step, k_cn_push_sorted with its per-warp
+    window, histories and exports through the permutation) on the same vectors."""
     g = dict(np.load(path))
     out = _histories(g)
     T = int(g["T"])
     picard = np.zeros(T, np.int64)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
-    rc = emu_mt.emu_cn_run(C.byref(_params_of(g)), ptr(x0), ptr(v0), T, int(g["cn_substeps"]), int(g["cn_max_iterations"]), float(g["cn_tolerance"]),
-                           reload_at, *[ptr(out[k]) for k in KEYS], ptr(picard))
+    run = emu_mt.emu_cn_sorted_run if push == "sorted" else emu_mt.emu_cn_run
+    rc = run(C.byref(_params_of(g)), ptr(x0), ptr(v0), T, int(g["cn_substeps"]), int(g["cn_max_iterations"]), float(g["cn_tolerance"]),
+             reload_at, *[ptr(out[k]) for k in KEYS], ptr(picard))
     assert rc == 0
     for k in KEYS:
         assert relerr(out[k], g[k]) < 1e-9, k
@@ -348,10 +354,12 @@ def test_field_solver_on_two_emulated_ranks(emu_mt, seed):
             assert rc == -2 or relerr(wrong["electric_field"], ref["electric_field"]) > 1e-6
 
 
+@pytest.mark.parametrize("push", ["unsorted", "sorted"])
 @pytest.mark.parametrize("seed", range(FUZZ(24)))
-def test_crank_nicolson_source_against_the_oracle_on_random_configurations(emu_mt, seed):
+def test_crank_nicolson_source_against_the_oracle_on_random_configurations(emu_mt, seed, push):
     """The implicit stepper's source over random boundary combinations, grids from 3 cells, 1-3 sub-steps, tight and loose Picard tolerances,
-    against oracle/literal.py (pinned to the reference's CN_step by the refsrc vectors); odd seeds reload the CN carry after two steps."""
+    against oracle/literal.py (pinned to the reference's CN_step by the refsrc vectors); odd seeds reload the CN carry after two steps.
+    Both pushes: on these small grids the sorted one's warps span the whole box, so its window and its direct path both see traffic."""
     from oracle import literal as L
     g = _random_case(900 + seed)
     rng = np.random.default_rng(seed)
@@ -369,10 +377,10 @@ def test_crank_nicolson_source_against_the_oracle_on_random_configurations(emu_m
     picard = np.zeros(T, np.int64)
     ptr = lambda a: a.ctypes.data_as(C_.c_void_p)  # noqa: E731
     x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
-    assert emu_mt.emu_cn_run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), T, n_sub, max_iter, tol, 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS],
-                             ptr(picard)) == 0
+    run = emu_mt.emu_cn_sorted_run if push == "sorted" else emu_mt.emu_cn_run
+    assert run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), T, n_sub, max_iter, tol, 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS], ptr(picard)) == 0
     assert all(np.isfinite(ref[k]).all() for k in KEYS)
-    info = {kk: g[kk] for kk in ("G", "bcs", "T")} | dict(n_sub=n_sub, max_iter=max_iter, tol=tol)
+    info = {kk: g[kk] for kk in ("G", "bcs", "T")} | dict(n_sub=n_sub, max_iter=max_iter, tol=tol, push=push)
     for k in KEYS:
         assert relerr(out[k], ref[k]) < 1e-7, (k, info)
     # the Picard loop ends on `delta > tol`; with tolerances at round-off level the last iteration is decided by the summation order

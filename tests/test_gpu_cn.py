@@ -12,7 +12,14 @@ pytestmark = pytest.mark.gpu
 KEYS = ("electric_field", "magnetic_field", "current_density", "charge_density", "positions", "velocities")
 
 
-def run_gpu_cn(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, dtype=torch.float64, steps_per_graph=0, split=None, deposit="auto"):
+@pytest.fixture
+def sorted_push(monkeypatch):
+    """Contexts created inside the test take the cell-sorted Crank-Nicolson push (csrc/jic_cn_sorted.cuh) whatever their size: the
+    library reads the threshold (default 200000 particles) when the context is created."""
+    monkeypatch.setenv("JIC_CN_SORTED_MIN", "0")
+
+
+def run_gpu_cn(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, dtype=torch.float64, steps_per_graph=0, split=None, deposit="auto", kinetic=False):
     from jaxincell_b200 import HotPath
     s = {"max_number_of_Picard_iterations_implicit_CN": 20, "number_of_particle_substeps_implicit_CN": 2,
          "tolerance_Picard_iterations_implicit_CN": 1e-6, "filter_passes": 5, "filter_alpha": 0.5, "filter_strides": (1, 2, 4), **(solver or {})}
@@ -25,11 +32,11 @@ def run_gpu_cn(p, *, length, G, dt, T, bcs=(0, 0, 0, 0), solver=None, dtype=torc
     hp.initialize(p["x0"], p["v0"])
     iters = []
     if split:
-        a = hp.run(split, particles=True); iters.append(hp.picard_iterations())
-        b = hp.run(T - split, particles=True)
+        a = hp.run(split, particles=True, kinetic=kinetic); iters.append(hp.picard_iterations())
+        b = hp.run(T - split, particles=True, kinetic=kinetic)
         out = {k: torch.cat([a[k], b[k]]) for k in a}
     else:
-        out = hp.run(T, particles=True)
+        out = hp.run(T, particles=True, kinetic=kinetic)
     iters.append(hp.picard_iterations())
     res = {k: v.cpu().numpy().astype(np.float64) for k, v in out.items()}
     E0, B0, vi = hp.initial()
@@ -74,6 +81,61 @@ def test_cn_picard_stopping_rules(tol, max_iter, substeps):
     got = run_gpu_cn(p, length=length, G=G, dt=dt, T=T, solver=solver)
     assert got["iters"][-1][1] == ref["picard_iterations"].sum()
     assert_parity(got, ref, 1e-5)
+
+
+@pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2), (1, 2, 1, 2)])
+def test_cn_sorted_push_matches_the_oracle_all_boundaries(bcs, sorted_push):
+    """The large-run variant (counting sort by cell every step, deposit aggregated per warp in shared memory) on the same cases: the
+    histories come back in input order through the permutation, the Picard counts are the oracle's, the kinetic-energy history is
+    0.5 m v^2 of the velocity history."""
+    G, length, T = 24, 0.01, 12
+    p = two_species(1500, 1500, length=length, G=G, seed=13, vth_e=0.2, vth_yz=0.1, drift=4e7, plus_minus=True, gpdl=0.008)
+    dt = cfl_dt(length, G, 0.3)
+    solver = dict(tolerance_Picard_iterations_implicit_CN=1e-9, max_number_of_Picard_iterations_implicit_CN=12, number_of_particle_substeps_implicit_CN=3)
+    ref = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, pbl=bcs[0], pbr=bcs[1], fbl=bcs[2],
+                   fbr=bcs[3], solver=solver)
+    got = run_gpu_cn(p, length=length, G=G, dt=dt, T=T, bcs=bcs, solver=solver, steps_per_graph=5, split=7, kinetic=True)
+    assert got["hp"].store_stats()["cn_sorted"] == 1
+    assert_parity(got, ref, 1e-5)
+    assert got["iters"][-1][0] == ref["picard_iterations"][-1]
+    assert got["iters"][-1][1] == ref["picard_iterations"].sum()
+    assert got["iters"][0][1] == ref["picard_iterations"][:7].sum()
+    v, m = got["velocities"], p["m"]
+    ne = p["species"][0]["count"]
+    want = np.stack([0.5 * (m[:ne] * (v[:, :ne] ** 2).sum(-1)).sum(-1), 0.5 * (m[ne:] * (v[:, ne:] ** 2).sum(-1)).sum(-1)], axis=1)
+    np.testing.assert_allclose(got["kinetic_energy"], want, rtol=1e-12)
+    x, vv, alive = (t.cpu().numpy() for t in got["hp"].particles())
+    np.testing.assert_allclose(x, ref["positions"][-1], rtol=0, atol=1e-9 * length)
+    np.testing.assert_allclose(vv, ref["velocities"][-1], rtol=1e-7, atol=1e-9 * np.abs(ref["velocities"]).max())
+    ke = float(got["hp"].kinetic_energy().cpu()[0])
+    np.testing.assert_allclose(ke, want[-1].sum(), rtol=1e-10)
+
+
+def test_cn_kinetic_energy_history_unsorted():
+    """jic_outputs.kinetic_energy of the unsorted stepper: the row is the step's (the field kernel advances the row counter first)."""
+    G, length, T = 16, 0.01, 6
+    p = two_species(400, 300, length=length, G=G, seed=2, vth_e=0.1, vth_yz=0.05, drift=3e7, plus_minus=True, gpdl=0.05)
+    got = run_gpu_cn(p, length=length, G=G, dt=cfl_dt(length, G, 0.8), T=T, kinetic=True, split=2)
+    assert got["hp"].store_stats()["cn_sorted"] == 0
+    v, m = got["velocities"], p["m"]
+    want = np.stack([0.5 * (m[:400] * (v[:, :400] ** 2).sum(-1)).sum(-1), 0.5 * (m[400:] * (v[:, 400:] ** 2).sum(-1)).sum(-1)], axis=1)
+    np.testing.assert_allclose(got["kinetic_energy"], want, rtol=1e-12)
+
+
+def test_cn_sorted_push_many_cells_wide_warps(sorted_push):
+    """Few particles per cell: a warp spans more cells than its shared-memory window holds, so most contributions take the direct
+    path -- the result must not depend on how good the order is.  (The Picard iteration on the fields diverges beyond the light
+    CFL, in the reference as well, so particles cannot be made to jump many cells per step.)"""
+    G, length, T = 256, 0.05, 8
+    p = two_species(700, 650, length=length, G=G, seed=21, vth_e=0.3, vth_yz=0.1, drift=1e8, plus_minus=True, gpdl=0.02)
+    dt = cfl_dt(length, G, 0.9)
+    solver = dict(tolerance_Picard_iterations_implicit_CN=1e-8, max_number_of_Picard_iterations_implicit_CN=15, number_of_particle_substeps_implicit_CN=2)
+    ref = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=solver)
+    assert np.isfinite(ref["electric_field"]).all()
+    got = run_gpu_cn(p, length=length, G=G, dt=dt, T=T, solver=solver)
+    assert got["hp"].store_stats()["cn_sorted"] == 1
+    assert_parity(got, ref, 1e-5)
+    assert got["iters"][-1][1] == ref["picard_iterations"].sum()
 
 
 def test_cn_conserves_energy_and_fp32_mode():
