@@ -16,13 +16,40 @@
 
 namespace jic {
 
-constexpr int kCnWin = 8;            // nodes per warp window
+#ifndef JIC_CN_WIN
+#define JIC_CN_WIN 6
+#endif
+#ifndef JIC_CN_SORTED_MINBLOCKS
+#define JIC_CN_SORTED_MINBLOCKS 7
+#endif
+constexpr int kCnWin = JIC_CN_WIN;   // nodes per warp window: a warp whose particles share a cell c touches nodes c-3 .. c+2 (a particle
+                                     // moves less than a cell per step: the Picard iteration needs c dt <= dx)
 constexpr int kCnWinComps = 4;       // J_x, J_y, J_z, rho
 constexpr int kCnColStride = 32;     // a row (node, component) holds one real per lane: the bank of an element depends on the lane alone
-constexpr int kCnSortedThreads = 256;
-static_assert(kCnWin * kCnWinComps == 32, "one (node, component) row per lane in the window reduction");
+#ifndef JIC_CN_SORTED_THREADS
+#define JIC_CN_SORTED_THREADS 128
+#endif
+constexpr int kCnSortedThreads = JIC_CN_SORTED_THREADS;
+static_assert(kCnWin * kCnWinComps <= 32, "at most one (node, component) row per lane in the window reduction");
 template <typename R>
 __host__ __device__ constexpr size_t cn_sorted_smem_bytes() { return (size_t)(kCnSortedThreads / 32) * kCnWin * kCnWinComps * kCnColStride * sizeof(R); }
+
+#ifndef JIC_CN_PREFETCH
+#define JIC_CN_PREFETCH 2
+#endif
+// hint: bring the line of `ptr` towards the SM (2: L1, 1: L2) for the warp's NEXT chunk -- no register is tied up, unlike a software
+// pipeline of loads (the kernel sits at the register limit of its occupancy)
+__device__ __forceinline__ void cn_prefetch(const void* ptr) {
+#ifdef __CUDA_ARCH__
+#if JIC_CN_PREFETCH == 2
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#elif JIC_CN_PREFETCH == 1
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#endif
+#else
+  (void)ptr;
+#endif
+}
 
 template <typename R>
 __device__ __forceinline__ int cn_cell(R x, const DevParams<R>& p) {
@@ -136,7 +163,7 @@ template <> struct CnPair<float> { using type = float2; };
 
 // One Picard iteration on sorted particles (see the header).  Same per-particle arithmetic as k_cn_push.
 template <typename R>
-__global__ void __launch_bounds__(kCnSortedThreads, 3) k_cn_push_sorted(const DevParams<R> p, CnState<R> cur, CnState<R> nxt, R* __restrict__ stag, int n_sub,
+__global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_cn_push_sorted(const DevParams<R> p, CnState<R> cur, CnState<R> nxt, R* __restrict__ stag, int n_sub,
                                                                         int it, const double* __restrict__ Eavg, const double* __restrict__ Bavg,
                                                                         R* __restrict__ acc, const uint8_t* __restrict__ alive,
                                                                         const uint8_t* __restrict__ sp_of, const CnControl* __restrict__ cn) {
@@ -168,6 +195,15 @@ __global__ void __launch_bounds__(kCnSortedThreads, 3) k_cn_push_sorted(const De
     }
     const int base = __reduce_min_sync(0xffffffffu, c0) - 3;
     __syncwarp();
+    {  // the next chunk of this warp: its state, staggered positions and bytes on their way while this one is computed
+      const long long in = i + (long long)gridDim.x * blockDim.x;
+      if (in < p.N) {
+        cn_prefetch(cur.x + in); cn_prefetch(cur.y + in); cn_prefetch(cur.z + in);
+        cn_prefetch(cur.vx + in); cn_prefetch(cur.vy + in); cn_prefetch(cur.vz + in);
+        if (it != 0) for (int s = 0; s < n_sub; ++s) cn_prefetch(stag + (size_t)s * p.N + in);
+        if ((lane & 7) == 0) { cn_prefetch(sp_of + in); cn_prefetch(alive + in); }
+      }
+    }
     // add w3[j] * (a0, a1, a2) to J (with_j) or w3[j] * a0 to rho on nodes k-1, k, k+1 (UNWRAPPED index k; idx = the wrapped ones)
     auto deposit3 = [&](int k, const R w3[3], const int idx[3], R a0, R a1, R a2, bool with_j) {
       const int rel0 = k - 1 - base;
@@ -249,7 +285,7 @@ __global__ void __launch_bounds__(kCnSortedThreads, 3) k_cn_push_sorted(const De
     __syncwarp();
     // lane l sums row l (node l / 4, component l % 4) over the 32 columns, two at a time; the XOR with the lane spreads the lanes of
     // a quarter warp over the eight 16-byte bank groups
-    {
+    if (lane < kRows) {
       const R2* row = win2 + lane * (kCnColStride / 2);
       R s0 = R(0), s1 = R(0);
 #pragma unroll

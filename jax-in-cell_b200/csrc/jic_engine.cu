@@ -115,6 +115,7 @@ struct EngineT : Engine {
   // cell-sorted Crank-Nicolson push (csrc/jic_cn_sorted.cuh): permutation (slot -> input index), species and alive bytes per slot,
   // their scatter targets, and the counting sort's histogram / offsets
   bool cn_sorted = false;
+  int cn_sort_every = 4, cn_age = 0;  // sort at steps 0, every, 2 every ... since initialisation (JIC_CN_SORT_EVERY)
   int *cn_perm = nullptr, *cn_perm2 = nullptr;
   uint8_t *cn_sp = nullptr, *cn_sp2 = nullptr, *cn_alive2 = nullptr;
   unsigned *cn_hist = nullptr, *cn_off = nullptr;
@@ -177,6 +178,7 @@ struct EngineT : Engine {
         // large runs: sorted push with warp-aggregated deposit (JIC_CN_SORTED_MIN overrides the particle-count threshold; 0 = always)
         long long min_n = 200000;
         if (const char* env = getenv("JIC_CN_SORTED_MIN")) min_n = atoll(env);
+        if (const char* env = getenv("JIC_CN_SORT_EVERY")) cn_sort_every = atoi(env) < 1 ? 1 : (atoi(env) > 64 ? 64 : atoi(env));
         cn_sorted = (long long)N >= min_n && G >= 8 && N < (1ull << 31);
         if (cn_sorted) {
           if ((rc = alloc(&cn_perm, N)) || (rc = alloc(&cn_perm2, N)) || (rc = alloc(&cn_sp, N)) || (rc = alloc(&cn_sp2, N)) ||
@@ -521,6 +523,7 @@ struct EngineT : Engine {
     JIC_CUDA(cudaMemsetAsync(ctl, 0, sizeof(RunControl), st));
     JIC_CUDA(cudaMemsetAsync(&ctl->push_t0, 0xFF, sizeof(unsigned long long), st));
     par = 0;
+    cn_age = 0;
     return JIC_OK;
   }
 
@@ -633,22 +636,28 @@ struct EngineT : Engine {
   }
 
   // one CN step reading particle buffer `p`: max_iter x (push, all-reduce, fields); iterations after convergence return at once
-  // sorted variant: the state of buffer p is scattered, cell by cell, into buffer p ^ 1 (with the permutation and the per-slot bytes),
-  // the Picard iterations read p ^ 1 and write p, so the step ends where it began and `par` does not flip
-  int enqueue_step_cn_sorted(cudaStream_t st, int p) {
+  // sorted variant, a step that sorts: the state of buffer p is scattered, cell by cell, into buffer p ^ 1 (with the permutation and
+  // the per-slot bytes), the Picard iterations read p ^ 1 and write p, so the step ends where it began.  A step that does not sort
+  // (particles move less than a cell per step, so the order stays good for a few steps: cn_sort_every) reads p and writes p ^ 1 like
+  // the unsorted stepper; slot i stays slot i, the permutation and the bytes stand.
+  int enqueue_step_cn_sorted(cudaStream_t st, int p, bool sort) {
     const int g = grid_for(dp.N, 256, 8);
     const size_t N = (size_t)dp.N;
-    k_cn_hist<R><<<g, 256, 0, st>>>(dp, cn_s[p].x, cn_hist);
-    k_cn_scan<<<1, 1024, 0, st>>>(dp.G, cn_hist, cn_off);
-    k_cn_scatter<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive, cn_alive2, cn_off, cn_hist);
-    JIC_CUDA(cudaMemsetAsync(cn_hist, 0, sizeof(unsigned) * dp.G, st));  // (the scatter used it as its cursors)
-    JIC_CUDA(cudaMemcpyAsync(cn_perm, cn_perm2, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
-    JIC_CUDA(cudaMemcpyAsync(cn_sp, cn_sp2, N, cudaMemcpyDeviceToDevice, st));
-    JIC_CUDA(cudaMemcpyAsync(cn_alive, cn_alive2, N, cudaMemcpyDeviceToDevice, st));
-    launches += 3;
-    const int gs = grid_for(dp.N, kCnSortedThreads, 3);
+    int src = p, dst = p ^ 1;  // the iterations read src and write dst
+    if (sort) {
+      k_cn_hist<R><<<g, 256, 0, st>>>(dp, cn_s[p].x, cn_hist);
+      k_cn_scan<<<1, 1024, 0, st>>>(dp.G, cn_hist, cn_off);
+      k_cn_scatter<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_s[p ^ 1], cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive, cn_alive2, cn_off, cn_hist);
+      JIC_CUDA(cudaMemsetAsync(cn_hist, 0, sizeof(unsigned) * dp.G, st));  // (the scatter used it as its cursors)
+      JIC_CUDA(cudaMemcpyAsync(cn_perm, cn_perm2, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      JIC_CUDA(cudaMemcpyAsync(cn_sp, cn_sp2, N, cudaMemcpyDeviceToDevice, st));
+      JIC_CUDA(cudaMemcpyAsync(cn_alive, cn_alive2, N, cudaMemcpyDeviceToDevice, st));
+      launches += 3;
+      src = p ^ 1; dst = p;
+    }
+    const int gs = grid_for(dp.N, kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS);
     for (int it = 0; it < prm.cn_max_iterations; ++it) {
-      k_cn_push_sorted<R><<<gs, kCnSortedThreads, cn_sorted_smem_bytes<R>(), st>>>(dp, cn_s[p ^ 1], cn_s[p], cn_stag, prm.cn_substeps, it, cn_Eavg,
+      k_cn_push_sorted<R><<<gs, kCnSortedThreads, cn_sorted_smem_bytes<R>(), st>>>(dp, cn_s[src], cn_s[dst], cn_stag, prm.cn_substeps, it, cn_Eavg,
                                                                                     cn_Bavg, acc, cn_alive, cn_sp, cn_ctl);
       int rc = allreduce(st, 0, true);
       if (rc) return rc;
@@ -656,17 +665,21 @@ struct EngineT : Engine {
       launches += 2;
     }
     if (ke_hist) {
-      k_cn_kinetic_sorted<R><<<g, 256, 0, st>>>(dp, cn_s[p].vx, cn_s[p].vy, cn_s[p].vz, cn_sp, nullptr, ctl, 1);
+      k_cn_kinetic_sorted<R><<<g, 256, 0, st>>>(dp, cn_s[dst].vx, cn_s[dst].vy, cn_s[dst].vz, cn_sp, nullptr, ctl, 1);
       launches += 1;
     }
-    k_cn_record_sorted<R><<<g, 256, 0, st>>>(dp, cn_s[p], cn_perm, ctl);
+    k_cn_record_sorted<R><<<g, 256, 0, st>>>(dp, cn_s[dst], cn_perm, ctl);
     launches += 1;
     JIC_CUDA(cudaGetLastError());
     return JIC_OK;
   }
+  // host-side cursor of the sorted stepper: (buffer that holds x_n, steps since the last sort) after one more step
+  static void cn_sorted_advance(int& p, int& age, int every) {
+    if (age != 0) p ^= 1;
+    age = (age + 1) % every;
+  }
 
   int enqueue_step_cn(cudaStream_t st, int p) {
-    if (cn_sorted) return enqueue_step_cn_sorted(st, p);
     const int g = grid_for(dp.N, 256, 8);
     int per_sm = (int)((size_t)200 * 1024 / (shared_bytes + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
@@ -815,11 +828,12 @@ struct EngineT : Engine {
     int rc = JIC_OK;
     for (long long s = 0; s < n && rc == JIC_OK; ++s) {
       cudaEventRecord(ev[3 * s], st);
-      rc = cn ? enqueue_step_cn(st, par) : enqueue_push(st, par);
+      rc = cn ? (cn_sorted ? enqueue_step_cn_sorted(st, par, cn_age == 0) : enqueue_step_cn(st, par)) : enqueue_push(st, par);
       cudaEventRecord(ev[3 * s + 1], st);
       if (rc == JIC_OK && !cn) rc = enqueue_fields(st, par);
       cudaEventRecord(ev[3 * s + 2], st);
       if (flips()) par ^= 1;
+      if (cn_sorted) cn_sorted_advance(par, cn_age, cn_sort_every);
     }
     cudaError_t ce = cudaStreamSynchronize(st);
     double a = 0, b = 0;
@@ -839,7 +853,8 @@ struct EngineT : Engine {
   }
 
   int get_graph(int steps, cudaStream_t st, cudaGraphExec_t* exec) {
-    const int key = (steps * 2 + par) * 2 + (ke_hist ? 1 : 0);  // the buffer pointers baked into the graph depend on the starting parity
+    // the buffer pointers baked into the graph depend on the starting parity (and, sorted CN, on which of its steps sort)
+    const int key = ((steps * 2 + par) * 2 + (ke_hist ? 1 : 0)) * 64 + (cn_sorted ? cn_age : 0);
     auto it = graphs.find(key);
     if (it != graphs.end()) { *exec = it->second; return JIC_OK; }
     cudaStream_t cs;
@@ -848,7 +863,15 @@ struct EngineT : Engine {
     cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     int rc = JIC_OK;
     if (e == cudaSuccess) {
-      for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, flips() ? (par ^ (s & 1)) : (cn ? par : 0));
+      if (cn_sorted) {
+        int p = par, age = cn_age;
+        for (int s = 0; s < steps && rc == JIC_OK; ++s) {
+          rc = enqueue_step_cn_sorted(cs, p, age == 0);
+          cn_sorted_advance(p, age, cn_sort_every);
+        }
+      } else {
+        for (int s = 0; s < steps && rc == JIC_OK; ++s) rc = enqueue_step(cs, flips() ? (par ^ (s & 1)) : (cn ? par : 0));
+      }
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
@@ -901,11 +924,17 @@ struct EngineT : Engine {
       launches += per_step * steps;
       done += steps;
       if (flips()) par ^= steps & 1;
+      if (cn_sorted) {
+        for (int k = 0; k < steps; ++k) {
+          if (cn_age == 0) launches += 3;  // (hist, scan, scatter of a step that sorts)
+          cn_sorted_advance(par, cn_age, cn_sort_every);
+        }
+      }
     }
     return JIC_OK;
   }
-  // do consecutive steps alternate between the ping-pong buffers?  (multi-CTA field kernel; unsorted CN state.  The sorted CN step
-  // scatters p -> p ^ 1 and iterates p ^ 1 -> p: it ends where it began.)
+  // do consecutive steps alternate between the ping-pong buffers?  (multi-CTA field kernel; unsorted CN state.  The sorted CN stepper
+  // keeps its own cursor: cn_sorted_advance.)
   bool flips() const { return mc || (cn && !cn_sorted); }
 
   // device-timed push kernel: summed %globaltimer span (first CTA in, last CTA out) of the launches since the last reset
@@ -950,7 +979,7 @@ struct EngineT : Engine {
   }
 
   long long count_launches_per_step() const {
-    if (cn) return 1 + (cn_sorted ? 3 : 0) + (ke_hist ? 1 : 0) + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
+    if (cn) return 1 + (ke_hist ? 1 : 0) + (long long)prm.cn_max_iterations * (2 + (world > 1 ? 1 : 0));
     long long k = 2 + ((world > 1 && !fused()) ? 1 : 0) + dp.stag + (ke_hist ? 1 : 0);
     if (prm.engine == JIC_ENGINE_BINNED) k += bins.extra_launches_per_step();
     return k;

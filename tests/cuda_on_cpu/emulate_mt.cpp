@@ -218,6 +218,9 @@ __attribute__((visibility("default"))) int emu_fs_run_two_ranks(const EmuParams*
   return 0;
 }
 
+static int g_cn_sort_every = 1;  // EngineT::cn_sort_every (JIC_CN_SORT_EVERY)
+extern "C" __attribute__((visibility("default"))) void emu_set_cn_sort_every(int k) { g_cn_sort_every = k < 1 ? 1 : k; }
+
 static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, const double* v0, int T, int n_sub, int max_iter, double tol,
                            int reload_at, double* hE, double* hB, double* hJ, double* hrho, double* hx, double* hv, long long* picard) {
   long long N;
@@ -251,7 +254,7 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
   emu_launch(1, kThreads, [&] { k_fields<R>(gs.field_args(ep, true, false)); });
   gs.E = gs.E0; gs.B = gs.B0;
   emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(0, true)); });
-  int par = 0;
+  int par = 0, age = 0;
   for (int t = 0; t < T; ++t) {
     if (t == reload_at && t > 0) {
       std::vector<R> x(3 * n), v(3 * n), E_c(gs.E.begin(), gs.E.end()), B_c(gs.B.begin(), gs.B.end());
@@ -272,7 +275,7 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
       std::fill(gs.acc.begin(), gs.acc.end(), 0.0);
       const CnControl keep = cn;
       std::memset(&cn, 0, sizeof(cn));
-      par = 0;  // EngineT::load_carry_cn
+      par = 0; age = 0;  // EngineT::load_carry_cn
       emu_launch(2, kThreads, [&] { k_cn_load<R>(p, x.data(), v.data(), alive_in.data(), cs[0], v_init.data(), alive.data()); });
       if (sorted) emu_launch(2, kThreads, [&] { k_cn_meta_init<R>(p, perm.data(), sp.data()); });
       emu_launch(1, kThreads, [&] { k_carry_copy_fields<R>(E_c.data(), B_c.data(), gs.E.data(), gs.B.data(), gs.E0.data(), gs.B0.data(), (int)(G * 3)); });
@@ -280,21 +283,27 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
       cn.total_iters = keep.total_iters;
     }
     gs.ctl.hist[0] = hE; gs.ctl.hist[1] = hB; gs.ctl.hist[2] = hJ; gs.ctl.hist[3] = hrho; gs.ctl.hist[4] = hx; gs.ctl.hist[5] = hv;
-    if (sorted) {  // EngineT::enqueue_step_cn_sorted
-      emu_launch(3, kThreads, [&] { k_cn_hist<R>(p, cs[par].x, hist.data()); });
-      emu_launch(1, kThreads, [&] { k_cn_scan((int)G, hist.data(), off.data()); });
-      emu_launch(3, kThreads, [&] { k_cn_scatter<R>(p, cs[par], cs[par ^ 1], perm.data(), perm2.data(), sp.data(), sp2.data(), alive.data(), alive2.data(),
-                                                    off.data(), hist.data()); });
-      std::fill(hist.begin(), hist.end(), 0u);
-      perm = perm2; sp = sp2; alive = alive2;
+    if (sorted) {  // EngineT::enqueue_step_cn_sorted + cn_sorted_advance
+      int src = par, dst = par ^ 1;
+      if (age == 0) {
+        emu_launch(3, kThreads, [&] { k_cn_hist<R>(p, cs[par].x, hist.data()); });
+        emu_launch(1, kThreads, [&] { k_cn_scan((int)G, hist.data(), off.data()); });
+        emu_launch(3, kThreads, [&] { k_cn_scatter<R>(p, cs[par], cs[par ^ 1], perm.data(), perm2.data(), sp.data(), sp2.data(), alive.data(), alive2.data(),
+                                                      off.data(), hist.data()); });
+        std::fill(hist.begin(), hist.end(), 0u);
+        perm = perm2; sp = sp2; alive = alive2;
+        src = par ^ 1; dst = par;
+      }
       for (int it = 0; it < max_iter; ++it) {
-        emu_launch(3, kThreads, [&] { k_cn_push_sorted<R>(p, cs[par ^ 1], cs[par], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(),
-                                                                  alive.data(), sp.data(), &cn); });
+        emu_launch(3, kThreads, [&] { k_cn_push_sorted<R>(p, cs[src], cs[dst], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(),
+                                                          alive.data(), sp.data(), &cn); });
         emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(it, false)); });
       }
-      emu_launch(2, kThreads, [&] { k_cn_record_sorted<R>(p, cs[par], perm.data(), &gs.ctl); });
+      emu_launch(2, kThreads, [&] { k_cn_record_sorted<R>(p, cs[dst], perm.data(), &gs.ctl); });
       if (picard) picard[t] = cn.last_iters;
-      continue;  // (the step ends in the buffer it began in)
+      if (age != 0) par ^= 1;
+      age = (age + 1) % g_cn_sort_every;
+      continue;
     }
     for (int it = 0; it < max_iter; ++it) {  // EngineT::enqueue_step_cn
       emu_launch(3, kThreads, [&] { k_cn_push<R, false>(p, cs[par], cs[par ^ 1], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(), alive.data(), &cn); });

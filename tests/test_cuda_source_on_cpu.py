@@ -185,6 +185,7 @@ def emu_mt(tmp_path_factory):
     lib.emu_cn_run.argtypes = [C.POINTER(EmuParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 7
     lib.emu_cn_sorted_run.restype = C.c_int
     lib.emu_cn_sorted_run.argtypes = lib.emu_cn_run.argtypes
+    lib.emu_set_cn_sort_every.argtypes = [C.c_int]
     return lib
 
 
@@ -248,6 +249,7 @@ def test_crank_nicolson_source_on_the_threaded_emulation(emu_mt, path, reload_at
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
     run = emu_mt.emu_cn_sorted_run if push == "sorted" else emu_mt.emu_cn_run
+    emu_mt.emu_set_cn_sort_every(4 if reload_at > 0 else 1)  # (the engine's default is a sort every fourth step)
     rc = run(C.byref(_params_of(g)), ptr(x0), ptr(v0), T, int(g["cn_substeps"]), int(g["cn_max_iterations"]), float(g["cn_tolerance"]),
              reload_at, *[ptr(out[k]) for k in KEYS], ptr(picard))
     assert rc == 0
@@ -378,6 +380,7 @@ def test_crank_nicolson_source_against_the_oracle_on_random_configurations(emu_m
     ptr = lambda a: a.ctypes.data_as(C_.c_void_p)  # noqa: E731
     x0, v0 = np.ascontiguousarray(g["x0"], np.float64), np.ascontiguousarray(g["v0"], np.float64)
     run = emu_mt.emu_cn_sorted_run if push == "sorted" else emu_mt.emu_cn_run
+    emu_mt.emu_set_cn_sort_every(1 + seed % 4)
     assert run(C_.byref(_params_of(g)), ptr(x0), ptr(v0), T, n_sub, max_iter, tol, 2 if seed % 2 else -1, *[ptr(out[k]) for k in KEYS], ptr(picard)) == 0
     assert all(np.isfinite(ref[k]).all() for k in KEYS)
     info = {kk: g[kk] for kk in ("G", "bcs", "T")} | dict(n_sub=n_sub, max_iter=max_iter, tol=tol, push=push)
