@@ -173,6 +173,7 @@ struct CnFieldArgs {
   double *En, *Bn;         // fields at the start of the step (G,3); replaced when the step ends
   double *Eg, *Bnext;      // current guess of E^{n+1}; B^{n+1} of the current iteration
   double *Eavg, *Bavg;     // what the push gathers
+  double* EB;              // optional (sorted push): the same packed per node, (E_avg[k], B_avg[k + 1]) -- see cn_prepare
   double *J, *rho;         // outputs of the step
   CnControl* cn;
   RunControl* ctl;
@@ -194,8 +195,10 @@ __device__ __forceinline__ double block_reduce(double v, bool take_max, double* 
 }
 
 // Faraday with the averaged E and the tables the push gathers: _algorithms.py:133-142
+// EB (optional): row k = (E_avg[k], B_avg[(k + 1) mod G]).  The faces of B sit one node left of those of E (_algorithms.py:110-111), so
+// the B stencil of a particle is its E stencil shifted by one node with the same weights: one packed row per stencil node serves both.
 __device__ __forceinline__ void cn_prepare(const double* En, const double* Bn, const double* Eg, double* Bnext, double* Eavg, double* Bavg,
-                                           int G, int fbl, double dx, double dt) {
+                                           int G, int fbl, double dx, double dt, double* EB = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int k = tid; k < G * 3; k += nt) Eavg[k] = 0.5 * (En[k] + Eg[k]);
   __syncthreads();
@@ -210,6 +213,13 @@ __device__ __forceinline__ void cn_prepare(const double* En, const double* Bn, c
     Bavg[i * 3] = 0.5 * (bn0 + b0); Bavg[i * 3 + 1] = 0.5 * (bn1 + b1); Bavg[i * 3 + 2] = 0.5 * (bn2 + b2);
   }
   __syncthreads();
+  if (EB) {
+    for (int i = tid; i < G; i += nt) {
+      const int ib = i + 1 < G ? i + 1 : 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { EB[i * 6 + c] = Eavg[i * 3 + c]; EB[i * 6 + 3 + c] = Bavg[ib * 3 + c]; }
+    }
+  }
 }
 
 template <typename R>
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(1024) k_cn_fields(const CnFieldArgs<R> a) {
     for (int k = tid; k < G * 3; k += nt) a.Eg[k] = a.En[k];
     if (tid == 0) { a.cn->converged = 0; a.cn->iter = 0; }
     __syncthreads();
-    cn_prepare(a.En, a.Bn, a.Eg, a.Bnext, a.Eavg, a.Bavg, G, a.fbl, a.dx, a.dt);
+    cn_prepare(a.En, a.Bn, a.Eg, a.Bnext, a.Eavg, a.Bavg, G, a.fbl, a.dx, a.dt, a.EB);
     return;
   }
   if (a.it > 0 && a.cn->converged) return;
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(1024) k_cn_fields(const CnFieldArgs<R> a) {
   __syncthreads();
   if (more) {
     if (tid == 0) { a.cn->iter = iter; a.cn->converged = 0; }
-    cn_prepare(a.En, a.Bn, a.Eg, a.Bnext, a.Eavg, a.Bavg, G, a.fbl, a.dx, a.dt);
+    cn_prepare(a.En, a.Bn, a.Eg, a.Bnext, a.Eavg, a.Bavg, G, a.fbl, a.dx, a.dt, a.EB);
     return;
   }
   // ---- the step ends: E^{n+1} = last E_calc, B^{n+1} = the B_next this iteration pushed with (:229-241)
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(1024) k_cn_fields(const CnFieldArgs<R> a) {
     a.ctl->hist_row = row + 1; a.ctl->step += 1;
   }
   // first Faraday of the next step (guess = the new E^n)
-  cn_prepare(a.En, a.Bn, a.Eg, a.Bnext, a.Eavg, a.Bavg, G, a.fbl, a.dx, a.dt);
+  cn_prepare(a.En, a.Bn, a.Eg, a.Bnext, a.Eavg, a.Bavg, G, a.fbl, a.dx, a.dt, a.EB);
 }
 
 }  // namespace jic

@@ -20,7 +20,7 @@ namespace jic {
 #define JIC_CN_WIN 6
 #endif
 #ifndef JIC_CN_SORTED_MINBLOCKS
-#define JIC_CN_SORTED_MINBLOCKS 7
+#define JIC_CN_SORTED_MINBLOCKS 6
 #endif
 constexpr int kCnWin = JIC_CN_WIN;   // nodes per warp window: a warp whose particles share a cell c touches nodes c-3 .. c+2 (a particle
                                      // moves less than a cell per step: the Picard iteration needs c dt <= dx)
@@ -164,8 +164,7 @@ template <> struct CnPair<float> { using type = float2; };
 // One Picard iteration on sorted particles (see the header).  Same per-particle arithmetic as k_cn_push.
 template <typename R>
 __global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_cn_push_sorted(const DevParams<R> p, CnState<R> cur, CnState<R> nxt, R* __restrict__ stag, int n_sub,
-                                                                        int it, const double* __restrict__ Eavg, const double* __restrict__ Bavg,
-                                                                        R* __restrict__ acc, const uint8_t* __restrict__ alive,
+                                                                        int it, const double* __restrict__ EB, R* __restrict__ acc, const uint8_t* __restrict__ alive,
                                                                         const uint8_t* __restrict__ sp_of, const CnControl* __restrict__ cn) {
   if (it > 0 && cn->converged) return;
   using R2 = typename CnPair<R>::type;
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_c
   R* win = reinterpret_cast<R*>(cn_sorted_smem) + (size_t)warp * kRows * kCnColStride;  // rows (node, comp) x 32 lanes
   R2* win2 = reinterpret_cast<R2*>(win);
   const R dtau = p.dt / R(n_sub), half_dtau = R(0.5) * dtau;
-  const R e_start = p.g0 + p.half_dx, b_start = p.g0 - p.half_dx;  // _algorithms.py:110-111
+  const R e_start = p.g0 + p.half_dx;  // _algorithms.py:110 (the B faces, :111, are the E faces shifted by one node: table EB)
   const R w_sub = dtau / p.dt;
   const GlobalGrid<R> grid{acc};
   for (long long i0 = (blockIdx.x * (long long)blockDim.x + warp * 32); i0 < p.N; i0 += (long long)gridDim.x * blockDim.x) {
@@ -240,18 +239,17 @@ __global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_c
         // (the staggered position of the NEXT sub-step is fetched before this one's is replaced: the store below would otherwise
         // fence the load behind it)
         const R xs_next = (it != 0 && s + 1 < n_sub) ? stag[(size_t)(s + 1) * p.N + i] : x_n;
-        int ie[3], ib[3];
-        R we[3], wb[3];
+        int ie[3];
+        R we[3];
         const int ke = cn_stencil_fast(xs, e_start, p, ie, we);  // unwrapped centre node of the face stencil
-        cn_stencil_fast(xs, b_start, p, ib, wb);
         R E[3] = {0, 0, 0}, B[3] = {0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            E[c] += we[k] * (R)__ldg(Eavg + ie[k] * 3 + c);
-            B[c] += wb[k] * (R)__ldg(Bavg + ib[k] * 3 + c);
-          }
+        for (int k = 0; k < 3; ++k) {  // row ie[k] of the packed table: E on face ie[k], B on the B face of the same stencil slot
+          const double2* row = reinterpret_cast<const double2*>(EB + ie[k] * 6);
+          const double2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
+          E[0] += we[k] * (R)r0.x; E[1] += we[k] * (R)r0.y; E[2] += we[k] * (R)r1.x;
+          B[0] += we[k] * (R)r1.y; B[1] += we[k] * (R)r2.x; B[2] += we[k] * (R)r2.y;
+        }
         R vnew[3] = {vel[0], vel[1], vel[2]};
         boris_velocity(vnew, E, B, qm, dtau);
         R vmid[3] = {R(0.5) * (vel[0] + vnew[0]), R(0.5) * (vel[1] + vnew[1]), R(0.5) * (vel[2] + vnew[2])};

@@ -119,6 +119,7 @@ struct EngineT : Engine {
   int *cn_perm = nullptr, *cn_perm2 = nullptr;
   uint8_t *cn_sp = nullptr, *cn_sp2 = nullptr, *cn_alive2 = nullptr;
   unsigned *cn_hist = nullptr, *cn_off = nullptr;
+  double* cn_EB = nullptr;  // (G,6) packed gather table of the sorted push: CnFieldArgs::EB
 
   int dtype() const override { return prm.dtype; }
   long long n_particles() const override { return dp.N; }
@@ -182,7 +183,7 @@ struct EngineT : Engine {
         cn_sorted = (long long)N >= min_n && G >= 8 && N < (1ull << 31);
         if (cn_sorted) {
           if ((rc = alloc(&cn_perm, N)) || (rc = alloc(&cn_perm2, N)) || (rc = alloc(&cn_sp, N)) || (rc = alloc(&cn_sp2, N)) ||
-              (rc = alloc(&cn_alive2, N)) || (rc = alloc(&cn_hist, G)) || (rc = alloc(&cn_off, G + 1)))
+              (rc = alloc(&cn_alive2, N)) || (rc = alloc(&cn_hist, G)) || (rc = alloc(&cn_off, G + 1)) || (rc = alloc(&cn_EB, G * 6)))
             return rc;
           JIC_CUDA(cudaFuncSetAttribute(k_cn_push_sorted<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cn_sorted_smem_bytes<R>()));
         }
@@ -291,7 +292,7 @@ struct EngineT : Engine {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (int k = 0; k < 2; ++k) { if (ev_copied[k]) cudaEventDestroy(ev_copied[k]); if (ev_used[k]) cudaEventDestroy(ev_used[k]); }
     for (int k = 0; k < 2; ++k) { void* q[] = {cn_s[k].x, cn_s[k].y, cn_s[k].z, cn_s[k].vx, cn_s[k].vy, cn_s[k].vz}; for (void* p : q) if (p) cudaFree(p); }
-    void* ptrs[] = {cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive2, cn_hist, cn_off, cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
+    void* ptrs[] = {cn_EB, cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive2, cn_hist, cn_off, cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
     for (void* p : ptrs) if (p) cudaFree(p);
     bins.destroy();
     if (comm && !comm_shared && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
@@ -611,7 +612,7 @@ struct EngineT : Engine {
     a.G = dp.G; a.fbl = dp.fbl; a.fbr = dp.fbr; a.it = it; a.max_iter = prm.cn_max_iterations; a.prepare_only = prepare_only ? 1 : 0;
     a.dx = prm.dx; a.dt = prm.dt; a.tol = prm.cn_tolerance;
     a.acc = acc; a.En = E; a.Bn = B; a.Eg = cn_Eg; a.Bnext = cn_Bnext; a.Eavg = cn_Eavg; a.Bavg = cn_Bavg; a.J = J; a.rho = rho;
-    a.cn = cn_ctl; a.ctl = ctl;
+    a.cn = cn_ctl; a.ctl = ctl; a.EB = cn_EB;
     return a;
   }
 
@@ -657,8 +658,8 @@ struct EngineT : Engine {
     }
     const int gs = grid_for(dp.N, kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS);
     for (int it = 0; it < prm.cn_max_iterations; ++it) {
-      k_cn_push_sorted<R><<<gs, kCnSortedThreads, cn_sorted_smem_bytes<R>(), st>>>(dp, cn_s[src], cn_s[dst], cn_stag, prm.cn_substeps, it, cn_Eavg,
-                                                                                    cn_Bavg, acc, cn_alive, cn_sp, cn_ctl);
+      k_cn_push_sorted<R><<<gs, kCnSortedThreads, cn_sorted_smem_bytes<R>(), st>>>(dp, cn_s[src], cn_s[dst], cn_stag, prm.cn_substeps, it, cn_EB,
+                                                                                    acc, cn_alive, cn_sp, cn_ctl);
       int rc = allreduce(st, 0, true);
       if (rc) return rc;
       k_cn_fields<R><<<1, 1024, 0, st>>>(cn_field_args(it, false));

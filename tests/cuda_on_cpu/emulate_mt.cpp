@@ -237,6 +237,8 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
   std::vector<int> perm(n), perm2(n);
   std::vector<unsigned> hist(G, 0u), off(G, 0u);
   std::vector<double> Eg(G * 3), Bnext(G * 3), Eavg(G * 3), Bavg(G * 3);
+  std::vector<double> EB_store(G * 6 + 2);
+  double* EB = sorted ? (double*)(((uintptr_t)EB_store.data() + 15) & ~(uintptr_t)15) : nullptr;  // (read 16 bytes at a time)
   CnControl cn;
   std::memset(&cn, 0, sizeof(cn));
   auto cn_args = [&](int it, bool prepare_only) {  // EngineT::cn_field_args
@@ -245,7 +247,7 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
     a.G = ep->G; a.fbl = ep->fbl; a.fbr = ep->fbr; a.it = it; a.max_iter = max_iter; a.prepare_only = prepare_only ? 1 : 0;
     a.dx = ep->dx; a.dt = ep->dt; a.tol = tol;
     a.acc = gs.acc.data(); a.En = gs.E.data(); a.Bn = gs.B.data(); a.Eg = Eg.data(); a.Bnext = Bnext.data(); a.Eavg = Eavg.data(); a.Bavg = Bavg.data();
-    a.J = gs.J.data(); a.rho = gs.rho.data(); a.cn = &cn; a.ctl = &gs.ctl;
+    a.J = gs.J.data(); a.rho = gs.rho.data(); a.cn = &cn; a.ctl = &gs.ctl; a.EB = EB;
     return a;
   };
   // EngineT::initialize_cn
@@ -272,6 +274,7 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
       for (int k = 0; k < 2; ++k) for (auto& b : buf[k]) std::fill(b.begin(), b.end(), 1e300);
       std::fill(alive.begin(), alive.end(), 7); std::fill(gs.E.begin(), gs.E.end(), 1e300); std::fill(gs.B.begin(), gs.B.end(), 1e300);
       std::fill(Eg.begin(), Eg.end(), 1e300); std::fill(Eavg.begin(), Eavg.end(), 1e300); std::fill(Bavg.begin(), Bavg.end(), 1e300);
+      std::fill(EB_store.begin(), EB_store.end(), 1e300);
       std::fill(gs.acc.begin(), gs.acc.end(), 0.0);
       const CnControl keep = cn;
       std::memset(&cn, 0, sizeof(cn));
@@ -295,7 +298,7 @@ static int emu_cn_run_impl(bool sorted, const EmuParams* ep, const double* x0, c
         src = par ^ 1; dst = par;
       }
       for (int it = 0; it < max_iter; ++it) {
-        emu_launch(3, kThreads, [&] { k_cn_push_sorted<R>(p, cs[src], cs[dst], stag.data(), n_sub, it, Eavg.data(), Bavg.data(), gs.acc.data(),
+        emu_launch(3, kThreads, [&] { k_cn_push_sorted<R>(p, cs[src], cs[dst], stag.data(), n_sub, it, EB, gs.acc.data(),
                                                           alive.data(), sp.data(), &cn); });
         emu_launch(1, kThreads, [&] { k_cn_fields<R>(cn_args(it, false)); });
       }
