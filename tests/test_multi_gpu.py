@@ -100,9 +100,13 @@ def _worker_modes(rank, world, port, mode, q):
         dt = cfl_dt(length, G, 0.3)
         x, v, idx = shard_particles(p["x0"], p["v0"], p["species"], rank, world)
         kw = dict(field_solver=1, engine="binned") if mode == "field_solver" else dict(time_evolution_algorithm=1, cn_max_iterations=6, cn_tolerance=1e-8)
+        if mode == "crank_nicolson_sorted":  # the large-run push (csrc/jic_cn_sorted.cuh) on every rank's shard, whatever its size
+            os.environ["JIC_CN_SORTED_MIN"] = "0"
         hp = HotPath(species=shard_species(p["species"], rank, world), length=length, G=G, dt=dt, **kw)
         hp.comm_init_from_torch()
         assert hp.comm_mode() == "nccl"
+        if mode != "field_solver":
+            assert hp.store_stats()["cn_sorted"] == (1 if mode == "crank_nicolson_sorted" else 0)
         hp.set_external_fields(None, None)
         hp.initialize(x, v)
         out = hp.run(T)
@@ -131,7 +135,7 @@ def _worker_modes(rank, world, port, mode, q):
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", ["field_solver", "crank_nicolson"])
+@pytest.mark.parametrize("mode", ["field_solver", "crank_nicolson", "crank_nicolson_sorted"])
 def test_n_gpus_field_solver_and_crank_nicolson(mode, world):
     import torch
     import torch.multiprocessing as mp
