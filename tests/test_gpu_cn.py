@@ -111,6 +111,18 @@ def test_cn_sorted_push_matches_the_oracle_all_boundaries(bcs, sorted_push):
     np.testing.assert_allclose(ke, want[-1].sum(), rtol=1e-10)
 
 
+def test_cn_sorted_push_fp32(sorted_push):
+    """The float instantiation of the sorted push (float window, float2 reduction) within the fp32 tolerance on E, J and rho."""
+    G, length, T = 32, 0.01, 10
+    p = two_species(4000, 4000, length=length, G=G, seed=5, vth_e=0.05, vth_yz=0.02, drift=5e7, plus_minus=True, gpdl=0.03)
+    dt = cfl_dt(length, G, 0.9)
+    solver = dict(tolerance_Picard_iterations_implicit_CN=1e-4, max_number_of_Picard_iterations_implicit_CN=25)
+    ref = L.run_CN(p["x0"], p["v0"], p["q"], p["m"], p["qm"], length=length, G=G, dt=dt, total_steps=T, solver=solver)
+    got = run_gpu_cn(p, length=length, G=G, dt=dt, T=T, solver=solver, dtype=torch.float32)
+    assert got["hp"].store_stats()["cn_sorted"] == 1
+    assert_parity(got, ref, 1e-3, keys=("electric_field", "current_density", "charge_density"))
+
+
 def test_cn_kinetic_energy_history_unsorted():
     """jic_outputs.kinetic_energy of the unsorted stepper: the row is the step's (the field kernel advances the row counter first)."""
     G, length, T = 16, 0.01, 6

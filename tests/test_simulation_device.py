@@ -60,6 +60,28 @@ def test_kinetic_energy_history_matches_the_particle_histories():
     assert dev["dominant_frequency"] == pytest.approx(full["dominant_frequency"], rel=1e-12)
 
 
+def test_crank_nicolson_device_resident_takes_the_sorted_push_and_matches_the_particle_histories():
+    """time_evolution_algorithm = 1 with 2.4e5 particles: above the library's threshold, so the device-resident run steps with the
+    cell-sorted Crank-Nicolson push; its fields and device-reduced kinetic energies against the host path of the same dictionary with
+    JIC_CN_SORTED_MIN raised (unsorted push, (T,N,3) histories kept, energies from the velocity history)."""
+    import os
+    from jaxincell_b200 import Simulation, diagnostics
+    cn = dict(time_evolution_algorithm=1, max_number_of_Picard_iterations_implicit_CN=8, tolerance_Picard_iterations_implicit_CN=1e-9,
+              number_of_particle_substeps_implicit_CN=2)
+    par = _parameters(n=120_000, T=10, **cn)
+    par["solver_parameters"].update(particle_history=True)
+    os.environ["JIC_CN_SORTED_MIN"] = str(1 << 40)
+    try:
+        full = diagnostics(Simulation(par).run())
+    finally:
+        del os.environ["JIC_CN_SORTED_MIN"]
+    dev = diagnostics(Simulation(_parameters(n=120_000, T=10, device_resident=True, kinetic_energy_history=True, **cn)).run())
+    for k in FIELDS:
+        assert _rel(dev[k], full[k]) < 1e-8, k
+    for k in ("kinetic_energy", "kinetic_energy_electrons", "kinetic_energy_ions", "total_energy"):
+        assert _rel(dev[k], full[k]) < 1e-8, k
+
+
 def test_kinetic_energy_history_through_the_c_abi_all_engines():
     """jic_outputs.kinetic_energy on both engines against 0.5 m v^2 of the velocity history (INDEXED keeps it)."""
     import torch
