@@ -288,7 +288,7 @@ def run_reference(args):
             "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference itself cannot run here (import jaxincell from baseline/_ref -> " + str(why_not) + "); "
                     "this is the oracle port of its algorithm (compiled C + OpenMP restatement, NumPy if no compiler) on the host cores"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def np_isfinite(a):
@@ -372,7 +372,30 @@ def timed_run(hp, torch, dist, world, K, outs, barrier):
     return ms, (kms / kn if kn else None), kn
 
 
+_JSON_FD = None
+
+
+def keep_stdout_for_the_json_line():
+    """Libraries write to stdout behind Python's back (NCCL prints its version line there at communicator creation): from here on
+    file descriptor 1 is stderr, and the ONE JSON line goes to the descriptor that was stdout when the process started."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.buffer.write(data); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -678,7 +701,7 @@ def main():
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
             rate, cores, sample, _ = cpu_port_rate(w, seconds_target=12.0)
             line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
