@@ -39,9 +39,9 @@ def build(force=False, verbose=False, out=None, defines=None):
         return OUT
     out = out or OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false".replace("=false", ""),
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-I", nccl_include(), "-o", out, os.path.join(CSRC, "jic_engine.cu"), "-ldl"]
-    cmd = [c for c in cmd if c != "--use_fast_math"]  # IEEE arithmetic: parity with the reference matters more than a few percent
+    # (no --use_fast_math: IEEE arithmetic -- parity with the reference matters more than a few percent)
     for macro in ("JIC_PUSH_THREADS", "JIC_PUSH_MINBLOCKS", "JIC_PUSH_THREADS_F32", "JIC_PUSH_MINBLOCKS_F32", "JIC_PUSH_STAGES", "JIC_PUSH_STAGES_F32", "JIC_PUSH_STAGE_BLOCKS", "JIC_PUSH_STAGE_BLOCKS_F32", "JIC_PUSH_RUN", "JIC_ITEMS_PER_WARP", "JIC_TAIL_SPLIT", "JIC_MAX_CHUNK"):  # tuning knobs of the binned push kernel
         val = (defines or {}).get(macro, os.environ.get(macro))
         if val is not None and val != "":

@@ -97,11 +97,26 @@ struct __align__(16) DestSlot {
   int bin;        // range index (2 * bin + half)
 };
 
+// Packed fp32 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 work on two floats in a 64-bit register pair and take ONE issue slot): the fp32
+// push is bound by instruction issue, and a lane carries two independent particles through phases B-C (push_stage_blocks = 2), so
+// their arithmetic pairs up.  Same IEEE roundings as the scalar instructions: results are bit-identical to the scalar path.
+#ifndef JIC_PUSH_F32X2
+#define JIC_PUSH_F32X2 1
+#endif
+struct F32x2 { unsigned long long u; };
+__device__ __forceinline__ F32x2 pk2(float lo, float hi) { F32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(F32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.u)); }
+__device__ __forceinline__ F32x2 fma2(F32x2 a, F32x2 b, F32x2 c) { F32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u)); return r; }
+__device__ __forceinline__ F32x2 add2(F32x2 a, F32x2 b) { F32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
+__device__ __forceinline__ F32x2 mul2(F32x2 a, F32x2 b) { F32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u)); return r; }
+template <typename R> struct PushWarpPacked {};                      // (empty base: the fp64 layout is untouched)
+template <> struct PushWarpPacked<float> { F32x2 coefp[24]; };       // coef[] with every value duplicated into both halves
+
 // one warp's shared memory
 constexpr int kPoolCap = 64;   // processed stayers waiting to fill holes (< 32 triggers a donor block, which adds at most 32)
 constexpr int kMixCap = 128;   // ring of movers: 32 frozen (claimed, not yet written) + up to 63 collecting
 template <typename R>
-struct __align__(128) PushWarpSmem {
+struct __align__(128) PushWarpSmem : PushWarpPacked<R> {
   R ring[push_stages<R>()][push_stage_blocks<R>()][kBlkElems];  // input: work-item blocks on their way in
   R pool[4][kPoolCap];                               // d, v_x, v_y, v_z of pooled stayers (a stack)
   R mix[4][kMixCap];                                 // t_new (unshifted), v_x, v_y, v_z of movers (a ring)
@@ -125,6 +140,7 @@ template <typename R, bool REL, bool STAG>
 __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p, const __grid_constant__ BinDev<R> bd,
                                                                        const R* __restrict__ F, R* __restrict__ acc, RunControl* __restrict__ ctl) {
   constexpr int NS = push_stages<R>(), KB = push_stage_blocks<R>(), RUN = kPushRun;
+  constexpr bool PACK = JIC_PUSH_F32X2 && std::is_same<R, float>::value && KB == 2 && !REL && !STAG;
   if (threadIdx.x == 0) atomicMin(&ctl->push_t0, global_timer_ns());
   constexpr unsigned kBlockBytes = kBlkElems * sizeof(R);
   constexpr unsigned FULL = 0xffffffffu;
@@ -209,6 +225,7 @@ __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p
         val *= hs;
       }
       sm.coef[lane] = val;
+      if constexpr (PACK) sm.coefp[lane] = pk2(val, val);
     } else if (lane < 27) {
       const int k = lane - 24;
       const int bk = k == 0 ? b : (k == 1 ? s * G + (c == 0 ? G - 1 : c - 1) : s * G + (c == G - 1 ? 0 : c + 1));
@@ -318,6 +335,36 @@ __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p
       __syncwarp();  // every lane has taken its particles: the ring slot can be refilled
       if (lane == 0 && g + NS < ngroups) load_group(g + NS);
       // ---- B. gather (quadratics in d), velocity update, move
+      if constexpr (PACK) {
+        // the two particles of the lane side by side in 64-bit registers; the same operations in the same order as the loop below
+        const F32x2* cp = sm.coefp;
+        const int hi0 = d[0] >= R(0) ? 3 : 2, hi1 = d[1] >= R(0) ? 3 : 2;
+        const F32x2 D = pk2(d[0], d[1]), NEG1 = pk2(-1.f, -1.f);
+        F32x2 E2[3], B2[3], nB2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          E2[k] = fma2(fma2(pk2(coef[8 * k + hi0], coef[8 * k + hi1]), D, cp[8 * k + 1]), D, cp[8 * k]);
+          B2[k] = fma2(fma2(cp[8 * k + 6], D, cp[8 * k + 5]), D, cp[8 * k + 4]);
+          nB2[k] = mul2(B2[k], NEG1);
+        }
+        const F32x2 vm0 = add2(pk2(v[0][0], v[1][0]), E2[0]), vm1 = add2(pk2(v[0][1], v[1][1]), E2[1]), vm2 = add2(pk2(v[0][2], v[1][2]), E2[2]);
+        const F32x2 R0 = fma2(vm1, B2[2], fma2(vm2, nB2[1], vm0)), R1 = fma2(vm2, B2[0], fma2(vm0, nB2[2], vm1)),
+                    R2 = fma2(vm0, B2[1], fma2(vm1, nB2[0], vm2));
+        const F32x2 Rt = fma2(R0, B2[0], fma2(R1, B2[1], mul2(R2, B2[2])));
+        const F32x2 den = fma2(B2[0], B2[0], fma2(B2[1], B2[1], fma2(B2[2], B2[2], pk2(1.f, 1.f))));
+        float den0, den1;
+        unpk2(den, den0, den1);
+        const F32x2 inv = pk2(rcp_fast(den0), rcp_fast(den1));
+        const F32x2 V0 = fma2(fma2(R1, B2[2], fma2(R2, nB2[1], fma2(Rt, B2[0], R0))), inv, E2[0]);
+        const F32x2 V1 = fma2(fma2(R2, B2[0], fma2(R0, nB2[2], fma2(Rt, B2[1], R1))), inv, E2[1]);
+        const F32x2 V2 = fma2(fma2(R0, B2[1], fma2(R1, nB2[0], fma2(Rt, B2[2], R2))), inv, E2[2]);
+        const F32x2 U = mul2(V0, pk2(cells_per_v, cells_per_v));
+        const F32x2 TN = add2(D, U), TM = fma2(pk2(0.5f, 0.5f), U, D);
+        unpk2(V0, v[0][0], v[1][0]); unpk2(V1, v[0][1], v[1][1]); unpk2(V2, v[0][2], v[1][2]);
+        unpk2(U, u[0], u[1]); unpk2(TN, tn[0], tn[1]); unpk2(TM, tm[0], tm[1]);
+        fast[0] = fast_bin && (fabs(tn[0]) < R(1.5));
+        fast[1] = fast_bin && (fabs(tn[1]) < R(1.5));
+      } else {
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         R E[3], B[3];
@@ -346,6 +393,7 @@ __global__ void JIC_PUSH_BOUNDS(R) k_push(const __grid_constant__ DevParams<R> p
         tm[kb] = fma(R(0.5), u[kb], d[kb]);
         fast[kb] = fast_bin && (fabs(tn[kb]) < R(1.5));
         if (STAG) fast[kb] = fast[kb] && (fabs(ts[kb]) < R(1.5));
+      }
       }
       // ---- C. deposit moments
       auto moments = [&](int kb) {
