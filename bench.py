@@ -551,6 +551,21 @@ def main():
                        f"histories, on an existing context; second of two identical passes (the first one creates the staging buffers)"}
         ok2 = bool(torch.isfinite(host_out["electric_field"][-1]).all().item())
         energy_ok = energy_ok and ok2
+        # what the link gives: one plain pinned -> device copy of the same x0 buffer, device-timed (the denominator of the upload time)
+        sink = torch.empty((N, 3), dtype=dtype, device=device)
+        sink.copy_(hx, non_blocking=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        sink.copy_(hx, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link = N * 3 * es / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        e2e["h2d_link_gbs_measured"] = link
+        e2e["upload_gbs_achieved"] = N * 6 * es / (t1 - t0) / 1e9
+        e2e["upload_note"] = ("upload_and_start_up moves x0,v0 at upload_gbs_achieved against h2d_link_gbs_measured for a bare cudaMemcpyAsync of "
+                              "the same pinned buffer on this box; the rest of it is the start-up kernel of the last chunk and the first field solve")
+        del sink
         del hx, hv, host_out, dev_out
     # ---- sustained: the same K-step replay repeated until the board has been under load for a while (power cap, clocks settle)
     sustained = None
