@@ -554,6 +554,59 @@ __global__ void __launch_bounds__(256) k_scatter_binned(const DevParams<R> p, co
   }
 }
 
+// The same scatter in two passes (large runs).  k_scatter_binned writes four 8-byte words per particle into four different 32-byte
+// sectors of a random block: every one of them is a partial-sector write that the memory system turns into a read-modify-write
+// (10.6 ms per 1e8 particles, 3x the time of the rest of the data movement of the start-up).  Here pass 1 writes ONE whole sector per
+// particle -- the record (d, v_x, v_y, v_z) at its final slot number in a temporary array-of-records -- and pass 2 streams each range's
+// records back (coalesced) and writes the blocks' rows (coalesced).  Slot order inside a bin differs from run to run either way (cursor
+// atomics); the sums the push forms over a bin do not depend on it beyond rounding.
+template <typename R>
+struct alignas(4 * sizeof(R)) BinRecord { R d, vx, vy, vz; };
+
+// The temporary lives in memory the store already owns: buffer 1 is the start-up's staging area (four linear arrays of cap_total reals of
+// which the first N are used), so each array has a free tail.  The record array is cut into four pieces, one per tail (the last one
+// shorter: the bin indices of the staging area sit at its end).  No allocation on the start-up path.
+template <typename R>
+struct RecordPieces {
+  BinRecord<R>* piece[4];
+  long long len012, len3;  // records per piece
+  __host__ __device__ long long capacity() const { return 3 * len012 + len3; }
+  __device__ __forceinline__ BinRecord<R>* at(long long k) const {
+    const int p = (k >= len012) + (k >= 2 * len012) + (k >= 3 * len012);
+    return piece[p] + (k - p * len012);
+  }
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_scatter_records(const DevParams<R> p, const BinDev<R> bd, const R* __restrict__ st_x,
+                                                         const R* __restrict__ st_vx, const R* __restrict__ st_vy, const R* __restrict__ st_vz,
+                                                         const int* __restrict__ st_bin, const RecordPieces<R> tmp) {
+  const long long tmp_n = tmp.capacity();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.N; i += (long long)gridDim.x * blockDim.x) {
+    const int b = st_bin[i];
+    if (b < 0) continue;
+    const int c = b % p.G;
+    const unsigned slot = atomicAdd(&bd.cur[0][2 * b], 1u);
+    const long long k = bd.off[0][2 * b] + slot;
+    const R d = (st_x[i] - node_pos(c, p)) * p.inv_dx;
+    if (k < bd.off[0][2 * b + 1] && k < tmp_n) *tmp.at(k) = BinRecord<R>{d, st_vx[i], st_vy[i], st_vz[i]};
+    else atomicExch(&bd.hdr->error, 2);  // (cannot happen: k_first_layout sized the ranges from the same histogram)
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_records_to_blocks(const BinDev<R> bd, const RecordPieces<R> tmp) {
+  // one warp per block of 32 slots, over all blocks of the first layout; slots past a range's population were preset to NaN (= holes)
+  const int lane = threadIdx.x & 31;
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_blocks = bd.off[0][2 * bd.nb] >> 5;
+  for (long long blk = w; blk < n_blocks; blk += nw) {
+    const BinRecord<R> rec = *tmp.at(blk * kBlk + lane);
+    R* q = bd.rec[0] + blk * (long long)kBlkElems + lane;
+    q[0] = rec.d; q[kBlk] = rec.vx; q[2 * kBlk] = rec.vy; q[3 * kBlk] = rec.vz;
+  }
+}
+
 // export / diagnostics over the current source buffer (holes, d = NaN, are skipped) ------------------------------
 // live particles per range: one warp per range
 template <typename R>
@@ -772,13 +825,39 @@ struct BinnedStore {
   // initial binning: staging (in buffer 1, which is free until the first push) -> histogram -> exact layout -> scatter.
   // Three parts, so that a pipelined host upload can feed the first kernel chunk by chunk.
   int* st_bin = nullptr;
+  bool st_bin_owned = false;      // st_bin came from cudaMallocAsync (the free tail of buffer 1 was too short)
+  RecordPieces<R> st_records{};   // capacity() == 0: one-pass scatter
   int start_begin(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
     cudaMemsetAsync(bd.hdr, 0, sizeof(PlanHeader), st);
     cudaMemsetAsync(bd.cur[0], 0, sizeof(unsigned) * 2 * bd.nb, st);
     cudaMemsetAsync(bd.slow0, 0, sizeof(unsigned) * bd.nb, st);
+    // scratch of the start-up inside buffer 1: [array a: N staged reals | free tail], a = 0..3; the bin indices go to the end of the last
+    // tail, the record pieces of the two-pass scatter to the (aligned) starts of the four tails
+    const long long free_tail = bd.cap_total - dp.N;  // reals per array
+    const long long bin_reals = ((long long)sizeof(int) * dp.N + sizeof(R) - 1) / (long long)sizeof(R) + 8;
+    R* const stage = bd.rec[1];
     st_bin = nullptr;
-    cudaError_t ce = cudaMallocAsync((void**)&st_bin, sizeof(int) * (size_t)(dp.N ? dp.N : 1), st);
-    if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("staging allocation: %s", cudaGetErrorString(ce)));
+    st_bin_owned = false;
+    st_records = RecordPieces<R>{};
+    if (free_tail >= bin_reals + 8) {
+      uintptr_t a = (uintptr_t)(stage + 4 * bd.cap_total - bin_reals);
+      st_bin = (int*)((a + 15) & ~(uintptr_t)15);
+      const char* env = getenv("JIC_SCATTER_RECORDS");  // 0: never, 1 (default): from 2^20 particles up, 2: whenever the tails hold it
+      const int mode = env ? atoi(env) : 1;
+      const long long len012 = (free_tail - 8) / 4, len3 = (free_tail - bin_reals - 16) / 4;
+      const long long need = dp.N + 32ll * bd.nb + 32;  // ranges are padded to whole blocks: at most 31 more slots per block range
+      if ((mode == 2 || (mode == 1 && dp.N >= (1ll << 20))) && len3 > 0 && 3 * len012 + len3 >= need) {
+        for (int a4 = 0; a4 < 4; ++a4) {
+          const uintptr_t b = (uintptr_t)(stage + a4 * bd.cap_total + dp.N), al = 4 * sizeof(R);
+          st_records.piece[a4] = (BinRecord<R>*)((b + al - 1) / al * al);
+        }
+        st_records.len012 = len012; st_records.len3 = len3;
+      }
+    } else {
+      cudaError_t ce = cudaMallocAsync((void**)&st_bin, sizeof(int) * (size_t)(dp.N ? dp.N : 1), st);
+      if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("staging allocation: %s", cudaGetErrorString(ce)));
+      st_bin_owned = true;
+    }
     return JIC_OK;
   }
   int start_chunk(Engine& e, const DevParams<R>& dp, const R* x0, const R* v0, long long i0, long long n, R* acc, cudaStream_t st) {
@@ -791,9 +870,19 @@ struct BinnedStore {
   int start_end(Engine& e, const DevParams<R>& dp, cudaStream_t st) {
     R* sx = bd.rec[1]; R* svx = sx + bd.cap_total; R* svy = svx + bd.cap_total; R* svz = svy + bd.cap_total;
     k_first_layout<R><<<1, 1024, 0, st>>>(bd);
-    k_scatter_binned<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, bd, sx, svx, svy, svz, st_bin);
-    cudaFreeAsync(st_bin, st);
+    if (st_records.capacity() > 0) {
+      // two-pass scatter through whole-sector records (see k_scatter_records); all-ones words are NaNs: unclaimed slots read back as holes
+      for (int a4 = 0; a4 < 4; ++a4)
+        cudaMemsetAsync(st_records.piece[a4], 0xFF, sizeof(BinRecord<R>) * (size_t)(a4 < 3 ? st_records.len012 : st_records.len3), st);
+      k_scatter_records<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, bd, sx, svx, svy, svz, st_bin, st_records);
+      k_records_to_blocks<R><<<grid_for(dp.N + 32ll * bd.nb + 32, 256, 8), 256, 0, st>>>(bd, st_records);
+      e.launches += 1;
+    } else {
+      k_scatter_binned<R><<<grid_for(dp.N, 256, 8), 256, 0, st>>>(dp, bd, sx, svx, svy, svz, st_bin);
+    }
+    if (st_bin_owned) cudaFreeAsync(st_bin, st);
     st_bin = nullptr;
+    st_bin_owned = false;
     e.launches += 2;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("binned start: %s", cudaGetErrorString(ce)));

@@ -216,9 +216,13 @@ def _sorted_particles(x, v, alive):
     return x[order, 0], v[order]
 
 
+@pytest.mark.parametrize("scatter", ["one_pass", "records"])
 @pytest.mark.parametrize("bcs", [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2), (1, 2, 1, 2), (2, 0, 2, 0)])
-def test_binned_engine_all_boundaries(bcs):
-    """Cell-binned store (fast path + general path in wall cells + re-binning) against the oracle, fields AND particles."""
+def test_binned_engine_all_boundaries(bcs, scatter, monkeypatch):
+    """Cell-binned store (fast path + general path in wall cells + re-binning) against the oracle, fields AND particles.
+    scatter: the start-up's way into the bins -- the one-pass kernel (default below 2^20 particles) or the two-pass one through
+    whole-sector records (default above; forced here)."""
+    monkeypatch.setenv("JIC_SCATTER_RECORDS", "2" if scatter == "records" else "0")
     G, length, T = 24, 0.01, 30
     p = two_species(3000, 3000, length=length, G=G, seed=41, vth_e=0.3, vth_yz=0.2, drift=5e7, plus_minus=True, gpdl=0.5)
     dt = cfl_dt(length, G, 0.9)
