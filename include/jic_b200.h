@@ -198,6 +198,11 @@ int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, 
  * Crank-Nicolson contexts (no binned store): out[0] = 1 when the context runs the cell-sorted push (csrc/jic_cn_sorted.cuh; contexts of
  * at least JIC_CN_SORTED_MIN particles, an environment variable read at creation, default 200000), 0 for the unsorted one; the rest 0. */
 int jic_store_stats(jic_context* ctx, int64_t out[8], void* stream);
+/* The large device buffers of a context (>= 32 MiB each: particle stores, per-particle arrays, upload staging) come from a stream-ordered
+ * memory pool the library owns, one per device, which keeps freed memory so that the next context of the process does not pay
+ * cudaMalloc / cudaFree again (28 ms per 1e8-particle context).  jic_trim_memory hands everything the pools hold and nobody uses back to
+ * the driver.  Environment JIC_POOL=0: no pool, plain cudaMalloc / cudaFree. */
+void jic_trim_memory(void);
 /* Number of kernel launches issued by this context so far (for the bench's gpu_launches figure). */
 int64_t jic_launch_count(const jic_context* ctx);
 

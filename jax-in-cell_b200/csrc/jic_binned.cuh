@@ -747,11 +747,11 @@ struct BinnedStore {
   bool built = false;
 
   template <typename T>
-  int alloc(Engine& e, T** ptr, size_t n) {
+  int alloc(Engine& e, T** ptr, size_t n, bool zero = true) {
     void* p = nullptr;
-    cudaError_t ce = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    cudaError_t ce = DevicePool::get().malloc(&p, (n ? n : 1) * sizeof(T));
     if (ce != cudaSuccess) return e.fail(JIC_ERR_CUDA, format("cudaMalloc(%zu bytes) for the particle bins: %s", n * sizeof(T), cudaGetErrorString(ce)));
-    cudaMemset(p, 0, (n ? n : 1) * sizeof(T));
+    if (zero) cudaMemset(p, 0, (n ? n : 1) * sizeof(T));
     owned.push_back(p);
     *ptr = (T*)p;
     return JIC_OK;
@@ -812,7 +812,7 @@ struct BinnedStore {
   }
 
   void destroy() {
-    for (void* p : owned) cudaFree(p);
+    for (void* p : owned) DevicePool::get().free(p);  // (the engine's destructor has synchronised the device)
     owned.clear();
   }
 

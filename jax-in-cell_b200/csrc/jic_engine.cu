@@ -127,7 +127,7 @@ struct EngineT : Engine {
 
   template <typename T>
   int alloc(T** p, size_t n) {
-    JIC_CUDA(cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)));
+    JIC_CUDA(DevicePool::get().malloc((void**)p, (n ? n : 1) * sizeof(T)));
     JIC_CUDA(cudaMemset(*p, 0, (n ? n : 1) * sizeof(T)));
     return JIC_OK;
   }
@@ -288,12 +288,13 @@ struct EngineT : Engine {
       cudaDeviceSynchronize();
       for (int r = 0; r < world; ++r) if (r != rank && peer_block[r]) cudaIpcCloseMemHandle(peer_block[r]);
     }
-    for (R* b : hstage) if (b) cudaFree(b);
+    cudaDeviceSynchronize();  // pooled buffers are freed stream-ordered: nothing of this context may still be running
+    for (R* b : hstage) if (b) DevicePool::get().free(b);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (int k = 0; k < 2; ++k) { if (ev_copied[k]) cudaEventDestroy(ev_copied[k]); if (ev_used[k]) cudaEventDestroy(ev_used[k]); }
-    for (int k = 0; k < 2; ++k) { void* q[] = {cn_s[k].x, cn_s[k].y, cn_s[k].z, cn_s[k].vx, cn_s[k].vy, cn_s[k].vz}; for (void* p : q) if (p) cudaFree(p); }
+    for (int k = 0; k < 2; ++k) { void* q[] = {cn_s[k].x, cn_s[k].y, cn_s[k].z, cn_s[k].vx, cn_s[k].vy, cn_s[k].vz}; for (void* p : q) if (p) DevicePool::get().free(p); }
     void* ptrs[] = {cn_EB, cn_perm, cn_perm2, cn_sp, cn_sp2, cn_alive2, cn_hist, cn_off, cn_alive, cn_stag, cn_Eg, cn_Bnext, cn_Eavg, cn_Bavg, cn_ctl, xh, yh, zh, vx, vy, vz, v_init, shared_block, F, E, B, E2, B2, E_int, B_int, J, rho, extE, extB, s0, s1, E0, B0, ctl, mc_done, gauss_h, ExC};
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) if (p) DevicePool::get().free(p);
     bins.destroy();
     if (comm && !comm_shared && nccl_api().CommDestroy) nccl_api().CommDestroy(comm);
     if (caller_device >= 0 && caller_device != device) cudaSetDevice(caller_device);
@@ -475,8 +476,8 @@ struct EngineT : Engine {
     if (const char* env = getenv("JIC_HOST_CHUNK")) chunk = std::max(1ll, atoll(env));
     chunk = std::min(chunk, dp.N);
     if (hstage_n < chunk) {
-      for (R*& b : hstage) { if (b) cudaFree(b); b = nullptr; }
-      for (R*& b : hstage) JIC_CUDA(cudaMalloc((void**)&b, (size_t)chunk * 3 * sizeof(R)));
+      for (R*& b : hstage) { if (b) { cudaDeviceSynchronize(); DevicePool::get().free(b); } b = nullptr; }
+      for (R*& b : hstage) JIC_CUDA(DevicePool::get().malloc((void**)&b, (size_t)chunk * 3 * sizeof(R)));
       hstage_n = chunk;
     }
     if (!copy_stream) {
@@ -1142,6 +1143,7 @@ int jic_push_kernel_time(jic_context* ctx, double* ms_sum, int64_t* n_launches, 
   if (n_launches) *n_launches = n;
   return rc;
 }
+void jic_trim_memory(void) { DevicePool::get().trim(); }
 int jic_store_stats(jic_context* ctx, int64_t out[8], void* st) {
   CTX_OR_FAIL(ctx);
   long long tmp[8] = {0};

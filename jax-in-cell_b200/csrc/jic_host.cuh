@@ -4,7 +4,10 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/jic_b200.h"
 
@@ -26,6 +29,69 @@ inline std::string format(const char* fmt, ...) {
     cudaError_t _e = (expr);                                                                             \
     if (_e != cudaSuccess) return fail(JIC_ERR_CUDA, format("%s -> %s", #expr, cudaGetErrorString(_e))); \
   } while (0)
+
+// Device memory of the large buffers (particle stores, per-particle arrays).  cudaMalloc / cudaFree of 17 GB cost ~8 ms and ~20 ms per
+// context at 1e8 particles -- a third of a 20-step Simulation.run().  They come from a library-owned stream-ordered memory pool per
+// device instead, whose release threshold keeps freed memory in the pool: the next context of the process gets it back at once.
+// jic_trim_memory() hands it back to the driver; JIC_POOL=0 switches the pool off.  Small buffers, and the block other ranks map
+// through CUDA IPC, stay with cudaMalloc.
+struct DevicePool {
+  static constexpr size_t kMinBytes = 32u << 20;
+  std::mutex mu;
+  std::unordered_map<int, cudaMemPool_t> pools;      // device -> pool
+  std::unordered_map<void*, int> owned;              // pointer -> device
+  bool enabled() const { const char* v = getenv("JIC_POOL"); return !(v && atoi(v) == 0); }
+  static DevicePool& get() { static DevicePool p; return p; }
+  cudaError_t malloc(void** ptr, size_t bytes) {
+    if (bytes >= kMinBytes && enabled()) {
+      std::lock_guard<std::mutex> lock(mu);
+      int dev = 0;
+      cudaGetDevice(&dev);
+      auto it = pools.find(dev);
+      if (it == pools.end()) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+          it = pools.emplace(dev, pool).first;
+        } else {
+          (void)cudaGetLastError();
+        }
+      }
+      if (it != pools.end()) {
+        cudaError_t e = cudaMallocFromPoolAsync(ptr, bytes, it->second, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);  // from here on the memory is good on every stream
+        if (e == cudaSuccess) { owned[*ptr] = dev; return cudaSuccess; }
+        (void)cudaGetLastError();
+        cudaMemPoolTrimTo(it->second, 0);  // out of memory with a full pool: give it back and take the plain road
+      }
+    }
+    return cudaMalloc(ptr, bytes);
+  }
+  // the caller has synchronised the work that used `ptr`
+  void free(void* ptr) {
+    if (!ptr) return;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      auto it = owned.find(ptr);
+      if (it != owned.end()) {
+        owned.erase(it);
+        cudaFreeAsync(ptr, cudaStreamPerThread);
+        return;
+      }
+    }
+    cudaFree(ptr);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lock(mu);
+    cudaStreamSynchronize(cudaStreamPerThread);
+    for (auto& kv : pools) cudaMemPoolTrimTo(kv.second, 0);
+  }
+};
 
 struct Engine {
   virtual ~Engine() {}

@@ -266,6 +266,11 @@ class HotPath:
             pass
 
 
+def trim_memory():
+    """Hand the device memory that the library's pools keep for the next context back to the driver (jic_trim_memory)."""
+    _lib.load().jic_trim_memory()
+
+
 def sample_particles(species_sampling, box_size, *, dtype=torch.float64, device=None, threefry_partitionable=True, rank=0, world=1):
     """jic_sample_particles[_slice]: initial (x0, v0) device tensors from the reference's formulas and jax.random's streams
     (jaxincell/_state_initialization.py:51-85).  `species_sampling`: dicts with count, seed_position, seed_velocity and per-axis

@@ -75,6 +75,7 @@ SYMBOLS = [
     ("jic_check_status", C.c_int, [_P, _P]),
     ("jic_push_kernel_time", C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32, _P]),
     ("jic_store_stats", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
+    ("jic_trim_memory", None, []),
     ("jic_launch_count", C.c_int64, [_P]),
     ("jic_sample_particles", C.c_int, [C.c_int32, C.c_int32, C.POINTER(SpeciesSampling), C.POINTER(C.c_double), C.c_int32, _P, _P, _P]),
     ("jic_sample_particles_slice", C.c_int, [C.c_int32, C.c_int32, C.POINTER(SpeciesSampling), C.POINTER(C.c_int64), C.POINTER(C.c_int64),

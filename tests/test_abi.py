@@ -22,7 +22,7 @@ def lib():
 
 def test_header_symbols_are_exported_and_bound(lib):
     header = open(os.path.join(ROOT, "include", "jic_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(jic_[a-z_0-9]+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|void|const char\*)\s+(jic_[a-z_0-9]+)\s*\(", header, flags=re.M))
     assert len(declared) >= 14
     bound = {name for name, _, _ in lib.SYMBOLS}
     assert declared == bound, declared ^ bound

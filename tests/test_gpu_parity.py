@@ -410,3 +410,31 @@ def test_all_particles_in_one_cell_binned():
     assert_parity(got, ref, FIELD_KEYS, 1e-5)
     x, v, alive = (t.cpu().numpy() for t in got["hp"].particles())
     assert int(alive.sum()) == 10000
+
+
+def test_device_memory_pool_keeps_freed_buffers_until_trimmed():
+    """The large buffers of a context come from a library-owned memory pool that keeps them after jic_destroy (the next context of the
+    process starts without cudaMalloc); jic_trim_memory hands them back."""
+    from jaxincell_b200 import HotPath, trim_memory
+    trim_memory()
+    G, length = 256, 0.01
+    p = two_species(1_000_000, 1_000_000, length=length, G=G, seed=3, vth_e=0.05, vth_yz=0.01, drift=3e7, plus_minus=True, gpdl=0.5)
+    dt = cfl_dt(length, G, 0.9)
+    x0, v0 = torch.as_tensor(p["x0"], device="cuda"), torch.as_tensor(p["v0"], device="cuda")
+    torch.cuda.synchronize()
+    free_before = torch.cuda.mem_get_info()[0]
+    fields = []
+    for _ in range(2):  # the second context runs on recycled memory: same result
+        hp = HotPath(species=p["species"], length=length, G=G, dt=dt, engine="binned")
+        hp.set_external_fields(None, None)
+        hp.initialize(x0, v0)
+        fields.append(hp.run(3)["electric_field"].cpu().numpy())
+        hp.check_status()
+        hp.close()
+    torch.cuda.synchronize()
+    kept = free_before - torch.cuda.mem_get_info()[0]
+    assert kept > 100 << 20, kept          # 2 x 2.25 x 2e6 slots x 32 B of particle store stay with the pool
+    trim_memory()
+    assert free_before - torch.cuda.mem_get_info()[0] < 32 << 20
+    scale = np.abs(fields[0]).max()
+    assert np.abs(fields[1] - fields[0]).max() < 1e-9 * scale
