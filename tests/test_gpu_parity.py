@@ -254,7 +254,8 @@ def test_binned_engine_large_cfl_multi_cell_jumps():
     assert_parity(got, ref, FIELD_KEYS, 1e-5)
 
 
-def test_binned_engine_relativistic_and_fp32():
+def test_binned_engine_relativistic_and_fp32(monkeypatch):
+    monkeypatch.setenv("JIC_SCATTER_RECORDS", "2")  # (the two-pass start-up scatter with 16-byte records in the fp32 leg)
     G, length, T = 32, 0.02, 25
     p = two_species(4000, 4000, length=length, G=G, seed=31, vth_e=0.4, vth_yz=0.2, gpdl=0.5)
     speed = np.linalg.norm(p["v0"], axis=1, keepdims=True)
