@@ -26,6 +26,10 @@ constexpr int kCnWin = JIC_CN_WIN;   // nodes per warp window: a warp whose part
                                      // moves less than a cell per step: the Picard iteration needs c dt <= dx)
 constexpr int kCnWinComps = 4;       // J_x, J_y, J_z, rho
 constexpr int kCnColStride = 32;     // a row (node, component) holds one real per lane: the bank of an element depends on the lane alone
+#ifndef JIC_CN_PER_LANE
+#define JIC_CN_PER_LANE 8
+#endif
+constexpr int kCnPerLane = JIC_CN_PER_LANE;  // consecutive 32-particle groups a warp runs through one window (zeroed and summed once)
 #ifndef JIC_CN_SORTED_THREADS
 #define JIC_CN_SORTED_THREADS 128
 #endif
@@ -177,32 +181,14 @@ __global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_c
   const R e_start = p.g0 + p.half_dx;  // _algorithms.py:110 (the B faces, :111, are the E faces shifted by one node: table EB)
   const R w_sub = dtau / p.dt;
   const GlobalGrid<R> grid{acc};
-  for (long long i0 = (blockIdx.x * (long long)blockDim.x + warp * 32); i0 < p.N; i0 += (long long)gridDim.x * blockDim.x) {
-    const long long i = i0 + lane;
-    const bool have = i < p.N;
-    // zero the window (the warp together, 16 bytes per lane and store); find its first node: three left of the warp's lowest cell
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5), warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  constexpr long long kChunk = 32ll * kCnPerLane;  // particles per warp and window pass
+  for (long long i0 = warp_global * kChunk; i0 < p.N; i0 += warps_total * kChunk) {
+    // zero the window (the warp together, 16 bytes per lane and store)
 #pragma unroll
     for (int t = 0; t < kRows * kCnColStride / 64; ++t) win2[t * 32 + lane] = R2{R(0), R(0)};
-    R pos[3] = {R(0), R(0), R(0)}, vel[3] = {R(0), R(0), R(0)};
-    int c0 = 0x3fffffff;
-    R xs = R(0);
-    if (have) {
-      pos[0] = cur.x[i]; pos[1] = cur.y[i]; pos[2] = cur.z[i];
-      vel[0] = cur.vx[i]; vel[1] = cur.vy[i]; vel[2] = cur.vz[i];
-      xs = it == 0 ? pos[0] : stag[i];
-      c0 = cn_cell(pos[0], p);
-    }
-    const int base = __reduce_min_sync(0xffffffffu, c0) - 3;
-    __syncwarp();
-    {  // the next chunk of this warp: its state, staggered positions and bytes on their way while this one is computed
-      const long long in = i + (long long)gridDim.x * blockDim.x;
-      if (in < p.N) {
-        cn_prefetch(cur.x + in); cn_prefetch(cur.y + in); cn_prefetch(cur.z + in);
-        cn_prefetch(cur.vx + in); cn_prefetch(cur.vy + in); cn_prefetch(cur.vz + in);
-        if (it != 0) for (int s = 0; s < n_sub; ++s) cn_prefetch(stag + (size_t)s * p.N + in);
-        if ((lane & 7) == 0) { cn_prefetch(sp_of + in); cn_prefetch(alive + in); }
-      }
-    }
+    int base = 0;  // first node of the window: three left of the lowest cell of the chunk's first 32 particles (the order is ascending;
+                   // whatever falls outside the window -- stale order, sparse cells -- takes the direct path)
     // add w3[j] * (a0, a1, a2) to J (with_j) or w3[j] * a0 to rho on nodes k-1, k, k+1 (UNWRAPPED index k; idx = the wrapped ones)
     auto deposit3 = [&](int k, const R w3[3], const int idx[3], R a0, R a1, R a2, bool with_j) {
       const int rel0 = k - 1 - base;
@@ -229,6 +215,32 @@ __global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_c
         }
       }
     };
+    for (int h = 0; h < kCnPerLane; ++h) {
+    if (i0 + 32ll * h >= p.N) break;  // (warp-uniform)
+    const long long i = i0 + 32ll * h + lane;
+    const bool have = i < p.N;
+    R pos[3] = {R(0), R(0), R(0)}, vel[3] = {R(0), R(0), R(0)};
+    int c0 = 0x3fffffff;
+    R xs = R(0);
+    if (have) {
+      pos[0] = cur.x[i]; pos[1] = cur.y[i]; pos[2] = cur.z[i];
+      vel[0] = cur.vx[i]; vel[1] = cur.vy[i]; vel[2] = cur.vz[i];
+      xs = it == 0 ? pos[0] : stag[i];
+      c0 = cn_cell(pos[0], p);
+    }
+    if (h == 0) {
+      base = __reduce_min_sync(0xffffffffu, c0) - 3;
+      __syncwarp();  // (the window is zero for every lane from here on)
+    }
+    {  // what this warp reads next -- the chunk's next 32 particles, or the first 32 of its next chunk -- on its way meanwhile
+      const long long in = h + 1 < kCnPerLane ? i + 32 : i0 + warps_total * kChunk + lane;
+      if (in < p.N) {
+        cn_prefetch(cur.x + in); cn_prefetch(cur.y + in); cn_prefetch(cur.z + in);
+        cn_prefetch(cur.vx + in); cn_prefetch(cur.vy + in); cn_prefetch(cur.vz + in);
+        if (it != 0) for (int s = 0; s < n_sub; ++s) cn_prefetch(stag + (size_t)s * p.N + in);
+        if ((lane & 7) == 0) { cn_prefetch(sp_of + in); cn_prefetch(alive + in); }
+      }
+    }
     if (have) {
       const int sp = sp_of[i];
       const bool live = alive[i] != 0;
@@ -280,6 +292,7 @@ __global__ void __launch_bounds__(kCnSortedThreads, JIC_CN_SORTED_MINBLOCKS) k_c
         deposit_cloud(grid, cl, p.G, R(0), R(0), ar, false);
       }
     }
+    }  // h
     __syncwarp();
     // lane l sums row l (node l / 4, component l % 4) over the 32 columns, two at a time; the XOR with the lane spreads the lanes of
     // a quarter warp over the eight 16-byte bank groups
