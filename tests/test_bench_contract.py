@@ -29,3 +29,15 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
                          capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip() == ""
+
+
+def test_the_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: on a machine without a CUDA device the product arm stops with a message and prints no result line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("needs a machine without a GPU")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode != 0
+    assert res.stdout.strip() == ""
+    assert "GPU" in res.stderr
